@@ -1,0 +1,97 @@
+"""ctypes binding of libdmg_b200.so (the C ABI declared in include/dmg_b200.h).
+
+There is no CPU path and no fallback: if the library is missing or cannot be loaded, importing the
+symbols raises.  The .so is built in-tree by ``deepmusicgeneration_b200.build`` (nvcc, sm_100a).
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+c_i32, c_i64, c_u32, c_u64, c_f32, c_f64, c_vp = C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float, C.c_double, C.c_void_p
+
+ARCH_TXL, ARCH_BERT = 0, 1
+F32, BF16 = 0, 1
+GEMM_AUTO, GEMM_SIMT = 0, 1
+LOGITS_NONE, LOGITS_ALL, LOGITS_LAST = 0, 1, 2
+SAMPLE_EARLY_STOP, SAMPLE_MASK_UNUSED, SAMPLE_REMIX_FILTER = 1, 2, 4
+
+
+class Config(C.Structure):
+    _fields_ = [(n, c_i32) for n in ('arch', 'dtype', 'vocab', 'd_model', 'n_layers', 'n_heads', 'd_head', 'd_inner',
+                                     'mem_len', 'attn_bias', 'encode_position', 'max_batch', 'max_seq', 'max_rows',
+                                     'keep_hidden', 'gemm_backend')] + [('reserved', c_i32 * 4)]
+
+
+class VocabLayout(C.Structure):
+    _fields_ = [(n, c_i32) for n in ('bos', 'pad', 'eos', 'mask', 'ni', 'sep', 'special_lo', 'special_hi', 'note_lo',
+                                     'note_hi', 'dur_lo', 'dur_hi', 'ins_lo', 'ins_hi')]
+
+
+class SamplerParams(C.Structure):
+    _fields_ = [('temperatures', c_f64 * 3), ('min_bars', c_i32), ('top_k', c_i32), ('top_p', c_f32),
+                ('n_words', c_i32), ('allowed_ins_mask', c_u32), ('flags', c_i32), ('seed', c_u64)]
+
+
+# name -> (restype, argtypes): every symbol include/dmg_b200.h declares
+SYMBOLS = {
+    'dmg_last_error': (C.c_char_p, []),
+    'dmg_abi_version': (c_i32, []),
+    'dmg_create': (c_i32, [C.POINTER(Config), c_i32, C.POINTER(c_vp)]),
+    'dmg_destroy': (None, [c_vp]),
+    'dmg_set_weight': (c_i32, [c_vp, C.c_char_p, c_vp, c_i64]),
+    'dmg_get_weight': (c_i32, [c_vp, C.c_char_p, c_vp, c_i64]),
+    'dmg_commit_weights': (c_i32, [c_vp]),
+    'dmg_reset': (c_i32, [c_vp, c_i32]),
+    'dmg_select_hidden': (c_i32, [c_vp, c_vp, c_i32]),
+    'dmg_mem_count': (c_i32, [c_vp]),
+    'dmg_forward': (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    'dmg_get_hidden': (c_i32, [c_vp, c_i32, c_vp, c_vp]),
+    'dmg_sampler_init': (c_i32, [c_vp, C.POINTER(VocabLayout), C.POINTER(SamplerParams), c_vp, c_vp, c_i32]),
+    'dmg_generate': (c_i32, [c_vp, c_i32, c_vp, c_vp]),
+    'dmg_generate_step_host': (c_i32, [c_vp, c_vp, c_vp, c_vp]),
+    'dmg_sample_logits': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, C.POINTER(VocabLayout), C.POINTER(SamplerParams),
+                                  c_u64, c_vp, c_vp, c_vp]),
+    'dmg_device_bytes': (c_i64, [c_vp]),
+    'dmg_launch_count': (c_i64, []),
+    'dmg_uses_tcgen05': (c_i32, [c_vp]),
+    'dmg_gemm_bf16': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+}
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    "Load (building first if the sources changed and nvcc is around) and type every exported symbol."
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not _build.is_current():
+        try:
+            _build.build()
+        except Exception as e:   # no nvcc on the box: use the shipped .so if there is one
+            if not os.path.exists(path):
+                raise RuntimeError(f'libdmg_b200.so is missing and could not be built: {e}') from e
+    if not os.path.exists(path):
+        raise RuntimeError(f'{path} not found: the CUDA extension is required, there is no fallback path')
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)     # AttributeError if the library does not export it
+        fn.restype, fn.argtypes = res, args
+    _LIB = lib
+    return lib
+
+
+class DmgError(RuntimeError):
+    pass
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = load().dmg_last_error()
+        raise DmgError(f'{what}: {msg.decode() if msg else "error"} (rc={rc})')

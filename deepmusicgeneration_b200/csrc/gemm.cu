@@ -1,0 +1,294 @@
+// GEMM kernels: C[M,N] = A[M,K] * W[N,K]^T (+bias)(tanh-GeLU).
+//
+//  * gemm_tc_kernel  - the bf16 product path: TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ->
+//    tcgen05.mma (cta_group::1, M=128) with fp32 accumulators in TMEM -> tcgen05.ld epilogue.
+//    Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator + epilogue, warps 3-5 epilogue.
+//  * gemm_simt_kernel - fp32 parity mode (and a bf16 debugging reference): plain FFMA tiles.
+//
+// Replaces the eager nn.Linear calls of the reference hot path: fastai MultiHeadRelativeAttention.attention /
+// .out / .r_attn, feed_forward's two Linears, LinearDecoder.decoder and
+// q_wgt/k_wgt/v_wgt/r_attn of deep_music_remix.py:2034-2040.
+#include <cuda.h>
+#include <cstdarg>
+#include "kernels.cuh"
+
+namespace dmg {
+
+long long g_launch_count = 0;
+
+// ---------------------------------------------------------------------------------------------
+// SIMT tile GEMM (64x64x16, 256 threads, 4x4 per thread)
+// ---------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W,
+                                                        int ldw, const float* __restrict__ bias, void* __restrict__ C,
+                                                        int ldc, int M, int N, int K, int gelu, int out_bf16) {
+  __shared__ float As[16][68];
+  __shared__ float Ws[16][68];
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+
+  const int lr = t >> 2, lk = (t & 3) * 4;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int k = k0 + lk + i;
+      int ra = m0 + lr, rw = n0 + lr;
+      As[lk + i][lr] = (ra < M && k < K) ? to_f32(A[(size_t)ra * lda + k]) : 0.f;
+      Ws[lk + i][lr] = (rw < N && k < K) ? to_f32(W[(size_t)rw * ldw + k]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; kk++) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = Ws[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int r = m0 + ty * 4 + i;
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      int c = n0 + tx * 4 + j;
+      if (c >= N) continue;
+      float v = acc[i][j] + (bias ? bias[c] : 0.f);
+      if (gelu) v = gelu_tanh(v);
+      if (out_bf16) ((bf16*)C)[(size_t)r * ldc + c] = __float2bfloat16_rn(v);
+      else ((float*)C)[(size_t)r * ldc + c] = v;
+    }
+  }
+}
+
+template <class T>
+int gemm_simt(const T* A, int lda, const T* W, int ldw, const float* bias, void* C, int ldc, int M, int N, int K,
+              int gelu, int out_bf16, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return 0;
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  gemm_simt_kernel<T><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, gelu, out_bf16);
+  g_launch_count++;
+  DMG_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+template int gemm_simt<float>(const float*, int, const float*, int, const float*, void*, int, int, int, int, int, int,
+                              cudaStream_t);
+template int gemm_simt<bf16>(const bf16*, int, const bf16*, int, const float*, void*, int, int, int, int, int, int,
+                             cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------
+// TMA tensor maps (driver entry point fetched through the runtime: no link-time libcuda dependency)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+int make_tmap_bf16(TensorMap2D* out, const void* base, long long cols, long long rows, long long ld, int box_rows) {
+  static_assert(sizeof(CUtensorMap) <= sizeof(TensorMap2D), "CUtensorMap size");
+  PFN_encodeTiled enc = get_encode();
+  DMG_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  DMG_CHECK(cols % 64 == 0, "tensor map: inner dimension %lld is not a multiple of 64", cols);
+  DMG_CHECK(((uintptr_t)base & 15) == 0 && (ld * 2) % 16 == 0, "tensor map: base/stride not 16-byte aligned");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc((CUtensorMap*)out->bytes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                   gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DMG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 GEMM
+// ---------------------------------------------------------------------------------------------
+// K-major operand tile in shared memory written by TMA with 128B swizzle: rows of 128 bytes (64 bf16), 8-row
+// groups 1024 bytes apart (SBO), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BN, int STAGES>
+struct GemmTcSmem {
+  static constexpr int A_BYTES = 128 * 64 * 2;
+  static constexpr int B_BYTES = BN * 64 * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = TILE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const float* __restrict__ bias, void* __restrict__ C, int ldc, int M, int N, int K, int gelu,
+               int out_bf16) {
+  using L = GemmTcSmem<BN, STAGES>;
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(tiles + L::TILE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_holder = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * 128;
+  const int num_kb = K / 64;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], L::STAGE_BYTES);
+        uint8_t* a_dst = tiles + s * L::STAGE_BYTES;
+        tma_load_2d(a_dst, &tmA, kb * 64, m0, &full[s]);
+        tma_load_2d(a_dst + L::A_BYTES, &tmW, kb * 64, n0, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    // instruction descriptor: D fp32 (bit 4), A bf16 (bit 7), B bf16 (bit 10), K-major both, N>>3 @17, M>>4 @24
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+    for (int kb = 0; kb < num_kb; kb++) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(tiles + s * L::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {   // UMMA_K = 16 bf16 = 32 bytes inside the 128B swizzle atom
+          umma_bf16(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                    (uint32_t)((kb | k) != 0));
+        }
+        umma_commit(&empty[s]);                       // frees the smem stage when these MMAs retire
+        if (kb == num_kb - 1) umma_commit(tmem_full);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;                 // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+      tmem_ld_wait();
+      const int col0 = n0 + c;
+      if (row < M && col0 < N) {
+        float vals[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          float x = __uint_as_float(r[j]);
+          if (bias) x += (col0 + j < N) ? bias[col0 + j] : 0.f;
+          if (gelu) x = gelu_tanh(x);
+          vals[j] = x;
+        }
+        if (col0 + 32 <= N) {
+          if (out_bf16) {
+            uint4* dst = (uint4*)((bf16*)C + (size_t)row * ldc + col0);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              dst[j] = make_uint4(pack_bf16x2(vals[8 * j], vals[8 * j + 1]), pack_bf16x2(vals[8 * j + 2], vals[8 * j + 3]),
+                                  pack_bf16x2(vals[8 * j + 4], vals[8 * j + 5]), pack_bf16x2(vals[8 * j + 6], vals[8 * j + 7]));
+          } else {
+            float4* dst = (float4*)((float*)C + (size_t)row * ldc + col0);
+#pragma unroll
+            for (int j = 0; j < 8; j++) dst[j] = make_float4(vals[4 * j], vals[4 * j + 1], vals[4 * j + 2], vals[4 * j + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            if (col0 + j < N) {
+              if (out_bf16) ((bf16*)C)[(size_t)row * ldc + col0 + j] = __float2bfloat16_rn(vals[j]);
+              else ((float*)C)[(size_t)row * ldc + col0 + j] = vals[j];
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const TensorMap2D* tmA, const TensorMap2D* tmW, const float* bias, void* C, int ldc, int M, int N,
+                     int K, int gelu, int out_bf16, cudaStream_t st) {
+  using L = GemmTcSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    DMG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (M + 127) / 128);
+  gemm_tc_kernel<BN, STAGES><<<grid, 192, L::TOTAL, st>>>(*(const CUtensorMap*)tmA->bytes, *(const CUtensorMap*)tmW->bytes,
+                                                         bias, C, ldc, M, N, K, gelu, out_bf16);
+  g_launch_count++;
+  DMG_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int gemm_tc(const TensorMap2D* tmA, const TensorMap2D* tmW, int BN, const float* bias, void* C, int ldc, int M, int N,
+            int K, int gelu, int out_bf16, cudaStream_t st) {
+  DMG_CHECK(K % 64 == 0 && K >= 64, "gemm_tc: K=%d must be a positive multiple of 64", K);
+  if (M <= 0 || N <= 0) return 0;
+  if (out_bf16) DMG_CHECK(ldc % 8 == 0, "gemm_tc: bf16 output needs ldc %% 8 == 0 (ldc=%d)", ldc);
+  else DMG_CHECK(ldc % 4 == 0, "gemm_tc: fp32 output needs ldc %% 4 == 0 (ldc=%d)", ldc);
+  if (BN == 32) return launch_tc<32, 8>(tmA, tmW, bias, C, ldc, M, N, K, gelu, out_bf16, st);
+  if (BN == 128) return launch_tc<128, 6>(tmA, tmW, bias, C, ldc, M, N, K, gelu, out_bf16, st);
+  DMG_CHECK(false, "gemm_tc: unsupported BN=%d", BN);
+  return 0;
+}
+
+}  // namespace dmg

@@ -1,0 +1,99 @@
+// Internal launcher declarations shared by the .cu files of libdmg_b200.so.
+#pragma once
+#include "common.cuh"
+
+namespace dmg {
+
+extern long long g_launch_count;   // kernels launched by this library (process-wide)
+
+// ------------------------------------------------------------------ GEMM: C[M,N] = A[M,K] * W[N,K]^T (+bias)(gelu)
+// nn.Linear layout: both operands are K-major, which is what tcgen05 wants.
+struct TensorMap2D {
+  alignas(64) unsigned char bytes[128];   // CUtensorMap
+};
+// bf16 row-major [rows, cols] (row stride `ld` elements); box = [box_rows, 64 cols], 128B swizzle.
+int make_tmap_bf16(TensorMap2D* out, const void* base, long long cols, long long rows, long long ld, int box_rows);
+
+template <class T>
+int gemm_simt(const T* A, int lda, const T* W, int ldw, const float* bias, void* C, int ldc, int M, int N, int K,
+              int gelu, int out_bf16, cudaStream_t st);
+
+// BN in {32, 128}; tmA box rows = 128, tmW box rows = BN. K % 64 == 0.
+int gemm_tc(const TensorMap2D* tmA, const TensorMap2D* tmW, int BN, const float* bias, void* C, int ldc, int M, int N,
+            int K, int gelu, int out_bf16, cudaStream_t st);
+
+// ------------------------------------------------------------------ elementwise / small kernels
+// x32[row] = emb[id] (+ beat[pos%32] + bar[min(pos/32 % 1024, 1023)]); xa = T(x32)
+template <class T>
+int embed(const long long* ids, const long long* pos, const float* emb, const float* beat, const float* bar, float* x32,
+          T* xa, int rows, int d, int vocab, cudaStream_t st);
+
+// x32 = LayerNorm(x32 + add) * w + b (eps 1e-5); xa = T(x32).  TAdd = float (GEMM output) or T (BERT: attention output)
+template <class T, class TAdd>
+int residual_layernorm(float* x32, const TAdd* add, const float* w, const float* b, T* xa, int rows, int d,
+                       cudaStream_t st);
+
+// PositionalEncoding table pe[dist][d] = cat(sin(dist*f), cos(dist*f)), f_k = 10000^(-2k/d); dist = 0..n-1
+template <class T>
+int posenc_table(T* pe, int n, int d, cudaStream_t st);
+
+// [n, H*Dh] fp32 (GEMM output) -> [H][n][Dh] T   (rel-pos key cache layout)
+template <class T>
+int rd_relayout(const float* src, T* dst, int n, int H, int Dh, cudaStream_t st);
+
+template <class T>
+int cast_f32(const float* src, T* dst, long long n, cudaStream_t st);
+
+// gather rows: dst[r] = src[idx(r)] with idx(r) = r*stride + offset   (last position of every stream)
+template <class T>
+int gather_rows(const T* src, T* dst, int rows, int d, int stride, int offset, cudaStream_t st);
+
+// ------------------------------------------------------------------ memory rings
+// Device-side ring state read by graph-captured kernels: [0] = pos_total (tokens appended since reset),
+// [1] = mem_count (valid memory positions, <= M).
+template <class T>
+int ring_append_kv(const float* qkv, T* kring, T* vring, int B, int T_len, int H, int Dh, int M, long long pos_total,
+                   int b0, int Bcap, cudaStream_t st);
+// hidden-state mems (model[0].hidden): ring [B][M][d] fp32
+int ring_append_hidden(const float* x32, float* hring, int B, int T_len, int d, int M, long long pos_total, int b0,
+                       cudaStream_t st);
+int ring_export_hidden(const float* hring, float* out, int B, int d, int M, long long pos_total, int mem_count,
+                       cudaStream_t st);
+int state_advance(int* dev_state, int T_len, int M, cudaStream_t st);
+
+// ------------------------------------------------------------------ attention
+struct AttnGeneralArgs {
+  const float* qkv;     // [rows, 3*H*Dh] fp32, row = b*T + i
+  const void* kring;    // T [Bcap][H][M][Dh]
+  const void* vring;
+  const void* rd;       // T [H][Dcap][Dh] relative-position keys by distance
+  const float* u;       // [H*Dh]
+  const float* v;
+  void* out;            // T [rows, H*Dh]
+  int B, T, H, M, Dcap;
+  int mem_count;        // valid memory positions
+  long long pos_total;  // tokens appended since reset (ring slot = token index mod M)
+  int b0;               // first stream of this chunk (ring offset)
+  int bert;             // 1: no mask, _line_shift wrap-around live (deep_music_remix.py:2096, r_mask=False)
+  int win, k;           // window_mask (win_size, k); eval = (1, 1)
+  float scale;          // 1/sqrt(Dh)
+};
+template <class T>
+int attn_general(const AttnGeneralArgs& a, cudaStream_t st);
+
+struct AttnDecodeArgs {
+  const float* qkv;     // [B, 3*H*Dh] fp32 (the new token)
+  bf16* kring;          // [Bcap][H][M][64]
+  bf16* vring;
+  const bf16* rd;       // [H][Dcap][64]
+  const float* u;
+  const float* v;
+  bf16* out;            // [B, H*64]
+  const int* dev_state; // [0] pos_total, [1] mem_count
+  int B, H, M, Dcap;
+  float scale;
+};
+int attn_decode(const AttnDecodeArgs& a, cudaStream_t st);
+bool attn_decode_supported(int Dh, int M);
+
+}  // namespace dmg

@@ -1,0 +1,150 @@
+/*
+ * dmg_b200.h - C ABI of the B200-native DeepMusicGeneration hot path (libdmg_b200.so).
+ *
+ * The reference (AniketRajpoot/DeepMusicGeneration) is pure Python: it has no plugin / FFI layer, its
+ * boundary is the Python call surface of the model and the learner.  Each entry point below names the
+ * reference call it stands behind (paths relative to the reference checkout).  The Python host package
+ * `deepmusicgeneration_b200` binds these with ctypes and re-creates that call surface on top.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success, non-zero on error
+ * (message via dmg_last_error()); no exceptions cross the ABI; no internal threads; all device work is
+ * enqueued on the caller's stream (a cudaStream_t passed as void*, NULL = legacy default stream);
+ * "_dev" pointers are device memory of the model's device, "_host" pointers are host memory;
+ * the caller owns every buffer it passes; the model owns weights, the K/V memory rings, the
+ * relative-position key cache and its workspaces.
+ */
+#ifndef DMG_B200_H
+#define DMG_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dmg_model dmg_model;
+
+enum { DMG_ARCH_TXL = 0,   /* MusicTransformerXL + LinearDecoder   (deep_music_genre.py:1603-1647, fastai TransformerXL) */
+       DMG_ARCH_BERT = 1   /* MultiTransformer 'msk' branch: MTEncoder + MTLinearDecoder (deep_music_remix.py:1864-2104) */ };
+enum { DMG_F32 = 0, DMG_BF16 = 1 };
+enum { DMG_GEMM_AUTO = 0,  /* bf16: tcgen05/TMEM/TMA kernel; f32: SIMT fp32 kernel */
+       DMG_GEMM_SIMT = 1   /* debugging: SIMT kernel for every dtype */ };
+enum { DMG_LOGITS_NONE = 0, DMG_LOGITS_ALL = 1, DMG_LOGITS_LAST = 2 };
+
+/* Model hyper-parameters: the keys of the reference config dicts (app_utils.py:13-63, fastai tfmerXL_lm_config). */
+typedef struct dmg_config {
+  int32_t arch;             /* DMG_ARCH_*                                                                 */
+  int32_t dtype;            /* DMG_F32 (parity mode) or DMG_BF16 (fast path)                              */
+  int32_t vocab;            /* len(vocab.itos) = 324                                                      */
+  int32_t d_model, n_layers, n_heads, d_head, d_inner;
+  int32_t mem_len;          /* TXL segment-recurrence memory (config['mem_len']); 0 for the BERT encoder  */
+  int32_t attn_bias;        /* config['bias']: bias on attention / r_attn (/ out) Linears                  */
+  int32_t encode_position;  /* BeatPositionEncoder / TransformerEmbedding beat+bar embeddings             */
+  int32_t max_batch;        /* streams whose K/V rings stay resident in HBM                               */
+  int32_t max_seq;          /* longest x_len of one forward call                                          */
+  int32_t max_rows;         /* activation workspace rows per chunk; 0 = max_batch*max_seq                 */
+  int32_t keep_hidden;      /* also keep the reference's hidden-state mems (model[0].hidden) for export   */
+  int32_t gemm_backend;     /* DMG_GEMM_*                                                                 */
+  int32_t reserved[4];
+} dmg_config;
+
+/* Index layout of MusicVocab (deep_music_genre.py:812-890); ranges are [lo, hi). */
+typedef struct dmg_vocab_layout {
+  int32_t bos, pad, eos, mask, ni, sep;
+  int32_t special_lo, special_hi;    /* SPECIAL_TOKS */
+  int32_t note_lo, note_hi, dur_lo, dur_hi, ins_lo, ins_hi;
+} dmg_vocab_layout;
+
+enum { DMG_SAMPLE_EARLY_STOP = 1,    /* the loop's break rules (deep_music_genre.py:1951-1963)                         */
+       DMG_SAMPLE_MASK_UNUSED = 2,   /* also forbid ids >= ins_hi (mt*, dummy*), which the reference never filters      */
+       DMG_SAMPLE_REMIX_FILTER = 4   /* filter_invalid_indexes of deep_music_remix.py:2394-2437 instead of the genre one */ };
+
+/* Arguments of MusicLearner.predict (deep_music_genre.py:1853-1855). */
+typedef struct dmg_sampler_params {
+  double temperatures[3];    /* [0] after instrument/pad, [1] after note/xxsep, [2] after duration (:1913-1918);
+                                Python floats in the reference, hence double                                   */
+  int32_t min_bars;
+  int32_t top_k;
+  float top_p;
+  int32_t n_words;
+  uint32_t allowed_ins_mask; /* bit i set = instrument i allowed; 0 = allowed_ins is None                    */
+  int32_t flags;             /* DMG_SAMPLE_*                                                                 */
+  uint64_t seed;             /* Philox key of the device multinomial                                         */
+} dmg_sampler_params;
+
+const char* dmg_last_error(void);
+int dmg_abi_version(void);
+
+/* get_language_model / get_multitask_model (deep_music_genre.py:1793, deep_music_remix.py:1851-1862): allocate
+ * the model on CUDA device `device`. */
+int dmg_create(const dmg_config* cfg, int device, dmg_model** out);
+void dmg_destroy(dmg_model* m);
+
+/* load_state_dict(state['model'], strict=False) (deep_music_genre.py:1800): one call per tensor, fastai
+ * state-dict key names, fp32 host data in nn.Module layout.  Unknown names return 1
+ * (ignored, like strict=False) without setting an error. */
+int dmg_set_weight(dmg_model* m, const char* name, const float* data_host, int64_t numel);
+int dmg_get_weight(dmg_model* m, const char* name, float* out_host, int64_t numel);
+/* Must follow the last dmg_set_weight: makes bf16 copies, runs the rel-pos R-projection (r_attn over
+ * PositionalEncoding) into the per-layer key cache, builds the TMA tensor maps. */
+int dmg_commit_weights(dmg_model* m);
+
+/* SequentialRNN.reset() -> TransformerXL.reset() (deep_music_genre.py:1857): drop all memory; `batch`
+ * streams become active. */
+int dmg_reset(dmg_model* m, int batch);
+/* TransformerXL.select_hidden(idxs) (used by beam_search, deep_music_genre.py:1847): new stream j takes
+ * the memory of old stream idx[j]. */
+int dmg_select_hidden(dmg_model* m, const int32_t* idx_host, int n);
+/* hidden[0].size(1) of the reference: number of memory positions currently held. */
+int dmg_mem_count(dmg_model* m);
+
+/* model(x) (deep_music_genre.py:1617-1647 + LinearDecoder; deep_music_remix.py:1874-1881 for DMG_ARCH_BERT).
+ * ids_dev/pos_dev: int64 [bs, x_len] (pos_dev may be NULL unless encode_position).  mask_win/mask_k: the
+ * (win_size, k) pair of window_mask (:1577-1584); eval mode is (1, 1).  logits_dev: fp32 [bs, x_len, V]
+ * (DMG_LOGITS_ALL) or [bs, V] (DMG_LOGITS_LAST) or NULL.  core_out_dev: fp32 [bs, x_len, d_model] or NULL.
+ * Appends the segment to the memory exactly like _update_mems. */
+int dmg_forward(dmg_model* m, const int64_t* ids_dev, const int64_t* pos_dev, int bs, int x_len, int mask_win,
+                int mask_k, int logits_mode, float* logits_dev, float* core_out_dev, void* stream);
+
+/* raw_outputs[level] of the reference forward (= model[0].hidden[level]): fp32 [bs, mem_count, d_model].
+ * Needs cfg.keep_hidden. */
+int dmg_get_hidden(dmg_model* m, int level, float* out_dev, void* stream);
+
+/* MusicLearner.predict state (deep_music_genre.py:1856-1881): per stream the previous token (item.data[-1]),
+ * last_pos = pos[-1]; start_pos = last_pos. */
+int dmg_sampler_init(dmg_model* m, const dmg_vocab_layout* vocab, const dmg_sampler_params* params,
+                     const int32_t* prev_idx_host, const int64_t* last_pos_host, int bs);
+
+/* The body of the `for i in range(n_words)` loop (deep_music_genre.py:1883-1967), n_steps times, entirely on
+ * the device: sample from the logits of the latest forward (temperature, grammar filter, top-k/top-p,
+ * multinomial), then run the one-token forward on the sampled ids.  dmg_forward(..., DMG_LOGITS_LAST, NULL)
+ * (the prefill of the seed) must precede the first call.  tokens_dev: int32 [n_steps, bs]; -1 marks a stream
+ * that has stopped (BOS predicted / bar rule); -2 marks a stream whose previous token has no temperature class
+ * (the reference raises AssertionError there, :1920-1925). */
+int dmg_generate(dmg_model* m, int n_steps, int32_t* tokens_dev, void* stream);
+/* Same loop body, ONE step, through host buffers: copies ids_host (int64 [bs], may be NULL to keep the sampled
+ * ids) in, runs sample+forward, copies the bs sampled tokens out to tokens_host and synchronises the stream. */
+int dmg_generate_step_host(dmg_model* m, const int64_t* ids_host, int32_t* tokens_host, void* stream);
+
+/* Sampling only (top_k_top_p + filter + multinomial over caller-provided logits), for predict_mask
+ * (deep_music_remix.py:2586-2609; temperatures[0] after duration/pad else [1], the ten special ids forbidden,
+ * the remix filter): logits_dev fp32 [n, V]; prev_idx_dev, repeat_count_dev int32 [n]; out_dev (sampled ids) and
+ * num_choices_dev (non-zero probabilities, drives repeat_count) int32 [n]. */
+int dmg_sample_logits(dmg_model* m, const float* logits_dev, const int32_t* prev_idx_dev,
+                      const int32_t* repeat_count_dev, int n, const dmg_vocab_layout* vocab,
+                      const dmg_sampler_params* params, uint64_t offset, int32_t* out_dev, int32_t* num_choices_dev,
+                      void* stream);
+
+/* Introspection for tests / bench. */
+int64_t dmg_device_bytes(dmg_model* m);          /* bytes of HBM owned by the model */
+int64_t dmg_launch_count(void);                  /* kernels launched by this library so far (process-wide) */
+int dmg_uses_tcgen05(dmg_model* m);              /* 1 when GEMMs run on the tcgen05 kernel */
+
+/* Stand-alone GEMM entry (unit tests / micro-benchmarks): C[M,N] = A[M,K] * W[N,K]^T (+bias) (gelu),
+ * bf16 inputs on the device, fp32 or bf16 output.  backend: DMG_GEMM_AUTO = tcgen05, DMG_GEMM_SIMT. */
+int dmg_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_dev, void* c_dev, int M, int N, int K,
+                  int gelu, int out_bf16, int backend, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMG_B200_H */
