@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched incremental generation with the Transformer-XL of BASELINE.json.
+
+Workload (BASELINE.json configs[1], "C2"): musicautobot-default Transformer-XL (d_model 512, 16 layers, 8 heads x 64,
+d_inner 2048, mem_len 512, vocab 324, random init), 256 independent streams per GPU, memory filled by a 512-token
+prefill of synthetic tokens, then one-token steps (S = 513) with top-k/top-p sampling on the device, bf16.
+A "step" = one generated token for every stream.  `value` = generated tokens/s over all GPUs (weak scaling:
+256 streams per GPU, no collective on the data path).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            this repo's CUDA path
+  python bench.py --impl reference [--steps K] [--warmup W]      the reference's algorithm on the host CPU cores
+                                                                  (the oracle restatement: the reference itself needs
+                                                                  fastai==1.0.61/music21, not installable offline)
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC, UNIT = 'generated_tokens_per_sec', 'tokens/s'
+B_PER_GPU, PREFILL, V = 256, 512, 324
+CFG = dict(d_model=512, n_layers=16, n_heads=8, d_head=64, d_inner=2048, mem_len=512)
+WORKLOAD = ('C2: Transformer-XL d_model 512, 16 layers, 8 heads x 64, d_inner 2048, mem_len 512, vocab 324; '
+            '256 streams/GPU, one-token steps over a full 512-slot memory (S=513), top_k 30 / top_p 0.65 sampling')
+
+
+def measured_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def attention_bytes_per_launch(B, H=8, Dh=64, M=512, e=2):
+    "Algorithmic bytes of ONE fused decode-attention launch (one layer): K and V rings read once, new K/V written, "
+    "rel-pos key cache once, q/k/v of the new token read, output written (DESIGN.md section 5)."
+    kv_read = B * H * M * 2 * Dh * e
+    kv_write = B * H * 2 * Dh * e
+    rcache = H * (M + 1) * Dh * e
+    qkv_in = B * 3 * H * Dh * 4
+    out = B * H * Dh * e
+    return kv_read + kv_write + rcache + qkv_in + out
+
+
+def step_bytes(B, L=16, d=512, H=8, Dh=64, di=2048, M=512, e=2):
+    "Algorithmic HBM bytes of one whole decode step (SURVEY.md 8d): K/V read+write, weights once, rel-pos cache."
+    HD = H * Dh
+    kv = B * L * M * 2 * HD * e + B * L * 2 * HD * e
+    w = (L * (d * 3 * HD + HD * d + d * di + di * d) + V * d) * e
+    r = L * (M + 1) * HD * e
+    return kv + w + r
+
+
+class ClockSampler:
+    "nvidia-smi clocks + throttle reasons sampled DURING the timed region."
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(',')]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, val in zip(names, r[2:6]):
+                if val.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference(batch, steps, warmup, budget_s):
+    """The reference algorithm on the host: eager PyTorch fp32, hidden-state memory re-projected to K/V every step,
+    materialised _line_shift (oracle/txl.py).  Memory is pre-filled with random hidden states (its contents do not
+    change the cost).  Returns (tokens/s, steps actually timed, threads)."""
+    from oracle import txl
+    torch.manual_seed(0)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model = txl.get_language_model(V, txl.baseline_config()).eval()
+    enc = model[0]
+    enc.reset(); enc.init = True
+    enc.hidden = [torch.randn(batch, CFG['mem_len'], CFG['d_model']) for _ in range(CFG['n_layers'] + 1)]
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randint(0, V, (batch, 1), generator=g)
+    t_begin = time.time()
+    with torch.no_grad():
+        for _ in range(warmup):
+            x = model(x)[0][:, -1].argmax(-1, keepdim=True)
+            if time.time() - t_begin > budget_s / 3:
+                break
+        done, t0 = 0, time.time()
+        for _ in range(steps):
+            x = model(x)[0][:, -1].argmax(-1, keepdim=True)
+            done += 1
+            if time.time() - t_begin > budget_s:
+                break
+        dt = time.time() - t0
+    return batch * done / dt, done, threads, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    batch = 8
+    value, done, threads, dt = cpu_reference(batch, args.steps, min(args.warmup, 2), budget_s=150.0)
+    sample = (f'{batch} streams x {done} one-token steps over a full 512-slot memory, greedy, fp32 eager PyTorch oracle '
+              f'(reference algorithm: hidden-state mems re-projected every step), {threads} threads')
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': done,
+            'warmup': min(args.warmup, 2), 'ms_per_step': 1e3 * dt / max(done, 1), 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'cpu_batch': batch},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- CUDA arm
+def run_b200(args):
+    from deepmusicgeneration_b200 import _lib, sharding
+    from deepmusicgeneration_b200.app_utils import baseline_config
+    from deepmusicgeneration_b200.codec import MusicDataBunch
+    from deepmusicgeneration_b200.learner import MusicLearner, sampler_params, vocab_layout
+    from deepmusicgeneration_b200.model import _ptr, get_language_model
+
+    rank, local_rank, world = sharding.init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device - the CUDA path has no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    lib = _lib.load()
+
+    cfg = baseline_config()
+    model = get_language_model(V, cfg, dtype='bf16', device=local_rank, max_batch=B, max_seq=PREFILL, max_rows=B * 64,
+                               keep_hidden=False, seed=0)
+    data = MusicDataBunch.empty('')
+    learn = MusicLearner(data, model)
+    e = model._e
+
+    # synthetic LakhMIDI-shaped seeds: (note, duration, instrument) triplets; every stream ends on an instrument token
+    g = torch.Generator().manual_seed(1234 + rank)
+    trip = torch.stack([torch.randint(12, 140, (B, PREFILL // 3 + 1), generator=g),
+                        torch.randint(140, 301, (B, PREFILL // 3 + 1), generator=g),
+                        torch.randint(301, 308, (B, PREFILL // 3 + 1), generator=g)], dim=2).reshape(B, -1)
+    seeds = trip[:, -PREFILL:].contiguous()
+    assert seeds.shape == (B, PREFILL) and int(seeds[0, -1]) >= 301
+    seeds_pinned = seeds.pin_memory()
+
+    model.reset()
+    learn._prefill(seeds_pinned.to(dev, non_blocking=True), None)
+    vl = vocab_layout(data.vocab)
+    params = sampler_params(data.vocab, 10 ** 9, (1.0, 1.0, 1.0), 10 ** 6, 30, 0.65, None, flags=_lib.SAMPLE_MASK_UNUSED, seed=7)
+    prev = np.ascontiguousarray(seeds[:, -1].numpy().astype(np.int32))
+    lp = np.zeros(B, dtype=np.int64)
+    _lib.check(lib.dmg_sampler_init(e.h, C.byref(vl), C.byref(params), prev.ctypes.data_as(C.c_void_p),
+                                    lp.ctypes.data_as(C.c_void_p), B), 'dmg_sampler_init')
+    toks = torch.empty(max(K, W), B, dtype=torch.int32, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def generate(n):
+        _lib.check(lib.dmg_generate(e.h, n, _ptr(toks), stream), 'dmg_generate')
+
+    generate(W)                                   # warm-up (also captures the CUDA graph of the one-token forward)
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, device-resident (inputs already in HBM)
+    sharding.barrier(); torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = lib.dmg_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    ev0.record()
+    generate(K)
+    ev1.record()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    sharding.barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = int(lib.dmg_launch_count() - launches0)
+    clock_info = clocks.stop(t0, t1) if clocks else None
+    ms_max = sharding.max_over_ranks(ms, device=dev)
+    value = B * world * K / (ms_max / 1e3)
+    good = int((toks[:K] >= 0).all().item())
+
+    # ---- end to end through the C ABI with HOST buffers: H2D of the step's input ids, D2H of the sampled tokens
+    Ke = min(K, 512)
+    ids_host = torch.empty(B, dtype=torch.int64).pin_memory()
+    tok_host = torch.empty(B, dtype=torch.int32).pin_memory()
+    ids_host.copy_(toks[K - 1].to(torch.int64).clamp_min(1).cpu())
+    for _ in range(3):
+        _lib.check(lib.dmg_generate_step_host(e.h, C.c_void_p(ids_host.data_ptr()), C.c_void_p(tok_host.data_ptr()), stream), 'step_host')
+        ids_host.copy_(tok_host.to(torch.int64).clamp_min(1))
+    sharding.barrier(); torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(Ke):
+        _lib.check(lib.dmg_generate_step_host(e.h, C.c_void_p(ids_host.data_ptr()), C.c_void_p(tok_host.data_ptr()), stream), 'step_host')
+        ids_host.copy_(tok_host.to(torch.int64).clamp_min(1))        # the host's view of x = new_tensor([idx])
+    ev1.record()
+    torch.cuda.synchronize()
+    e2e_ms = sharding.max_over_ranks(ev0.elapsed_time(ev1), device=dev)
+    e2e_value = B * world * Ke / (e2e_ms / 1e3)
+
+    # ---- roofline of the dominant kernel (fused decode attention), timed alone with CUDA events on its stream.
+    # 16 launches touch 16 different layers' rings (4.3 GB) -> every launch reads cold data (L2 = 126 MB).
+    L = cfg['n_layers']
+    for l in range(L):
+        _lib.check(lib.dmg_attn_decode_layer(e.h, l, stream), 'attn_decode_layer')
+    torch.cuda.synchronize()
+    reps = 8
+    ev0.record()
+    for _ in range(reps):
+        for l in range(L):
+            lib.dmg_attn_decode_layer(e.h, l, stream)
+    ev1.record()
+    torch.cuda.synchronize()
+    attn_ms = ev0.elapsed_time(ev1) / (reps * L)
+    peak, peak_src = measured_peaks()
+    abytes = attention_bytes_per_launch(B)
+    achieved = abytes / (attn_ms / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'attn_decode_traffic.json')
+    if os.path.exists(tpath):
+        try: traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
+        except Exception: traffic = None
+    roofline = {'bound': 'hbm', 'kernel': 'attn_decode_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': abytes, 'kernel_ms': attn_ms,
+                'kernel_share_of_step': attn_ms * L / (ms / K),
+                'step_algorithmic_bytes': step_bytes(B), 'step_frac': step_bytes(B) / (ms / K / 1e3) / 1e9 / peak}
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, done, threads, dt = cpu_reference(8, 24, 1, budget_s=40.0)
+        cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+               'sample': f'8 streams x {done} one-token steps over a full 512-slot memory, fp32 eager-PyTorch oracle '
+                         f'(reference algorithm), {dt:.1f} s'}
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms_max / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+            'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'global_batch': B * world, 'prefill': PREFILL,
+                       'parallelism': f'streams sharded over {world} GPU(s), no collective',
+                       'l2': 'inputs larger than L2: every step streams 4.3 GB of K/V through a 126 MB L2',
+                       'tcgen05_gemm': bool(lib.dmg_uses_tcgen05(e.h)), 'all_streams_alive': bool(good)},
+            'roofline': roofline, 'cpu_baseline': cpu,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': B * 8, 'd2h_bytes_per_step': B * 4, 'steps': Ke},
+            'gpu_launches': launches, 'clocks': clock_info}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=2048)
+    ap.add_argument('--warmup', type=int, default=32)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=B_PER_GPU, help='streams per GPU')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -408,7 +408,8 @@ int dmg_create(const dmg_config* cfg, int device, dmg_model** out) {
     for (int l = 0; l <= L; l++) TRY(dalloc(m, &m->hrings[l], (size_t)c.max_batch * c.mem_len * d));
   }
   // workspaces
-  const size_t R = (size_t)m->max_rows;
+  const size_t R = (size_t)(m->max_rows < 128 ? 128 : m->max_rows);   // TMA boxes are 128 rows tall
+  const size_t RB = (size_t)(c.max_batch < 128 ? 128 : c.max_batch);
   TRY(dalloc(m, &m->x32, R * d));
   if (m->is_bf16) { bf16* t = nullptr; TRY(dalloc(m, &t, R * d)); m->xa = t; } else m->xa = m->x32;
   TRY(dalloc(m, &m->qkv, R * 3 * HD));
@@ -417,7 +418,7 @@ int dmg_create(const dmg_config* cfg, int device, dmg_model** out) {
     TRY(dalloc(m, &m->proj, R * d));
     char* t = nullptr; TRY(dalloc(m, &t, R * c.d_inner * m->esz)); m->hbuf = t;
   }
-  { char* t = nullptr; TRY(dalloc(m, &t, (size_t)c.max_batch * d * m->esz)); m->xlast = t; }
+  { char* t = nullptr; TRY(dalloc(m, &t, RB * d * m->esz)); m->xlast = t; }
   TRY(dalloc(m, &m->logits_buf, (size_t)c.max_batch * V));
   TRY(dalloc(m, &m->dev_state, 4));
   TRY(dalloc(m, &m->ids_buf, (size_t)c.max_batch));
@@ -432,10 +433,10 @@ int dmg_create(const dmg_config* cfg, int device, dmg_model** out) {
   TRY(dalloc(m, &m->samp.step, (size_t)c.max_batch));
   TRY(dalloc(m, &m->samp.status, (size_t)c.max_batch));
   if (!rc && m->use_tc) {
-    m->a_rows[A_XA] = m->max_rows; m->a_cols[A_XA] = d;
-    m->a_rows[A_ATTN] = m->max_rows; m->a_cols[A_ATTN] = HD;
-    m->a_rows[A_H] = m->max_rows; m->a_cols[A_H] = c.d_inner;
-    m->a_rows[A_XLAST] = c.max_batch; m->a_cols[A_XLAST] = d;
+    m->a_rows[A_XA] = (int)R; m->a_cols[A_XA] = d;
+    m->a_rows[A_ATTN] = (int)R; m->a_cols[A_ATTN] = HD;
+    m->a_rows[A_H] = (int)R; m->a_cols[A_H] = c.d_inner;
+    m->a_rows[A_XLAST] = (int)RB; m->a_cols[A_XLAST] = d;
     void* bufs[A_COUNT] = {m->xa, m->attn, m->hbuf, m->xlast};
     for (int i = 0; i < A_COUNT && !rc; i++) {
       if (bufs[i] == nullptr || m->a_cols[i] % 64 != 0) continue;
@@ -641,6 +642,23 @@ int dmg_sample_logits(dmg_model* m, const float* logits_dev, const int32_t* prev
   a.out_tokens = out_dev;
   a.num_choices = num_choices_dev;
   return sample_launch(a, n, (cudaStream_t)stream);
+}
+
+int dmg_attn_decode_layer(dmg_model* m, int layer, void* stream) {
+  DMG_CHECK(m, "dmg_attn_decode_layer: null model");
+  const dmg_config& c = m->cfg;
+  DMG_CHECK(layer >= 0 && layer < c.n_layers, "dmg_attn_decode_layer: layer %d out of range", layer);
+  DMG_CHECK(m->is_bf16 && c.arch == DMG_ARCH_TXL && attn_decode_supported(c.d_head, c.mem_len),
+            "dmg_attn_decode_layer: the fused decode kernel needs bf16, d_head 64 and mem_len %% 128 == 0");
+  DMG_CHECK(m->batch >= 1 && m->batch <= m->max_rows, "dmg_attn_decode_layer: no active streams");
+  DMG_CUDA_OK(cudaSetDevice(m->device));
+  LayerW& L = m->layers[layer];
+  AttnDecodeArgs a;
+  a.qkv = m->qkv; a.kring = (bf16*)L.kring; a.vring = (bf16*)L.vring; a.rd = (const bf16*)L.rd;
+  a.u = m->u; a.v = m->v; a.out = (bf16*)m->attn; a.dev_state = m->dev_state;
+  a.B = m->batch; a.H = c.n_heads; a.M = c.mem_len; a.Dcap = m->Dcap;
+  a.scale = 1.f / sqrtf((float)c.d_head);
+  return attn_decode(a, (cudaStream_t)stream);
 }
 
 int dmg_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_dev, void* c_dev, int M, int N, int K, int gelu,

@@ -139,6 +139,10 @@ int64_t dmg_device_bytes(dmg_model* m);          /* bytes of HBM owned by the mo
 int64_t dmg_launch_count(void);                  /* kernels launched by this library so far (process-wide) */
 int dmg_uses_tcgen05(dmg_model* m);              /* 1 when GEMMs run on the tcgen05 kernel */
 
+/* Measurement hook for bench.py's roofline: re-launch ONLY the fused decode-attention kernel of `layer` on the
+ * current ring state and the q/k/v of the latest one-token forward (idempotent: the ring position is not advanced). */
+int dmg_attn_decode_layer(dmg_model* m, int layer, void* stream);
+
 /* Stand-alone GEMM entry (unit tests / micro-benchmarks): C[M,N] = A[M,K] * W[N,K]^T (+bias) (gelu),
  * bf16 inputs on the device, fp32 or bf16 output.  backend: DMG_GEMM_AUTO = tcgen05, DMG_GEMM_SIMT. */
 int dmg_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_dev, void* c_dev, int M, int N, int K,
