@@ -14,7 +14,7 @@ c_i32, c_i64, c_u32, c_u64, c_f32, c_f64, c_vp = C.c_int32, C.c_int64, C.c_uint3
 
 ARCH_TXL, ARCH_BERT = 0, 1
 F32, BF16 = 0, 1
-GEMM_AUTO, GEMM_SIMT = 0, 1
+GEMM_AUTO, GEMM_SIMT, GEMM_TC_TILE = 0, 1, 2
 LOGITS_NONE, LOGITS_ALL, LOGITS_LAST = 0, 1, 2
 SAMPLE_EARLY_STOP, SAMPLE_MASK_UNUSED, SAMPLE_REMIX_FILTER = 1, 2, 4
 

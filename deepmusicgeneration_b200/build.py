@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libdmg_b200.so')
-SOURCES = ['gemm.cu', 'elementwise.cu', 'attention.cu', 'sampling.cu', 'model.cu']
+SOURCES = ['gemm.cu', 'elementwise.cu', 'attention.cu', 'attention_decode2.cu', 'sampling.cu', 'model.cu']
 HEADERS = ['common.cuh', 'kernels.cuh', 'sampling.cuh', os.path.join('..', '..', 'include', 'dmg_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']

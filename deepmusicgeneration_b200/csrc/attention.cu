@@ -16,6 +16,7 @@
 //  * attn_general_kernel - any x_len (prefill, training-shape forward, BERT encoder), fp32 or bf16 ring,
 //    flash-style online softmax over 32x32 tiles on the FFMA pipe.
 #include "kernels.cuh"
+#include "launch.cuh"
 
 namespace dmg {
 
@@ -46,6 +47,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(AttnDecodeArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int h = blockIdx.x, b = blockIdx.y;
   const int H = a.H, HD = H * 64;
+  pdl_launch_dependents();
+  pdl_wait();
   const int pos_total = a.dev_state[0], mc = a.dev_state[1];
   const int head = pos_total % M;
   const int nK = M / 64, nV = M / 128, nItems = nK + nV;
@@ -228,10 +231,7 @@ int attn_decode(const AttnDecodeArgs& a, cudaStream_t st) {
     DMG_CUDA_OK(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  attn_decode_kernel<<<dim3(a.H, a.B), 128, smem, st>>>(a);
-  g_launch_count++;
-  DMG_CUDA_OK(cudaGetLastError());
-  return 0;
+  return launch_k(attn_decode_kernel, dim3(a.H, a.B), dim3(128), smem, st, 1, a);
 }
 
 // =============================================================================================
@@ -257,6 +257,8 @@ __global__ void __launch_bounds__(128) attn_general_kernel(AttnGeneralArgs a) {
   float* P = RU + (BERT ? 63 * GLD : 0);
 
   const int tid = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   const int i0 = blockIdx.x * GQ, h = blockIdx.y, b = blockIdx.z;
   const int T_len = a.T, H = a.H, HD = H * 64, M = a.M;
   const int m = a.mem_count, S = m + T_len;
@@ -429,10 +431,7 @@ static int launch_general(const AttnGeneralArgs& a, cudaStream_t st) {
     configured = true;
   }
   dim3 grid((a.T + GQ - 1) / GQ, a.H, a.B);
-  attn_general_kernel<T, BERT><<<grid, 128, smem, st>>>(a);
-  g_launch_count++;
-  DMG_CUDA_OK(cudaGetLastError());
-  return 0;
+  return launch_k(attn_general_kernel<T, BERT>, grid, dim3(128), smem, st, 1, a);
 }
 
 template <class T>

@@ -6,6 +6,7 @@
 // (fastai MultiHeadAttention.forward / feed_forward; deep_music_remix.py:2052), PositionalEncoding (fastai),
 // TransformerXL._update_mems (fastai; cat + slice every step -> ring append).
 #include "kernels.cuh"
+#include "launch.cuh"
 
 namespace dmg {
 
@@ -17,6 +18,8 @@ __global__ void embed_kernel(const long long* __restrict__ ids, const long long*
                              int vocab) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= rows) return;
   long long id = ids[row];
   if (id < 0) id = 0;
@@ -50,10 +53,7 @@ int embed(const long long* ids, const long long* pos, const float* emb, const fl
           T* xa, int rows, int d, int vocab, cudaStream_t st) {
   if (rows <= 0) return 0;
   const int wpb = 8;
-  embed_kernel<T><<<(rows + wpb - 1) / wpb, wpb * 32, 0, st>>>(ids, pos, emb, beat, bar, x32, xa, rows, d, vocab);
-  g_launch_count++;
-  DMG_CUDA_OK(cudaGetLastError());
-  return 0;
+  return launch_k(embed_kernel<T>, dim3((rows + wpb - 1) / wpb), dim3(wpb * 32), 0, st, 1, ids, pos, emb, beat, bar, x32, xa, rows, d, vocab);
 }
 template int embed<float>(const long long*, const long long*, const float*, const float*, const float*, float*, float*,
                           int, int, int, cudaStream_t);
@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(256) residual_ln_kernel(float* __restrict__ x3
                                                           T* __restrict__ xa, int rows, int d) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= rows) return;
   float v[NV * 4];
   float s = 0.f;
@@ -117,13 +119,10 @@ int residual_layernorm(float* x32, const TAdd* add, const float* w, const float*
   switch (d / 128) {
 #define DMG_LN_CASE(NV)                                                                                    \
   case NV:                                                                                                 \
-    residual_ln_kernel<T, TAdd, NV><<<grid, block, 0, st>>>(x32, add, w, b, xa, rows, d);                  \
-    break;
+    return launch_k(residual_ln_kernel<T, TAdd, NV>, grid, block, 0, st, 1, x32, add, w, b, xa, rows, d);
     DMG_LN_CASE(1) DMG_LN_CASE(2) DMG_LN_CASE(3) DMG_LN_CASE(4) DMG_LN_CASE(5) DMG_LN_CASE(6) DMG_LN_CASE(7) DMG_LN_CASE(8)
 #undef DMG_LN_CASE
   }
-  g_launch_count++;
-  DMG_CUDA_OK(cudaGetLastError());
   return 0;
 }
 template int residual_layernorm<float, float>(float*, const float*, const float*, const float*, float*, int, int, cudaStream_t);
@@ -197,6 +196,8 @@ template int cast_f32<bf16>(const float*, bf16*, long long, cudaStream_t);
 template <class T>
 __global__ void gather_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, int rows, int d, int stride, int offset) {
   const int r = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   const T* s = src + ((size_t)r * stride + offset) * d;
   T* o = dst + (size_t)r * d;
   for (int c = threadIdx.x; c < d; c += blockDim.x) o[c] = s[c];
@@ -204,10 +205,7 @@ __global__ void gather_rows_kernel(const T* __restrict__ src, T* __restrict__ ds
 template <class T>
 int gather_rows(const T* src, T* dst, int rows, int d, int stride, int offset, cudaStream_t st) {
   if (rows <= 0) return 0;
-  gather_rows_kernel<T><<<rows, 128, 0, st>>>(src, dst, rows, d, stride, offset);
-  g_launch_count++;
-  DMG_CUDA_OK(cudaGetLastError());
-  return 0;
+  return launch_k(gather_rows_kernel<T>, dim3(rows), dim3(128), 0, st, 1, src, dst, rows, d, stride, offset);
 }
 template int gather_rows<float>(const float*, float*, int, int, int, int, cudaStream_t);
 template int gather_rows<bf16>(const bf16*, bf16*, int, int, int, int, cudaStream_t);
@@ -285,15 +283,14 @@ int ring_export_hidden(const float* hring, float* out, int B, int d, int M, long
 }
 
 __global__ void state_advance_kernel(int* st, int T_len, int M) {
+  pdl_launch_dependents();
+  pdl_wait();
   st[0] += T_len;
   int m = st[1] + T_len;
   st[1] = m > M ? M : m;
 }
 int state_advance(int* dev_state, int T_len, int M, cudaStream_t st) {
-  state_advance_kernel<<<1, 1, 0, st>>>(dev_state, T_len, M);
-  g_launch_count++;
-  DMG_CUDA_OK(cudaGetLastError());
-  return 0;
+  return launch_k(state_advance_kernel, dim3(1), dim3(1), 0, st, 1, dev_state, T_len, M);
 }
 
 }  // namespace dmg

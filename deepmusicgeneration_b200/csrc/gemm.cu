@@ -11,6 +11,7 @@
 #include <cuda.h>
 #include <cstdarg>
 #include "kernels.cuh"
+#include "launch.cuh"
 
 namespace dmg {
 
@@ -25,6 +26,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
                                                         int ldc, int M, int N, int K, int gelu, int out_bf16) {
   __shared__ float As[16][68];
   __shared__ float Ws[16][68];
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   float acc[4][4];
@@ -78,10 +81,7 @@ int gemm_simt(const T* A, int lda, const T* W, int ldw, const float* bias, void*
               int gelu, int out_bf16, cudaStream_t st) {
   if (M <= 0 || N <= 0) return 0;
   dim3 grid((N + 63) / 64, (M + 63) / 64);
-  gemm_simt_kernel<T><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, C, ldc, M, N, K, gelu, out_bf16);
-  g_launch_count++;
-  DMG_CUDA_OK(cudaGetLastError());
-  return 0;
+  return launch_k(gemm_simt_kernel<T>, grid, dim3(256), 0, st, 1, A, lda, W, ldw, bias, C, ldc, M, N, K, gelu, out_bf16);
 }
 template int gemm_simt<float>(const float*, int, const float*, int, const float*, void*, int, int, int, int, int, int,
                               cudaStream_t);
@@ -158,6 +158,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * 128;
   const int num_kb = K / 64;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -176,6 +177,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();   // activations (A) and the output buffer belong to the predecessor chain until here
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -272,11 +274,8 @@ static int launch_tc(const TensorMap2D* tmA, const TensorMap2D* tmW, const float
     configured = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + 127) / 128);
-  gemm_tc_kernel<BN, STAGES><<<grid, 192, L::TOTAL, st>>>(*(const CUtensorMap*)tmA->bytes, *(const CUtensorMap*)tmW->bytes,
-                                                         bias, C, ldc, M, N, K, gelu, out_bf16);
-  g_launch_count++;
-  DMG_CUDA_OK(cudaGetLastError());
-  return 0;
+  return launch_k(gemm_tc_kernel<BN, STAGES>, grid, dim3(192), L::TOTAL, st, 1, *(const CUtensorMap*)tmA->bytes,
+                  *(const CUtensorMap*)tmW->bytes, bias, C, ldc, M, N, K, gelu, out_bf16);
 }
 
 int gemm_tc(const TensorMap2D* tmA, const TensorMap2D* tmW, int BN, const float* bias, void* C, int ldc, int M, int N,
@@ -289,6 +288,204 @@ int gemm_tc(const TensorMap2D* tmA, const TensorMap2D* tmW, int BN, const float*
   if (BN == 128) return launch_tc<128, 6>(tmA, tmW, bias, C, ldc, M, N, K, gelu, out_bf16, st);
   DMG_CHECK(false, "gemm_tc: unsupported BN=%d", BN);
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Skinny-M GEMM (decode: M = number of streams <= 512): split-K over a thread-block cluster.
+//
+// profiles/r1a_launches_decode_step.csv: with one CTA per 128x32 output tile the four per-layer GEMMs took
+// 9-18 us each - 16..64 CTAs each pulling 160-640 KB through one SM's TMA path, the A tile re-read by every
+// N-tile.  Here KSPLIT CTAs of a cluster each own K/KSPLIT of the reduction for the same 128xBN tile (40-80 KB per
+// CTA, 128-512 CTAs per GEMM), accumulate in TMEM, park the partial tile in their shared memory and reduce it
+// through distributed shared memory: CTA r finalises rows [r*128/KSPLIT, (r+1)*128/KSPLIT) by summing the KSPLIT
+// partials (ld.shared::cluster), then applies bias / GeLU and stores.  Deterministic (fixed summation order).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+constexpr int SK_BN = 32;
+constexpr int SK_MAXKB = 8;                       // k-blocks (of 64) per CTA
+constexpr int SK_RED_LD = SK_BN + 4;              // padded row stride of the partial tile (floats)
+constexpr int SK_STAGE = 128 * 64 * 2 + SK_BN * 64 * 2;
+__host__ __device__ constexpr int sk_smem_bytes(int num_kb) {
+  return num_kb * SK_STAGE + 128 * SK_RED_LD * 4 + 1024 + 256;
+}
+
+template <int KSPLIT>
+__global__ void __launch_bounds__(192)
+gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                      const float* __restrict__ bias, void* __restrict__ C, int ldc, int M, int N, int K, int gelu,
+                      int out_bf16) {
+  extern __shared__ __align__(1024) uint8_t sk_smem[];
+  uint8_t* tiles = sk_smem + ((1024u - (smem_u32(sk_smem) & 1023u)) & 1023u);
+  const int num_kb = K / 64 / KSPLIT;            // k-blocks of this CTA (<= SK_MAXKB)
+  float* red = (float*)(tiles + num_kb * SK_STAGE);
+  uint64_t* full = (uint64_t*)(red + 128 * SK_RED_LD);
+  uint64_t* tmem_full = full + SK_MAXKB;
+  uint32_t* tmem_holder = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t krank = cluster_ctarank();
+  const int n0 = (blockIdx.x / KSPLIT) * SK_BN, m0 = blockIdx.y * 128;
+  const int kb0 = krank * num_kb;
+  pdl_launch_dependents();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < num_kb; s++) mbar_init(&full[s], 1);
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<32>(tmem_holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {   // every stage is used once: issue all loads up front - the WEIGHT tiles even before the
+                       // predecessor kernel has finished (they never change), the activation tiles after pdl_wait
+      for (int kb = 0; kb < num_kb; kb++) {
+        mbar_expect_tx(&full[kb], SK_STAGE);
+        tma_load_2d(tiles + kb * SK_STAGE + 128 * 64 * 2, &tmW, (kb0 + kb) * 64, n0, &full[kb]);
+      }
+      pdl_wait();
+      for (int kb = 0; kb < num_kb; kb++) tma_load_2d(tiles + kb * SK_STAGE, &tmA, (kb0 + kb) * 64, m0, &full[kb]);
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SK_BN >> 3) << 17) | ((128u >> 4) << 24);
+    for (int kb = 0; kb < num_kb; kb++) {
+      mbar_wait(&full[kb], 0);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(tiles + kb * SK_STAGE);
+        const uint32_t b_addr = a_addr + 128 * 64 * 2;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          umma_bf16(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                    (uint32_t)((kb | k) != 0));
+        if (kb == num_kb - 1) umma_commit(tmem_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // partial tile: TMEM -> registers -> this CTA's shared memory (padded rows: conflict-free 16-byte stores)
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    uint32_t r[32];
+    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16), r);
+    tmem_ld_wait();
+    float4* dst = (float4*)(red + (q * 32 + lane) * SK_RED_LD);
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                           __uint_as_float(r[4 * j + 3]));
+  }
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();          // all partial tiles of the cluster are in shared memory
+  pdl_wait();                  // the output buffer may still be read by the predecessor chain until here
+
+  if (warp >= 2) {
+    constexpr int ROWS = 128 / KSPLIT;          // rows finalised by this CTA
+    const int te = threadIdx.x - 64;            // 0..127
+    const int rr = te >> 2, cg = (te & 3) * 8;  // 4 threads per row, 8 columns each
+    if (rr < ROWS) {
+      const int row_l = krank * ROWS + rr;
+      const uint32_t laddr = smem_u32(red + row_l * SK_RED_LD + cg);
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int r2 = 0; r2 < KSPLIT; r2++) {
+        const uint32_t ra = mapa_shared(laddr, (uint32_t)r2);
+        const float4 x = ld_dsmem_f4(ra), y = ld_dsmem_f4(ra + 16);
+        v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w;
+        v[4] += y.x; v[5] += y.y; v[6] += y.z; v[7] += y.w;
+      }
+      const int row = m0 + row_l, col0 = n0 + cg;
+      if (row < M && col0 < N) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          if (bias && col0 + j < N) v[j] += bias[col0 + j];
+          if (gelu) v[j] = gelu_tanh(v[j]);
+        }
+        if (col0 + 8 <= N) {
+          if (out_bf16) {
+            *(uint4*)((bf16*)C + (size_t)row * ldc + col0) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          } else {
+            float4* o = (float4*)((float*)C + (size_t)row * ldc + col0);
+            o[0] = make_float4(v[0], v[1], v[2], v[3]);
+            o[1] = make_float4(v[4], v[5], v[6], v[7]);
+          }
+        } else {
+          for (int j = 0; j < 8; j++)
+            if (col0 + j < N) {
+              if (out_bf16) ((bf16*)C)[(size_t)row * ldc + col0 + j] = __float2bfloat16_rn(v[j]);
+              else ((float*)C)[(size_t)row * ldc + col0 + j] = v[j];
+            }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  cluster_sync_all();          // nobody may exit while a peer still reads its shared memory
+  if (warp == 2) tmem_dealloc<32>(tmem_base);
+}
+
+template <int KSPLIT>
+static int launch_splitk(const TensorMap2D* tmA, const TensorMap2D* tmW, const float* bias, void* C, int ldc, int M, int N,
+                         int K, int gelu, int out_bf16, cudaStream_t st) {
+  const int num_kb = K / 64 / KSPLIT;
+  const int smem = sk_smem_bytes(num_kb);
+  static int configured = 0;
+  if (configured < smem) {
+    DMG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_splitk_kernel<KSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  return launch_k(gemm_tc_splitk_kernel<KSPLIT>, dim3(((N + SK_BN - 1) / SK_BN) * KSPLIT, (M + 127) / 128, 1), dim3(192), smem, st,
+                  KSPLIT, *(const CUtensorMap*)tmA->bytes, *(const CUtensorMap*)tmW->bytes, bias, C, ldc, M, N, K, gelu, out_bf16);
+}
+
+// Picks the split: K/64 k-blocks spread over 4 or 8 CTAs (at most SK_MAXKB blocks each).  Returns 0 when the shape
+// does not qualify (caller falls back to gemm_tc).
+int gemm_tc_splitk_ways(int K) {
+  if (K % 64) return 0;
+  const int kb = K / 64;
+  if (kb % 8 == 0 && kb / 8 >= 2 && kb / 8 <= SK_MAXKB) return 8;
+  if (kb % 4 == 0 && kb / 4 >= 1 && kb / 4 <= SK_MAXKB) return 4;
+  return 0;
+}
+
+int gemm_tc_splitk(const TensorMap2D* tmA, const TensorMap2D* tmW32, const float* bias, void* C, int ldc, int M, int N,
+                   int K, int gelu, int out_bf16, cudaStream_t st) {
+  const int ways = gemm_tc_splitk_ways(K);
+  DMG_CHECK(ways != 0, "gemm_tc_splitk: K=%d does not split", K);
+  if (M <= 0 || N <= 0) return 0;
+  if (out_bf16) DMG_CHECK(ldc % 8 == 0, "gemm_tc_splitk: bf16 output needs ldc %% 8 == 0 (ldc=%d)", ldc);
+  else DMG_CHECK(ldc % 4 == 0, "gemm_tc_splitk: fp32 output needs ldc %% 4 == 0 (ldc=%d)", ldc);
+  return ways == 8 ? launch_splitk<8>(tmA, tmW32, bias, C, ldc, M, N, K, gelu, out_bf16, st)
+                   : launch_splitk<4>(tmA, tmW32, bias, C, ldc, M, N, K, gelu, out_bf16, st);
 }
 
 }  // namespace dmg

@@ -21,6 +21,11 @@ int gemm_simt(const T* A, int lda, const T* W, int ldw, const float* bias, void*
 // BN in {32, 128}; tmA box rows = 128, tmW box rows = BN. K % 64 == 0.
 int gemm_tc(const TensorMap2D* tmA, const TensorMap2D* tmW, int BN, const float* bias, void* C, int ldc, int M, int N,
             int K, int gelu, int out_bf16, cudaStream_t st);
+// Skinny-M variant: split-K over a 4- or 8-CTA cluster, partial tiles reduced through distributed shared memory.
+// tmW32 = weight map with 32-row boxes.  gemm_tc_splitk_ways(K) == 0 -> shape not supported.
+int gemm_tc_splitk_ways(int K);
+int gemm_tc_splitk(const TensorMap2D* tmA, const TensorMap2D* tmW32, const float* bias, void* C, int ldc, int M, int N,
+                   int K, int gelu, int out_bf16, cudaStream_t st);
 
 // ------------------------------------------------------------------ elementwise / small kernels
 // x32[row] = emb[id] (+ beat[pos%32] + bar[min(pos/32 % 1024, 1023)]); xa = T(x32)
@@ -95,5 +100,10 @@ struct AttnDecodeArgs {
 };
 int attn_decode(const AttnDecodeArgs& a, cudaStream_t st);
 bool attn_decode_supported(int Dh, int M);
+// v2: persistent, TMA-2D swizzled K/V tiles, resident rel-pos keys, mma.sync dot products (attention_decode2.cu).
+// tmK/tmV: ring viewed as [max_batch*H*M rows, 64 cols]; tmR: Rd viewed as [H*Dcap rows, 64 cols]; 64-row boxes.
+int attn_decode2(const TensorMap2D* tmK, const TensorMap2D* tmV, const TensorMap2D* tmR, const AttnDecodeArgs& a, int b0,
+                 int num_sms, cudaStream_t st);
+bool attn_decode2_supported(int Dh, int M);
 
 }  // namespace dmg

@@ -36,6 +36,8 @@ struct LayerW {
   void* rd = nullptr;      // [H][Dcap][Dh] compute dtype: r_attn(PositionalEncoding(dist))
   void* kring = nullptr;   // [max_batch][H][M][Dh] compute dtype
   void* vring = nullptr;
+  TensorMap2D tmK, tmV, tmR;   // 64-row boxes over the rings / the rel-pos cache (decode attention v2)
+  bool has_ring_tm = false;
 };
 
 struct RegEntry {
@@ -53,7 +55,7 @@ struct dmg_model {
   dmg_config cfg;
   int device = 0;
   bool is_bf16 = false, use_tc = false, committed = false;
-  int HD = 0, Dcap = 0, max_rows = 0, esz = 4;
+  int HD = 0, Dcap = 0, max_rows = 0, esz = 4, num_sms = 148;
   Weight emb;   // [V, d] (tied head)
   float *beat = nullptr, *bar = nullptr, *u = nullptr, *v = nullptr, *head_b = nullptr;
   std::vector<LayerW> layers;
@@ -116,6 +118,8 @@ static int linear(dmg_model* m, int abuf, const void* A, const Weight& w, const 
   if (!m->is_bf16) return gemm_simt<float>((const float*)A, K, w.f32, K, bias, C, ldc, M, N, K, gelu, out_bf16, st);
   if (m->use_tc && w.has_tm && K % 64 == 0) {
     const bool skinny = M <= 512;
+    if (skinny && gemm_tc_splitk_ways(K) && !getenv("DMG_NO_SPLITK"))
+      return gemm_tc_splitk(&m->tmA[abuf], &w.tm32, bias, C, ldc, M, N, K, gelu, out_bf16, st);
     return gemm_tc(&m->tmA[abuf], skinny ? &w.tm32 : &w.tm128, skinny ? 32 : 128, bias, C, ldc, M, N, K, gelu, out_bf16, st);
   }
   return gemm_simt<bf16>((const bf16*)A, K, w.b16, K, bias, C, ldc, M, N, K, gelu, out_bf16, st);
@@ -130,7 +134,9 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
   T* xa = (T*)m->xa;
   if (embed<T>(ids, c.encode_position ? pos : nullptr, m->emb.f32, m->beat, m->bar, m->x32, xa, rows, d, c.vocab, st)) return -1;
   if (c.keep_hidden && M > 0 && ring_append_hidden(m->x32, m->hrings[0], nb, T_len, d, M, m->pos_total, b0, st)) return -1;
-  const bool fast_decode = m->is_bf16 && !bert && T_len == 1 && attn_decode_supported(c.d_head, M) && !getenv("DMG_NO_DECODE_KERNEL");
+  const bool v2_ok = !bert && M > 0 && m->layers[0].has_ring_tm && attn_decode2_supported(c.d_head, M) && !getenv("DMG_DECODE_V1");
+  const bool fast_decode = m->is_bf16 && !bert && T_len == 1 && (v2_ok || attn_decode_supported(c.d_head, M)) &&
+                           !getenv("DMG_NO_DECODE_KERNEL");
   for (int l = 0; l < c.n_layers; l++) {
     LayerW& L = m->layers[l];
     if (linear(m, A_XA, xa, L.wqkv, L.bqkv, m->qkv, 3 * HD, rows, 0, 0, st)) return -1;
@@ -145,7 +151,11 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
       a.dev_state = m->dev_state;
       a.B = nb; a.H = c.n_heads; a.M = M; a.Dcap = m->Dcap;
       a.scale = 1.f / sqrtf((float)c.d_head);
-      if (attn_decode(a, st)) return -1;
+      if (v2_ok) {
+        if (attn_decode2(&L.tmK, &L.tmV, &L.tmR, a, b0, m->num_sms, st)) return -1;
+      } else {
+        if (attn_decode(a, st)) return -1;
+      }
     } else {
       AttnGeneralArgs a;
       a.qkv = m->qkv; a.kring = L.kring; a.vring = L.vring; a.rd = L.rd; a.u = m->u; a.v = m->v; a.out = m->attn;
@@ -171,7 +181,7 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
     DMG_CUDA_OK(cudaMemcpyAsync(core_out + (size_t)b0 * T_len * d, m->x32, (size_t)rows * d * 4, cudaMemcpyDeviceToDevice, st));
   if (logits_mode == DMG_LOGITS_ALL && logits) {
     if (linear(m, A_XA, xa, m->emb, m->head_b, logits + (size_t)b0 * T_len * c.vocab, c.vocab, rows, 0, 0, st)) return -1;
-  } else if (logits_mode == DMG_LOGITS_LAST) {
+  } else if (logits_mode == DMG_LOGITS_LAST && !(T_len == 1 && nb == m->batch)) {
     if (gather_rows<T>(xa, (T*)m->xlast + (size_t)b0 * d, nb, d, T_len, T_len - 1, st)) return -1;
   }
   return 0;
@@ -197,7 +207,8 @@ static int forward_impl(dmg_model* m, const long long* ids, const long long* pos
     if (rc) return rc;
   }
   if (logits_mode == DMG_LOGITS_LAST) {
-    if (linear(m, A_XLAST, m->xlast, m->emb, m->head_b, m->logits_buf, c.vocab, bs, 0, 0, st)) return -1;
+    const bool direct = T_len == 1 && cb >= bs;   // one-token step in a single chunk: the last rows ARE the rows
+    if (linear(m, direct ? A_XA : A_XLAST, direct ? m->xa : m->xlast, m->emb, m->head_b, m->logits_buf, c.vocab, bs, 0, 0, st)) return -1;
     if (logits) DMG_CUDA_OK(cudaMemcpyAsync(logits, m->logits_buf, (size_t)bs * c.vocab * 4, cudaMemcpyDeviceToDevice, st));
     m->logits_valid = true;
   }
@@ -252,7 +263,8 @@ static int decode_forward(dmg_model* m, int bs, cudaStream_t st) {
 // dev_state on the device, so replay stays valid while the memory advances).
 static int decode_forward_graphed(dmg_model* m, int bs, cudaStream_t st) {
   const bool graph_ok = m->is_bf16 && m->cfg.arch == DMG_ARCH_TXL && !m->cfg.keep_hidden && m->cfg.max_rows >= bs &&
-                        attn_decode_supported(m->cfg.d_head, m->cfg.mem_len) && !getenv("DMG_NO_GRAPH") &&
+                        (attn_decode_supported(m->cfg.d_head, m->cfg.mem_len) ||
+                         attn_decode2_supported(m->cfg.d_head, m->cfg.mem_len)) && !getenv("DMG_NO_GRAPH") &&
                         !getenv("DMG_NO_DECODE_KERNEL");
   if (!graph_ok) return decode_forward(m, bs, st);
   if (m->step_graph == nullptr || m->graph_bs != bs) {
@@ -337,6 +349,7 @@ int dmg_create(const dmg_config* cfg, int device, dmg_model** out) {
   m->device = device;
   m->is_bf16 = c.dtype == DMG_BF16;
   m->use_tc = m->is_bf16 && c.gemm_backend != DMG_GEMM_SIMT && !getenv("DMG_GEMM_SIMT");
+  m->num_sms = prop.multiProcessorCount;
   m->esz = m->is_bf16 ? 2 : 4;
   m->HD = c.n_heads * c.d_head;
   m->Dcap = c.mem_len + c.max_seq + 1;
@@ -401,6 +414,13 @@ int dmg_create(const dmg_config* cfg, int device, dmg_model** out) {
       const size_t rb = (size_t)c.max_batch * c.n_heads * c.mem_len * c.d_head * m->esz;
       p8 = nullptr; TRY(dalloc(m, &p8, rb)); W.kring = p8;
       p8 = nullptr; TRY(dalloc(m, &p8, rb)); W.vring = p8;
+      if (!rc && m->is_bf16 && attn_decode2_supported(c.d_head, c.mem_len)) {
+        const long long ring_rows = (long long)c.max_batch * c.n_heads * c.mem_len;
+        TRY(make_tmap_bf16(&W.tmK, W.kring, 64, ring_rows, 64, 64));
+        TRY(make_tmap_bf16(&W.tmV, W.vring, 64, ring_rows, 64, 64));
+        TRY(make_tmap_bf16(&W.tmR, W.rd, 64, (long long)c.n_heads * m->Dcap, 64, 64));
+        W.has_ring_tm = !rc;
+      }
     }
   }
   if (c.keep_hidden && c.mem_len > 0) {
@@ -648,8 +668,9 @@ int dmg_attn_decode_layer(dmg_model* m, int layer, void* stream) {
   DMG_CHECK(m, "dmg_attn_decode_layer: null model");
   const dmg_config& c = m->cfg;
   DMG_CHECK(layer >= 0 && layer < c.n_layers, "dmg_attn_decode_layer: layer %d out of range", layer);
-  DMG_CHECK(m->is_bf16 && c.arch == DMG_ARCH_TXL && attn_decode_supported(c.d_head, c.mem_len),
-            "dmg_attn_decode_layer: the fused decode kernel needs bf16, d_head 64 and mem_len %% 128 == 0");
+  DMG_CHECK(m->is_bf16 && c.arch == DMG_ARCH_TXL &&
+                (attn_decode_supported(c.d_head, c.mem_len) || attn_decode2_supported(c.d_head, c.mem_len)),
+            "dmg_attn_decode_layer: the fused decode kernels need bf16, d_head 64 and mem_len %% 64 == 0");
   DMG_CHECK(m->batch >= 1 && m->batch <= m->max_rows, "dmg_attn_decode_layer: no active streams");
   DMG_CUDA_OK(cudaSetDevice(m->device));
   LayerW& L = m->layers[layer];
@@ -658,6 +679,8 @@ int dmg_attn_decode_layer(dmg_model* m, int layer, void* stream) {
   a.u = m->u; a.v = m->v; a.out = (bf16*)m->attn; a.dev_state = m->dev_state;
   a.B = m->batch; a.H = c.n_heads; a.M = c.mem_len; a.Dcap = m->Dcap;
   a.scale = 1.f / sqrtf((float)c.d_head);
+  if (L.has_ring_tm && attn_decode2_supported(c.d_head, c.mem_len) && !getenv("DMG_DECODE_V1"))
+    return attn_decode2(&L.tmK, &L.tmV, &L.tmR, a, 0, m->num_sms, (cudaStream_t)stream);
   return attn_decode(a, (cudaStream_t)stream);
 }
 
@@ -671,6 +694,8 @@ int dmg_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_dev, v
   const int BN = M <= 512 ? 32 : 128;
   if (make_tmap_bf16(&ta, a_dev, K, M, K, 128)) return -1;
   if (make_tmap_bf16(&tw, w_dev, K, N, K, BN)) return -1;
+  if (backend == DMG_GEMM_AUTO && M <= 512 && gemm_tc_splitk_ways(K))
+    return gemm_tc_splitk(&ta, &tw, bias_dev, c_dev, N, M, N, K, gelu, out_bf16, st);
   return gemm_tc(&ta, &tw, BN, bias_dev, c_dev, N, M, N, K, gelu, out_bf16, st);
 }
 

@@ -6,6 +6,7 @@
 // predict_mask's sampling deep_music_remix.py:2586-2609.
 #include "kernels.cuh"
 #include "sampling.cuh"
+#include "launch.cuh"
 
 namespace dmg {
 
@@ -94,6 +95,8 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(SampleArgs a) {
   __shared__ int sh_int[4];
 
   const int sidx = blockIdx.x, tid = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   const int V = a.V;
   const dmg_vocab_layout vl = a.vocab;
   const dmg_sampler_params sp = a.params;
@@ -322,10 +325,7 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(SampleArgs a) {
 int sample_launch(const SampleArgs& a, int n, cudaStream_t st) {
   DMG_CHECK(a.V <= SAMP_MAXV, "sampler: vocab %d exceeds %d", a.V, SAMP_MAXV);
   if (n <= 0) return 0;
-  sample_kernel<<<n, SAMP_THREADS, 0, st>>>(a);
-  g_launch_count++;
-  DMG_CUDA_OK(cudaGetLastError());
-  return 0;
+  return launch_k(sample_kernel, dim3(n), dim3(SAMP_THREADS), 0, st, 1, a);
 }
 
 }  // namespace dmg

@@ -26,8 +26,9 @@ typedef struct dmg_model dmg_model;
 enum { DMG_ARCH_TXL = 0,   /* MusicTransformerXL + LinearDecoder   (deep_music_genre.py:1603-1647, fastai TransformerXL) */
        DMG_ARCH_BERT = 1   /* MultiTransformer 'msk' branch: MTEncoder + MTLinearDecoder (deep_music_remix.py:1864-2104) */ };
 enum { DMG_F32 = 0, DMG_BF16 = 1 };
-enum { DMG_GEMM_AUTO = 0,  /* bf16: tcgen05/TMEM/TMA kernel; f32: SIMT fp32 kernel */
-       DMG_GEMM_SIMT = 1   /* debugging: SIMT kernel for every dtype */ };
+enum { DMG_GEMM_AUTO = 0,  /* bf16: tcgen05/TMEM/TMA kernels (cluster split-K for <= 512 rows); f32: SIMT fp32 kernel */
+       DMG_GEMM_SIMT = 1,  /* debugging: SIMT kernel for every dtype */
+       DMG_GEMM_TC_TILE = 2 /* dmg_gemm_bf16 only: the one-CTA-per-tile tcgen05 kernel even for skinny shapes */ };
 enum { DMG_LOGITS_NONE = 0, DMG_LOGITS_ALL = 1, DMG_LOGITS_LAST = 2 };
 
 /* Model hyper-parameters: the keys of the reference config dicts (app_utils.py:13-63, fastai tfmerXL_lm_config). */

@@ -30,6 +30,9 @@ def _p(t):
     (1000, 2048, 512, 1, 1, True),     # M > 512 -> 128x128 tiles
     (4096, 1536, 512, 0, 0, False),    # prefill-sized
     (640, 512, 3072, 0, 0, True),      # long K (48 k-blocks through a 6-stage ring)
+    (256, 512, 3072, 0, 0, True),      # split-K 8 x 6 k-blocks
+    (64, 2048, 768, 1, 1, True),       # split-K 4 x 3 k-blocks, GeLU + bf16 out
+    (300, 324, 2048, 0, 0, True),      # 3 M-tiles, ragged N, split-K 8
 ])
 def test_gemm_tcgen05_vs_fp32(M, N, K, gelu, out_bf16, bias):
     L, lib = _lib()
@@ -41,7 +44,7 @@ def test_gemm_tcgen05_vs_fp32(M, N, K, gelu, out_bf16, bias):
     if bias: ref = ref + b
     if gelu:
         ref = 0.5 * ref * (1 + torch.tanh(0.7978845608028654 * (ref + 0.044715 * ref ** 3)))
-    for backend in (L.GEMM_AUTO, L.GEMM_SIMT):
+    for backend in (L.GEMM_AUTO, L.GEMM_TC_TILE, L.GEMM_SIMT):   # AUTO = cluster split-K when M <= 512
         c = torch.full((M, N), float('nan'), device='cuda', dtype=torch.bfloat16 if out_bf16 else torch.float32)
         rc = lib.dmg_gemm_bf16(_p(a), _p(w), _p(b), _p(c), M, N, K, gelu, out_bf16, backend, C.c_void_p(0))
         assert rc == 0, lib.dmg_last_error()
@@ -50,16 +53,6 @@ def test_gemm_tcgen05_vs_fp32(M, N, K, gelu, out_bf16, bias):
         tol = 2e-2 * max(1.0, ref.abs().max().item()) if out_bf16 else 2e-3 * max(1.0, ref.abs().max().item())
         assert not torch.isnan(c.float()).any(), f'backend {backend}: NaN left in output (tile not written)'
         assert err < tol, f'backend {backend}: max err {err} (tol {tol})'
-
-
-def _sample(lib, L, logits, prev, rc, params, offset=0):
-    n = logits.shape[0]
-    from deepmusicgeneration_b200.learner import vocab_layout
-    from deepmusicgeneration_b200.codec import MusicVocab
-    vl = vocab_layout(MusicVocab.create())
-    out = torch.zeros(n, dtype=torch.int32, device='cuda'); nc = torch.zeros(n, dtype=torch.int32, device='cuda')
-    # any engine handle works for the stateless sampler; build the smallest one
-    return vl, out, nc
 
 
 @pytest.fixture(scope='module')
