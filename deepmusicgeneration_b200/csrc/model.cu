@@ -134,13 +134,15 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
   T* xa = (T*)m->xa;
   if (embed<T>(ids, c.encode_position ? pos : nullptr, m->emb.f32, m->beat, m->bar, m->x32, xa, rows, d, c.vocab, st)) return -1;
   if (c.keep_hidden && M > 0 && ring_append_hidden(m->x32, m->hrings[0], nb, T_len, d, M, m->pos_total, b0, st)) return -1;
+  static const int skip = getenv("DMG_DEBUG_SKIP") ? atoi(getenv("DMG_DEBUG_SKIP")) : 0;   // timing experiments only
   const bool v2_ok = !bert && M > 0 && m->layers[0].has_ring_tm && attn_decode2_supported(c.d_head, M) && !getenv("DMG_DECODE_V1");
   const bool fast_decode = m->is_bf16 && !bert && T_len == 1 && (v2_ok || attn_decode_supported(c.d_head, M)) &&
                            !getenv("DMG_NO_DECODE_KERNEL");
   for (int l = 0; l < c.n_layers; l++) {
     LayerW& L = m->layers[l];
-    if (linear(m, A_XA, xa, L.wqkv, L.bqkv, m->qkv, 3 * HD, rows, 0, 0, st)) return -1;
-    if (fast_decode) {
+    if (!(skip & 1) && linear(m, A_XA, xa, L.wqkv, L.bqkv, m->qkv, 3 * HD, rows, 0, 0, st)) return -1;
+    if (skip & 2) {
+    } else if (fast_decode) {
       AttnDecodeArgs a;
       a.qkv = m->qkv;
       a.kring = (bf16*)L.kring + (size_t)b0 * c.n_heads * M * 64;
@@ -169,11 +171,11 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
     if (bert) {
       if (residual_layernorm<T, T>(m->x32, (const T*)m->attn, L.ln1w, L.ln1b, xa, rows, d, st)) return -1;
     } else {
-      if (linear(m, A_ATTN, m->attn, L.wo, L.bo, m->proj, d, rows, 0, 0, st)) return -1;
-      if (residual_layernorm<T, float>(m->x32, m->proj, L.ln1w, L.ln1b, xa, rows, d, st)) return -1;
-      if (linear(m, A_XA, xa, L.w1, L.b1, m->hbuf, c.d_inner, rows, 1, m->is_bf16 ? 1 : 0, st)) return -1;
-      if (linear(m, A_H, m->hbuf, L.w2, L.b2, m->proj, d, rows, 0, 0, st)) return -1;
-      if (residual_layernorm<T, float>(m->x32, m->proj, L.ln2w, L.ln2b, xa, rows, d, st)) return -1;
+      if (!(skip & 4) && linear(m, A_ATTN, m->attn, L.wo, L.bo, m->proj, d, rows, 0, 0, st)) return -1;
+      if (!(skip & 8) && residual_layernorm<T, float>(m->x32, m->proj, L.ln1w, L.ln1b, xa, rows, d, st)) return -1;
+      if (!(skip & 16) && linear(m, A_XA, xa, L.w1, L.b1, m->hbuf, c.d_inner, rows, 1, m->is_bf16 ? 1 : 0, st)) return -1;
+      if (!(skip & 32) && linear(m, A_H, m->hbuf, L.w2, L.b2, m->proj, d, rows, 0, 0, st)) return -1;
+      if (!(skip & 64) && residual_layernorm<T, float>(m->x32, m->proj, L.ln2w, L.ln2b, xa, rows, d, st)) return -1;
     }
     if (c.keep_hidden && M > 0 && ring_append_hidden(m->x32, m->hrings[l + 1], nb, T_len, d, M, m->pos_total, b0, st)) return -1;
   }
