@@ -35,6 +35,11 @@ class SamplerParams(C.Structure):
                 ('n_words', c_i32), ('allowed_ins_mask', c_u32), ('flags', c_i32), ('seed', c_u64)]
 
 
+class TrainConfig(C.Structure):
+    _fields_ = [('batch', c_i32), ('bptt', c_i32), ('resid_p', c_f32), ('attn_p', c_f32), ('ff_p', c_f32), ('embed_p', c_f32),
+                ('output_p', c_f32), ('alpha', c_f32), ('beta', c_f32), ('seed', c_u64), ('reserved', c_i32 * 4)]
+
+
 # name -> (restype, argtypes): every symbol include/dmg_b200.h declares
 SYMBOLS = {
     'dmg_last_error': (C.c_char_p, []),
@@ -59,6 +64,25 @@ SYMBOLS = {
     'dmg_uses_tcgen05': (c_i32, [c_vp]),
     'dmg_attn_decode_layer': (c_i32, [c_vp, c_i32, c_vp]),
     'dmg_gemm_bf16': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    # training step
+    'dmg_train_param_count': (c_i64, [c_vp]),
+    'dmg_train_create': (c_i32, [c_vp, C.POINTER(TrainConfig), c_vp]),
+    'dmg_train_destroy': (None, [c_vp]),
+    'dmg_train_reset': (c_i32, [c_vp]),
+    'dmg_train_forward': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, c_vp]),
+    'dmg_train_backward': (c_i32, [c_vp, c_i32, c_i32, c_vp]),
+    'dmg_train_grad_span': (c_i32, [c_vp, c_i32, c_i32, C.POINTER(c_i64), C.POINTER(c_i64)]),
+    'dmg_train_optimizer_step': (c_i32, [c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp]),
+    'dmg_train_losses': (c_i32, [c_vp, c_vp, c_vp]),
+    'dmg_train_get_grad': (c_i32, [c_vp, C.c_char_p, c_vp, c_i64]),
+    'dmg_train_dropout_mask': (c_i32, [c_vp, c_i32, c_i32, c_i64, c_vp, c_i64, c_vp]),
+    'dmg_train_grad_buffer': (c_vp, [c_vp]),
+    'dmg_gemm_train': (c_i32, [c_vp, c_i32, c_i64, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_i64,
+                               c_i32, c_vp, c_i64, c_i32, c_vp, c_i64, c_f32, c_u32, c_vp]),
+    'dmg_attn_train_fwd': (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32,
+                                   c_i32, c_i32, c_f32, c_u32, c_vp]),
+    'dmg_attn_train_bwd': (c_i32, [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32,
+                                   c_i32, c_i32, c_i32, c_f32, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 
 

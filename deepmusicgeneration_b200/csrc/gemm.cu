@@ -123,6 +123,24 @@ int make_tmap_bf16(TensorMap2D* out, const void* base, long long cols, long long
   return 0;
 }
 
+// General form (training GEMMs): any inner length (out-of-bounds box elements read as zero), 64-element inner box.
+int make_tmap_bf16_ex(TensorMap2D* out, const void* base, long long inner, long long rows, long long ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  DMG_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  DMG_CHECK(((uintptr_t)base & 15) == 0 && (ld * 2) % 16 == 0, "tensor map: base/stride not 16-byte aligned (ld=%lld)", ld);
+  DMG_CHECK(box_rows >= 1 && box_rows <= 256, "tensor map: box_rows %d outside [1, 256]", box_rows);
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc((CUtensorMap*)out->bytes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                   gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DMG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner %lld rows %lld ld %lld box %d)", (int)r,
+            inner, rows, ld, box_rows);
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05 GEMM
 // ---------------------------------------------------------------------------------------------

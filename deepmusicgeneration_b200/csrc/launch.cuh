@@ -49,4 +49,19 @@ int launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaS
   return 0;
 }
 
+// Plain stream-ordered launch (training kernels: no programmatic dependent launch, so no pdl_wait() obligations).
+template <class... KArgs, class... Args>
+int launch_np(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = nullptr;
+  cfg.numAttrs = 0;
+  DMG_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
+  g_launch_count++;
+  return 0;
+}
+
 }  // namespace dmg

@@ -7,9 +7,8 @@
 #include <string>
 #include <vector>
 
-#include "../../include/dmg_b200.h"
-#include "kernels.cuh"
-#include "sampling.cuh"
+#include "model.cuh"
+#include "launch.cuh"
 
 namespace dmg {
 
@@ -21,81 +20,12 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-struct Weight {
-  float* f32 = nullptr;   // master copy, nn.Linear layout [rows(out), cols(in)]
-  bf16* b16 = nullptr;
-  int rows = 0, cols = 0;
-  TensorMap2D tm32, tm128;   // TMA maps with 32- and 128-row boxes
-  bool has_tm = false;
-};
-
-struct LayerW {
-  Weight wqkv, wr, wo, w1, w2;
-  float *bqkv = nullptr, *br = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
-  float *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr;
-  void* rd = nullptr;      // [H][Dcap][Dh] compute dtype: r_attn(PositionalEncoding(dist))
-  void* kring = nullptr;   // [max_batch][H][M][Dh] compute dtype
-  void* vring = nullptr;
-  TensorMap2D tmK, tmV, tmR;   // 64-row boxes over the rings / the rel-pos cache (decode attention v2)
-  bool has_ring_tm = false;
-};
-
-struct RegEntry {
-  float* dst;
-  long long numel;
-};
-
-enum ABuf { A_XA = 0, A_ATTN = 1, A_H = 2, A_XLAST = 3, A_COUNT = 4 };
-
 }  // namespace dmg
 
 using namespace dmg;
 
-struct dmg_model {
-  dmg_config cfg;
-  int device = 0;
-  bool is_bf16 = false, use_tc = false, committed = false;
-  int HD = 0, Dcap = 0, max_rows = 0, esz = 4, num_sms = 148;
-  Weight emb;   // [V, d] (tied head)
-  float *beat = nullptr, *bar = nullptr, *u = nullptr, *v = nullptr, *head_b = nullptr;
-  std::vector<LayerW> layers;
-  std::vector<float*> hrings;   // (L+1) x [max_batch][M][d] fp32 when keep_hidden
-  std::map<std::string, RegEntry> reg;
-  std::vector<void*> allocs;
-  long long bytes = 0;
-  // memory state
-  long long pos_total = 0;
-  int mem_count = 0, batch = 0;
-  int* dev_state = nullptr;
-  // workspaces
-  float *x32 = nullptr, *qkv = nullptr, *proj = nullptr, *logits_buf = nullptr;
-  void *xa = nullptr, *attn = nullptr, *hbuf = nullptr, *xlast = nullptr;
-  TensorMap2D tmA[A_COUNT];
-  int a_rows[A_COUNT], a_cols[A_COUNT];
-  // generation loop
-  bool samp_ready = false, logits_valid = false;
-  SampleArgs samp;
-  long long *ids_buf = nullptr, *pos_buf = nullptr;
-  int* tok_buf = nullptr;
-  cudaStream_t cap_stream = nullptr;
-  cudaGraphExec_t step_graph = nullptr;
-  int graph_bs = -1;
-  long long graph_launches = 0;
-};
-
 namespace dmg {
 
-template <class T>
-static int dalloc(dmg_model* m, T** p, size_t n, bool zero = true) {
-  void* q = nullptr;
-  const size_t bytes = (n ? n : 1) * sizeof(T);
-  DMG_CUDA_OK(cudaMalloc(&q, bytes));
-  if (zero) DMG_CUDA_OK(cudaMemset(q, 0, bytes));
-  m->allocs.push_back(q);
-  m->bytes += (long long)bytes;
-  *p = (T*)q;
-  return 0;
-}
 
 static int alloc_weight(dmg_model* m, Weight& w, int rows, int cols, const std::string& name) {
   w.rows = rows;
@@ -317,6 +247,7 @@ int dmg_mem_count(dmg_model* m) { return m ? m->mem_count : -1; }
 void dmg_destroy(dmg_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
+  dmg_train_destroy(m);
   if (m->step_graph) cudaGraphExecDestroy(m->step_graph);
   if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
   for (void* p : m->allocs) cudaFree(p);

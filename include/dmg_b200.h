@@ -149,6 +149,71 @@ int dmg_attn_decode_layer(dmg_model* m, int layer, void* stream);
 int dmg_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_dev, void* c_dev, int M, int N, int K,
                   int gelu, int out_bf16, int backend, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training step: what fastai's Learner.fit does around the reference model for one batch -
+ * model(x) in train mode (deep_music_genre.py:1617-1647 with dropout and rand_window_mask :1586-1590), CrossEntropyFlat
+ * + RNNTrainer's AR/TAR terms, loss.backward(), Adam with decoupled weight decay.  bf16 compute (tcgen05 GEMMs, mma.sync
+ * flash attention with the rel-pos term), fp32 master weights / residual stream / gradients.  Needs a DMG_BF16
+ * DMG_ARCH_TXL model.  Data-parallel training: every rank runs forward/backward on its own sequences and all-reduces the
+ * flat gradient buffer (dmg_train_grad_span tells which slice is final after which backward call) before the step.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct dmg_train_config {
+  int32_t batch;            /* sequences per step on this GPU (each keeps its own memory, like bs rows of the reference batch) */
+  int32_t bptt;             /* tokens per sequence and step (x_len), a multiple of 64                                          */
+  float resid_p, attn_p, ff_p, embed_p, output_p;   /* dropout probabilities, already multiplied by drop_mult (App. A.1/A.2)    */
+  float alpha, beta;        /* RNNTrainer activation regularisation (AR) and temporal AR (TAR, value only), App. A.7           */
+  uint64_t seed;            /* base seed of the counter-based dropout masks                                                    */
+  int32_t reserved[4];
+} dmg_train_config;
+
+/* Allocates activations / gradient / Adam state.  grad_flat_dev: caller-owned fp32 device buffer of
+ * dmg_train_param_count() elements that receives the gradients (e.g. a torch tensor handed to NCCL), or NULL to let the
+ * model own one.  Call dmg_train_param_count first (it works before dmg_train_create). */
+int64_t dmg_train_param_count(dmg_model* m);
+int dmg_train_create(dmg_model* m, const dmg_train_config* cfg, float* grad_flat_dev);
+void dmg_train_destroy(dmg_model* m);
+/* RNNTrainer.on_epoch_begin -> model.reset(): forget the training memory (hidden states of the previous segments). */
+int dmg_train_reset(dmg_model* m);
+/* model(x) in train mode + loss.  ids/targets (and pos when encode_position): int64 [batch, bptt] on the device.
+ * (mask_win, mask_k): what rand_window_mask drew on the host, (1,1) or (w,0).  training = 0 disables every dropout
+ * (model.eval() semantics with the training memory).  `step` keys the dropout masks. */
+int dmg_train_forward(dmg_model* m, const int64_t* ids_dev, const int64_t* pos_dev, const int64_t* targets_dev, int mask_win,
+                      int mask_k, int training, int64_t step, void* stream);
+/* loss.backward() in slices so that the gradient all-reduce can overlap: runs the head (when layer_hi == n_layers) and
+ * the layers layer_hi-1 ... layer_lo; layer_lo == 0 also runs the embedding and finishes the step (memory update).
+ * Slices must be issued in descending order and cover n_layers..0 exactly once per forward. */
+int dmg_train_backward(dmg_model* m, int layer_hi, int layer_lo, void* stream);
+/* Flat-gradient slice that is final once dmg_train_backward(m, layer_hi, layer_lo) has run. */
+int dmg_train_grad_span(dmg_model* m, int layer_hi, int layer_lo, int64_t* offset, int64_t* count);
+/* Adam(betas, eps) with fastai's true_wd (p *= 1 - lr*wd first), gradients scaled by grad_scale (1/world_size after a
+ * SUM all-reduce) and clipped to global norm `clip` (<= 0: no clipping); refreshes the bf16 weight copies.
+ * Inference entry points need dmg_commit_weights() again afterwards (the rel-pos key cache follows r_attn). */
+int dmg_train_optimizer_step(dmg_model* m, float lr, float beta1, float beta2, float eps, float wd, float clip,
+                             float grad_scale, void* stream);
+/* Synchronises the stream and returns {cross-entropy (mean), alpha*AR, beta*TAR, gradient norm (after grad_scale; 0 before
+ * the first optimizer step)} of the latest step. */
+int dmg_train_losses(dmg_model* m, float* out4_host, void* stream);
+/* Tests: gradient of one parameter by its state-dict name; the dropout mask (keep ? 1/(1-p) : 0) of a site as the kernels
+ * generate it (site 0 embedding [rows,d], 1 attention [B,H,T,S], 2 attention-residual [rows,d], 3 FFN inner [rows,d_inner],
+ * 4 FFN residual [rows,d], 5 output RNN dropout [B,d]); the device pointer of the owned gradient buffer. */
+int dmg_train_get_grad(dmg_model* m, const char* name, float* out_host, int64_t numel);
+int dmg_train_dropout_mask(dmg_model* m, int site, int layer, int64_t step, float* out_dev, int64_t numel, void* stream);
+float* dmg_train_grad_buffer(dmg_model* m);
+/* Unit-test entry of the training GEMM (persistent tcgen05 kernel): C[M,N] = op(A) op(B); a_mn / b_mn = 1 when the
+ * reduction index is the slow one in memory; out_mode 0 fp32, 1 bf16, 2 fp32 atomic accumulate (split-K allowed);
+ * aux_mode 0 none, 1 multiply by gelu'(aux bf16), 2 add aux bf16, 3 add aux fp32. */
+int dmg_gemm_train(const void* a_dev, int a_mn, int64_t lda, const void* b_dev, int b_mn, int64_t ldb, int M, int N, int K,
+                   int splitk, const float* bias_dev, int gelu, const void* aux_dev, int64_t ld_aux, int aux_mode, void* out_dev,
+                   int64_t ldc, int out_mode, void* out2_dev, int64_t ld2, float drop_p, uint32_t drop_seed, void* stream);
+/* Unit-test entries of the training attention kernels (attention_train.cu): see AttnTrainArgs for the layouts. */
+int dmg_attn_train_fwd(const void* qkv_x, int64_t ldx, const void* kv_m, int64_t ldm, const void* rk, const float* u,
+                       const float* v, void* out, float* lse, int B, int T, int H, int M, int mem_count, int win, int k,
+                       float drop_p, uint32_t drop_seed, void* stream);
+int dmg_attn_train_bwd(const void* qkv_x, int64_t ldx, const void* kv_m, int64_t ldm, const void* rk, const float* u,
+                       const float* v, const void* out, const float* lse, const void* dout, int B, int T, int H, int M,
+                       int mem_count, int win, int k, float drop_p, uint32_t drop_seed, float* delta, void* dqkv_x, void* dkv_m,
+                       void* ds_dist, float* du, float* dv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,158 @@
+"""GPU parity of the whole training step (dmg_train_*) against the oracle's restatement of the fastai step
+(oracle/train.py on oracle/txl.py): loss parts, every parameter gradient, the Adam update and the memory carried into the
+next step, with and without dropout (the oracle is fed the very masks the kernels draw)."""
+import numpy as np
+import pytest
+import torch
+
+from deepmusicgeneration_b200.model import get_language_model
+from deepmusicgeneration_b200.training import TXLTrainer, one_cycle_lr, rand_window_mask_size
+from oracle import train as otrain
+from oracle import txl
+
+pytestmark = pytest.mark.gpu
+
+V = 324
+
+
+def small_config(**kw):
+    c = dict(txl.default_config(), n_layers=2, d_model=128, n_heads=2, d_head=64, d_inner=256, mem_len=64, ctx_len=64,
+             encode_position=False, mask_steps=1)
+    c.update(kw)
+    return c
+
+
+def build_pair(cfg, bs, bptt, drop_mult, seed=0, alpha=2., beta=1.):
+    torch.manual_seed(seed)
+    om = txl.get_language_model(V, cfg, drop_mult=drop_mult)
+    pm = get_language_model(V, cfg, dtype='bf16', device=0, max_batch=bs, max_seq=max(bptt, 64), keep_hidden=False, init=False)
+    pm.load_state_dict(om.state_dict())
+    tr = TXLTrainer(pm, bs, bptt, cfg, drop_mult=drop_mult, alpha=alpha, beta=beta, seed=1234, distributed=False)
+    return om, pm, tr
+
+
+def set_oracle_mask(monkeypatch, size):
+    def fixed(x_len, m_len, device, max_size=None, p=0.2, is_eval=False, rng=None):
+        return txl.window_mask(x_len, device, m_len, size=size)
+    monkeypatch.setattr(txl, 'rand_window_mask', fixed)
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20)).item()
+
+
+def compare_grads(tr, om, tol, skip=()):
+    got = tr.grads()
+    ref = {n: p.grad for n, p in om.state_dict(keep_vars=True).items() if getattr(p, 'grad', None) is not None}
+    checked = 0
+    worst = (0., None)
+    for name, g in got.items():
+        if name in skip:
+            continue
+        r = ref.get(name)
+        if r is None and name == '0.encoder.weight':
+            r = ref.get('1.decoder.weight')
+        assert r is not None, f'oracle has no gradient for {name}'
+        e = rel(g, r.reshape(g.shape))
+        if e > worst[0]:
+            worst = (e, name)
+        checked += 1
+    assert worst[0] < tol, f'worst gradient mismatch {worst}'
+    print('worst gradient rel err', worst)
+    return checked
+
+
+def install_masks(tr, sites, cfg, bs, bptt, m_len, step):
+    "give the oracle the masks the kernels will draw for `step`"
+    d, H, di, M = cfg['d_model'], cfg['n_heads'], cfg['d_inner'], cfg['mem_len']
+    S = M + bptt
+    sites['embed'][0].mask = tr.dropout_mask(0, 0, (bs, bptt, d), step).cpu()
+    sites['out'][0].mask = tr.dropout_mask(5, 0, (bs, 1, d), step).cpu()
+    for l in range(cfg['n_layers']):
+        full = tr.dropout_mask(1, l, (bs, H, bptt, S), step)
+        sites['attn'][l].mask = full[..., M - m_len:].cpu()
+        sites['res1'][l].mask = tr.dropout_mask(2, l, (bs, bptt, d), step).cpu()
+        sites['ff'][l].mask = tr.dropout_mask(3, l, (bs, bptt, di), step).cpu()
+        sites['res2'][l].mask = tr.dropout_mask(4, l, (bs, bptt, d), step).cpu()
+
+
+@pytest.mark.parametrize('drop_mult,encode_position,mask_size', [(0., False, (1, 1)), (0., True, (1, 0)), (1., False, (1, 1)),
+                                                                 (1., True, (2, 0))])
+def test_training_step_matches_oracle(monkeypatch, drop_mult, encode_position, mask_size):
+    cfg = small_config(encode_position=encode_position, mask_steps=2)
+    bs, bptt, steps = 3, 64, 3
+    om, pm, tr = build_pair(cfg, bs, bptt, drop_mult)
+    om.train(); om.reset()
+    sites = otrain.install_dropout_masks(om)
+    set_oracle_mask(monkeypatch, mask_size)
+    opt = otrain.AdamTrueWD(otrain.unique_params(om), eps=1e-3)
+    sd0 = {k: v.clone() for k, v in om.state_dict().items()}
+    tr.reset()
+    g = torch.Generator().manual_seed(5)
+    lr = 1e-3
+    for s in range(steps):
+        x = torch.randint(0, V, (bs, bptt), generator=g)
+        y = torch.randint(0, V, (bs, bptt), generator=g)
+        pos = torch.cumsum(torch.randint(0, 9, (bs, bptt), generator=g), 1) + 40 * s if encode_position else None
+        m_len = min(cfg['mem_len'], s * bptt)
+        if drop_mult > 0:
+            install_masks(tr, sites, cfg, bs, bptt, m_len, s)
+        ref = otrain.train_step(om, {'x': x, 'pos': pos} if encode_position else x, y, opt, lr, wd=0.01, clip=0.5)
+        tr.forward(x, y, pos, mask_size=mask_size)
+        tr.backward()
+        got = tr.losses()
+        assert abs(got['ce'] - ref['ce']) < 2e-2 * max(1., abs(ref['ce'])), (s, got, ref)
+        assert abs(got['ar'] - ref['ar']) < 2e-2 * max(1e-3, abs(ref['ar'])), (s, got, ref)
+        assert abs(got['tar'] - ref['tar']) < 3e-2 * max(1e-3, abs(ref['tar'])), (s, got, ref)
+        n = compare_grads(tr, om, tol=2e-2)
+        assert n >= 4 + 11 * cfg['n_layers']
+        tr.optimizer_step(lr, betas=(0.9, 0.99), eps=1e-3, wd=0.01, clip=0.5)
+        got = tr.losses()
+        assert abs(got['grad_norm'] - ref['grad_norm']) < 3e-2 * ref['grad_norm'], (s, got, ref)
+    # parameter movement after three Adam steps (eps is large in this test so that the update is a smooth function of the
+    # gradient: with the default 1e-8 an update is lr*sign(g) and bf16 noise on near-zero gradients flips signs)
+    sd_ref, sd_got = om.state_dict(), pm.state_dict()
+    for name, w in sd_got.items():
+        d_got, d_ref = w - sd0[name].reshape(w.shape), (sd_ref[name] - sd0[name]).reshape(w.shape)
+        assert rel(d_got, d_ref) < 0.1, (name, rel(d_got, d_ref))
+    tr.close()
+
+
+def test_training_reduces_loss_and_inference_follows():
+    "a few hundred steps on a repeating pattern: the loss must fall; afterwards the inference path sees the trained weights"
+    cfg = small_config()
+    bs, bptt = 4, 64
+    om, pm, tr = build_pair(cfg, bs, bptt, drop_mult=1.0, alpha=2., beta=1.)
+    base = torch.arange(bs * bptt * 40) % 37 + 12
+    data = base.view(bs, -1)
+    tr.reset()
+    first = last = None
+    n = data.shape[1] // bptt - 1
+    for ep in range(3):
+        tr.reset()
+        for i in range(n):
+            x = data[:, i * bptt:(i + 1) * bptt]
+            y = data[:, i * bptt + 1:(i + 1) * bptt + 1]
+            lr, mom = one_cycle_lr(ep * n + i, 3 * n, 3e-3)
+            tr.step(x, y, lr=lr, betas=(mom, 0.99))
+            if first is None:
+                first = tr.losses()['ce']
+    last = tr.losses()['ce']
+    assert first > 4.0 and last < 0.5 * first, (first, last)
+    tr.sync_for_inference()
+    pm.reset()
+    logits = pm(data[:, :bptt].cuda())[0]
+    pred = logits.argmax(-1).cpu()
+    acc = (pred[:, 8:] == data[:, 9:bptt + 1]).float().mean().item()
+    assert acc > 0.9, acc
+    tr.close()
+
+
+def test_rand_window_mask_size_follows_reference_draws():
+    rng = np.random.RandomState(0)
+    ref = np.random.RandomState(0)
+    for _ in range(200):
+        got = rand_window_mask_size(4, p=0.2, is_eval=False, rng=rng)
+        exp = (1, 1) if ref.rand() >= 0.2 else (ref.randint(0, 4) + 1, 0)
+        assert got == exp
+    assert rand_window_mask_size(4, is_eval=True) == (1, 1)
