@@ -44,13 +44,13 @@ __device__ __forceinline__ bool visible(const MaskP& mp, int i, int j) {
 
 // (q + bias) A-fragments: a[ks] covers k = 16*ks..16*ks+15; registers hold (g,2t..),(g+8,2t..),(g,2t+8..),(g+8,2t+8..)
 __device__ __forceinline__ uint32_t add_bias2(uint32_t w, float b0, float b1) { return pack_bf16x2(bf16lo(w) + b0, bf16hi(w) + b1); }
-__device__ __forceinline__ void q_frags(uint32_t sQ, int w, int lane, const float* __restrict__ u, const float* __restrict__ v,
+__device__ __forceinline__ void q_frags(uint32_t sQ, int w, int lane, const LaneOff& L, const float* __restrict__ u, const float* __restrict__ v,
                                         uint32_t (&qu)[4][4], uint32_t (&qv)[4][4]) {
   const int t = lane & 3;
 #pragma unroll
   for (int ks = 0; ks < 4; ks++) {
     uint32_t a[4];
-    frag_a(sQ, 16 * w, 16 * ks, lane, a);
+    frag_a(sQ, 16 * w, ks, L, a);
     const int c0 = 16 * ks + 2 * t;
     const float u0 = u[c0], u1 = u[c0 + 1], u8 = u[c0 + 8], u9 = u[c0 + 9];
     const float v0 = v[c0], v1 = v[c0 + 1], v8 = v[c0 + 8], v9 = v[c0 + 9];
@@ -64,19 +64,18 @@ __device__ __forceinline__ void q_frags(uint32_t sQ, int w, int lane, const floa
 // s[nt][e] = AC + BD (unscaled) for the warp's 16 query rows x the tile's 64 keys.
 // sR0 / sR1: the two Rk tiles of the window (distances D0-64..D0-1 and D0..D0+63).
 __device__ __forceinline__ void scores_tile(const uint32_t (&qu)[4][4], const uint32_t (&qv)[4][4], uint32_t sK, uint32_t sR0,
-                                            uint32_t sR1, float* skew, int w, int lane, float (&s)[8][4]) {
+                                            uint32_t sR1, float* skew, int w, int lane, const LaneOff& L, float (&s)[8][4]) {
   const int g = lane >> 2, t = lane & 3;
   // position term: 16 rows x 80 distances (window columns 16w .. 16w+79)
 #pragma unroll
   for (int p = 0; p < 5; p++) {
     const int wc = 16 * w + 16 * p;                 // first window column of this pair of n-tiles
-    const uint32_t sR = wc < 64 ? sR0 : sR1;
-    const int n0 = wc & 63;
+    const uint32_t sR = (wc < 64 ? sR0 : sR1) + (wc & 63) * 128;
     float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
     for (int ks = 0; ks < 4; ks++) {
       uint32_t r[4];
-      frag_b(sR, n0, 16 * ks, lane, r);
+      frag_b(sR, 0, ks, L, r);
       mma_bf16(acc[0], qv[ks], r[0], r[1]);
       mma_bf16(acc[1], qv[ks], r[2], r[3]);
     }
@@ -96,7 +95,7 @@ __device__ __forceinline__ void scores_tile(const uint32_t (&qu)[4][4], const ui
 #pragma unroll
     for (int np = 0; np < 4; np++) {
       uint32_t r[4];
-      frag_b(sK, 16 * np, 16 * ks, lane, r);
+      frag_b(sK, 16 * np, ks, L, r);
       mma_bf16(s[2 * np], qu[ks], r[0], r[1]);
       mma_bf16(s[2 * np + 1], qu[ks], r[2], r[3]);
     }
@@ -137,57 +136,79 @@ __device__ __forceinline__ float quad_sum(float v) {
 // =============================================================================================
 // forward
 // =============================================================================================
-constexpr int FWD_SMEM = 3 * TILE_BYTES /*Q,K,V*/ + 2 * TILE_BYTES /*R ring*/ + 4 * 16 * SKEW_LD * 4;
+// Pipeline: K / V tiles in an NST-deep ring (cp.async groups, prefetch distance NST-1), Rk tiles in an (NST+1)-slot ring
+// (tile rt lives in slot rt % (NST+1)): iteration jt needs Rk tiles rt_hi = (M+i0)/64 - jt and rt_hi - 1, and each
+// iteration's load group brings exactly one new Rk tile (the very first brings two).
+constexpr int ATT_NST = 3;
+constexpr int ATT_NR = ATT_NST + 1;
+constexpr int FWD_SMEM = TILE_BYTES /*Q*/ + 2 * ATT_NST * TILE_BYTES /*K,V ring*/ + ATT_NR * TILE_BYTES /*R ring*/ + 4 * 16 * SKEW_LD * 4;
 
 __global__ void __launch_bounds__(128) attn_train_fwd_kernel(const AttnTrainArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + TILE_BYTES;
-  uint8_t* sV = sK + TILE_BYTES;
-  uint8_t* sR = sV + TILE_BYTES;                    // 2 tiles: Rk tile rt lives in slot rt & 1
-  float* skew_all = (float*)(sR + 2 * TILE_BYTES);
+  uint8_t* sKV = sQ + TILE_BYTES;                   // stage s: K at sKV + 2*s*TILE, V right behind it
+  uint8_t* sR = sKV + 2 * ATT_NST * TILE_BYTES;
+  float* skew_all = (float*)(sR + ATT_NR * TILE_BYTES);
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   float* skew = skew_all + w * 16 * SKEW_LD;
+  LaneOff L;
+  lane_off_init(L, lane, w);
 
   const int nT = a.T / 64;
   const int it = nT - 1 - (blockIdx.x % nT);        // heavy (late) query tiles first
   const int bh = blockIdx.x / nT, b = bh / a.H, h = bh % a.H;
   const int i0 = it * 64, HD = a.H * 64, S = a.M + a.T;
   const MaskP mp = {a.M, a.mem_count, a.win, a.k};
+  const int jt_lo = (a.M - a.mem_count) / 64, jt_hi = (a.M + i0) / 64;
+  const int rt_top = (a.M + i0) / 64;               // rt_hi of iteration jt is rt_top - jt
+
+  auto load_stage = [&](int jt) {                   // one cp.async group: K, V of key tile jt and the new Rk tile(s)
+    if (jt <= jt_hi) {
+      const int st = (jt - jt_lo) % ATT_NST;
+      long long ld;
+      const bf16* kp = kv_tile_ptr(a, b, h, jt, 0, &ld);
+      tile_load_async(sKV + 2 * st * TILE_BYTES, kp, ld, tid, 128);
+      const bf16* vp = kv_tile_ptr(a, b, h, jt, 1, &ld);
+      tile_load_async(sKV + (2 * st + 1) * TILE_BYTES, vp, ld, tid, 128);
+      const int rt_hi = rt_top - jt;
+      if (jt == jt_lo) tile_load_async(sR + (rt_hi % ATT_NR) * TILE_BYTES, a.rk + (long long)rt_hi * 64 * HD + h * 64, HD, tid, 128);
+      if (rt_hi > 0) tile_load_async(sR + ((rt_hi - 1) % ATT_NR) * TILE_BYTES, a.rk + (long long)(rt_hi - 1) * 64 * HD + h * 64, HD, tid, 128);
+    }
+    cp_async_commit();
+  };
 
   tile_load_async(sQ, a.qkv_x + ((long long)b * a.T + i0) * a.ldx + h * 64, a.ldx, tid, 128);
   cp_async_commit();
-  cp_async_wait<0>();
+#pragma unroll
+  for (int s = 0; s < ATT_NST - 1; s++) load_stage(jt_lo + s);
+  cp_async_wait<ATT_NST - 1>();                     // Q has landed (the stage groups may still be in flight)
   __syncthreads();
   uint32_t qu[4][4], qv[4][4];
-  q_frags(smem_u32(sQ), w, lane, a.u + h * 64, a.v + h * 64, qu, qv);
+  q_frags(smem_u32(sQ), w, lane, L, a.u + h * 64, a.v + h * 64, qu, qv);
 
   float o[8][4];
 #pragma unroll
   for (int nt = 0; nt < 8; nt++) { o[nt][0] = 0.f; o[nt][1] = 0.f; o[nt][2] = 0.f; o[nt][3] = 0.f; }
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   const float c = a.scale * LOG2E;
-  const int jt_lo = (a.M - a.mem_count) / 64, jt_hi = (a.M + i0) / 64;
   const int row_g[2] = {i0 + 16 * w + g, i0 + 16 * w + g + 8};
+  // dropout pair index of (row, key j) = ((bh*T + row)*S + j) / 2 = drop_base[row] + j/2   (S is even; this thread's j/2 = j0/2 + 4*nt + t)
+  const uint32_t drop_base[2] = {(uint32_t)((((long long)bh * a.T + row_g[0]) * S) >> 1) + t,
+                                 (uint32_t)((((long long)bh * a.T + row_g[1]) * S) >> 1) + t};
 
   for (int jt = jt_lo; jt <= jt_hi; jt++) {
     const int j0 = jt * 64;
-    const int rt_hi = (a.M + i0 - j0) / 64, rt_lo = rt_hi > 0 ? rt_hi - 1 : 0;
-    __syncthreads();                                 // everybody is done with the previous K / V / R tiles
-    long long ld;
-    const bf16* kp = kv_tile_ptr(a, b, h, jt, 0, &ld);
-    tile_load_async(sK, kp, ld, tid, 128);
-    const bf16* vp = kv_tile_ptr(a, b, h, jt, 1, &ld);
-    tile_load_async(sV, vp, ld, tid, 128);
-    if (jt == jt_lo) tile_load_async(sR + (rt_hi & 1) * TILE_BYTES, a.rk + (long long)rt_hi * 64 * HD + h * 64, HD, tid, 128);
-    if (rt_hi > 0) tile_load_async(sR + (rt_lo & 1) * TILE_BYTES, a.rk + (long long)rt_lo * 64 * HD + h * 64, HD, tid, 128);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
+    const int rt_hi = rt_top - jt, rt_lo = rt_hi > 0 ? rt_hi - 1 : 0;
+    cp_async_wait<ATT_NST - 2>();                    // tile jt has landed
+    __syncthreads();                                 // ... for everybody; and everybody is done with tile jt-1
+    load_stage(jt + ATT_NST - 1);                    // refill the stage tile jt-1 used
+    const int st = (jt - jt_lo) % ATT_NST;
+    uint8_t* sK = sKV + 2 * st * TILE_BYTES;
+    uint8_t* sV = sK + TILE_BYTES;
 
     float s[8][4];
-    scores_tile(qu, qv, smem_u32(sK), smem_u32(sR + (rt_lo & 1) * TILE_BYTES), smem_u32(sR + (rt_hi & 1) * TILE_BYTES), skew, w,
-                lane, s);
+    scores_tile(qu, qv, smem_u32(sK), smem_u32(sR + (rt_lo % ATT_NR) * TILE_BYTES), smem_u32(sR + (rt_hi % ATT_NR) * TILE_BYTES),
+                skew, w, lane, L, s);
     const bool need_mask = (j0 + 63 >= a.M) || (j0 < a.M - a.mem_count);
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
@@ -204,7 +225,7 @@ __global__ void __launch_bounds__(128) attn_train_fwd_kernel(const AttnTrainArgs
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       const float m_new = fmaxf(m_run[r], quad_max(mx[r]));
-      alpha[r] = (m_new == -INFINITY) ? 1.f : exp2f(m_run[r] - m_new);
+      alpha[r] = (m_new == -INFINITY) ? 1.f : ex2_fast(m_run[r] - m_new);
       m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;
       m_run[r] = m_new;
     }
@@ -215,14 +236,13 @@ __global__ void __launch_bounds__(128) attn_train_fwd_kernel(const AttnTrainArgs
       float p[4];
 #pragma unroll
       for (int e = 0; e < 4; e++) {
-        p[e] = exp2f(s[nt][e] - m_use[e >> 1]);
+        p[e] = ex2_fast(s[nt][e] - m_use[e >> 1]);
         rs[e >> 1] += p[e];
       }
       if (a.drop_thresh) {
 #pragma unroll
         for (int r = 0; r < 2; r++) {
-          const uint32_t e0 = (uint32_t)(((long long)bh * a.T + row_g[r]) * S + j0 + 8 * nt + 2 * t);
-          const uint32_t hb = drop_pair_bits(a.drop_seed, e0 >> 1);
+          const uint32_t hb = drop_pair_bits(a.drop_seed, drop_base[r] + (uint32_t)(j0 >> 1) + 4 * nt);
           p[2 * r] = ((hb & 0xFFFFu) >= a.drop_thresh) ? p[2 * r] * a.drop_scale : 0.f;
           p[2 * r + 1] = ((hb >> 16) >= a.drop_thresh) ? p[2 * r + 1] * a.drop_scale : 0.f;
         }
@@ -242,7 +262,7 @@ __global__ void __launch_bounds__(128) attn_train_fwd_kernel(const AttnTrainArgs
 #pragma unroll
       for (int np = 0; np < 4; np++) {
         uint32_t r[4];
-        frag_b_t(sVa, 16 * np, 16 * ks, lane, r);
+        frag_b_t(sVa, np, 16 * ks, L, r);
         mma_bf16(o[2 * np], pa[ks], r[0], r[1]);
         mma_bf16(o[2 * np + 1], pa[ks], r[2], r[3]);
       }
@@ -281,7 +301,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
 // recompute P (normalised), dP and dS for one tile; returns ds (scaled gradient wrt AC+BD) and pd (dropped P) in s / pd
 __device__ __forceinline__ void bwd_tile_math(const AttnTrainArgs& a, const MaskP& mp, float (&s)[8][4], float (&dpd)[8][4],
                                               const int (&row_g)[2], const float (&lse2)[2], const float (&dl)[2], int j0,
-                                              long long bhT, int S, int t, bool want_pd, float (&pd)[8][4]) {
+                                              const uint32_t (&drop_base)[2], int t, bool want_pd, float (&pd)[8][4]) {
   const float c = a.scale * LOG2E;
   const bool need_mask = (j0 + 63 >= a.M) || (j0 < a.M - a.mem_count);
 #pragma unroll
@@ -290,8 +310,7 @@ __device__ __forceinline__ void bwd_tile_math(const AttnTrainArgs& a, const Mask
     if (a.drop_thresh) {
 #pragma unroll
       for (int r = 0; r < 2; r++) {
-        const uint32_t e0 = (uint32_t)((bhT + row_g[r]) * S + j0 + 8 * nt + 2 * t);
-        const uint32_t hb = drop_pair_bits(a.drop_seed, e0 >> 1);
+        const uint32_t hb = drop_pair_bits(a.drop_seed, drop_base[r] + (uint32_t)(j0 >> 1) + 4 * nt);
         keep[2 * r] = ((hb & 0xFFFFu) >= a.drop_thresh) ? a.drop_scale : 0.f;
         keep[2 * r + 1] = ((hb >> 16) >= a.drop_thresh) ? a.drop_scale : 0.f;
       }
@@ -299,7 +318,7 @@ __device__ __forceinline__ void bwd_tile_math(const AttnTrainArgs& a, const Mask
 #pragma unroll
     for (int e = 0; e < 4; e++) {
       const int r = e >> 1;
-      float p = exp2f(s[nt][e] * c - lse2[r]);
+      float p = ex2_fast(s[nt][e] * c - lse2[r]);
       if (need_mask && !visible(mp, row_g[r], j0 + 8 * nt + 2 * t + (e & 1))) p = 0.f;
       const float dp = dpd[nt][e] * keep[e];
       s[nt][e] = p * (dp - dl[r]) * a.scale;
@@ -308,19 +327,20 @@ __device__ __forceinline__ void bwd_tile_math(const AttnTrainArgs& a, const Mask
   }
 }
 
-constexpr int DQ_SMEM = 2 * TILE_BYTES /*K,V (Q and dO staged here first)*/ + 2 * TILE_BYTES /*R*/ + 4 * 16 * SKEW_LD * 4 +
-                        4 * 16 * DSK_LD * 2;
+constexpr int DQ_SMEM = 2 * ATT_NST * TILE_BYTES /*K,V ring (Q and dO are staged in its last stage first)*/ + ATT_NR * TILE_BYTES /*R*/ +
+                        4 * 16 * SKEW_LD * 4 + 4 * 16 * DSK_LD * 2;
 
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnTrainBwdArgs ba) {
   const AttnTrainArgs& a = ba.f;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sK = smem;
-  uint8_t* sV = sK + TILE_BYTES;
-  uint8_t* sR = sV + TILE_BYTES;
-  float* skew_all = (float*)(sR + 2 * TILE_BYTES);
+  uint8_t* sKV = smem;
+  uint8_t* sR = sKV + 2 * ATT_NST * TILE_BYTES;
+  float* skew_all = (float*)(sR + ATT_NR * TILE_BYTES);
   bf16* dsk_all = (bf16*)(skew_all + 4 * 16 * SKEW_LD);
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   float* skew = skew_all + w * 16 * SKEW_LD;
+  LaneOff L;
+  lane_off_init(L, lane, w);
   bf16* dsk = dsk_all + w * 16 * DSK_LD;
 
   const int nT = a.T / 64;
@@ -329,20 +349,42 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnTrainBwdArgs
   const int i0 = it * 64, HD = a.H * 64, S = a.M + a.T;
   const MaskP mp = {a.M, a.mem_count, a.win, a.k};
   const long long bhT = (long long)bh * a.T;
+  const int jt_lo = (a.M - a.mem_count) / 64, jt_hi = (a.M + i0) / 64;
+  const int rt_top = (a.M + i0) / 64;
 
-  // stage Q and dO through the K / V buffers to build the A fragments
-  tile_load_async(sK, a.qkv_x + ((long long)b * a.T + i0) * a.ldx + h * 64, a.ldx, tid, 128);
-  tile_load_async(sV, ba.dout + ((long long)b * a.T + i0) * HD + h * 64, HD, tid, 128);
+  auto load_stage = [&](int jt) {
+    if (jt <= jt_hi) {
+      const int st = (jt - jt_lo) % ATT_NST;
+      long long ld;
+      const bf16* kp = kv_tile_ptr(a, b, h, jt, 0, &ld);
+      tile_load_async(sKV + 2 * st * TILE_BYTES, kp, ld, tid, 128);
+      const bf16* vp = kv_tile_ptr(a, b, h, jt, 1, &ld);
+      tile_load_async(sKV + (2 * st + 1) * TILE_BYTES, vp, ld, tid, 128);
+      const int rt_hi = rt_top - jt;
+      if (jt == jt_lo) tile_load_async(sR + (rt_hi % ATT_NR) * TILE_BYTES, a.rk + (long long)rt_hi * 64 * HD + h * 64, HD, tid, 128);
+      if (rt_hi > 0) tile_load_async(sR + ((rt_hi - 1) % ATT_NR) * TILE_BYTES, a.rk + (long long)(rt_hi - 1) * 64 * HD + h * 64, HD, tid, 128);
+    }
+    cp_async_commit();
+  };
+
+  // stage Q and dO through the LAST ring stage (the prologue fills stages 0 .. NST-2) to build the A fragments
+  uint8_t* sQst = sKV + 2 * (ATT_NST - 1) * TILE_BYTES;
+  uint8_t* sdOst = sQst + TILE_BYTES;
+  tile_load_async(sQst, a.qkv_x + ((long long)b * a.T + i0) * a.ldx + h * 64, a.ldx, tid, 128);
+  tile_load_async(sdOst, ba.dout + ((long long)b * a.T + i0) * HD + h * 64, HD, tid, 128);
   cp_async_commit();
+#pragma unroll
+  for (int s2 = 0; s2 < ATT_NST - 1; s2++) load_stage(jt_lo + s2);
   for (int i = lane; i < 16 * DSK_LD; i += 32) dsk[i] = __float2bfloat16_rn(0.f);   // off-band entries stay zero
-  cp_async_wait<0>();
+  cp_async_wait<ATT_NST - 1>();
   __syncthreads();
   uint32_t qu[4][4], qv[4][4], dof[4][4];
-  q_frags(smem_u32(sK), w, lane, a.u + h * 64, a.v + h * 64, qu, qv);
+  q_frags(smem_u32(sQst), w, lane, L, a.u + h * 64, a.v + h * 64, qu, qv);
 #pragma unroll
-  for (int ks = 0; ks < 4; ks++) frag_a(smem_u32(sV), 16 * w, 16 * ks, lane, dof[ks]);
+  for (int ks = 0; ks < 4; ks++) frag_a(smem_u32(sdOst), 16 * w, ks, L, dof[ks]);
 
   const int row_g[2] = {i0 + 16 * w + g, i0 + 16 * w + g + 8};
+  const uint32_t drop_base[2] = {(uint32_t)(((bhT + row_g[0]) * S) >> 1) + t, (uint32_t)(((bhT + row_g[1]) * S) >> 1) + t};
   float lse2[2], dl[2];
 #pragma unroll
   for (int r = 0; r < 2; r++) {
@@ -355,7 +397,6 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnTrainBwdArgs
 #pragma unroll
     for (int e = 0; e < 4; e++) { dq_ac[nt][e] = 0.f; dq_bd[nt][e] = 0.f; }
 
-  const int jt_lo = (a.M - a.mem_count) / 64, jt_hi = (a.M + i0) / 64;
   // distances that no key tile of this row produces (beyond the oldest visible key) must read as zero in the dRk GEMM
   {
     const long long HS = (long long)a.H * S;
@@ -371,21 +412,16 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnTrainBwdArgs
     const int j0 = jt * 64;
     const int D0 = a.M + i0 - j0;
     const int rt_hi = D0 / 64, rt_lo = rt_hi > 0 ? rt_hi - 1 : 0;
-    __syncthreads();
-    long long ld;
-    const bf16* kp = kv_tile_ptr(a, b, h, jt, 0, &ld);
-    tile_load_async(sK, kp, ld, tid, 128);
-    const bf16* vp = kv_tile_ptr(a, b, h, jt, 1, &ld);
-    tile_load_async(sV, vp, ld, tid, 128);
-    if (jt == jt_lo) tile_load_async(sR + (rt_hi & 1) * TILE_BYTES, a.rk + (long long)rt_hi * 64 * HD + h * 64, HD, tid, 128);
-    if (rt_hi > 0) tile_load_async(sR + (rt_lo & 1) * TILE_BYTES, a.rk + (long long)rt_lo * 64 * HD + h * 64, HD, tid, 128);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-    const uint32_t sR0 = smem_u32(sR + (rt_lo & 1) * TILE_BYTES), sR1 = smem_u32(sR + (rt_hi & 1) * TILE_BYTES);
+    cp_async_wait<ATT_NST - 2>();
+    __syncthreads();                                 // tile jt visible to all; tile jt-1 (and the Q/dO staging) released
+    load_stage(jt + ATT_NST - 1);
+    const int st = (jt - jt_lo) % ATT_NST;
+    uint8_t* sK = sKV + 2 * st * TILE_BYTES;
+    uint8_t* sV = sK + TILE_BYTES;
+    const uint32_t sR0 = smem_u32(sR + (rt_lo % ATT_NR) * TILE_BYTES), sR1 = smem_u32(sR + (rt_hi % ATT_NR) * TILE_BYTES);
 
     float s[8][4], dpd[8][4], unused[8][4];
-    scores_tile(qu, qv, smem_u32(sK), sR0, sR1, skew, w, lane, s);
+    scores_tile(qu, qv, smem_u32(sK), sR0, sR1, skew, w, lane, L, s);
     // dPd = dO V^T
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) { dpd[nt][0] = 0.f; dpd[nt][1] = 0.f; dpd[nt][2] = 0.f; dpd[nt][3] = 0.f; }
@@ -395,12 +431,12 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnTrainBwdArgs
 #pragma unroll
       for (int np = 0; np < 4; np++) {
         uint32_t r[4];
-        frag_b(sVa, 16 * np, 16 * ks, lane, r);
+        frag_b(sVa, 16 * np, ks, L, r);
         mma_bf16(dpd[2 * np], dof[ks], r[0], r[1]);
         mma_bf16(dpd[2 * np + 1], dof[ks], r[2], r[3]);
       }
     }
-    bwd_tile_math(a, mp, s, dpd, row_g, lse2, dl, j0, bhT, S, t, false, unused);   // s := dS
+    bwd_tile_math(a, mp, s, dpd, row_g, lse2, dl, j0, drop_base, t, false, unused);   // s := dS
 
     // dS into the skewed strip (bf16): strip[row][64 + row - jl]
 #pragma unroll
@@ -425,7 +461,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnTrainBwdArgs
 #pragma unroll
       for (int np = 0; np < 4; np++) {
         uint32_t r[4];
-        frag_b_t(sKa, 16 * np, 16 * ks, lane, r);
+        frag_b_t(sKa, np, 16 * ks, L, r);
         mma_bf16(dq_ac[2 * np], dsa[ks], r[0], r[1]);
         mma_bf16(dq_ac[2 * np + 1], dsa[ks], r[2], r[3]);
       }
@@ -442,7 +478,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnTrainBwdArgs
 #pragma unroll
       for (int np = 0; np < 4; np++) {
         uint32_t r[4];
-        frag_b_t(sRx, 16 * np, wc & 63, lane, r);
+        frag_b_t(sRx, np, wc & 63, L, r);
         mma_bf16(dq_bd[2 * np], af, r[0], r[1]);
         mma_bf16(dq_bd[2 * np + 1], af, r[2], r[3]);
       }
@@ -489,22 +525,27 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnTrainBwdArgs
   }
 }
 
-constexpr int DKV_SMEM = 7 * TILE_BYTES /*K,V,Q,dO,Qu,P,dS*/ + 2 * TILE_BYTES /*R*/ + 4 * 16 * SKEW_LD * 4;
+// Q / dO tiles double-buffered, Rk tiles in a 3-slot ring (the window slides UP with the query tile: iteration `it` needs
+// rt_hi = (M + i0 - j0)/64 and rt_hi - 1 and loads exactly one new tile, rt_hi); (q+u) overwrites Q in place.
+constexpr int DKV_NST = 2;
+constexpr int DKV_NR = 3;
+constexpr int DKV_SMEM = 2 * TILE_BYTES /*K,V*/ + 2 * DKV_NST * TILE_BYTES /*Q,dO ring*/ + 2 * TILE_BYTES /*P,dS*/ + DKV_NR * TILE_BYTES +
+                         4 * 16 * SKEW_LD * 4;
 
 __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnTrainBwdArgs ba) {
   const AttnTrainArgs& a = ba.f;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sK = smem;
   uint8_t* sV = sK + TILE_BYTES;
-  uint8_t* sQ = sV + TILE_BYTES;
-  uint8_t* sdO = sQ + TILE_BYTES;
-  uint8_t* sQu = sdO + TILE_BYTES;
-  uint8_t* sP = sQu + TILE_BYTES;
+  uint8_t* sQdO = sV + TILE_BYTES;                  // stage s: Q at sQdO + 2*s*TILE, dO right behind it
+  uint8_t* sP = sQdO + 2 * DKV_NST * TILE_BYTES;
   uint8_t* sdS = sP + TILE_BYTES;
   uint8_t* sR = sdS + TILE_BYTES;
-  float* skew_all = (float*)(sR + 2 * TILE_BYTES);
+  float* skew_all = (float*)(sR + DKV_NR * TILE_BYTES);
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   float* skew = skew_all + w * 16 * SKEW_LD;
+  LaneOff L;
+  lane_off_init(L, lane, w);
 
   const int nS = (a.M + a.T) / 64;
   const int jt = blockIdx.x % nS;                     // memory tiles (longest loops) come first
@@ -534,12 +575,33 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnTrainBwdArg
     return;
   }
 
-  long long ld;
-  const bf16* kp = kv_tile_ptr(a, b, h, jt, 0, &ld);
-  tile_load_async(sK, kp, ld, tid, 128);
-  const bf16* vp = kv_tile_ptr(a, b, h, jt, 1, &ld);
-  tile_load_async(sV, vp, ld, tid, 128);
-  cp_async_commit();
+  const int nT = a.T / 64;
+  const int it_lo = j0 < a.M ? 0 : (j0 - a.M) / 64;
+  const int rt_base = (a.M - j0) / 64;              // rt_hi of iteration `it` is rt_base + it (>= 0 from it_lo on)
+
+  auto load_stage = [&](int it) {                   // one cp.async group: Q, dO of query tile `it` and the new Rk tile(s)
+    if (it < nT) {
+      const int st = (it - it_lo) % DKV_NST;
+      const int i0 = it * 64;
+      tile_load_async(sQdO + 2 * st * TILE_BYTES, a.qkv_x + ((long long)b * a.T + i0) * a.ldx + h * 64, a.ldx, tid, 128);
+      tile_load_async(sQdO + (2 * st + 1) * TILE_BYTES, ba.dout + ((long long)b * a.T + i0) * HD + h * 64, HD, tid, 128);
+      const int rt_hi = rt_base + it;
+      tile_load_async(sR + (rt_hi % DKV_NR) * TILE_BYTES, a.rk + (long long)rt_hi * 64 * HD + h * 64, HD, tid, 128);
+      if (it == it_lo && rt_hi > 0)
+        tile_load_async(sR + ((rt_hi - 1) % DKV_NR) * TILE_BYTES, a.rk + (long long)(rt_hi - 1) * 64 * HD + h * 64, HD, tid, 128);
+    }
+    cp_async_commit();
+  };
+
+  {
+    long long ld;
+    const bf16* kp = kv_tile_ptr(a, b, h, jt, 0, &ld);
+    tile_load_async(sK, kp, ld, tid, 128);
+    const bf16* vp = kv_tile_ptr(a, b, h, jt, 1, &ld);
+    tile_load_async(sV, vp, ld, tid, 128);
+  }
+#pragma unroll
+  for (int s2 = 0; s2 < DKV_NST - 1; s2++) load_stage(it_lo + s2);     // K, V ride in the first group
 
   float dk[8][4], dv[8][4];
 #pragma unroll
@@ -547,28 +609,22 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnTrainBwdArg
 #pragma unroll
     for (int e = 0; e < 4; e++) { dk[nt][e] = 0.f; dv[nt][e] = 0.f; }
 
-  const int nT = a.T / 64;
-  const int it_lo = j0 < a.M ? 0 : (j0 - a.M) / 64;
   for (int it = it_lo; it < nT; it++) {
     const int i0 = it * 64;
-    const int D0 = a.M + i0 - j0;
-    const int rt_hi = D0 / 64, rt_lo = rt_hi > 0 ? rt_hi - 1 : 0;
-    __syncthreads();
-    tile_load_async(sQ, a.qkv_x + ((long long)b * a.T + i0) * a.ldx + h * 64, a.ldx, tid, 128);
-    tile_load_async(sdO, ba.dout + ((long long)b * a.T + i0) * HD + h * 64, HD, tid, 128);
-    // window slides upwards with the query tile: the new upper tile replaces the old lower one
-    tile_load_async(sR + (rt_hi & 1) * TILE_BYTES, a.rk + (long long)rt_hi * 64 * HD + h * 64, HD, tid, 128);
-    if (it == it_lo && rt_hi > 0)
-      tile_load_async(sR + (rt_lo & 1) * TILE_BYTES, a.rk + (long long)rt_lo * 64 * HD + h * 64, HD, tid, 128);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-    const uint32_t sR0 = smem_u32(sR + (rt_lo & 1) * TILE_BYTES), sR1 = smem_u32(sR + (rt_hi & 1) * TILE_BYTES);
+    const int rt_hi = rt_base + it, rt_lo = rt_hi > 0 ? rt_hi - 1 : 0;
+    cp_async_wait<DKV_NST - 2>();
+    __syncthreads();                                 // tile `it` visible; everybody finished iteration it-1 (sP, sdS, old stage)
+    load_stage(it + DKV_NST - 1);
+    const int st = (it - it_lo) % DKV_NST;
+    uint8_t* sQ = sQdO + 2 * st * TILE_BYTES;
+    uint8_t* sdO = sQ + TILE_BYTES;
+    uint8_t* sQu = sQ;                               // (q+u) replaces q in place once the fragments are in registers
+    const uint32_t sR0 = smem_u32(sR + (rt_lo % DKV_NR) * TILE_BYTES), sR1 = smem_u32(sR + (rt_hi % DKV_NR) * TILE_BYTES);
 
     uint32_t qu[4][4], qv[4][4], dof[4][4];
-    q_frags(smem_u32(sQ), w, lane, a.u + h * 64, a.v + h * 64, qu, qv);
+    q_frags(smem_u32(sQ), w, lane, L, a.u + h * 64, a.v + h * 64, qu, qv);
 #pragma unroll
-    for (int ks = 0; ks < 4; ks++) frag_a(smem_u32(sdO), 16 * w, 16 * ks, lane, dof[ks]);
+    for (int ks = 0; ks < 4; ks++) frag_a(smem_u32(sdO), 16 * w, ks, L, dof[ks]);
     // (q+u) tile for the dK contraction (B operand, [k = query][n = dh])
 #pragma unroll
     for (int ks = 0; ks < 4; ks++) {
@@ -578,6 +634,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnTrainBwdArg
       *(uint32_t*)(sQu + tile_off(16 * w + g + 8, 2 * ks + 1) + 4 * t) = qu[ks][3];
     }
     const int row_g[2] = {i0 + 16 * w + g, i0 + 16 * w + g + 8};
+    const uint32_t drop_base[2] = {(uint32_t)(((bhT + row_g[0]) * S) >> 1) + t, (uint32_t)(((bhT + row_g[1]) * S) >> 1) + t};
     float lse2[2], dl[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
@@ -585,7 +642,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnTrainBwdArg
       dl[r] = ba.delta[bhT + row_g[r]];
     }
     float s[8][4], dpd[8][4], pd[8][4];
-    scores_tile(qu, qv, smem_u32(sK), sR0, sR1, skew, w, lane, s);
+    scores_tile(qu, qv, smem_u32(sK), sR0, sR1, skew, w, lane, L, s);
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) { dpd[nt][0] = 0.f; dpd[nt][1] = 0.f; dpd[nt][2] = 0.f; dpd[nt][3] = 0.f; }
     const uint32_t sVa = smem_u32(sV);
@@ -594,12 +651,12 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnTrainBwdArg
 #pragma unroll
       for (int np = 0; np < 4; np++) {
         uint32_t r[4];
-        frag_b(sVa, 16 * np, 16 * ks, lane, r);
+        frag_b(sVa, 16 * np, ks, L, r);
         mma_bf16(dpd[2 * np], dof[ks], r[0], r[1]);
         mma_bf16(dpd[2 * np + 1], dof[ks], r[2], r[3]);
       }
     }
-    bwd_tile_math(a, mp, s, dpd, row_g, lse2, dl, j0, bhT, S, t, true, pd);   // s := dS, pd := dropped P
+    bwd_tile_math(a, mp, s, dpd, row_g, lse2, dl, j0, drop_base, t, true, pd);   // s := dS, pd := dropped P
     // P and dS tiles [query][key] for the transposed contractions
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) {
@@ -614,15 +671,15 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnTrainBwdArg
 #pragma unroll
     for (int ks = 0; ks < 4; ks++) {
       uint32_t ap[4], as[4];
-      frag_a_t(sPa, 16 * w, 16 * ks, lane, ap);
-      frag_a_t(sdSa, 16 * w, 16 * ks, lane, as);
+      frag_a_t(sPa, 16 * ks, L, ap);
+      frag_a_t(sdSa, 16 * ks, L, as);
 #pragma unroll
       for (int np = 0; np < 4; np++) {
         uint32_t r[4];
-        frag_b_t(sdOa, 16 * np, 16 * ks, lane, r);
+        frag_b_t(sdOa, np, 16 * ks, L, r);
         mma_bf16(dv[2 * np], ap, r[0], r[1]);
         mma_bf16(dv[2 * np + 1], ap, r[2], r[3]);
-        frag_b_t(sQua, 16 * np, 16 * ks, lane, r);
+        frag_b_t(sQua, np, 16 * ks, L, r);
         mma_bf16(dk[2 * np], as, r[0], r[1]);
         mma_bf16(dk[2 * np + 1], as, r[2], r[3]);
       }

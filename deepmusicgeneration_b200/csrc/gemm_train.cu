@@ -49,6 +49,7 @@ struct GemmTParams {
   void* out; long long ldc; int out_mode;
   bf16* out2; long long ld2;
   uint32_t drop_thresh, drop_seed; float drop_scale;
+  int groups; int a_gs, b_gs; long long c_gs;
 };
 
 template <int BN>
@@ -68,7 +69,8 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_mn = p.num_m * p.num_n;
-  const int total = tiles_mn * p.splitk;
+  const int tiles_g = tiles_mn * p.splitk;
+  const int total = tiles_g * p.groups;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -96,8 +98,9 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       uint32_t it = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int ks = t / tiles_mn, r = t - ks * tiles_mn;
-        const int m0 = (r % p.num_m) * GT_BM, n0 = (r / p.num_m) * BN;
+        const int grp = t / tiles_g, tg = t - grp * tiles_g;
+        const int ks = tg / tiles_mn, r = tg - ks * tiles_mn;
+        const int m0 = (r % p.num_m) * GT_BM + grp * p.a_gs, n0 = (r / p.num_m) * BN + grp * p.b_gs;
         const int kb_lo = ks * p.kb_per_split;
         const int kb_hi = min(p.num_kb, kb_lo + p.kb_per_split);
         for (int kb = kb_lo; kb < kb_hi; kb++, it++) {
@@ -130,7 +133,7 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t b_lbo = p.b_mn ? 8192u : 16u, b_kstep = p.b_mn ? 2048u : 32u;
     uint32_t it = 0, tile_i = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, tile_i++) {
-      const int ks = t / tiles_mn;
+      const int ks = (t % tiles_g) / tiles_mn;
       const int kb_lo = ks * p.kb_per_split;
       const int kb_hi = min(p.num_kb, kb_lo + p.kb_per_split);
       const uint32_t acc = tile_i & 1, acc_ph = (tile_i >> 1) & 1;
@@ -164,8 +167,10 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr int HALF_COLS = BN / 2;
     uint32_t tile_i = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, tile_i++) {
-      const int ks = t / tiles_mn, r = t - ks * tiles_mn;
+      const int grp = t / tiles_g, tg = t - grp * tiles_g;
+      const int ks = tg / tiles_mn, r = tg - ks * tiles_mn;
       const int m0 = (r % p.num_m) * GT_BM, n0 = (r / p.num_m) * BN;
+      const long long c_off = (long long)grp * p.c_gs;
       const uint32_t acc = tile_i & 1, acc_ph = (tile_i >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
@@ -189,8 +194,16 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = __uint_as_float(rr[j]);
         if (p.bias && first_split) {
+          if (nval == 32) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) v[j] += (j < nval) ? __ldg(p.bias + col0 + j) : 0.f;
+            for (int j = 0; j < 8; j++) {
+              const float4 bq = __ldg((const float4*)(p.bias + col0) + j);
+              v[4 * j] += bq.x; v[4 * j + 1] += bq.y; v[4 * j + 2] += bq.z; v[4 * j + 3] += bq.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] += (j < nval) ? __ldg(p.bias + col0 + j) : 0.f;
+          }
         }
         if (p.out2) {
           bf16* o2 = p.out2 + (size_t)row * p.ld2 + col0;
@@ -200,12 +213,14 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               ((uint4*)o2)[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                                            pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
           } else {
-            for (int j = 0; j < nval; j++) o2[j] = __float2bfloat16_rn(v[j]);
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+              if (j < nval) o2[j] = __float2bfloat16_rn(v[j]);
           }
         }
         if (p.act) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) v[j] = gelu_tanh(v[j]);
+          for (int j = 0; j < 32; j++) v[j] = gelu_tanh_fast(v[j]);
         }
         if (p.aux_mode == GEMM_AUX_GELU_GRAD || p.aux_mode == GEMM_AUX_ADD_BF16) {
           const bf16* ax = (const bf16*)p.aux + (size_t)row * p.ld_aux + col0;
@@ -223,7 +238,7 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           if (p.aux_mode == GEMM_AUX_GELU_GRAD) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) v[j] *= gelu_tanh_grad(a[j]);
+            for (int j = 0; j < 32; j++) v[j] *= gelu_tanh_grad_fast(a[j]);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; j++) v[j] += a[j];
@@ -252,25 +267,29 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         if (p.out_mode == GEMM_OUT_BF16) {
-          bf16* o = (bf16*)p.out + (size_t)row * p.ldc + col0;
+          bf16* o = (bf16*)p.out + (size_t)row * p.ldc + col0 + c_off;
           if (nval == 32) {
 #pragma unroll
             for (int j = 0; j < 4; j++)
               ((uint4*)o)[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
           } else {
-            for (int j = 0; j < nval; j++) o[j] = __float2bfloat16_rn(v[j]);
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+              if (j < nval) o[j] = __float2bfloat16_rn(v[j]);
           }
         } else if (p.out_mode == GEMM_OUT_F32) {
-          float* o = (float*)p.out + (size_t)row * p.ldc + col0;
+          float* o = (float*)p.out + (size_t)row * p.ldc + col0 + c_off;
           if (nval == 32) {
 #pragma unroll
             for (int j = 0; j < 8; j++) ((float4*)o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
-            for (int j = 0; j < nval; j++) o[j] = v[j];
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+              if (j < nval) o[j] = v[j];
           }
         } else {
-          float* o = (float*)p.out + (size_t)row * p.ldc + col0;
+          float* o = (float*)p.out + (size_t)row * p.ldc + col0 + c_off;
 #pragma unroll
           for (int j = 0; j < 32; j++)
             if (j < nval) atomicAdd(o + j, v[j]);
@@ -331,7 +350,8 @@ int gemm_bf16_tc(const bf16* A, int a_mn, long long lda, const bf16* B, int b_mn
   // tile width: widest tile that still yields at least ~one wave of tiles
   const int num_m = (M + GT_BM - 1) / GT_BM;
   int BN = 256;
-  while (BN > 64 && ((long long)num_m * ((N + BN - 1) / BN) * splitk < num_sms || N <= BN / 2)) BN >>= 1;
+  const int groups = e.groups < 1 ? 1 : e.groups;
+  while (BN > 64 && ((long long)num_m * ((N + BN - 1) / BN) * splitk * groups < num_sms || N <= BN / 2)) BN >>= 1;
   const int num_n = (N + BN - 1) / BN;
   GemmTParams p;
   p.M = M; p.N = N; p.K = K; p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
@@ -343,12 +363,15 @@ int gemm_bf16_tc(const bf16* A, int a_mn, long long lda, const bf16* B, int b_mn
   p.bias = e.bias; p.act = e.act; p.aux = e.aux; p.ld_aux = e.ld_aux; p.aux_mode = e.aux_mode;
   p.out = e.out; p.ldc = e.ldc; p.out_mode = e.out_mode; p.out2 = e.out2; p.ld2 = e.ld2;
   p.drop_thresh = e.drop_thresh; p.drop_seed = e.drop_seed; p.drop_scale = e.drop_scale;
+  p.groups = e.groups < 1 ? 1 : e.groups; p.a_gs = (int)e.a_gs; p.b_gs = (int)e.b_gs; p.c_gs = e.c_gs;
+  DMG_CHECK(p.groups == 1 || (!e.out2 && e.aux_mode == GEMM_AUX_NONE && !e.bias && !e.drop_thresh), "gemm_bf16_tc: grouped launches take the plain epilogue only");
   const TensorMap2D *ta = nullptr, *tb = nullptr;
-  if (!a_mn) { if (get_tmap(A, K, M, lda, GT_BM, &ta)) return -1; }
-  else       { if (get_tmap(A, M, K, lda, 64, &ta)) return -1; }
-  if (!b_mn) { if (get_tmap(B, K, N, ldb, BN, &tb)) return -1; }
-  else       { if (get_tmap(B, N, K, ldb, 64, &tb)) return -1; }
-  const long long total = (long long)num_m * num_n * p.splitk;
+  const long long Mext = M + (long long)(groups - 1) * e.a_gs, Next = N + (long long)(groups - 1) * e.b_gs;   // tensor extents
+  if (!a_mn) { if (get_tmap(A, K, Mext, lda, GT_BM, &ta)) return -1; }
+  else       { if (get_tmap(A, Mext, K, lda, 64, &ta)) return -1; }
+  if (!b_mn) { if (get_tmap(B, K, Next, ldb, BN, &tb)) return -1; }
+  else       { if (get_tmap(B, Next, K, ldb, 64, &tb)) return -1; }
+  const long long total = (long long)num_m * num_n * p.splitk * groups;
   const int grid = (int)(total < num_sms ? total : num_sms);
   if (BN == 256) return launch_gt<256>(ta, tb, p, grid, st);
   if (BN == 128) return launch_gt<128>(ta, tb, p, grid, st);

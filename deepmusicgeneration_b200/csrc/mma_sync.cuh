@@ -32,29 +32,55 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
 constexpr int TILE_BYTES = 64 * 64 * 2;
 __device__ __forceinline__ uint32_t tile_off(int r, int chunk) { return (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4)); }
 
-// all `nthreads` threads of the CTA copy a 64-row x 64-col bf16 block (row stride ld elements) into a tile
+// 128 threads copy a 64-row x 64-col bf16 block (row stride ld elements) into a tile: thread t moves the 16-byte chunk
+// (t & 7) of rows (t >> 3) + 16 k, k = 0..3 - the swizzled chunk position is the same for all four (row & 7 is unchanged)
 __device__ __forceinline__ void tile_load_async(uint8_t* tile, const bf16* g, long long ld, int tid, int nthreads) {
-  for (int i = tid; i < 512; i += nthreads) {
-    const int r = i >> 3, c = i & 7;
-    cp_async16(tile + tile_off(r, c), g + (long long)r * ld + c * 8);
-  }
+  (void)nthreads;
+  const int r = tid >> 3, c = tid & 7;
+  uint8_t* dst = tile + tile_off(r, c);
+  const bf16* src = g + (long long)r * ld + c * 8;
+#pragma unroll
+  for (int k = 0; k < 4; k++) cp_async16(dst + k * 2048, src + (long long)k * 16 * ld);
 }
 
-// A fragment (16 rows m0.., 16 k k0..) from a tile stored [m][k]
-__device__ __forceinline__ void frag_a(uint32_t tile_addr, int m0, int k0, int lane, uint32_t (&a)[4]) {
-  ldsm_x4(tile_addr + tile_off(m0 + (lane & 15), (k0 >> 3) + (lane >> 4)), a);
+// Per-lane byte offsets of the ldmatrix row addresses inside a tile, computed once per kernel: the XOR swizzle only mixes
+// lane-constant bits (row & 7 == lane & 7 for every fragment shape below) with the 16-byte chunk index.
+struct LaneOff {
+  uint32_t b[4];    // [ks] B fragment from a [n][k] tile:  tile + n0*128 + b[ks]     (k0 = 16*ks)
+  uint32_t bt[4];   // [np] B fragment from a [k][n] tile:  tile + k0*128 + bt[np]    (n0 = 16*np)
+  uint32_t a[4];    // [ks] A fragment from a [m][k] tile:  tile + m0*128 + a[ks]
+  uint32_t at;      //      A fragment from a [k][m] tile:  tile + k0*128 + at        (m0 = 16*warp, folded in)
+};
+__device__ __forceinline__ void lane_off_init(LaneOff& L, int lane, int warp) {
+  const uint32_t sw = lane & 7;
+  const uint32_t rB = (lane & 7) + ((lane >> 4) << 3), kb = (lane >> 3) & 1;      // frag_b / frag_a_t row, chunk bit
+  const uint32_t rT = (lane & 7) + (((lane >> 3) & 1) << 3), hb = lane >> 4;      // frag_b_t row, chunk bit
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    L.b[i] = rB * 128 + (((2 * i + kb) ^ sw) << 4);
+    L.bt[i] = rT * 128 + (((2 * i + hb) ^ sw) << 4);
+    L.a[i] = (lane & 15) * 128 + (((2 * i + hb) ^ sw) << 4);
+  }
+  L.at = rB * 128 + (((2 * warp + kb) ^ sw) << 4);
 }
-// A fragment from a tile stored [k][m] (transposed read)
-__device__ __forceinline__ void frag_a_t(uint32_t tile_addr, int m0, int k0, int lane, uint32_t (&a)[4]) {
-  ldsm_x4_t(tile_addr + tile_off(k0 + (lane & 7) + ((lane >> 4) << 3), (m0 >> 3) + ((lane >> 3) & 1)), a);
+// n0, k0, m0: multiples of 16 (compile-time constants at the call sites -> folded into the ldmatrix immediate)
+__device__ __forceinline__ void frag_b(uint32_t tile_addr, int n0, int ks, const LaneOff& L, uint32_t (&r)[4]) {
+  ldsm_x4(tile_addr + n0 * 128 + L.b[ks], r);
 }
-// B fragments of two neighbouring n-tiles (n0..n0+15) x 16 k from a tile stored [n][k]: (r0,r1) -> n-tile 0, (r2,r3) -> n-tile 1
-__device__ __forceinline__ void frag_b(uint32_t tile_addr, int n0, int k0, int lane, uint32_t (&r)[4]) {
-  ldsm_x4(tile_addr + tile_off(n0 + (lane & 7) + ((lane >> 4) << 3), (k0 >> 3) + ((lane >> 3) & 1)), r);
+__device__ __forceinline__ void frag_b_t(uint32_t tile_addr, int np, int k0, const LaneOff& L, uint32_t (&r)[4]) {
+  ldsm_x4_t(tile_addr + k0 * 128 + L.bt[np], r);
 }
-// same from a tile stored [k][n] (transposed read)
-__device__ __forceinline__ void frag_b_t(uint32_t tile_addr, int n0, int k0, int lane, uint32_t (&r)[4]) {
-  ldsm_x4_t(tile_addr + tile_off(k0 + (lane & 7) + (((lane >> 3) & 1) << 3), (n0 >> 3) + (lane >> 4)), r);
+__device__ __forceinline__ void frag_a(uint32_t tile_addr, int m0, int ks, const LaneOff& L, uint32_t (&a)[4]) {
+  ldsm_x4(tile_addr + m0 * 128 + L.a[ks], a);
+}
+__device__ __forceinline__ void frag_a_t(uint32_t tile_addr, int k0, const LaneOff& L, uint32_t (&a)[4]) {
+  ldsm_x4_t(tile_addr + k0 * 128 + L.at, a);
+}
+
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 }  // namespace dmg

@@ -64,6 +64,9 @@ struct dmg_train {
   int opt_steps = 0;
   int next_layer = -1;                       // backward progress: next layer_hi expected (-1: no forward pending)
   bool mem_pending = false;
+  AdamTensor* adam_tensors = nullptr;
+  AdamChunk* adam_chunks = nullptr;
+  int n_adam_chunks = 0;
   std::vector<void*> allocs;
   long long bytes = 0;
 };
@@ -153,10 +156,12 @@ int ensure_wr_b16(dmg_model* m, dmg_train* t) {
   return 0;
 }
 
+// split-K factor of a weight-gradient GEMM: as many K slices as fit in ONE wave of 128x256 tiles (the epilogue adds
+// fp32 atomics per slice, so more slices than needed only add traffic), at least 8 k-blocks per slice
 int pick_splitk(int M, int N, int K, int num_sms) {
   const long long tiles = (long long)((M + 127) / 128) * ((N + 255) / 256);
   const int num_kb = (K + 63) / 64;
-  long long s = (2ll * num_sms + tiles - 1) / tiles;
+  long long s = num_sms / tiles;
   if (s > num_kb / 8) s = num_kb / 8;
   if (s < 1) s = 1;
   return (int)s;
@@ -297,7 +302,7 @@ int backward_head(dmg_model* m, dmg_train* t, cudaStream_t st) {
   DMG_CUDA_OK(cudaMemsetAsync(t->G, 0, (size_t)t->total * sizeof(float), st));
   // tied decoder weight: dE += dlogits^T xdrop ; bias ; input gradient
   if (grad_w(m, t, t->dlogits, t->Vp, t->xdrop, d, c.vocab, d, rows, t->g_emb, st)) return -1;
-  if (train_colsum_bf16(t->dlogits, t->Vp, rows, c.vocab, t->G + t->g_head_b, t->partial, st)) return -1;
+  if (train_colsum_bf16(t->dlogits, t->Vp, rows, c.vocab, t->G + t->g_head_b, st)) return -1;
   {
     GemmEpi e; e.out = t->dadd; e.ldc = d; e.out_mode = GEMM_OUT_BF16;
     if (gemm_bf16_tc(t->dlogits, 0, t->Vp, m->emb.b16, 1, d, rows, d, c.vocab, 1, e, ns, st)) return -1;
@@ -313,30 +318,27 @@ int backward_layer(dmg_model* m, dmg_train* t, int l, cudaStream_t st) {
   LayerW& W = m->layers[l];
   LayerAct& A = t->act[l];
   const LayerGrad& g = t->lg[l];
-  int nblk = 0;
   // ---- FFN block
   {
     const Drop d4 = make_drop(t, t->cfg.ff_p, SITE_RES2, l);
-    if (train_ln_bwd(t->dx32, A.z2, A.st2, W.ln2w, t->dadd, t->partial, &nblk, rows, d, d4.thresh, d4.seed, d4.scale, st)) return -1;
-    if (train_partial_finish(t->partial, nblk, d, t->G + g.ln2w, t->G + g.ln2b, st)) return -1;
+    if (train_ln_bwd(t->dx32, A.z2, A.st2, W.ln2w, t->dadd, t->G + g.ln2w, t->G + g.ln2b, rows, d, d4.thresh, d4.seed, d4.scale, st)) return -1;
     if (grad_w(m, t, t->dadd, d, A.hact, di, d, di, rows, g.w2, st)) return -1;
-    if (train_colsum_bf16(t->dadd, d, rows, d, t->G + g.b2, t->partial, st)) return -1;
+    if (train_colsum_bf16(t->dadd, d, rows, d, t->G + g.b2, st)) return -1;
     const Drop d3 = make_drop(t, t->cfg.ff_p, SITE_FF, l);
     GemmEpi e; e.aux = A.hpre; e.ld_aux = di; e.aux_mode = GEMM_AUX_GELU_GRAD; e.out = t->dh; e.ldc = di; e.out_mode = GEMM_OUT_BF16;
     e.drop_thresh = d3.thresh; e.drop_seed = d3.seed; e.drop_scale = d3.scale;
     if (gemm_bf16_tc(t->dadd, 0, d, W.w2.b16, 1, di, rows, di, d, 1, e, ns, st)) return -1;
     if (grad_w(m, t, t->dh, di, A.xa1, d, di, d, rows, g.w1, st)) return -1;
-    if (train_colsum_bf16(t->dh, di, rows, di, t->G + g.b1, t->partial, st)) return -1;
+    if (train_colsum_bf16(t->dh, di, rows, di, t->G + g.b1, st)) return -1;
     GemmEpi e2; e2.aux = t->dx32; e2.ld_aux = d; e2.aux_mode = GEMM_AUX_ADD_F32; e2.out = t->dx32; e2.ldc = d; e2.out_mode = GEMM_OUT_F32;
     if (gemm_bf16_tc(t->dh, 0, di, W.w1.b16, 1, d, rows, d, di, 1, e2, ns, st)) return -1;
   }
   // ---- attention block
   {
     const Drop d2 = make_drop(t, t->cfg.resid_p, SITE_RES1, l);
-    if (train_ln_bwd(t->dx32, A.z1, A.st1, W.ln1w, t->dadd, t->partial, &nblk, rows, d, d2.thresh, d2.seed, d2.scale, st)) return -1;
-    if (train_partial_finish(t->partial, nblk, d, t->G + g.ln1w, t->G + g.ln1b, st)) return -1;
+    if (train_ln_bwd(t->dx32, A.z1, A.st1, W.ln1w, t->dadd, t->G + g.ln1w, t->G + g.ln1b, rows, d, d2.thresh, d2.seed, d2.scale, st)) return -1;
     if (grad_w(m, t, t->dadd, d, A.attn, HD, d, HD, rows, g.wo, st)) return -1;
-    if (g.bo >= 0 && train_colsum_bf16(t->dadd, d, rows, d, t->G + g.bo, t->partial, st)) return -1;
+    if (g.bo >= 0 && train_colsum_bf16(t->dadd, d, rows, d, t->G + g.bo, st)) return -1;
     GemmEpi e; e.out = t->dattn; e.ldc = HD; e.out_mode = GEMM_OUT_BF16;
     if (gemm_bf16_tc(t->dadd, 0, d, W.wo.b16, 1, HD, rows, HD, d, 1, e, ns, st)) return -1;
 
@@ -348,20 +350,23 @@ int backward_layer(dmg_model* m, dmg_train* t, int l, cudaStream_t st) {
     // dRk[h] = dS_dist[:, h]^T (q + v)[:, h]  ->  dWr = dRk^T PE
     if (train_q_plus_bias(A.qkv_x, 3 * HD, m->v, t->qv, rows, HD, st)) return -1;
     DMG_CUDA_OK(cudaMemsetAsync(t->drk32, 0, (size_t)S * HD * sizeof(float), st));
-    for (int h = 0; h < c.n_heads; h++) {
-      GemmEpi er; er.out = t->drk32 + h * 64; er.ldc = HD; er.out_mode = GEMM_OUT_ATOMIC;
-      if (gemm_bf16_tc(t->ds_dist + (size_t)h * S, 1, (long long)c.n_heads * S, t->qv + h * 64, 1, HD, S, 64, rows,
-                       pick_splitk(S, 64, rows, ns), er, ns, st)) return -1;
+    {   // one grouped launch: group h reads dS_dist columns [h*S, (h+1)*S) and (q+v) columns [h*64, (h+1)*64)
+      GemmEpi er; er.out = t->drk32; er.ldc = HD; er.out_mode = GEMM_OUT_ATOMIC;
+      er.groups = c.n_heads; er.a_gs = S; er.b_gs = 64; er.c_gs = 64;
+      int sk = (2 * ns) / (c.n_heads * ((S + 127) / 128));
+      if (sk < 1) sk = 1;
+      if (sk > rows / 512) sk = rows / 512 > 0 ? rows / 512 : 1;
+      if (gemm_bf16_tc(t->ds_dist, 1, (long long)c.n_heads * S, t->qv, 1, HD, S, 64, rows, sk, er, ns, st)) return -1;
     }
     if (train_cast_bf16(t->drk32, t->drk16, (long long)S * HD, st)) return -1;
     if (grad_w(m, t, t->drk16, HD, t->pe, d, HD, d, S, g.wr, st)) return -1;
-    if (g.br >= 0 && train_colsum_bf16(t->drk16, HD, S, HD, t->G + g.br, t->partial, st)) return -1;
+    if (g.br >= 0 && train_colsum_bf16(t->drk16, HD, S, HD, t->G + g.br, st)) return -1;
     // dWqkv: segment rows, then the memory rows' k|v part
     if (grad_w(m, t, t->dqkv_x, 3 * HD, A.xa_in, d, 3 * HD, d, rows, g.wqkv, st)) return -1;
-    if (g.bqkv >= 0 && train_colsum_bf16(t->dqkv_x, 3 * HD, rows, 3 * HD, t->G + g.bqkv, t->partial, st)) return -1;
+    if (g.bqkv >= 0 && train_colsum_bf16(t->dqkv_x, 3 * HD, rows, 3 * HD, t->G + g.bqkv, st)) return -1;
     if (t->mem_count > 0) {
       if (grad_w(m, t, t->dkv_m, 2 * HD, t->mem[l], d, 2 * HD, d, t->B * M, g.wqkv + (long long)HD * d, st)) return -1;
-      if (g.bqkv >= 0 && train_colsum_bf16(t->dkv_m, 2 * HD, t->B * M, 2 * HD, t->G + g.bqkv + HD, t->partial, st)) return -1;
+      if (g.bqkv >= 0 && train_colsum_bf16(t->dkv_m, 2 * HD, t->B * M, 2 * HD, t->G + g.bqkv + HD, st)) return -1;
     }
     GemmEpi e2; e2.aux = t->dx32; e2.ld_aux = d; e2.aux_mode = GEMM_AUX_ADD_F32; e2.out = t->dx32; e2.ldc = d; e2.out_mode = GEMM_OUT_F32;
     if (gemm_bf16_tc(t->dqkv_x, 0, 3 * HD, W.wqkv.b16, 1, d, rows, d, 3 * HD, 1, e2, ns, st)) return -1;
@@ -476,6 +481,24 @@ int dmg_train_create(dmg_model* m, const dmg_train_config* cfg, float* grad_flat
   TRY(talloc(t, &t->dkv_m, BM * 2 * HD));
   TRY(talloc(t, &t->ds_dist, (size_t)rows * c.n_heads * S));
   TRY(talloc(t, &t->qv, (size_t)rows * HD));
+  {   // multi-tensor Adam tables
+    std::vector<AdamTensor> ht;
+    std::vector<AdamChunk> hc;
+    for (size_t i = 0; i < t->params.size(); i++) {
+      const ParamRef& p = t->params[i];
+      AdamTensor at; at.p = p.p; at.p16 = p.p16; at.off = p.off;
+      ht.push_back(at);
+      for (long long s0 = 0; s0 < p.n; s0 += 16384) {
+        AdamChunk ch; ch.t = (int)i; ch.start = (int)s0; ch.len = (int)(p.n - s0 < 16384 ? p.n - s0 : 16384);
+        hc.push_back(ch);
+      }
+    }
+    t->n_adam_chunks = (int)hc.size();
+    TRY(talloc(t, &t->adam_tensors, ht.size()));
+    TRY(talloc(t, &t->adam_chunks, hc.size()));
+    if (!rc && cudaMemcpy(t->adam_tensors, ht.data(), ht.size() * sizeof(AdamTensor), cudaMemcpyHostToDevice) != cudaSuccess) rc = -1;
+    if (!rc && cudaMemcpy(t->adam_chunks, hc.data(), hc.size() * sizeof(AdamChunk), cudaMemcpyHostToDevice) != cudaSuccess) rc = -1;
+  }
   TRY(train_posenc(t->pe, S, d, 0));
   TRY(ensure_wr_b16(m, t));
 #undef TRY
@@ -559,9 +582,8 @@ int dmg_train_optimizer_step(dmg_model* m, float lr, float beta1, float beta2, f
   DMG_CUDA_OK(cudaMemsetAsync(t->acc + 3, 0, sizeof(float), st));
   if (train_sumsq(t->G, t->total, t->acc + 3, st)) return -1;
   t->opt_steps++;
-  for (auto& p : t->params)
-    if (train_adam(p.p, t->G + p.off, t->m1 + p.off, t->m2 + p.off, p.p16, p.n, lr, beta1, beta2, eps, wd, t->opt_steps, clip, t->acc + 3,
-                   grad_scale, st)) return -1;
+  if (train_adam(t->adam_tensors, t->adam_chunks, t->n_adam_chunks, t->G, t->m1, t->m2, lr, beta1, beta2, eps, wd, t->opt_steps, clip,
+                 t->acc + 3, grad_scale, st)) return -1;
   m->committed = false;   // the inference rel-pos key cache is stale now
   return 0;
 }

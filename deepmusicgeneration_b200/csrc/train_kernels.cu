@@ -142,12 +142,13 @@ __global__ void __launch_bounds__(256) train_res_ln_fwd_kernel(float* __restrict
 }
 
 // LayerNorm backward; dy is overwritten by dz.  Each block walks rows with stride gridDim.x*8 and keeps per-lane column
-// partials of dw / db, reduced over the block's 8 warps at the end -> partial[blk][0|1][d].
+// partials of dw / db, reduced over the block's 8 warps at the end and added to dw_out / db_out (one atomic per column and block).
 template <int NV>
 __global__ void __launch_bounds__(256) train_ln_bwd_kernel(float* __restrict__ dy, const bf16* __restrict__ zsave,
                                                            const float2* __restrict__ stats, const float* __restrict__ w,
-                                                           bf16* __restrict__ dadd, float* __restrict__ partial, int rows,
-                                                           uint32_t thresh, uint32_t seed, float scale) {
+                                                           bf16* __restrict__ dadd, float* __restrict__ dw_out,
+                                                           float* __restrict__ db_out, int rows, uint32_t thresh, uint32_t seed,
+                                                           float scale) {
   constexpr int d = NV * 128;
   __shared__ float red[8][128];
   const int wp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -210,27 +211,39 @@ __global__ void __launch_bounds__(256) train_ln_bwd_kernel(float* __restrict__ d
         float s = 0.f;
 #pragma unroll
         for (int q = 0; q < 8; q++) s += red[q][threadIdx.x];
-        partial[((long long)blockIdx.x * 2 + which) * d + k * 128 + threadIdx.x] = s;
+        atomicAdd((which ? db_out : dw_out) + k * 128 + threadIdx.x, s);
       }
     }
   }
 }
 
 // dst0[c] += sum_blk partial[blk][0][c]; dst1[c] += sum_blk partial[blk][1][c]   (dst1 may be NULL: single plane)
+// 32 columns per block, 8 row-groups of threads walk the partial blocks, shared-memory tree at the end (coalesced reads).
 __global__ void __launch_bounds__(256) train_partial_finish_kernel(const float* __restrict__ partial, int nblk, int n,
                                                                    float* __restrict__ dst0, float* __restrict__ dst1) {
-  const int c = blockIdx.x * 256 + threadIdx.x;
+  __shared__ float red[8][33];
   const int planes = dst1 ? 2 : 1;
-  if (c >= n * planes) return;
-  const int which = c / n, col = c % n;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int b = 0; b < nblk; b++) s += partial[((long long)b * planes + which) * n + col];
-  (which ? dst1 : dst0)[col] += s;
+  if (c < n * planes) {
+    const int which = c / n, col = c % n;
+    for (int b = ty; b < nblk; b += 8) s += partial[((long long)b * planes + which) * n + col];
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < n * planes) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; q++) t += red[q][tx];
+    const int which = c / n, col = c % n;
+    (which ? dst1 : dst0)[col] += t;
+  }
 }
 
 // column sums of a bf16 matrix: block = 256 threads x 2 columns, blockIdx.y = row chunk
 __global__ void __launch_bounds__(256) train_colsum_kernel(const bf16* __restrict__ x, long long ld, int rows, int n,
-                                                           float* __restrict__ partial) {
+                                                           float* __restrict__ dst) {
   const int c = (blockIdx.x * 256 + threadIdx.x) * 2;
   if (c >= n) return;
   const int chunk = (rows + gridDim.y - 1) / gridDim.y;
@@ -240,8 +253,8 @@ __global__ void __launch_bounds__(256) train_colsum_kernel(const bf16* __restric
     const uint32_t v = *(const uint32_t*)(x + (long long)r * ld + c);
     s0 += bf16lo(v); s1 += bf16hi(v);
   }
-  partial[(long long)blockIdx.y * n + c] = s0;
-  if (c + 1 < n) partial[(long long)blockIdx.y * n + c + 1] = s1;
+  atomicAdd(dst + c, s0);
+  if (c + 1 < n) atomicAdd(dst + c + 1, s1);
 }
 
 // ------------------------------------------------------------------ loss
@@ -404,23 +417,47 @@ __global__ void __launch_bounds__(256) train_posenc_kernel(bf16* __restrict__ pe
   }
 }
 
-__global__ void __launch_bounds__(256) train_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m1,
-                                                         float* __restrict__ m2, bf16* __restrict__ p16, long long n, float lr,
-                                                         float beta1, float beta2, float eps, float wd, float bc1, float bc2,
-                                                         float clip, const float* __restrict__ gnorm2, float gscale) {
+// Multi-tensor Adam: one launch for every parameter tensor.  chunk c covers elements [start, start + len) of tensor
+// desc[c].t; gradients / moments live in flat buffers at desc.off.
+__global__ void __launch_bounds__(256) train_adam_kernel(const AdamTensor* __restrict__ tensors, const AdamChunk* __restrict__ chunks,
+                                                         const float* __restrict__ G, float* __restrict__ M1, float* __restrict__ M2,
+                                                         float lr, float beta1, float beta2, float eps, float wd, float bc1,
+                                                         float bc2, float clip, const float* __restrict__ gnorm2, float gscale) {
+  const AdamChunk ch = chunks[blockIdx.x];
+  const AdamTensor tn = tensors[ch.t];
   float coef = gscale;
   if (clip > 0.f && gnorm2) {
     const float nrm = sqrtf(gnorm2[0]) * gscale;
     coef *= fminf(1.f, clip / (nrm + 1e-6f));
   }
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+  float* p = tn.p + ch.start;
+  bf16* p16 = tn.p16 ? tn.p16 + ch.start : nullptr;
+  const float* g = G + tn.off + ch.start;
+  float* m1 = M1 + tn.off + ch.start;
+  float* m2 = M2 + tn.off + ch.start;
+  const float decay = 1.f - lr * wd, ib1 = 1.f / bc1, ib2 = 1.f / bc2;
+  const int n4 = ch.len >> 2;                       // chunk starts are multiples of 4 and tensors are 16-byte aligned
+  for (int i = threadIdx.x; i < n4; i += 256) {
+    const float4 gr = ((const float4*)g)[i];
+    float4 w = ((float4*)p)[i], a = ((float4*)m1)[i], b = ((float4*)m2)[i];
+    float wv[4] = {w.x, w.y, w.z, w.w}, av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+    const float gv[4] = {gr.x * coef, gr.y * coef, gr.z * coef, gr.w * coef};
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      av[e] = beta1 * av[e] + (1.f - beta1) * gv[e];
+      bv[e] = beta2 * bv[e] + (1.f - beta2) * gv[e] * gv[e];
+      wv[e] = wv[e] * decay - lr * (av[e] * ib1) / (sqrtf(bv[e] * ib2) + eps);   // fastai true_wd: decay, then Adam
+    }
+    ((float4*)p)[i] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+    ((float4*)m1)[i] = make_float4(av[0], av[1], av[2], av[3]);
+    ((float4*)m2)[i] = make_float4(bv[0], bv[1], bv[2], bv[3]);
+    if (p16) ((uint2*)p16)[i] = make_uint2(pack_bf16x2(wv[0], wv[1]), pack_bf16x2(wv[2], wv[3]));
+  }
+  for (int i = n4 * 4 + threadIdx.x; i < ch.len; i += 256) {
     const float gr = g[i] * coef;
-    float w = p[i] * (1.f - lr * wd);                   // fastai true_wd: decoupled decay before the Adam update
-    const float a = beta1 * m1[i] + (1.f - beta1) * gr;
-    const float b = beta2 * m2[i] + (1.f - beta2) * gr * gr;
-    m1[i] = a; m2[i] = b;
-    w -= lr * (a / bc1) / (sqrtf(b / bc2) + eps);
-    p[i] = w;
+    const float a = beta1 * m1[i] + (1.f - beta1) * gr, b = beta2 * m2[i] + (1.f - beta2) * gr * gr;
+    const float w = p[i] * decay - lr * (a * ib1) / (sqrtf(b * ib2) + eps);
+    m1[i] = a; m2[i] = b; p[i] = w;
     if (p16) p16[i] = __float2bfloat16_rn(w);
   }
 }
@@ -466,19 +503,18 @@ int train_residual_ln_fwd(float* x32, const bf16* add, const float* w, const flo
   return -2;
 }
 
-int train_ln_bwd(float* dy, const bf16* zsave, const float2* stats, const float* w, bf16* dadd, float* partial, int* nblk_out,
-                 int rows, int d, uint32_t thresh, uint32_t seed, float scale, cudaStream_t st) {
+int train_ln_bwd(float* dy, const bf16* zsave, const float2* stats, const float* w, bf16* dadd, float* dw, float* db, int rows, int d,
+                 uint32_t thresh, uint32_t seed, float scale, cudaStream_t st) {
   int nblk = (rows + 7) / 8;
   if (nblk > 148 * 2) nblk = 148 * 2;
-  *nblk_out = nblk;
   const dim3 grid(nblk), block(256);
   switch (d / 128) {
-    case 1: return launch_np(train_ln_bwd_kernel<1>, grid, block, 0, st, dy, zsave, stats, w, dadd, partial, rows, thresh, seed, scale);
-    case 2: return launch_np(train_ln_bwd_kernel<2>, grid, block, 0, st, dy, zsave, stats, w, dadd, partial, rows, thresh, seed, scale);
-    case 3: return launch_np(train_ln_bwd_kernel<3>, grid, block, 0, st, dy, zsave, stats, w, dadd, partial, rows, thresh, seed, scale);
-    case 4: return launch_np(train_ln_bwd_kernel<4>, grid, block, 0, st, dy, zsave, stats, w, dadd, partial, rows, thresh, seed, scale);
-    case 6: return launch_np(train_ln_bwd_kernel<6>, grid, block, 0, st, dy, zsave, stats, w, dadd, partial, rows, thresh, seed, scale);
-    case 8: return launch_np(train_ln_bwd_kernel<8>, grid, block, 0, st, dy, zsave, stats, w, dadd, partial, rows, thresh, seed, scale);
+    case 1: return launch_np(train_ln_bwd_kernel<1>, grid, block, 0, st, dy, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
+    case 2: return launch_np(train_ln_bwd_kernel<2>, grid, block, 0, st, dy, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
+    case 3: return launch_np(train_ln_bwd_kernel<3>, grid, block, 0, st, dy, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
+    case 4: return launch_np(train_ln_bwd_kernel<4>, grid, block, 0, st, dy, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
+    case 6: return launch_np(train_ln_bwd_kernel<6>, grid, block, 0, st, dy, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
+    case 8: return launch_np(train_ln_bwd_kernel<8>, grid, block, 0, st, dy, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
   }
   DMG_CHECK(false, "training LayerNorm backward: d_model=%d unsupported", d);
   return -2;
@@ -486,16 +522,15 @@ int train_ln_bwd(float* dy, const bf16* zsave, const float2* stats, const float*
 
 int train_partial_finish(const float* partial, int nblk, int n, float* dst0, float* dst1, cudaStream_t st) {
   const int tot = n * (dst1 ? 2 : 1);
-  return launch_np(train_partial_finish_kernel, dim3((tot + 255) / 256), dim3(256), 0, st, partial, nblk, n, dst0, dst1);
+  return launch_np(train_partial_finish_kernel, dim3((tot + 31) / 32), dim3(256), 0, st, partial, nblk, n, dst0, dst1);
 }
 
-int train_colsum_bf16(const bf16* x, long long ld, int rows, int n, float* dst, float* partial, cudaStream_t st) {
+int train_colsum_bf16(const bf16* x, long long ld, int rows, int n, float* dst, cudaStream_t st) {
   const int gx = (n + 511) / 512;
   int gy = (148 * 4 + gx - 1) / gx;
   if (gy > rows) gy = rows;
   if (gy < 1) gy = 1;
-  if (launch_np(train_colsum_kernel, dim3(gx, gy), dim3(256), 0, st, x, ld, rows, n, partial)) return -1;
-  return train_partial_finish(partial, gy, n, dst, nullptr, st);
+  return launch_np(train_colsum_kernel, dim3(gx, gy), dim3(256), 0, st, x, ld, rows, n, dst);
 }
 
 int train_ce_loss(const float* logits, long long ldl, const long long* targets, bf16* dlogits, float* loss_acc, int rows, int V,
@@ -542,10 +577,10 @@ int train_posenc(bf16* pe, int n, int d, cudaStream_t st) {
   return launch_np(train_posenc_kernel, dim3(grid_for((long long)n * d / 2)), dim3(256), 0, st, pe, n, d);
 }
 
-int train_adam(float* p, const float* g, float* m1, float* m2, bf16* p16, long long n, float lr, float beta1, float beta2,
-               float eps, float wd, int step, float clip, const float* gnorm2, float gscale, cudaStream_t st) {
+int train_adam(const AdamTensor* tensors_dev, const AdamChunk* chunks_dev, int nchunks, const float* G, float* M1, float* M2, float lr,
+               float beta1, float beta2, float eps, float wd, int step, float clip, const float* gnorm2, float gscale, cudaStream_t st) {
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
-  return launch_np(train_adam_kernel, dim3(grid_for(n, 148 * 8)), dim3(256), 0, st, p, g, m1, m2, p16, n, lr, beta1, beta2, eps, wd,
+  return launch_np(train_adam_kernel, dim3(nchunks), dim3(256), 0, st, tensors_dev, chunks_dev, G, M1, M2, lr, beta1, beta2, eps, wd,
                    bc1, bc2, clip, gnorm2, gscale);
 }
 

@@ -36,6 +36,21 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
   return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * k * (1.f + 3.f * c * x * x);
 }
 
+// single-instruction tanh (MUFU): abs error ~5e-4, used where the result is rounded to bf16 anyway
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  return 0.5f * x * (1.f + tanh_fast(0.7978845608028654f * (x + 0.044715f * x * x * x)));
+}
+__device__ __forceinline__ float gelu_tanh_grad_fast(float x) {
+  const float k = 0.7978845608028654f, c = 0.044715f;
+  const float t = tanh_fast(k * (x + c * x * x * x));
+  return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * k * (1.f + 3.f * c * x * x);
+}
+
 // ------------------------------------------------------------------ persistent tcgen05 GEMM
 // C[M,N] = A * B with the reduction over K; operand storage:
 //   a_mn = 0: A is [M, K] row-major (K contiguous, "K-major")      a_mn = 1: A is [K, M] row-major ("MN-major")
@@ -60,6 +75,10 @@ struct GemmEpi {
   uint32_t drop_thresh = 0;      // dropout applied last (after act / aux): 0 = none
   uint32_t drop_seed = 0;
   float drop_scale = 1.f;
+  // grouped launch: `groups` independent problems of the same shape in one grid; group g reads A at M-coordinate
+  // g*a_gs, B at N-coordinate g*b_gs and writes at column offset g*c_gs (the per-head dRk contraction)
+  int groups = 1;
+  long long a_gs = 0, b_gs = 0, c_gs = 0;
 };
 int gemm_bf16_tc(const bf16* A, int a_mn, long long lda, const bf16* B, int b_mn, long long ldb, int M, int N, int K,
                  int splitk, const GemmEpi& e, int num_sms, cudaStream_t st);
@@ -105,12 +124,12 @@ int train_residual_ln_fwd(float* x32, const bf16* add, const float* w, const flo
                           float2* stats, int rows, int d, uint32_t thresh, uint32_t seed, float scale, cudaStream_t st);
 // LayerNorm backward: dy (fp32 [rows,d], in/out: becomes dz = gradient wrt z, which is also the residual-branch
 // gradient); dadd = bf16(dropout_mask * scale * dz) (gradient wrt the GEMM output that was added);
-// partial sums of dw/db are written to `partial` [nblk][2][d] and folded into dw/db by train_colsum_finish.
-int train_ln_bwd(float* dy, const bf16* zsave, const float2* stats, const float* w, bf16* dadd, float* partial,
-                 int* nblk_out, int rows, int d, uint32_t thresh, uint32_t seed, float scale, cudaStream_t st);
+// dw[d] / db[d] += the affine-parameter gradients (one atomic per column and block).
+int train_ln_bwd(float* dy, const bf16* zsave, const float2* stats, const float* w, bf16* dadd, float* dw, float* db, int rows, int d,
+                 uint32_t thresh, uint32_t seed, float scale, cudaStream_t st);
 int train_partial_finish(const float* partial, int nblk, int n, float* dst0, float* dst1, cudaStream_t st);   // dst += sums
 // column sums of a bf16 matrix [rows, n] (row stride ld) added into dst[n] (bias gradients)
-int train_colsum_bf16(const bf16* x, long long ld, int rows, int n, float* dst, float* partial, cudaStream_t st);
+int train_colsum_bf16(const bf16* x, long long ld, int rows, int n, float* dst, cudaStream_t st);
 // column sums of a fp32 matrix, added into dst (du/dv from dq accumulators are not needed: attention does them)
 // head: logits fp32 [rows, ldl] -> per-row CE loss (sum into loss_acc[0]) and dlogits bf16 [rows, ldl] = (softmax - onehot) * gscale
 int train_ce_loss(const float* logits, long long ldl, const long long* targets, bf16* dlogits, float* loss_acc,
@@ -137,10 +156,13 @@ int train_mem_update(bf16* mem, const bf16* x, int B, int T, int M, int d, cudaS
 int train_mem_update2(bf16* dst, const bf16* src, const bf16* x, int B, int T, int M, int d, cudaStream_t st);   // dst != src
 // PositionalEncoding table in bf16 [n, d]
 int train_posenc(bf16* pe, int n, int d, cudaStream_t st);
-// fused Adam (decoupled weight decay, bias correction) over the flat parameter buffer; grads are multiplied by
-// min(1, clip / ||g||) with ||g||^2 read from gnorm2[0] on the device; also refreshes the bf16 copy.
-int train_adam(float* p, const float* g, float* m1, float* m2, bf16* p16, long long n, float lr, float beta1, float beta2,
-               float eps, float wd, int step, float clip, const float* gnorm2, float gscale, cudaStream_t st);
+// fused multi-tensor Adam (decoupled weight decay first - fastai true_wd -, bias correction): ONE launch for all
+// parameter tensors; gradients are multiplied by grad_scale * min(1, clip / ||grad_scale * g||) with ||g||^2 read from
+// gnorm2[0] on the device; refreshes the bf16 copies.  chunks: <= 16384 elements each, starts multiples of 4.
+struct AdamTensor { float* p; bf16* p16; long long off; };
+struct AdamChunk { int t; int start; int len; };
+int train_adam(const AdamTensor* tensors_dev, const AdamChunk* chunks_dev, int nchunks, const float* G, float* M1, float* M2, float lr,
+               float beta1, float beta2, float eps, float wd, int step, float clip, const float* gnorm2, float gscale, cudaStream_t st);
 // dropout mask export for the tests: out[i] = keep(seed, i) ? scale : 0
 int train_export_mask(float* out, long long n, uint32_t thresh, uint32_t seed, float scale, cudaStream_t st);
 
