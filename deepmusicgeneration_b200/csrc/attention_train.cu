@@ -210,23 +210,26 @@ __global__ void __launch_bounds__(128) attn_train_fwd_kernel(const AttnTrainArgs
     scores_tile(qu, qv, smem_u32(sK), smem_u32(sR + (rt_lo % ATT_NR) * TILE_BYTES), smem_u32(sR + (rt_hi % ATT_NR) * TILE_BYTES),
                 skew, w, lane, L, s);
     const bool need_mask = (j0 + 63 >= a.M) || (j0 < a.M - a.mem_count);
+    // running max kept on the RAW scores (the scale is positive); exp2((s - m) * c) is one FFMA + one MUFU per element
     float mx[2] = {-INFINITY, -INFINITY};
+    if (need_mask) {
+#pragma unroll
+      for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+          if (!visible(mp, row_g[e >> 1], j0 + 8 * nt + 2 * t + (e & 1))) s[nt][e] = -INFINITY;
+    }
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) {
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        float x = s[nt][e] * c;
-        if (need_mask && !visible(mp, row_g[e >> 1], j0 + 8 * nt + 2 * t + (e & 1))) x = -INFINITY;
-        s[nt][e] = x;
-        mx[e >> 1] = fmaxf(mx[e >> 1], x);
-      }
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
     }
-    float alpha[2], m_use[2];
+    float alpha[2], neg_mc[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       const float m_new = fmaxf(m_run[r], quad_max(mx[r]));
-      alpha[r] = (m_new == -INFINITY) ? 1.f : ex2_fast(m_run[r] - m_new);
-      m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;
+      alpha[r] = (m_new == -INFINITY) ? 1.f : ex2_fast((m_run[r] - m_new) * c);
+      neg_mc[r] = (m_new == -INFINITY) ? 0.f : -m_new * c;
       m_run[r] = m_new;
     }
     float rs[2] = {0.f, 0.f};
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(128) attn_train_fwd_kernel(const AttnTrainArgs
       float p[4];
 #pragma unroll
       for (int e = 0; e < 4; e++) {
-        p[e] = ex2_fast(s[nt][e] - m_use[e >> 1]);
+        p[e] = ex2_fast(fmaf(s[nt][e], c, neg_mc[e >> 1]));
         rs[e >> 1] += p[e];
       }
       if (a.drop_thresh) {
@@ -252,9 +255,11 @@ __global__ void __launch_bounds__(128) attn_train_fwd_kernel(const AttnTrainArgs
     }
 #pragma unroll
     for (int r = 0; r < 2; r++) l_run[r] = l_run[r] * alpha[r] + rs[r];
+    if (__any_sync(0xffffffffu, alpha[0] != 1.f || alpha[1] != 1.f)) {   // the max settles after the first tiles: skip the rescale
 #pragma unroll
-    for (int nt = 0; nt < 8; nt++) {
-      o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0]; o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
+      for (int nt = 0; nt < 8; nt++) {
+        o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0]; o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
+      }
     }
     const uint32_t sVa = smem_u32(sV);
 #pragma unroll
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__(128) attn_train_fwd_kernel(const AttnTrainArgs
 #pragma unroll
     for (int nt = 0; nt < 8; nt++)
       *(uint32_t*)(orow + 8 * nt + 2 * t) = pack_bf16x2(o[nt][2 * r] * inv, o[nt][2 * r + 1] * inv);
-    if (t == 0) a.lse[(long long)bh * a.T + row_g[r]] = (m_run[r] + log2f(l)) * LN2;
+    if (t == 0) a.lse[(long long)bh * a.T + row_g[r]] = (m_run[r] * c + log2f(l)) * LN2;
   }
 }
 

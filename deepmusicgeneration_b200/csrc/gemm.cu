@@ -141,6 +141,24 @@ int make_tmap_bf16_ex(TensorMap2D* out, const void* base, long long inner, long 
   return 0;
 }
 
+// Output-side map (TMA stores of the training GEMM epilogue): 32-column x 32-row boxes (64-byte rows), 64B swizzle so the
+// row-per-lane staging writes are bank-conflict free.
+int make_tmap_bf16_store(TensorMap2D* out, const void* base, long long inner, long long rows, long long ld) {
+  PFN_encodeTiled enc = get_encode();
+  DMG_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  DMG_CHECK(((uintptr_t)base & 15) == 0 && (ld * 2) % 16 == 0, "store tensor map: base/stride not 16-byte aligned (ld=%lld)", ld);
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc((CUtensorMap*)out->bytes, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                   gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DMG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (store map) failed with CUresult %d (inner %lld rows %lld ld %lld)", (int)r, inner,
+            rows, ld);
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05 GEMM
 // ---------------------------------------------------------------------------------------------

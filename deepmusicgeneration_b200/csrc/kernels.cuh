@@ -15,6 +15,8 @@ struct TensorMap2D {
 int make_tmap_bf16(TensorMap2D* out, const void* base, long long cols, long long rows, long long ld, int box_rows);
 // same, any inner length (OOB box elements read as zero)
 int make_tmap_bf16_ex(TensorMap2D* out, const void* base, long long inner, long long rows, long long ld, int box_rows);
+// output map for TMA stores: 32 x 32 boxes, 64B swizzle
+int make_tmap_bf16_store(TensorMap2D* out, const void* base, long long inner, long long rows, long long ld);
 
 template <class T>
 int gemm_simt(const T* A, int lda, const T* W, int ldw, const float* bias, void* C, int ldc, int M, int N, int K,

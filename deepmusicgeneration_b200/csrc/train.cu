@@ -57,7 +57,8 @@ struct dmg_train {
   // workspaces
   float *x32 = nullptr, *dx32 = nullptr, *logits = nullptr, *delta = nullptr, *drk32 = nullptr, *partial = nullptr, *acc = nullptr;
   bf16 *proj = nullptr, *dadd = nullptr, *dh = nullptr, *dattn = nullptr, *dqkv_x = nullptr, *dkv_m = nullptr, *ds_dist = nullptr,
-       *qv = nullptr, *drk16 = nullptr, *dlogits = nullptr, *xdrop = nullptr;
+       *qv = nullptr, *drk16 = nullptr, *dlogits = nullptr, *xdrop = nullptr, *dbr = nullptr;
+  bool dbr_valid = false;                    // dbr holds a branch gradient still to be added to dx32
   const long long *ids = nullptr, *pos = nullptr;     // of the latest forward (caller-owned, must stay alive until backward ends)
   int win = 1, k = 1, training = 1;
   long long step = 0;
@@ -156,12 +157,12 @@ int ensure_wr_b16(dmg_model* m, dmg_train* t) {
   return 0;
 }
 
-// split-K factor of a weight-gradient GEMM: as many K slices as fit in ONE wave of 128x256 tiles (the epilogue adds
-// fp32 atomics per slice, so more slices than needed only add traffic), at least 8 k-blocks per slice
+// split-K factor of a weight-gradient GEMM: as many K slices as fit in ONE wave of 256 x 256 CTA-pair tiles (the epilogue
+// adds fp32 atomics per slice, so more slices than needed only add traffic), at least 8 k-blocks per slice
 int pick_splitk(int M, int N, int K, int num_sms) {
-  const long long tiles = (long long)((M + 127) / 128) * ((N + 255) / 256);
+  const long long tiles = (long long)((M + 255) / 256) * ((N + 255) / 256);
   const int num_kb = (K + 63) / 64;
-  long long s = num_sms / tiles;
+  long long s = (num_sms / 2) / tiles;
   if (s > num_kb / 8) s = num_kb / 8;
   if (s < 1) s = 1;
   return (int)s;
@@ -309,6 +310,7 @@ int backward_head(dmg_model* m, dmg_train* t, cudaStream_t st) {
   }
   const Drop dr = make_drop(t, t->cfg.output_p, SITE_OUT, 0);
   const float ar_coef = 2.f * t->cfg.alpha / ((float)rows * d);
+  t->dbr_valid = false;
   return train_head_bwd(t->dadd, t->x32, t->dx32, t->B, t->T, d, dr.thresh, dr.seed, dr.scale, ar_coef, st);
 }
 
@@ -321,7 +323,7 @@ int backward_layer(dmg_model* m, dmg_train* t, int l, cudaStream_t st) {
   // ---- FFN block
   {
     const Drop d4 = make_drop(t, t->cfg.ff_p, SITE_RES2, l);
-    if (train_ln_bwd(t->dx32, A.z2, A.st2, W.ln2w, t->dadd, t->G + g.ln2w, t->G + g.ln2b, rows, d, d4.thresh, d4.seed, d4.scale, st)) return -1;
+    if (train_ln_bwd(t->dx32, t->dbr_valid ? t->dbr : nullptr, A.z2, A.st2, W.ln2w, t->dadd, t->G + g.ln2w, t->G + g.ln2b, rows, d, d4.thresh, d4.seed, d4.scale, st)) return -1;
     if (grad_w(m, t, t->dadd, d, A.hact, di, d, di, rows, g.w2, st)) return -1;
     if (train_colsum_bf16(t->dadd, d, rows, d, t->G + g.b2, st)) return -1;
     const Drop d3 = make_drop(t, t->cfg.ff_p, SITE_FF, l);
@@ -330,13 +332,14 @@ int backward_layer(dmg_model* m, dmg_train* t, int l, cudaStream_t st) {
     if (gemm_bf16_tc(t->dadd, 0, d, W.w2.b16, 1, di, rows, di, d, 1, e, ns, st)) return -1;
     if (grad_w(m, t, t->dh, di, A.xa1, d, di, d, rows, g.w1, st)) return -1;
     if (train_colsum_bf16(t->dh, di, rows, di, t->G + g.b1, st)) return -1;
-    GemmEpi e2; e2.aux = t->dx32; e2.ld_aux = d; e2.aux_mode = GEMM_AUX_ADD_F32; e2.out = t->dx32; e2.ldc = d; e2.out_mode = GEMM_OUT_F32;
+    // input gradient of the FFN branch, bf16; the LayerNorm backward below adds it to the fp32 residual gradient
+    GemmEpi e2; e2.out = t->dbr; e2.ldc = d; e2.out_mode = GEMM_OUT_BF16;
     if (gemm_bf16_tc(t->dh, 0, di, W.w1.b16, 1, d, rows, d, di, 1, e2, ns, st)) return -1;
   }
   // ---- attention block
   {
     const Drop d2 = make_drop(t, t->cfg.resid_p, SITE_RES1, l);
-    if (train_ln_bwd(t->dx32, A.z1, A.st1, W.ln1w, t->dadd, t->G + g.ln1w, t->G + g.ln1b, rows, d, d2.thresh, d2.seed, d2.scale, st)) return -1;
+    if (train_ln_bwd(t->dx32, t->dbr, A.z1, A.st1, W.ln1w, t->dadd, t->G + g.ln1w, t->G + g.ln1b, rows, d, d2.thresh, d2.seed, d2.scale, st)) return -1;
     if (grad_w(m, t, t->dadd, d, A.attn, HD, d, HD, rows, g.wo, st)) return -1;
     if (g.bo >= 0 && train_colsum_bf16(t->dadd, d, rows, d, t->G + g.bo, st)) return -1;
     GemmEpi e; e.out = t->dattn; e.ldc = HD; e.out_mode = GEMM_OUT_BF16;
@@ -368,8 +371,10 @@ int backward_layer(dmg_model* m, dmg_train* t, int l, cudaStream_t st) {
       if (grad_w(m, t, t->dkv_m, 2 * HD, t->mem[l], d, 2 * HD, d, t->B * M, g.wqkv + (long long)HD * d, st)) return -1;
       if (g.bqkv >= 0 && train_colsum_bf16(t->dkv_m, 2 * HD, t->B * M, 2 * HD, t->G + g.bqkv + HD, st)) return -1;
     }
-    GemmEpi e2; e2.aux = t->dx32; e2.ld_aux = d; e2.aux_mode = GEMM_AUX_ADD_F32; e2.out = t->dx32; e2.ldc = d; e2.out_mode = GEMM_OUT_F32;
+    // input gradient of the attention branch, bf16: consumed by the next LayerNorm backward (or the embedding backward)
+    GemmEpi e2; e2.out = t->dbr; e2.ldc = d; e2.out_mode = GEMM_OUT_BF16;
     if (gemm_bf16_tc(t->dqkv_x, 0, 3 * HD, W.wqkv.b16, 1, d, rows, d, 3 * HD, 1, e2, ns, st)) return -1;
+    t->dbr_valid = true;
   }
   return 0;
 }
@@ -377,7 +382,7 @@ int backward_layer(dmg_model* m, dmg_train* t, int l, cudaStream_t st) {
 int backward_embed(dmg_model* m, dmg_train* t, cudaStream_t st) {
   const dmg_config& c = m->cfg;
   const Drop dr = make_drop(t, t->cfg.embed_p, SITE_EMBED, 0);
-  return train_embed_bwd(t->ids, c.encode_position ? t->pos : nullptr, t->dx32, t->G + t->g_emb,
+  return train_embed_bwd(t->ids, c.encode_position ? t->pos : nullptr, t->dx32, t->dbr_valid ? t->dbr : nullptr, t->G + t->g_emb,
                          t->g_beat >= 0 ? t->G + t->g_beat : nullptr, t->g_bar >= 0 ? t->G + t->g_bar : nullptr, t->rows, c.d_model,
                          c.vocab, dr.thresh, dr.seed, dr.scale, st);
 }
@@ -475,6 +480,7 @@ int dmg_train_create(dmg_model* m, const dmg_train_config* cfg, float* grad_flat
   TRY(talloc(t, &t->acc, 8));
   TRY(talloc(t, &t->proj, (size_t)rows * d));
   TRY(talloc(t, &t->dadd, (size_t)rows * d));
+  TRY(talloc(t, &t->dbr, (size_t)rows * d));
   TRY(talloc(t, &t->dh, (size_t)rows * di));
   TRY(talloc(t, &t->dattn, (size_t)rows * HD));
   TRY(talloc(t, &t->dqkv_x, (size_t)rows * 3 * HD));

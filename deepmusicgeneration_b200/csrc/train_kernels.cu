@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) train_embed_kernel(const long long* __res
 }
 
 __global__ void __launch_bounds__(256) train_embed_bwd_kernel(const long long* __restrict__ ids, const long long* __restrict__ pos,
-                                                              const float* __restrict__ dx, float* __restrict__ demb,
+                                                              const float* __restrict__ dx, const bf16* __restrict__ dbr, float* __restrict__ demb,
                                                               float* __restrict__ dbeat, float* __restrict__ dbar, int rows, int d,
                                                               int vocab, uint32_t thresh, uint32_t seed, float scale) {
   const int d4 = d >> 2;
@@ -70,6 +70,10 @@ __global__ void __launch_bounds__(256) train_embed_bwd_kernel(const long long* _
     long long id = ids[row];
     id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
     float4 g = *(const float4*)(dx + (long long)row * d + c);
+    if (dbr) {
+      const uint2 b2 = *(const uint2*)(dbr + (long long)row * d + c);
+      g.x += bf16lo(b2.x); g.y += bf16hi(b2.x); g.z += bf16lo(b2.y); g.w += bf16hi(b2.y);
+    }
     if (thresh) {
       float k[4];
       keep4(seed, (uint32_t)(row * d + c), thresh, scale, k);
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(256) train_res_ln_fwd_kernel(float* __restrict
 // LayerNorm backward; dy is overwritten by dz.  Each block walks rows with stride gridDim.x*8 and keeps per-lane column
 // partials of dw / db, reduced over the block's 8 warps at the end and added to dw_out / db_out (one atomic per column and block).
 template <int NV>
-__global__ void __launch_bounds__(256) train_ln_bwd_kernel(float* __restrict__ dy, const bf16* __restrict__ zsave,
+__global__ void __launch_bounds__(256) train_ln_bwd_kernel(float* __restrict__ dy, const bf16* __restrict__ dbr, const bf16* __restrict__ zsave,
                                                            const float2* __restrict__ stats, const float* __restrict__ w,
                                                            bf16* __restrict__ dadd, float* __restrict__ dw_out,
                                                            float* __restrict__ db_out, int rows, uint32_t thresh, uint32_t seed,
@@ -167,7 +171,11 @@ __global__ void __launch_bounds__(256) train_ln_bwd_kernel(float* __restrict__ d
 #pragma unroll
     for (int k = 0; k < NV; k++) {
       const int c = (lane + 32 * k) * 4;
-      const float4 y = *(const float4*)(dy + (long long)row * d + c);
+      float4 y = *(const float4*)(dy + (long long)row * d + c);
+      if (dbr) {   // branch gradient produced in bf16 by the preceding input-gradient GEMM
+        const uint2 b2 = *(const uint2*)(dbr + (long long)row * d + c);
+        y.x += bf16lo(b2.x); y.y += bf16hi(b2.x); y.z += bf16lo(b2.y); y.w += bf16hi(b2.y);
+      }
       const uint2 z2 = *(const uint2*)(zsave + (long long)row * d + c);
       const float zz[4] = {bf16lo(z2.x), bf16hi(z2.x), bf16lo(z2.y), bf16hi(z2.y)};
       const float yy[4] = {y.x, y.y, y.z, y.w};
@@ -482,9 +490,9 @@ int train_embed(const long long* ids, const long long* pos, const float* emb, co
                    rows, d, vocab, thresh, seed, scale);
 }
 
-int train_embed_bwd(const long long* ids, const long long* pos, const float* dx, float* demb, float* dbeat, float* dbar, int rows,
-                    int d, int vocab, uint32_t thresh, uint32_t seed, float scale, cudaStream_t st) {
-  return launch_np(train_embed_bwd_kernel, dim3(grid_for((long long)rows * d / 4)), dim3(256), 0, st, ids, pos, dx, demb, dbeat, dbar,
+int train_embed_bwd(const long long* ids, const long long* pos, const float* dx, const bf16* dbr, float* demb, float* dbeat, float* dbar,
+                    int rows, int d, int vocab, uint32_t thresh, uint32_t seed, float scale, cudaStream_t st) {
+  return launch_np(train_embed_bwd_kernel, dim3(grid_for((long long)rows * d / 4)), dim3(256), 0, st, ids, pos, dx, dbr, demb, dbeat, dbar,
                    rows, d, vocab, thresh, seed, scale);
 }
 
@@ -503,18 +511,18 @@ int train_residual_ln_fwd(float* x32, const bf16* add, const float* w, const flo
   return -2;
 }
 
-int train_ln_bwd(float* dy, const bf16* zsave, const float2* stats, const float* w, bf16* dadd, float* dw, float* db, int rows, int d,
+int train_ln_bwd(float* dy, const bf16* dbr, const bf16* zsave, const float2* stats, const float* w, bf16* dadd, float* dw, float* db, int rows, int d,
                  uint32_t thresh, uint32_t seed, float scale, cudaStream_t st) {
   int nblk = (rows + 7) / 8;
   if (nblk > 148 * 2) nblk = 148 * 2;
   const dim3 grid(nblk), block(256);
   switch (d / 128) {
-    case 1: return launch_np(train_ln_bwd_kernel<1>, grid, block, 0, st, dy, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
-    case 2: return launch_np(train_ln_bwd_kernel<2>, grid, block, 0, st, dy, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
-    case 3: return launch_np(train_ln_bwd_kernel<3>, grid, block, 0, st, dy, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
-    case 4: return launch_np(train_ln_bwd_kernel<4>, grid, block, 0, st, dy, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
-    case 6: return launch_np(train_ln_bwd_kernel<6>, grid, block, 0, st, dy, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
-    case 8: return launch_np(train_ln_bwd_kernel<8>, grid, block, 0, st, dy, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
+    case 1: return launch_np(train_ln_bwd_kernel<1>, grid, block, 0, st, dy, dbr, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
+    case 2: return launch_np(train_ln_bwd_kernel<2>, grid, block, 0, st, dy, dbr, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
+    case 3: return launch_np(train_ln_bwd_kernel<3>, grid, block, 0, st, dy, dbr, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
+    case 4: return launch_np(train_ln_bwd_kernel<4>, grid, block, 0, st, dy, dbr, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
+    case 6: return launch_np(train_ln_bwd_kernel<6>, grid, block, 0, st, dy, dbr, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
+    case 8: return launch_np(train_ln_bwd_kernel<8>, grid, block, 0, st, dy, dbr, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
   }
   DMG_CHECK(false, "training LayerNorm backward: d_model=%d unsupported", d);
   return -2;

@@ -122,10 +122,11 @@ int train_embed(const long long* ids, const long long* pos, const float* emb, co
 // z = x32 + dropout(add); save zsave = bf16(z), stats = (mean, rstd); x32 = LN(z)*w+b; xa = bf16(x32)
 int train_residual_ln_fwd(float* x32, const bf16* add, const float* w, const float* b, bf16* xa, bf16* zsave,
                           float2* stats, int rows, int d, uint32_t thresh, uint32_t seed, float scale, cudaStream_t st);
-// LayerNorm backward: dy (fp32 [rows,d], in/out: becomes dz = gradient wrt z, which is also the residual-branch
+// LayerNorm backward: incoming gradient = dy (fp32 [rows,d]) + dbr (bf16 [rows,d] or NULL: the branch gradient a preceding
+// input-gradient GEMM produced); dy is overwritten by dz = gradient wrt z, which is also the residual-branch
 // gradient); dadd = bf16(dropout_mask * scale * dz) (gradient wrt the GEMM output that was added);
 // dw[d] / db[d] += the affine-parameter gradients (one atomic per column and block).
-int train_ln_bwd(float* dy, const bf16* zsave, const float2* stats, const float* w, bf16* dadd, float* dw, float* db, int rows, int d,
+int train_ln_bwd(float* dy, const bf16* dbr, const bf16* zsave, const float2* stats, const float* w, bf16* dadd, float* dw, float* db, int rows, int d,
                  uint32_t thresh, uint32_t seed, float scale, cudaStream_t st);
 int train_partial_finish(const float* partial, int nblk, int n, float* dst0, float* dst1, cudaStream_t st);   // dst += sums
 // column sums of a bf16 matrix [rows, n] (row stride ld) added into dst[n] (bias gradients)
@@ -144,8 +145,8 @@ int train_head_bwd(const bf16* dxd, const float* core_out, float* dx32, int B, i
 int train_sumsq(const float* x, long long n, float* acc, cudaStream_t st);
 // TAR value: sum over b, t>=1 of (h[b,t]-h[b,t-1])^2 for h = bf16 [B, n, d] with stream stride bstride elements
 int train_tar(const bf16* h, long long bstride, int B, int n, int d, float* acc, cudaStream_t st);
-// embedding backward: demb[id] += mask * scale * dx (atomics); beat/bar likewise when pos != NULL
-int train_embed_bwd(const long long* ids, const long long* pos, const float* dx, float* demb, float* dbeat, float* dbar,
+// embedding backward: demb[id] += mask * scale * (dx + dbr) (atomics); beat/bar likewise when pos != NULL
+int train_embed_bwd(const long long* ids, const long long* pos, const float* dx, const bf16* dbr, float* demb, float* dbeat, float* dbar,
                     int rows, int d, int vocab, uint32_t thresh, uint32_t seed, float scale, cudaStream_t st);
 // fp32 [rows, d] -> bf16
 int train_cast_bf16(const float* src, bf16* dst, long long n, cudaStream_t st);
