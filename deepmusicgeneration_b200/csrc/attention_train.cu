@@ -255,11 +255,9 @@ __global__ void __launch_bounds__(128) attn_train_fwd_kernel(const AttnTrainArgs
     }
 #pragma unroll
     for (int r = 0; r < 2; r++) l_run[r] = l_run[r] * alpha[r] + rs[r];
-    if (__any_sync(0xffffffffu, alpha[0] != 1.f || alpha[1] != 1.f)) {   // the max settles after the first tiles: skip the rescale
 #pragma unroll
-      for (int nt = 0; nt < 8; nt++) {
-        o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0]; o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
-      }
+    for (int nt = 0; nt < 8; nt++) {
+      o[nt][0] *= alpha[0]; o[nt][1] *= alpha[0]; o[nt][2] *= alpha[1]; o[nt][3] *= alpha[1];
     }
     const uint32_t sVa = smem_u32(sV);
 #pragma unroll

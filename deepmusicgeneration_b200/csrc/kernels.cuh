@@ -31,6 +31,12 @@ int gemm_tc_splitk_ways(int K);
 int gemm_tc_splitk(const TensorMap2D* tmA, const TensorMap2D* tmW32, const float* bias, void* C, int ldc, int M, int N,
                    int K, int gelu, int out_bf16, cudaStream_t st);
 
+// Decode-step fusion (gemm_ln.cu): x32 = LayerNorm(x32 + A W^T + bias), xa = bf16(x32) in one 8-CTA-cluster kernel.
+// tmA16: activation map with 16-row boxes; tmW: weight map with (d/8)-row boxes.
+bool gemm_ln_supported(int d, int K);
+int gemm_ln(const TensorMap2D* tmA16, const TensorMap2D* tmW, const float* bias, float* x32, const float* ln_w, const float* ln_b,
+            bf16* xa, int M, int d, int K, cudaStream_t st);
+
 // ------------------------------------------------------------------ elementwise / small kernels
 // x32[row] = emb[id] (+ beat[pos%32] + bar[min(pos/32 % 1024, 1023)]); xa = T(x32)
 template <class T>

@@ -68,6 +68,10 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
   const bool v2_ok = !bert && M > 0 && m->layers[0].has_ring_tm && attn_decode2_supported(c.d_head, M) && !getenv("DMG_DECODE_V1");
   const bool fast_decode = m->is_bf16 && !bert && T_len == 1 && (v2_ok || attn_decode_supported(c.d_head, M)) &&
                            !getenv("DMG_NO_DECODE_KERNEL");
+  // Measured and rejected as the default (profiles/README.md, r1c): the 8-CTA-cluster GEMM + LayerNorm kernel is exact but
+  // slower than the split-K GEMM + LayerNorm pair at 256 rows (16 CTAs stream the whole K: 1.58 vs 1.46 ms/step at C2).
+  static const bool want_gemm_ln = getenv("DMG_GEMM_LN") != nullptr;
+  const bool fuse_ln = want_gemm_ln && m->is_bf16 && m->use_tc && !bert && rows <= 512;
   for (int l = 0; l < c.n_layers; l++) {
     LayerW& L = m->layers[l];
     if (!(skip & 1) && linear(m, A_XA, xa, L.wqkv, L.bqkv, m->qkv, 3 * HD, rows, 0, 0, st)) return -1;
@@ -101,11 +105,21 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
     if (bert) {
       if (residual_layernorm<T, T>(m->x32, (const T*)m->attn, L.ln1w, L.ln1b, xa, rows, d, st)) return -1;
     } else {
-      if (!(skip & 4) && linear(m, A_ATTN, m->attn, L.wo, L.bo, m->proj, d, rows, 0, 0, st)) return -1;
-      if (!(skip & 8) && residual_layernorm<T, float>(m->x32, m->proj, L.ln1w, L.ln1b, xa, rows, d, st)) return -1;
+      // one-token steps: projection + residual + LayerNorm in one cluster kernel (gemm_ln.cu)
+      const bool fuse1 = fuse_ln && L.wo.has_tmln && m->has_tmA16[A_ATTN], fuse2 = fuse_ln && L.w2.has_tmln && m->has_tmA16[A_H];
+      if (fuse1) {
+        if (!(skip & 4) && gemm_ln(&m->tmA16[A_ATTN], &L.wo.tmln, L.bo, m->x32, L.ln1w, L.ln1b, (bf16*)xa, rows, d, HD, st)) return -1;
+      } else {
+        if (!(skip & 4) && linear(m, A_ATTN, m->attn, L.wo, L.bo, m->proj, d, rows, 0, 0, st)) return -1;
+        if (!(skip & 8) && residual_layernorm<T, float>(m->x32, m->proj, L.ln1w, L.ln1b, xa, rows, d, st)) return -1;
+      }
       if (!(skip & 16) && linear(m, A_XA, xa, L.w1, L.b1, m->hbuf, c.d_inner, rows, 1, m->is_bf16 ? 1 : 0, st)) return -1;
-      if (!(skip & 32) && linear(m, A_H, m->hbuf, L.w2, L.b2, m->proj, d, rows, 0, 0, st)) return -1;
-      if (!(skip & 64) && residual_layernorm<T, float>(m->x32, m->proj, L.ln2w, L.ln2b, xa, rows, d, st)) return -1;
+      if (fuse2) {
+        if (!(skip & 32) && gemm_ln(&m->tmA16[A_H], &L.w2.tmln, L.b2, m->x32, L.ln2w, L.ln2b, (bf16*)xa, rows, d, c.d_inner, st)) return -1;
+      } else {
+        if (!(skip & 32) && linear(m, A_H, m->hbuf, L.w2, L.b2, m->proj, d, rows, 0, 0, st)) return -1;
+        if (!(skip & 64) && residual_layernorm<T, float>(m->x32, m->proj, L.ln2w, L.ln2b, xa, rows, d, st)) return -1;
+      }
     }
     if (c.keep_hidden && M > 0 && ring_append_hidden(m->x32, m->hrings[l + 1], nb, T_len, d, M, m->pos_total, b0, st)) return -1;
   }
@@ -181,6 +195,10 @@ static int commit_weight(dmg_model* m, Weight& w) {
     if (make_tmap_bf16(&w.tm32, w.b16, w.cols, w.rows, w.cols, 32)) return -1;
     if (make_tmap_bf16(&w.tm128, w.b16, w.cols, w.rows, w.cols, 128)) return -1;
     w.has_tm = true;
+    if (w.rows == m->cfg.d_model && gemm_ln_supported(w.rows, w.cols)) {
+      if (make_tmap_bf16(&w.tmln, w.b16, w.cols, w.rows, w.cols, w.rows / 8)) return -1;
+      w.has_tmln = true;
+    }
   }
   return 0;
 }
@@ -394,6 +412,8 @@ int dmg_create(const dmg_config* cfg, int device, dmg_model** out) {
     for (int i = 0; i < A_COUNT && !rc; i++) {
       if (bufs[i] == nullptr || m->a_cols[i] % 64 != 0) continue;
       TRY(make_tmap_bf16(&m->tmA[i], bufs[i], m->a_cols[i], m->a_rows[i], m->a_cols[i], 128));
+      TRY(make_tmap_bf16(&m->tmA16[i], bufs[i], m->a_cols[i], m->a_rows[i], m->a_cols[i], 16));
+      m->has_tmA16[i] = !rc;
     }
   }
   if (!rc && cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {

@@ -17,7 +17,8 @@ struct Weight {
   bf16* b16 = nullptr;
   int rows = 0, cols = 0;
   TensorMap2D tm32, tm128;   // TMA maps with 32- and 128-row boxes
-  bool has_tm = false;
+  TensorMap2D tmln;          // (rows/8)-row boxes: the fused GEMM + LayerNorm cluster kernel (weights with rows == d_model)
+  bool has_tm = false, has_tmln = false;
 };
 
 struct LayerW {
@@ -63,6 +64,8 @@ struct dmg_model {
   float *x32 = nullptr, *qkv = nullptr, *proj = nullptr, *logits_buf = nullptr;
   void *xa = nullptr, *attn = nullptr, *hbuf = nullptr, *xlast = nullptr;
   TensorMap2D tmA[A_COUNT];
+  TensorMap2D tmA16[A_COUNT];   // 16-row boxes (multicast slices of the fused GEMM + LayerNorm kernel)
+  bool has_tmA16[A_COUNT] = {false, false, false, false};
   int a_rows[A_COUNT], a_cols[A_COUNT];
   // generation loop
   bool samp_ready = false, logits_valid = false;

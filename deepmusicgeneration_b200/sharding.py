@@ -29,8 +29,21 @@ def init_distributed(backend=None):
             backend = 'nccl' if torch.cuda.is_available() else 'gloo'
         if backend == 'nccl':
             torch.cuda.set_device(local_rank)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+            dist.init_process_group(backend=backend, rank=rank, world_size=world, device_id=torch.device('cuda', local_rank))
+        else:
+            dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        import atexit
+        atexit.register(finalize)
     return rank, local_rank, world
+
+
+def finalize():
+    "destroy the process group (registered at exit by init_distributed)"
+    if dist.is_available() and dist.is_initialized():
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
 
 
 def barrier():

@@ -148,11 +148,28 @@ def test_training_reduces_loss_and_inference_follows():
     tr.close()
 
 
-def test_rand_window_mask_size_follows_reference_draws():
-    rng = np.random.RandomState(0)
-    ref = np.random.RandomState(0)
-    for _ in range(200):
-        got = rand_window_mask_size(4, p=0.2, is_eval=False, rng=rng)
-        exp = (1, 1) if ref.rand() >= 0.2 else (ref.randint(0, 4) + 1, 0)
-        assert got == exp
-    assert rand_window_mask_size(4, is_eval=True) == (1, 1)
+
+
+def test_grad_spans_tile_the_flat_buffer():
+    "backward slices (as the trainer issues them for the bucketed all-reduce) finalise disjoint spans that cover every gradient"
+    import ctypes as C
+    cfg = small_config(n_layers=5)
+    om, pm, tr = build_pair(cfg, 2, 64, 0.)
+    lib, h = tr.lib, tr.e.h
+    total = lib.dmg_train_param_count(h)
+    for bucket in (1, 2, 3, 5, 8):
+        spans, hi = [], 5
+        while True:
+            lo = max(0, hi - bucket)
+            off, cnt = C.c_int64(), C.c_int64()
+            assert lib.dmg_train_grad_span(h, hi, lo, C.byref(off), C.byref(cnt)) == 0
+            spans.append((off.value, cnt.value))
+            hi = lo
+            if hi == 0:
+                break
+        pos = 0
+        for off, cnt in spans:
+            assert off == pos and cnt > 0
+            pos += cnt
+        assert pos == total
+    tr.close()
