@@ -70,7 +70,7 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
                            !getenv("DMG_NO_DECODE_KERNEL");
   // Measured and rejected as the default (profiles/README.md, r1c): the 8-CTA-cluster GEMM + LayerNorm kernel is exact but
   // slower than the split-K GEMM + LayerNorm pair at 256 rows (16 CTAs stream the whole K: 1.58 vs 1.46 ms/step at C2).
-  static const bool want_gemm_ln = getenv("DMG_GEMM_LN") != nullptr;
+  const bool want_gemm_ln = getenv("DMG_GEMM_LN") != nullptr;
   const bool fuse_ln = want_gemm_ln && m->is_bf16 && m->use_tc && !bert && rows <= 512;
   for (int l = 0; l < c.n_layers; l++) {
     LayerW& L = m->layers[l];

@@ -58,6 +58,38 @@ class MusicLearner:
         torch.save(state, file)
         return file
 
+    # -- training: what fastai's Learner.fit_one_cycle does for this learner (notebook cell 70-73)
+    def trainer(self, bs, bptt, drop_mult=1., alpha=2., beta=1., seed=0, **kw):
+        "The training-step engine for this model (RNNLearner adds RNNTrainer(alpha=2, beta=1)); created once per (bs, bptt)."
+        from .training import TXLTrainer
+        key = (bs, bptt)
+        if getattr(self, '_trainer_key', None) != key:
+            if getattr(self, '_trainer', None) is not None:
+                self._trainer.close()
+            self._trainer = TXLTrainer(self.model, bs, bptt, self.config, drop_mult=drop_mult, alpha=alpha, beta=beta, seed=seed, **kw)
+            self._trainer_key = key
+        return self._trainer
+
+    def fit_one_cycle(self, cyc_len, max_lr, batches, bs=None, bptt=None, wd=0.01, clip=0.5, moms=(0.95, 0.85), drop_mult=1.,
+                      callback=None):
+        """learner.fit_one_cycle(epochs, lr) over `batches`, a list of (x, y[, pos]) LongTensors [bs, bptt] (the
+        MusicPreloader's contiguous streams, deep_music_genre.py:1088-1096): one-cycle LR / momentum schedule over all
+        cyc_len passes, memory reset at every epoch start (RNNTrainer.on_epoch_begin), Adam(true_wd), gradient clipping."""
+        from .training import one_cycle_lr
+        x0 = batches[0][0]
+        tr = self.trainer(bs or x0.shape[0], bptt or x0.shape[1], drop_mult=drop_mult)
+        total, i = cyc_len * len(batches), 0
+        for _ in range(cyc_len):
+            tr.reset()
+            for b in batches:
+                lr, mom = one_cycle_lr(i, total, max_lr, moms=moms)
+                tr.step(b[0], b[1], b[2] if len(b) > 2 else None, lr=lr, betas=(mom, 0.99), wd=wd, clip=clip)
+                if callback is not None:
+                    callback(i, tr)
+                i += 1
+        tr.sync_for_inference()
+        return tr.losses()
+
     def _prefill(self, x, pos):
         enc = self.model[0]
         enc._bs = x.shape[0]

@@ -126,6 +126,34 @@ def test_txl_bf16_logits_and_top1():
         assert _rel(p1, o1) <= 2e-2, s
 
 
+def test_fused_gemm_layernorm_cluster_kernel_matches_unfused_pair():
+    "DMG_GEMM_LN=1: out-projection / FFN-down GEMM + residual + LayerNorm in one 8-CTA-cluster kernel (gemm_ln.cu, opt-in)"
+    cfg = dict(txl.baseline_config(), n_layers=3)
+    om, pa = _pair(cfg, 'bf16', 130, 64, keep_hidden=False)       # 130 streams: two row tiles, the second one ragged
+    _, pb = _pair(cfg, 'bf16', 130, 64, keep_hidden=False)
+    g = torch.Generator().manual_seed(11)
+    x0 = torch.randint(0, V, (130, 40), generator=g)
+    om.reset()
+    with torch.no_grad(): om(x0)
+    for pm in (pa, pb):
+        pm.reset(); pm[0].forward(x0.cuda(), logits_mode=2)
+    worst = worst_o = 0.
+    for s in range(6):
+        xs = torch.randint(0, V, (130, 1), generator=g)
+        os.environ.pop('DMG_GEMM_LN', None)
+        la = pa[0].forward(xs.cuda(), logits_mode=1)[0].cpu()
+        try:
+            os.environ['DMG_GEMM_LN'] = '1'
+            lb = pb[0].forward(xs.cuda(), logits_mode=1)[0].cpu()
+        finally:
+            os.environ.pop('DMG_GEMM_LN', None)
+        with torch.no_grad(): lo = om(xs)[0]
+        worst = max(worst, (la - lb).abs().max().item())
+        worst_o = max(worst_o, _rel(lb, lo))
+    print(f'fused GEMM+LN vs unfused: max abs {worst:.3e}; vs oracle max rel {worst_o:.3e}')
+    assert worst < 1e-2 and worst_o <= 2e-2
+
+
 @pytest.mark.parametrize('M', [128, 64, 512])
 def test_decode_kernels_equal_general_kernel_and_oracle(M):
     """x_len==1 fast kernels (v2: persistent, TMA-2D tiles, resident Rd, mma.sync; v1: bulk-copy ring + FFMA) vs the

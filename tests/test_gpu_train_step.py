@@ -173,3 +173,21 @@ def test_grad_spans_tile_the_flat_buffer():
             pos += cnt
         assert pos == total
     tr.close()
+
+
+def test_learner_fit_one_cycle_surface():
+    "music_model_learner(...).fit_one_cycle(epochs, lr, batches): the notebook's training call on the CUDA engine"
+    from deepmusicgeneration_b200.codec import MusicDataBunch
+    from deepmusicgeneration_b200.learner import music_model_learner
+    cfg = small_config()
+    data = MusicDataBunch.empty('')
+    learn = music_model_learner(data, config=cfg, dtype='bf16', max_batch=4, max_seq=64, keep_hidden=False, seed=0)
+    base = (torch.arange(4 * 64 * 12) % 29 + 12).view(4, -1)
+    batches = [(base[:, i * 64:(i + 1) * 64], base[:, i * 64 + 1:(i + 1) * 64 + 1]) for i in range(11)]
+    seen = []
+    out = learn.fit_one_cycle(4, 3e-3, batches, callback=lambda i, tr: seen.append(i))
+    assert len(seen) == 44 and out['ce'] < 2.5, out
+    learn.model.reset()
+    logits = learn.model(base[:, :64].cuda())[0]
+    acc = (logits.argmax(-1).cpu()[:, 8:] == base[:, 9:65]).float().mean().item()
+    assert acc > 0.9, acc
