@@ -32,6 +32,10 @@ B_PER_GPU, PREFILL, V = 256, 512, 324
 CFG = dict(d_model=512, n_layers=16, n_heads=8, d_head=64, d_inner=2048, mem_len=512)
 WORKLOAD = ('C2: Transformer-XL d_model 512, 16 layers, 8 heads x 64, d_inner 2048, mem_len 512, vocab 324; '
             '256 streams/GPU, one-token steps over a full 512-slot memory (S=513), top_k 30 / top_p 0.65 sampling')
+# BASELINE.json configs[4] (not the headline; `--workload c5`): the scaled model, streams sharded over the GPUs
+CFG_C5 = dict(d_model=1024, n_layers=24, n_heads=16, d_head=64, d_inner=4096, mem_len=1024)
+WORKLOAD_C5 = ('C5: Transformer-XL d_model 1024, 24 layers, 16 heads x 64, d_inner 4096, mem_len 1024, vocab 324; '
+               '256 streams/GPU (K/V rings 25.8 GB), one-token steps over a full 1024-slot memory, top_k 30 / top_p 0.65 sampling')
 
 
 def measured_peaks():
@@ -166,7 +170,11 @@ def run_b200(args):
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
     lib = _lib.load()
 
-    cfg = baseline_config()
+    c5 = args.workload == 'c5'
+    shape = CFG_C5 if c5 else CFG
+    workload = WORKLOAD_C5 if c5 else WORKLOAD
+    PREFILL = shape['mem_len']                     # fills the memory ring exactly
+    cfg = dict(baseline_config(), **shape, ctx_len=PREFILL)
     model = get_language_model(V, cfg, dtype='bf16', device=local_rank, max_batch=B, max_seq=PREFILL, max_rows=B * 64,
                                keep_hidden=False, seed=0)
     data = MusicDataBunch.empty('')
@@ -251,7 +259,9 @@ def run_b200(args):
     torch.cuda.synchronize()
     attn_ms = ev0.elapsed_time(ev1) / (reps * L)
     peak, peak_src = measured_peaks()
-    abytes = attention_bytes_per_launch(B)
+    geo = dict(H=shape['n_heads'], Dh=shape['d_head'], M=shape['mem_len'])
+    abytes = attention_bytes_per_launch(B, **geo)
+    sbytes = step_bytes(B, L=shape['n_layers'], d=shape['d_model'], di=shape['d_inner'], **geo)
     achieved = abytes / (attn_ms / 1e3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'attn_decode_traffic.json')
@@ -262,12 +272,12 @@ def run_b200(args):
                 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': abytes, 'kernel_ms': attn_ms,
                 'kernel_share_of_step': attn_ms * L / (ms / K),
-                'step_algorithmic_bytes': step_bytes(B), 'step_frac': step_bytes(B) / (ms / K / 1e3) / 1e9 / peak}
+                'step_algorithmic_bytes': sbytes, 'step_frac': sbytes / (ms / K / 1e3) / 1e9 / peak}
 
     if rank != 0:
         return
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not c5:
         v, done, threads, dt = cpu_reference(8, 24, 1, budget_s=40.0)
         cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                'sample': f'8 streams x {done} one-token steps over a full 512-slot memory, fp32 eager-PyTorch oracle '
@@ -275,9 +285,9 @@ def run_b200(args):
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms_max / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
             'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'global_batch': B * world, 'prefill': PREFILL,
+            'config': {'workload': workload, 'batch_per_gpu': B, 'global_batch': B * world, 'prefill': PREFILL,
                        'parallelism': f'streams sharded over {world} GPU(s), no collective',
-                       'l2': 'inputs larger than L2: every step streams 4.3 GB of K/V through a 126 MB L2',
+                       'l2': f'inputs larger than L2: every step streams {sbytes / 1e9:.1f} GB of K/V through a 126 MB L2',
                        'tcgen05_gemm': bool(lib.dmg_uses_tcgen05(e.h)), 'all_streams_alive': bool(good)},
             'roofline': roofline, 'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': B * 8, 'd2h_bytes_per_step': B * 4, 'steps': Ke},
@@ -291,7 +301,7 @@ def main():
     ap.add_argument('--steps', type=int, default=None)
     ap.add_argument('--warmup', type=int, default=None)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=['c2', 'c3'],
+    ap.add_argument('--workload', default='c2', choices=['c2', 'c3', 'c5'],
                     help='c2 (default, the headline): batched incremental generation; c3: data-parallel training step')
     ap.add_argument('--batch', type=int, default=B_PER_GPU, help='c2: streams per GPU')
     ap.add_argument('--train-batch', type=int, default=32, help='c3: sequences per GPU and step')

@@ -213,38 +213,42 @@ template int gather_rows<bf16>(const bf16*, bf16*, int, int, int, int, cudaStrea
 // ------------------------------------------------------------------ memory rings
 // K/V of the last min(T, M) new tokens of every stream -> ring slot (token index mod M).
 // qkv row layout: [q (H*Dh) | k (H*Dh) | v (H*Dh)], ring layout [Bcap][H][M][Dh].
-template <class T>
-__global__ void ring_append_kv_kernel(const float* __restrict__ qkv, T* __restrict__ kring, T* __restrict__ vring, int T_len,
+template <class T, class TS>
+__global__ void ring_append_kv_kernel(const TS* __restrict__ qkv, T* __restrict__ kring, T* __restrict__ vring, int T_len,
                                       int H, int Dh, int M, long long pos_total, int b0, int first) {
   // grid: (T_len - first, B); block: H*Dh/4 threads (each 4 elements)
   const int i = first + blockIdx.x, b = blockIdx.y;
   const int HD = H * Dh;
   const int slot = (int)((pos_total + i) % M);
-  const float* row = qkv + ((size_t)b * T_len + i) * 3 * HD;
+  const TS* row = qkv + ((size_t)b * T_len + i) * 3 * HD;
   for (int e = threadIdx.x * 4; e < HD; e += blockDim.x * 4) {
     const int h = e / Dh, c = e % Dh;
-    const float4 kk = *(const float4*)(row + HD + e);
-    const float4 vv = *(const float4*)(row + 2 * HD + e);
+    const TS* kp = row + HD + e;
+    const TS* vp = row + 2 * HD + e;
     const size_t o = (((size_t)(b0 + b) * H + h) * M + slot) * Dh + c;
-    kring[o] = from_f32<T>(kk.x); kring[o + 1] = from_f32<T>(kk.y); kring[o + 2] = from_f32<T>(kk.z); kring[o + 3] = from_f32<T>(kk.w);
-    vring[o] = from_f32<T>(vv.x); vring[o + 1] = from_f32<T>(vv.y); vring[o + 2] = from_f32<T>(vv.z); vring[o + 3] = from_f32<T>(vv.w);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      kring[o + q] = from_f32<T>(to_f32(kp[q]));
+      vring[o + q] = from_f32<T>(to_f32(vp[q]));
+    }
   }
 }
-template <class T>
-int ring_append_kv(const float* qkv, T* kring, T* vring, int B, int T_len, int H, int Dh, int M, long long pos_total,
+template <class T, class TS>
+int ring_append_kv(const TS* qkv, T* kring, T* vring, int B, int T_len, int H, int Dh, int M, long long pos_total,
                    int b0, int Bcap, cudaStream_t st) {
   if (M <= 0 || B <= 0 || T_len <= 0) return 0;
   (void)Bcap;
   const int first = T_len > M ? T_len - M : 0;
   int threads = H * Dh / 4;
   if (threads > 256) threads = 256;
-  ring_append_kv_kernel<T><<<dim3(T_len - first, B), threads, 0, st>>>(qkv, kring, vring, T_len, H, Dh, M, pos_total, b0, first);
+  ring_append_kv_kernel<T, TS><<<dim3(T_len - first, B), threads, 0, st>>>(qkv, kring, vring, T_len, H, Dh, M, pos_total, b0, first);
   g_launch_count++;
   DMG_CUDA_OK(cudaGetLastError());
   return 0;
 }
-template int ring_append_kv<float>(const float*, float*, float*, int, int, int, int, int, long long, int, int, cudaStream_t);
-template int ring_append_kv<bf16>(const float*, bf16*, bf16*, int, int, int, int, int, long long, int, int, cudaStream_t);
+template int ring_append_kv<float, float>(const float*, float*, float*, int, int, int, int, int, long long, int, int, cudaStream_t);
+template int ring_append_kv<bf16, float>(const float*, bf16*, bf16*, int, int, int, int, int, long long, int, int, cudaStream_t);
+template int ring_append_kv<bf16, bf16>(const bf16*, bf16*, bf16*, int, int, int, int, int, long long, int, int, cudaStream_t);
 
 __global__ void ring_append_hidden_kernel(const float* __restrict__ x32, float* __restrict__ hring, int T_len, int d, int M,
                                           long long pos_total, int b0, int first) {

@@ -66,8 +66,8 @@ int gather_rows(const T* src, T* dst, int rows, int d, int stride, int offset, c
 // ------------------------------------------------------------------ memory rings
 // Device-side ring state read by graph-captured kernels: [0] = pos_total (tokens appended since reset),
 // [1] = mem_count (valid memory positions, <= M).
-template <class T>
-int ring_append_kv(const float* qkv, T* kring, T* vring, int B, int T_len, int H, int Dh, int M, long long pos_total,
+template <class T, class TS>
+int ring_append_kv(const TS* qkv, T* kring, T* vring, int B, int T_len, int H, int Dh, int M, long long pos_total,
                    int b0, int Bcap, cudaStream_t st);
 // hidden-state mems (model[0].hidden): ring [B][M][d] fp32
 int ring_append_hidden(const float* x32, float* hring, int B, int T_len, int d, int M, long long pos_total, int b0,
@@ -95,6 +95,11 @@ struct AttnGeneralArgs {
 };
 template <class T>
 int attn_general(const AttnGeneralArgs& a, cudaStream_t st);
+
+// Tensor-core flash attention for memory-less segments (attention_flash.cu): Transformer-XL prefill after reset() (causal) and
+// the BERT remix encoder (no mask, _line_shift wrap-around).  qkv: bf16 [B*T, 3*H*64]; rd: rel-pos key cache [H][Dcap][64].
+int attn_flash(const bf16* qkv, const bf16* rd, int Dcap, const float* u, const float* v, bf16* out, int B, int T, int H, int bert,
+               float scale, cudaStream_t st);
 
 struct AttnDecodeArgs {
   const float* qkv;     // [B, 3*H*Dh] fp32 (the new token)

@@ -68,14 +68,26 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
   const bool v2_ok = !bert && M > 0 && m->layers[0].has_ring_tm && attn_decode2_supported(c.d_head, M) && !getenv("DMG_DECODE_V1");
   const bool fast_decode = m->is_bf16 && !bert && T_len == 1 && (v2_ok || attn_decode_supported(c.d_head, M)) &&
                            !getenv("DMG_NO_DECODE_KERNEL");
+  // segments without memory (prefill after reset(), every BERT forward) in bf16: flash attention on the tensor cores
+  const bool flash = m->is_bf16 && m->use_tc && T_len > 1 && (bert || (m->mem_count == 0 && win == 1 && k == 1)) &&
+                     m->Dcap >= T_len && !getenv("DMG_NO_FLASH");
   // Measured and rejected as the default (profiles/README.md, r1c): the 8-CTA-cluster GEMM + LayerNorm kernel is exact but
   // slower than the split-K GEMM + LayerNorm pair at 256 rows (16 CTAs stream the whole K: 1.58 vs 1.46 ms/step at C2).
   const bool want_gemm_ln = getenv("DMG_GEMM_LN") != nullptr;
   const bool fuse_ln = want_gemm_ln && m->is_bf16 && m->use_tc && !bert && rows <= 512;
   for (int l = 0; l < c.n_layers; l++) {
     LayerW& L = m->layers[l];
-    if (!(skip & 1) && linear(m, A_XA, xa, L.wqkv, L.bqkv, m->qkv, 3 * HD, rows, 0, 0, st)) return -1;
-    if (skip & 2) {
+    if (flash) {
+      // memory-less segment: bf16 q|k|v straight from the GEMM epilogue, tensor-core flash attention (attention_flash.cu)
+      if (linear(m, A_XA, xa, L.wqkv, L.bqkv, m->qkv16, 3 * HD, rows, 0, 1, st)) return -1;
+      if (attn_flash(m->qkv16, (const bf16*)L.rd, m->Dcap, m->u, m->v, (bf16*)m->attn, nb, T_len, c.n_heads, bert ? 1 : 0,
+                     1.f / sqrtf((float)c.d_head), st)) return -1;
+      if (M > 0 && ring_append_kv<bf16, bf16>(m->qkv16, (bf16*)L.kring, (bf16*)L.vring, nb, T_len, c.n_heads, c.d_head, M,
+                                               m->pos_total, b0, c.max_batch, st)) return -1;
+    } else if (!(skip & 1) && linear(m, A_XA, xa, L.wqkv, L.bqkv, m->qkv, 3 * HD, rows, 0, 0, st)) {
+      return -1;
+    }
+    if (flash || (skip & 2)) {
     } else if (fast_decode) {
       AttnDecodeArgs a;
       a.qkv = m->qkv;
@@ -99,8 +111,8 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
       a.mem_count = m->mem_count; a.pos_total = m->pos_total; a.b0 = b0; a.bert = bert ? 1 : 0; a.win = win; a.k = k;
       a.scale = 1.f / sqrtf((float)c.d_head);
       if (attn_general<T>(a, st)) return -1;
-      if (M > 0 && ring_append_kv<T>(m->qkv, (T*)L.kring, (T*)L.vring, nb, T_len, c.n_heads, c.d_head, M, m->pos_total, b0,
-                                     c.max_batch, st)) return -1;
+      if (M > 0 && ring_append_kv<T, float>(m->qkv, (T*)L.kring, (T*)L.vring, nb, T_len, c.n_heads, c.d_head, M, m->pos_total, b0,
+                                            c.max_batch, st)) return -1;
     }
     if (bert) {
       if (residual_layernorm<T, T>(m->x32, (const T*)m->attn, L.ln1w, L.ln1b, xa, rows, d, st)) return -1;
@@ -384,6 +396,7 @@ int dmg_create(const dmg_config* cfg, int device, dmg_model** out) {
   TRY(dalloc(m, &m->x32, R * d));
   if (m->is_bf16) { bf16* t = nullptr; TRY(dalloc(m, &t, R * d)); m->xa = t; } else m->xa = m->x32;
   TRY(dalloc(m, &m->qkv, R * 3 * HD));
+  if (m->is_bf16) TRY(dalloc(m, &m->qkv16, R * 3 * HD));
   { char* t = nullptr; TRY(dalloc(m, &t, R * HD * m->esz)); m->attn = t; }
   if (!bert) {
     TRY(dalloc(m, &m->proj, R * d));

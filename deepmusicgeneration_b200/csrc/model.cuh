@@ -62,6 +62,7 @@ struct dmg_model {
   int* dev_state = nullptr;
   // workspaces
   float *x32 = nullptr, *qkv = nullptr, *proj = nullptr, *logits_buf = nullptr;
+  bf16* qkv16 = nullptr;        // bf16 q|k|v of a segment for the flash-attention path
   void *xa = nullptr, *attn = nullptr, *hbuf = nullptr, *xlast = nullptr;
   TensorMap2D tmA[A_COUNT];
   TensorMap2D tmA16[A_COUNT];   // 16-row boxes (multicast slices of the fused GEMM + LayerNorm kernel)

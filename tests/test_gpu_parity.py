@@ -126,6 +126,26 @@ def test_txl_bf16_logits_and_top1():
         assert _rel(p1, o1) <= 2e-2, s
 
 
+def test_scaled_model_c5_shapes_prefill_and_decode():
+    "BASELINE.json configs[4]: d_model 1024, 16 heads x 64, d_inner 4096, mem_len 1024 (2 of the 24 layers): prefill + ring decode"
+    cfg = dict(txl.baseline_config(), n_layers=2, d_model=1024, n_heads=16, d_head=64, d_inner=4096, mem_len=1024, ctx_len=1024)
+    om, pm = _pair(cfg, 'bf16', 3, 1024, keep_hidden=False)
+    g = torch.Generator().manual_seed(5)
+    x0 = torch.randint(0, V, (3, 1000), generator=g)
+    om.reset(); pm.reset()
+    with torch.no_grad(): ol = om(x0)[0][:, -1]
+    pl = pm[0].forward(x0.cuda(), logits_mode=2)[0].cpu()
+    assert _rel(pl, ol) <= 2e-2
+    worst = 0.
+    for s in range(40):                                        # crosses the point where the 1024-slot ring wraps
+        xs = torch.randint(0, V, (3, 1), generator=g)
+        with torch.no_grad(): lo = om(xs)[0][:, -1]
+        lp = pm[0].forward(xs.cuda(), logits_mode=1)[0].cpu()[:, -1]
+        worst = max(worst, _rel(lp, lo))
+    print(f'C5 shapes: decode max rel err {worst:.3e}')
+    assert worst <= 2e-2
+
+
 def test_fused_gemm_layernorm_cluster_kernel_matches_unfused_pair():
     "DMG_GEMM_LN=1: out-projection / FFN-down GEMM + residual + LayerNorm in one 8-CTA-cluster kernel (gemm_ln.cu, opt-in)"
     cfg = dict(txl.baseline_config(), n_layers=3)
@@ -276,6 +296,52 @@ def test_bert_encoder_bf16_app_config():
     top1 = (pl.argmax(-1) == ol.argmax(-1)).float().mean().item()
     print(f'bert bf16: max rel err {rel:.3e}, top-1 {top1:.4f}')
     assert rel <= 2e-2 and top1 >= 0.99
+
+
+@pytest.mark.parametrize('T', [2, 31, 64, 70, 130, 257, 320])
+def test_bert_flash_attention_bf16_ragged_lengths(T):
+    "attention_flash.cu, BERT mode (all three _line_shift lines live, ragged last tile) against the oracle and the general kernel"
+    cfg = dict(obert.multitask_config(), enc_layers=2, d_model=128, n_heads=2, d_head=64, d_inner=256)
+    om, pm = _bert_pair(cfg, 'bf16', 3, 320)
+    g = torch.Generator().manual_seed(T)
+    x = torch.randint(0, V, (3, T), generator=g)
+    pos = torch.cumsum(torch.randint(0, 9, (3, T), generator=g), 1)
+    with torch.no_grad():
+        ol = om({'msk': {'x': x, 'pos': pos.clone()}})['msk']
+    os.environ.pop('DMG_NO_FLASH', None)
+    pl = pm({'msk': {'x': x.cuda(), 'pos': pos.cuda()}})['msk'].cpu()
+    try:
+        os.environ['DMG_NO_FLASH'] = '1'
+        pg = pm({'msk': {'x': x.cuda(), 'pos': pos.cuda()}})['msk'].cpu()
+    finally:
+        os.environ.pop('DMG_NO_FLASH', None)
+    print(f'T={T}: flash vs oracle {_rel(pl, ol):.3e}, general vs oracle {_rel(pg, ol):.3e}, flash vs general {(pl - pg).abs().max():.3e}')
+    assert _rel(pl, ol) <= 2e-2 and (pl - pg).abs().max() < 3e-2
+
+
+@pytest.mark.parametrize('T', [2, 63, 64, 100, 300, 320])
+def test_txl_flash_prefill_bf16_ragged_lengths(T):
+    "attention_flash.cu, causal mode: prefill of a ragged seed after reset(), then ring decode continues from its K/V"
+    cfg = dict(SMALL, mem_len=128)
+    om, pm = _pair(cfg, 'bf16', 3, 320, keep_hidden=False)
+    _, pg = _pair(cfg, 'bf16', 3, 320, keep_hidden=False)
+    g = torch.Generator().manual_seed(100 + T)
+    x0 = torch.randint(0, V, (3, T), generator=g)
+    om.reset(); pm.reset(); pg.reset()
+    with torch.no_grad(): ol = om(x0)[0]
+    os.environ.pop('DMG_NO_FLASH', None)
+    pl = pm[0].forward(x0.cuda(), logits_mode=1)[0].cpu()
+    try:
+        os.environ['DMG_NO_FLASH'] = '1'
+        gl = pg[0].forward(x0.cuda(), logits_mode=1)[0].cpu()
+    finally:
+        os.environ.pop('DMG_NO_FLASH', None)
+    assert _rel(pl, ol) <= 2e-2 and (pl - gl).abs().max() < 3e-2
+    for s in range(5):
+        xs = torch.randint(0, V, (3, 1), generator=g)
+        with torch.no_grad(): lo = om(xs)[0]
+        lp = pm[0].forward(xs.cuda(), logits_mode=1)[0].cpu()
+        assert _rel(lp, lo) <= 2e-2, s
 
 
 def test_predict_mask_greedy_matches_oracle(golden_dir):
