@@ -50,9 +50,9 @@ __host__ __device__ inline D2Layout d2_layout(int M, int G, int n_stages) {
   return L;
 }
 
-static int d2_pick_stages(int M, int G) {
+static int d2_pick_stages(int M, int G, int max_stages = 16) {
   for (int s = 16; s >= 2; s >>= 1)
-    if (d2_layout(M, G, s).total <= 227 * 1024) return s;
+    if (s <= max_stages && d2_layout(M, G, s).total <= 227 * 1024) return s;
   return 0;
 }
 static int d2_pick_groups(int M) {
@@ -333,14 +333,15 @@ attn_decode2_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 
 template <int G>
 static int launch_d2(const TensorMap2D* tmK, const TensorMap2D* tmV, const TensorMap2D* tmR, const AttnDecodeArgs& a, int b0,
-                     int num_sms, cudaStream_t st) {
-  const int ns = d2_pick_stages(a.M, G);
+                     int num_sms, int max_stages, cudaStream_t st) {
+  const int ns = d2_pick_stages(a.M, G, max_stages > 0 ? max_stages : 16);
   const D2Layout L = d2_layout(a.M, G, ns);
   static int configured = 0;
   if (configured < L.total) {
     DMG_CUDA_OK(cudaFuncSetAttribute(attn_decode2_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     configured = L.total;
   }
+  DMG_CHECK(ns >= 2, "attn_decode2: no stage count fits (M=%d)", a.M);
   const long long NI = (long long)a.B * a.H;
   const int grid = (int)(NI < num_sms ? NI : num_sms);
   // a.kring / a.vring / a.qkv / a.out are chunk-local (offset by b0 streams); the TMA row coordinate adds b0
@@ -349,13 +350,13 @@ static int launch_d2(const TensorMap2D* tmK, const TensorMap2D* tmV, const Tenso
 }
 
 int attn_decode2(const TensorMap2D* tmK, const TensorMap2D* tmV, const TensorMap2D* tmR, const AttnDecodeArgs& a, int b0,
-                 int num_sms, cudaStream_t st) {
+                 int num_sms, int max_stages, cudaStream_t st) {
   DMG_CHECK(a.Dcap >= a.M + 1, "attn_decode2: rel-pos cache too small (%d < %d)", a.Dcap, a.M + 1);
   const int G = d2_pick_groups(a.M);
   DMG_CHECK(G > 0, "attn_decode2: mem_len %d not supported", a.M);
-  if (G == 4) return launch_d2<4>(tmK, tmV, tmR, a, b0, num_sms, st);
-  if (G == 2) return launch_d2<2>(tmK, tmV, tmR, a, b0, num_sms, st);
-  return launch_d2<1>(tmK, tmV, tmR, a, b0, num_sms, st);
+  if (G == 4) return launch_d2<4>(tmK, tmV, tmR, a, b0, num_sms, max_stages, st);
+  if (G == 2) return launch_d2<2>(tmK, tmV, tmR, a, b0, num_sms, max_stages, st);
+  return launch_d2<1>(tmK, tmV, tmR, a, b0, num_sms, max_stages, st);
 }
 
 }  // namespace dmg

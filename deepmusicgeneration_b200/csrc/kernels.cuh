@@ -117,8 +117,10 @@ int attn_decode(const AttnDecodeArgs& a, cudaStream_t st);
 bool attn_decode_supported(int Dh, int M);
 // v2: persistent, TMA-2D swizzled K/V tiles, resident rel-pos keys, mma.sync dot products (attention_decode2.cu).
 // tmK/tmV: ring viewed as [max_batch*H*M rows, 64 cols]; tmR: Rd viewed as [H*Dcap rows, 64 cols]; 64-row boxes.
+// max_stages > 0 caps the K/V tile ring (and with it the shared memory of the persistent CTA) so that the small GEMM kernels
+// of ANOTHER group of streams can share the SM while this kernel streams its rings (decode lanes, model.cu).
 int attn_decode2(const TensorMap2D* tmK, const TensorMap2D* tmV, const TensorMap2D* tmR, const AttnDecodeArgs& a, int b0,
-                 int num_sms, cudaStream_t st);
+                 int num_sms, int max_stages, cudaStream_t st);
 bool attn_decode2_supported(int Dh, int M);
 
 }  // namespace dmg

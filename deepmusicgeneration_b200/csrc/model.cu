@@ -100,7 +100,7 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
       a.B = nb; a.H = c.n_heads; a.M = M; a.Dcap = m->Dcap;
       a.scale = 1.f / sqrtf((float)c.d_head);
       if (v2_ok) {
-        if (attn_decode2(&L.tmK, &L.tmV, &L.tmR, a, b0, m->num_sms, st)) return -1;
+        if (attn_decode2(&L.tmK, &L.tmV, &L.tmR, a, b0, m->num_sms, m->lane_mode ? m->lane_stages : 0, st)) return -1;
       } else {
         if (attn_decode(a, st)) return -1;
       }
@@ -145,6 +145,65 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
   return 0;
 }
 
+// ---- decode lanes -------------------------------------------------------------------------------------------------
+static void lane_swap(dmg_model* m, dmg_model::Lane& ln) {
+  std::swap(m->x32, ln.x32); std::swap(m->qkv, ln.qkv); std::swap(m->proj, ln.proj);
+  std::swap(m->xa, ln.xa); std::swap(m->attn, ln.attn); std::swap(m->hbuf, ln.hbuf); std::swap(m->qkv16, ln.qkv16);
+  for (int i = 0; i < A_COUNT; i++) {
+    if (i == A_XLAST) continue;                       // the gathered last-position rows are shared by all lanes
+    std::swap(m->tmA[i], ln.tmA[i]); std::swap(m->tmA16[i], ln.tmA16[i]); std::swap(m->has_tmA16[i], ln.has_tmA16[i]);
+  }
+}
+
+static int ensure_lanes(dmg_model* m, int n_lanes, int rows_per_lane) {
+  const dmg_config& c = m->cfg;
+  const int d = c.d_model, HD = m->HD;
+  if ((int)m->lanes.size() >= n_lanes - 1 && m->lane_rows >= rows_per_lane) return 0;
+  DMG_CHECK(m->lanes.empty(), "decode lanes cannot be re-sized (asked for %d x %d rows)", n_lanes, rows_per_lane);
+  const size_t R = (size_t)((rows_per_lane + 127) / 128) * 128;
+  m->lanes.resize(n_lanes - 1);
+  int rc = 0;
+#define TRY(x) do { if (!rc && (x)) rc = -1; } while (0)
+  for (auto& ln : m->lanes) {
+    TRY(dalloc(m, &ln.x32, R * d));
+    { bf16* t = nullptr; TRY(dalloc(m, &t, R * d)); ln.xa = t; }
+    TRY(dalloc(m, &ln.qkv, R * 3 * HD));
+    TRY(dalloc(m, &ln.qkv16, R * 3 * HD));
+    { bf16* t = nullptr; TRY(dalloc(m, &t, R * HD)); ln.attn = t; }
+    TRY(dalloc(m, &ln.proj, R * d));
+    { bf16* t = nullptr; TRY(dalloc(m, &t, R * c.d_inner)); ln.hbuf = t; }
+    void* bufs[A_COUNT] = {ln.xa, ln.attn, ln.hbuf, nullptr};
+    const int cols[A_COUNT] = {d, HD, c.d_inner, 0};
+    for (int i = 0; i < A_COUNT && !rc; i++) {
+      if (!bufs[i] || cols[i] % 64) continue;
+      TRY(make_tmap_bf16(&ln.tmA[i], bufs[i], cols[i], (long long)R, cols[i], 128));
+      TRY(make_tmap_bf16(&ln.tmA16[i], bufs[i], cols[i], (long long)R, cols[i], 16));
+      ln.has_tmA16[i] = !rc;
+    }
+    if (!rc && cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking) != cudaSuccess) { set_error("lane stream creation failed"); rc = -1; }
+    if (!rc && cudaEventCreateWithFlags(&ln.ev, cudaEventDisableTiming) != cudaSuccess) { set_error("lane event creation failed"); rc = -1; }
+  }
+  if (!rc && !m->ev_fork && cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess) { set_error("fork event creation failed"); rc = -1; }
+#undef TRY
+  if (rc) return rc;
+  m->lane_rows = (int)R;
+  return 0;
+}
+
+static int decode_lane_count(dmg_model* m, int bs, int T_len) {
+  const dmg_config& c = m->cfg;
+  if (T_len != 1 || !m->is_bf16 || !m->use_tc || c.arch != DMG_ARCH_TXL || c.keep_hidden || c.mem_len <= 0) return 1;
+  if (!attn_decode2_supported(c.d_head, c.mem_len) || getenv("DMG_DECODE_V1") || getenv("DMG_NO_DECODE_KERNEL")) return 1;
+  // Opt-in (DMG_DECODE_LANES=2..4).  Measured at C2 (profiles/README.md, r1c): 1.480 ms/step with two lanes vs 1.461 ms
+  // with one - the "latency-bound" GEMM chain still wants every SM (256-512 CTAs per kernel), and next to a persistent
+  // attention CTA only one of its CTAs fits per SM instead of three, so the overlap buys nothing.
+  const char* e = getenv("DMG_DECODE_LANES");
+  int n = e ? atoi(e) : 1;
+  if (n > 4) n = 4;
+  while (n > 1 && bs / n < 64) n--;                    // a lane should fill at least half a 128-row GEMM tile
+  return n < 1 ? 1 : n;
+}
+
 static int forward_impl(dmg_model* m, const long long* ids, const long long* pos, int bs, int T_len, int win, int k,
                         int logits_mode, float* logits, float* core_out, cudaStream_t st) {
   const dmg_config& c = m->cfg;
@@ -157,7 +216,36 @@ static int forward_impl(dmg_model* m, const long long* ids, const long long* pos
   if (m->mem_count == 0) m->batch = bs;   // fastai: memory is (re)created by the first forward after reset()
   DMG_CHECK(bs == m->batch, "dmg_forward: batch %d does not match the %d streams held in memory", bs, m->batch);
   const int cb = m->max_rows / T_len;
-  for (int b0 = 0; b0 < bs; b0 += cb) {
+  const int n_lanes = decode_lane_count(m, bs, T_len);
+  bool laned = false;
+  if (n_lanes > 1 && cb >= bs) {
+    // one-token step in `n_lanes` groups of streams on parallel streams (graph-capturable: fork / join through events)
+    const int per = (bs + n_lanes - 1) / n_lanes;
+    if (ensure_lanes(m, n_lanes, per)) return -1;
+    DMG_CUDA_OK(cudaEventRecord(m->ev_fork, st));
+    m->lane_mode = true;
+    int rc = 0;
+    for (int i = 0; i < n_lanes && !rc; i++) {
+      const int b0 = i * per, nb = bs - b0 < per ? bs - b0 : per;
+      if (nb <= 0) break;
+      cudaStream_t s_i = i == 0 ? st : m->lanes[i - 1].st;
+      if (i > 0) {
+        if (cudaStreamWaitEvent(s_i, m->ev_fork, 0) != cudaSuccess) { set_error("lane fork failed"); rc = -1; break; }
+        lane_swap(m, m->lanes[i - 1]);
+      }
+      rc = forward_chunk<bf16>(m, ids + (size_t)b0, pos ? pos + (size_t)b0 : nullptr, b0, nb, 1, win, k, logits_mode, logits, core_out, s_i);
+      if (i > 0) {
+        lane_swap(m, m->lanes[i - 1]);
+        if (!rc && (cudaEventRecord(m->lanes[i - 1].ev, s_i) != cudaSuccess || cudaStreamWaitEvent(st, m->lanes[i - 1].ev, 0) != cudaSuccess)) {
+          set_error("lane join failed"); rc = -1;
+        }
+      }
+    }
+    m->lane_mode = false;
+    if (rc) return rc;
+    laned = true;
+  }
+  for (int b0 = 0; b0 < bs && !laned; b0 += cb) {
     const int nb = bs - b0 < cb ? bs - b0 : cb;
     const long long* p = pos ? pos + (size_t)b0 * T_len : nullptr;
     int rc = m->is_bf16 ? forward_chunk<bf16>(m, ids + (size_t)b0 * T_len, p, b0, nb, T_len, win, k, logits_mode, logits, core_out, st)
@@ -165,7 +253,7 @@ static int forward_impl(dmg_model* m, const long long* ids, const long long* pos
     if (rc) return rc;
   }
   if (logits_mode == DMG_LOGITS_LAST) {
-    const bool direct = T_len == 1 && cb >= bs;   // one-token step in a single chunk: the last rows ARE the rows
+    const bool direct = T_len == 1 && cb >= bs && !laned;   // one-token step in a single chunk: the last rows ARE the rows
     if (linear(m, direct ? A_XA : A_XLAST, direct ? m->xa : m->xlast, m->emb, m->head_b, m->logits_buf, c.vocab, bs, 0, 0, st)) return -1;
     if (logits) DMG_CUDA_OK(cudaMemcpyAsync(logits, m->logits_buf, (size_t)bs * c.vocab * 4, cudaMemcpyDeviceToDevice, st));
     m->logits_valid = true;
@@ -278,6 +366,11 @@ void dmg_destroy(dmg_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   dmg_train_destroy(m);
+  for (auto& ln : m->lanes) {
+    if (ln.st) cudaStreamDestroy(ln.st);
+    if (ln.ev) cudaEventDestroy(ln.ev);
+  }
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   if (m->step_graph) cudaGraphExecDestroy(m->step_graph);
   if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
   for (void* p : m->allocs) cudaFree(p);
@@ -313,6 +406,7 @@ int dmg_create(const dmg_config* cfg, int device, dmg_model** out) {
   m->is_bf16 = c.dtype == DMG_BF16;
   m->use_tc = m->is_bf16 && c.gemm_backend != DMG_GEMM_SIMT && !getenv("DMG_GEMM_SIMT");
   m->num_sms = prop.multiProcessorCount;
+  if (const char* ls = getenv("DMG_LANE_STAGES")) { m->lane_stages = atoi(ls); if (m->lane_stages < 2) m->lane_stages = 2; }
   m->esz = m->is_bf16 ? 2 : 4;
   m->HD = c.n_heads * c.d_head;
   m->Dcap = c.mem_len + c.max_seq + 1;
@@ -646,7 +740,8 @@ int dmg_attn_decode_layer(dmg_model* m, int layer, void* stream) {
   a.B = m->batch; a.H = c.n_heads; a.M = c.mem_len; a.Dcap = m->Dcap;
   a.scale = 1.f / sqrtf((float)c.d_head);
   if (L.has_ring_tm && attn_decode2_supported(c.d_head, c.mem_len) && !getenv("DMG_DECODE_V1"))
-    return attn_decode2(&L.tmK, &L.tmV, &L.tmR, a, 0, m->num_sms, (cudaStream_t)stream);
+    return attn_decode2(&L.tmK, &L.tmV, &L.tmR, a, 0, m->num_sms, decode_lane_count(m, m->batch, 1) > 1 ? m->lane_stages : 0,
+                        (cudaStream_t)stream);   // same ring depth as inside the (laned) step
   return attn_decode(a, (cudaStream_t)stream);
 }
 

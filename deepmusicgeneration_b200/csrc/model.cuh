@@ -77,6 +77,22 @@ struct dmg_model {
   cudaGraphExec_t step_graph = nullptr;
   int graph_bs = -1;
   long long graph_launches = 0;
+  // decode lanes: extra activation workspaces + streams so that the one-token step of one group of streams (latency-bound
+  // GEMM chain) overlaps the ring-streaming attention of another group (HBM-bound); lane 0 = the buffers above
+  struct Lane {
+    float *x32 = nullptr, *qkv = nullptr, *proj = nullptr;
+    void *xa = nullptr, *attn = nullptr, *hbuf = nullptr;
+    bf16* qkv16 = nullptr;
+    TensorMap2D tmA[A_COUNT], tmA16[A_COUNT];
+    bool has_tmA16[A_COUNT] = {false, false, false, false};
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev = nullptr;
+  };
+  std::vector<Lane> lanes;
+  cudaEvent_t ev_fork = nullptr;
+  int lane_rows = 0;
+  int lane_stages = 4;          // K/V tile ring depth of the decode-attention kernel while lanes overlap (DMG_LANE_STAGES)
+  bool lane_mode = false;       // set while a laned decode step is being issued
   dmg_train* train = nullptr;   // training state (train.cu), created by dmg_train_create
 };
 

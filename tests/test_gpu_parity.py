@@ -126,6 +126,29 @@ def test_txl_bf16_logits_and_top1():
         assert _rel(p1, o1) <= 2e-2, s
 
 
+def test_decode_lanes_match_single_lane():
+    "DMG_DECODE_LANES=2: the one-token step issued as two groups of streams on parallel streams (opt-in) gives the same logits"
+    cfg = dict(txl.baseline_config(), n_layers=2)
+    om, pa = _pair(cfg, 'bf16', 160, 64, keep_hidden=False)
+    _, pb = _pair(cfg, 'bf16', 160, 64, keep_hidden=False)
+    g = torch.Generator().manual_seed(21)
+    x0 = torch.randint(0, V, (160, 30), generator=g)
+    for pm in (pa, pb):
+        pm.reset(); pm[0].forward(x0.cuda(), logits_mode=2)
+    worst = 0.
+    for s in range(5):
+        xs = torch.randint(0, V, (160, 1), generator=g)
+        os.environ.pop('DMG_DECODE_LANES', None)
+        la = pa[0].forward(xs.cuda(), logits_mode=1)[0].cpu()
+        try:
+            os.environ['DMG_DECODE_LANES'] = '2'
+            lb = pb[0].forward(xs.cuda(), logits_mode=1)[0].cpu()
+        finally:
+            os.environ.pop('DMG_DECODE_LANES', None)
+        worst = max(worst, (la - lb).abs().max().item())
+    assert worst < 1e-3, worst
+
+
 def test_scaled_model_c5_shapes_prefill_and_decode():
     "BASELINE.json configs[4]: d_model 1024, 16 heads x 64, d_inner 4096, mem_len 1024 (2 of the 24 layers): prefill + ring decode"
     cfg = dict(txl.baseline_config(), n_layers=2, d_model=1024, n_heads=16, d_head=64, d_inner=4096, mem_len=1024, ctx_len=1024)
