@@ -17,6 +17,7 @@
 //   attn_bwd_dq_kernel: query-tile owner; recomputes P, forms dS, accumulates dQ (content + position parts -> du, dv),
 //                       writes dS in (row, distance) coordinates for the dRk GEMM (ds_dist)
 //   attn_bwd_dkv_kernel: key-tile owner; recomputes P and dS, accumulates dK, dV
+#include <cuda_fp16.h>
 #include "kernels.cuh"
 #include "launch.cuh"
 #include "mma_sync.cuh"
@@ -26,7 +27,8 @@ namespace dmg {
 
 namespace {
 
-constexpr int SKEW_LD = 84;    // floats per row of the warp-private skew strip (80 used)
+constexpr int SKEW_LD = 84;    // elements per row of the warp-private skew strip (80 used)
+typedef __half skew_t;         // fp16 strip (11-bit mantissa: rounding 5e-4 of the position term) - 2.7 KB per warp
 constexpr int DSK_LD = 88;     // bf16 per row of the warp-private dS strip (80 used); 176-byte rows keep ldmatrix aligned
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
@@ -64,7 +66,7 @@ __device__ __forceinline__ void q_frags(uint32_t sQ, int w, int lane, const Lane
 // s[nt][e] = AC + BD (unscaled) for the warp's 16 query rows x the tile's 64 keys.
 // sR0 / sR1: the two Rk tiles of the window (distances D0-64..D0-1 and D0..D0+63).
 __device__ __forceinline__ void scores_tile(const uint32_t (&qu)[4][4], const uint32_t (&qv)[4][4], uint32_t sK, uint32_t sR0,
-                                            uint32_t sR1, float* skew, int w, int lane, const LaneOff& L, float (&s)[8][4]) {
+                                            uint32_t sR1, skew_t* skew, int w, int lane, const LaneOff& L, float (&s)[8][4]) {
   const int g = lane >> 2, t = lane & 3;
   // position term: 16 rows x 80 distances (window columns 16w .. 16w+79)
 #pragma unroll
@@ -82,8 +84,8 @@ __device__ __forceinline__ void scores_tile(const uint32_t (&qu)[4][4], const ui
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       const int col = 16 * p + 8 * h + 2 * t;
-      *(float2*)(skew + g * SKEW_LD + col) = make_float2(acc[h][0], acc[h][1]);
-      *(float2*)(skew + (g + 8) * SKEW_LD + col) = make_float2(acc[h][2], acc[h][3]);
+      *(__half2*)(skew + g * SKEW_LD + col) = __floats2half2_rn(acc[h][0], acc[h][1]);
+      *(__half2*)(skew + (g + 8) * SKEW_LD + col) = __floats2half2_rn(acc[h][2], acc[h][3]);
     }
   }
   __syncwarp();
@@ -104,10 +106,10 @@ __device__ __forceinline__ void scores_tile(const uint32_t (&qu)[4][4], const ui
 #pragma unroll
   for (int nt = 0; nt < 8; nt++) {
     const int jl = 8 * nt + 2 * t;
-    s[nt][0] += skew[g * SKEW_LD + 64 + g - jl];
-    s[nt][1] += skew[g * SKEW_LD + 63 + g - jl];
-    s[nt][2] += skew[(g + 8) * SKEW_LD + 72 + g - jl];
-    s[nt][3] += skew[(g + 8) * SKEW_LD + 71 + g - jl];
+    s[nt][0] += __half2float(skew[g * SKEW_LD + 64 + g - jl]);
+    s[nt][1] += __half2float(skew[g * SKEW_LD + 63 + g - jl]);
+    s[nt][2] += __half2float(skew[(g + 8) * SKEW_LD + 72 + g - jl]);
+    s[nt][3] += __half2float(skew[(g + 8) * SKEW_LD + 71 + g - jl]);
   }
   __syncwarp();
 }
@@ -139,18 +141,21 @@ __device__ __forceinline__ float quad_sum(float v) {
 // Pipeline: K / V tiles in an NST-deep ring (cp.async groups, prefetch distance NST-1), Rk tiles in an (NST+1)-slot ring
 // (tile rt lives in slot rt % (NST+1)): iteration jt needs Rk tiles rt_hi = (M+i0)/64 - jt and rt_hi - 1, and each
 // iteration's load group brings exactly one new Rk tile (the very first brings two).
-constexpr int ATT_NST = 3;
+constexpr int ATT_NST = 3;                 // backward (dq) kernel
 constexpr int ATT_NR = ATT_NST + 1;
-constexpr int FWD_SMEM = TILE_BYTES /*Q*/ + 2 * ATT_NST * TILE_BYTES /*K,V ring*/ + ATT_NR * TILE_BYTES /*R ring*/ + 4 * 16 * SKEW_LD * 4;
+constexpr int FWD_NST = 2;                 // forward: 2 stages -> 74.75 KB -> three CTAs (12 warps) per SM
+constexpr int FWD_NR = FWD_NST + 1;
+constexpr int FWD_SMEM = TILE_BYTES /*Q*/ + 2 * FWD_NST * TILE_BYTES /*K,V ring*/ + FWD_NR * TILE_BYTES /*R ring*/ +
+                         4 * 16 * SKEW_LD * (int)sizeof(skew_t);
 
-__global__ void __launch_bounds__(128) attn_train_fwd_kernel(const AttnTrainArgs a) {
+__global__ void __launch_bounds__(128, 3) attn_train_fwd_kernel(const AttnTrainArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + TILE_BYTES;                   // stage s: K at sKV + 2*s*TILE, V right behind it
-  uint8_t* sR = sKV + 2 * ATT_NST * TILE_BYTES;
-  float* skew_all = (float*)(sR + ATT_NR * TILE_BYTES);
+  uint8_t* sR = sKV + 2 * FWD_NST * TILE_BYTES;
+  skew_t* skew_all = (skew_t*)(sR + FWD_NR * TILE_BYTES);
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  float* skew = skew_all + w * 16 * SKEW_LD;
+  skew_t* skew = skew_all + w * 16 * SKEW_LD;
   LaneOff L;
   lane_off_init(L, lane, w);
 
@@ -164,15 +169,15 @@ __global__ void __launch_bounds__(128) attn_train_fwd_kernel(const AttnTrainArgs
 
   auto load_stage = [&](int jt) {                   // one cp.async group: K, V of key tile jt and the new Rk tile(s)
     if (jt <= jt_hi) {
-      const int st = (jt - jt_lo) % ATT_NST;
+      const int st = (jt - jt_lo) % FWD_NST;
       long long ld;
       const bf16* kp = kv_tile_ptr(a, b, h, jt, 0, &ld);
       tile_load_async(sKV + 2 * st * TILE_BYTES, kp, ld, tid, 128);
       const bf16* vp = kv_tile_ptr(a, b, h, jt, 1, &ld);
       tile_load_async(sKV + (2 * st + 1) * TILE_BYTES, vp, ld, tid, 128);
       const int rt_hi = rt_top - jt;
-      if (jt == jt_lo) tile_load_async(sR + (rt_hi % ATT_NR) * TILE_BYTES, a.rk + (long long)rt_hi * 64 * HD + h * 64, HD, tid, 128);
-      if (rt_hi > 0) tile_load_async(sR + ((rt_hi - 1) % ATT_NR) * TILE_BYTES, a.rk + (long long)(rt_hi - 1) * 64 * HD + h * 64, HD, tid, 128);
+      if (jt == jt_lo) tile_load_async(sR + (rt_hi % FWD_NR) * TILE_BYTES, a.rk + (long long)rt_hi * 64 * HD + h * 64, HD, tid, 128);
+      if (rt_hi > 0) tile_load_async(sR + ((rt_hi - 1) % FWD_NR) * TILE_BYTES, a.rk + (long long)(rt_hi - 1) * 64 * HD + h * 64, HD, tid, 128);
     }
     cp_async_commit();
   };
@@ -180,8 +185,8 @@ __global__ void __launch_bounds__(128) attn_train_fwd_kernel(const AttnTrainArgs
   tile_load_async(sQ, a.qkv_x + ((long long)b * a.T + i0) * a.ldx + h * 64, a.ldx, tid, 128);
   cp_async_commit();
 #pragma unroll
-  for (int s = 0; s < ATT_NST - 1; s++) load_stage(jt_lo + s);
-  cp_async_wait<ATT_NST - 1>();                     // Q has landed (the stage groups may still be in flight)
+  for (int s = 0; s < FWD_NST - 1; s++) load_stage(jt_lo + s);
+  cp_async_wait<FWD_NST - 1>();                     // Q has landed (the stage groups may still be in flight)
   __syncthreads();
   uint32_t qu[4][4], qv[4][4];
   q_frags(smem_u32(sQ), w, lane, L, a.u + h * 64, a.v + h * 64, qu, qv);
@@ -199,15 +204,15 @@ __global__ void __launch_bounds__(128) attn_train_fwd_kernel(const AttnTrainArgs
   for (int jt = jt_lo; jt <= jt_hi; jt++) {
     const int j0 = jt * 64;
     const int rt_hi = rt_top - jt, rt_lo = rt_hi > 0 ? rt_hi - 1 : 0;
-    cp_async_wait<ATT_NST - 2>();                    // tile jt has landed
+    cp_async_wait<FWD_NST - 2>();                    // tile jt has landed
     __syncthreads();                                 // ... for everybody; and everybody is done with tile jt-1
-    load_stage(jt + ATT_NST - 1);                    // refill the stage tile jt-1 used
-    const int st = (jt - jt_lo) % ATT_NST;
+    load_stage(jt + FWD_NST - 1);                    // refill the stage tile jt-1 used
+    const int st = (jt - jt_lo) % FWD_NST;
     uint8_t* sK = sKV + 2 * st * TILE_BYTES;
     uint8_t* sV = sK + TILE_BYTES;
 
     float s[8][4];
-    scores_tile(qu, qv, smem_u32(sK), smem_u32(sR + (rt_lo % ATT_NR) * TILE_BYTES), smem_u32(sR + (rt_hi % ATT_NR) * TILE_BYTES),
+    scores_tile(qu, qv, smem_u32(sK), smem_u32(sR + (rt_lo % FWD_NR) * TILE_BYTES), smem_u32(sR + (rt_hi % FWD_NR) * TILE_BYTES),
                 skew, w, lane, L, s);
     const bool need_mask = (j0 + 63 >= a.M) || (j0 < a.M - a.mem_count);
     // running max kept on the RAW scores (the scale is positive); exp2((s - m) * c) is one FFMA + one MUFU per element
@@ -331,17 +336,17 @@ __device__ __forceinline__ void bwd_tile_math(const AttnTrainArgs& a, const Mask
 }
 
 constexpr int DQ_SMEM = 2 * ATT_NST * TILE_BYTES /*K,V ring (Q and dO are staged in its last stage first)*/ + ATT_NR * TILE_BYTES /*R*/ +
-                        4 * 16 * SKEW_LD * 4 + 4 * 16 * DSK_LD * 2;
+                        4 * 16 * SKEW_LD * (int)sizeof(skew_t) + 4 * 16 * DSK_LD * 2;
 
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnTrainBwdArgs ba) {
   const AttnTrainArgs& a = ba.f;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sKV = smem;
   uint8_t* sR = sKV + 2 * ATT_NST * TILE_BYTES;
-  float* skew_all = (float*)(sR + ATT_NR * TILE_BYTES);
+  skew_t* skew_all = (skew_t*)(sR + ATT_NR * TILE_BYTES);
   bf16* dsk_all = (bf16*)(skew_all + 4 * 16 * SKEW_LD);
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  float* skew = skew_all + w * 16 * SKEW_LD;
+  skew_t* skew = skew_all + w * 16 * SKEW_LD;
   LaneOff L;
   lane_off_init(L, lane, w);
   bf16* dsk = dsk_all + w * 16 * DSK_LD;
@@ -533,7 +538,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnTrainBwdArgs
 constexpr int DKV_NST = 2;
 constexpr int DKV_NR = 3;
 constexpr int DKV_SMEM = 2 * TILE_BYTES /*K,V*/ + 2 * DKV_NST * TILE_BYTES /*Q,dO ring*/ + 2 * TILE_BYTES /*P,dS*/ + DKV_NR * TILE_BYTES +
-                         4 * 16 * SKEW_LD * 4;
+                         4 * 16 * SKEW_LD * (int)sizeof(skew_t);
 
 __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnTrainBwdArgs ba) {
   const AttnTrainArgs& a = ba.f;
@@ -544,9 +549,9 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnTrainBwdArg
   uint8_t* sP = sQdO + 2 * DKV_NST * TILE_BYTES;
   uint8_t* sdS = sP + TILE_BYTES;
   uint8_t* sR = sdS + TILE_BYTES;
-  float* skew_all = (float*)(sR + DKV_NR * TILE_BYTES);
+  skew_t* skew_all = (skew_t*)(sR + DKV_NR * TILE_BYTES);
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  float* skew = skew_all + w * 16 * SKEW_LD;
+  skew_t* skew = skew_all + w * 16 * SKEW_LD;
   LaneOff L;
   lane_off_init(L, lane, w);
 

@@ -181,6 +181,10 @@ int apply_mem_update(dmg_model* m, dmg_train* t, cudaStream_t st, int level_lo, 
   const int M = c.mem_len;
   if (M <= 0) return 0;
   for (int l = level_lo; l <= level_hi; l++) {
+    if (t->T == M) {   // the whole memory is replaced: trade buffers instead of copying (the old memory becomes next step's scratch)
+      std::swap(t->mem[l], l < c.n_layers ? t->act[l].xa_in : t->xa_last);
+      continue;
+    }
     const bf16* x = l < c.n_layers ? t->act[l].xa_in : t->xa_last;
     if (t->T >= M) {
       if (train_mem_update(t->mem[l], x, t->B, t->T, M, c.d_model, st)) return -1;
@@ -323,9 +327,9 @@ int backward_layer(dmg_model* m, dmg_train* t, int l, cudaStream_t st) {
   // ---- FFN block
   {
     const Drop d4 = make_drop(t, t->cfg.ff_p, SITE_RES2, l);
-    if (train_ln_bwd(t->dx32, t->dbr_valid ? t->dbr : nullptr, A.z2, A.st2, W.ln2w, t->dadd, t->G + g.ln2w, t->G + g.ln2b, rows, d, d4.thresh, d4.seed, d4.scale, st)) return -1;
+    if (train_ln_bwd(t->dx32, t->dbr_valid ? t->dbr : nullptr, A.z2, A.st2, W.ln2w, t->dadd, t->G + g.ln2w, t->G + g.ln2b, t->G + g.b2, rows, d,
+                     d4.thresh, d4.seed, d4.scale, st)) return -1;   // also the FFN-down bias gradient
     if (grad_w(m, t, t->dadd, d, A.hact, di, d, di, rows, g.w2, st)) return -1;
-    if (train_colsum_bf16(t->dadd, d, rows, d, t->G + g.b2, st)) return -1;
     const Drop d3 = make_drop(t, t->cfg.ff_p, SITE_FF, l);
     GemmEpi e; e.aux = A.hpre; e.ld_aux = di; e.aux_mode = GEMM_AUX_GELU_GRAD; e.out = t->dh; e.ldc = di; e.out_mode = GEMM_OUT_BF16;
     e.drop_thresh = d3.thresh; e.drop_seed = d3.seed; e.drop_scale = d3.scale;
@@ -339,9 +343,9 @@ int backward_layer(dmg_model* m, dmg_train* t, int l, cudaStream_t st) {
   // ---- attention block
   {
     const Drop d2 = make_drop(t, t->cfg.resid_p, SITE_RES1, l);
-    if (train_ln_bwd(t->dx32, t->dbr, A.z1, A.st1, W.ln1w, t->dadd, t->G + g.ln1w, t->G + g.ln1b, rows, d, d2.thresh, d2.seed, d2.scale, st)) return -1;
+    if (train_ln_bwd(t->dx32, t->dbr, A.z1, A.st1, W.ln1w, t->dadd, t->G + g.ln1w, t->G + g.ln1b, g.bo >= 0 ? t->G + g.bo : nullptr, rows, d,
+                     d2.thresh, d2.seed, d2.scale, st)) return -1;
     if (grad_w(m, t, t->dadd, d, A.attn, HD, d, HD, rows, g.wo, st)) return -1;
-    if (g.bo >= 0 && train_colsum_bf16(t->dadd, d, rows, d, t->G + g.bo, st)) return -1;
     GemmEpi e; e.out = t->dattn; e.ldc = HD; e.out_mode = GEMM_OUT_BF16;
     if (gemm_bf16_tc(t->dadd, 0, d, W.wo.b16, 1, HD, rows, HD, d, 1, e, ns, st)) return -1;
 

@@ -151,18 +151,18 @@ template <int NV>
 __global__ void __launch_bounds__(256) train_ln_bwd_kernel(float* __restrict__ dy, const bf16* __restrict__ dbr, const bf16* __restrict__ zsave,
                                                            const float2* __restrict__ stats, const float* __restrict__ w,
                                                            bf16* __restrict__ dadd, float* __restrict__ dw_out,
-                                                           float* __restrict__ db_out, int rows, uint32_t thresh, uint32_t seed,
-                                                           float scale) {
+                                                           float* __restrict__ db_out, float* __restrict__ dsum_out, int rows,
+                                                           uint32_t thresh, uint32_t seed, float scale) {
   constexpr int d = NV * 128;
   __shared__ float red[8][128];
   const int wp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float dw[NV][4], db[NV][4], wv[NV][4];
+  float dw[NV][4], db[NV][4], ds[NV][4], wv[NV][4];   // ds: column sums of dadd = the bias gradient of the Linear whose output was added
 #pragma unroll
   for (int k = 0; k < NV; k++) {
     const float4 ww = *(const float4*)(w + (lane + 32 * k) * 4);
     wv[k][0] = ww.x; wv[k][1] = ww.y; wv[k][2] = ww.z; wv[k][3] = ww.w;
 #pragma unroll
-    for (int e = 0; e < 4; e++) { dw[k][e] = 0.f; db[k][e] = 0.f; }
+    for (int e = 0; e < 4; e++) { dw[k][e] = 0.f; db[k][e] = 0.f; ds[k][e] = 0.f; }
   }
   for (int row = blockIdx.x * 8 + wp; row < rows; row += gridDim.x * 8) {
     const float2 st = stats[row];
@@ -203,23 +203,26 @@ __global__ void __launch_bounds__(256) train_ln_bwd_kernel(float* __restrict__ d
         keep4(seed, (uint32_t)(row * d + c), thresh, scale, kp);
         dz[0] *= kp[0]; dz[1] *= kp[1]; dz[2] *= kp[2]; dz[3] *= kp[3];
       }
+      ds[k][0] += dz[0]; ds[k][1] += dz[1]; ds[k][2] += dz[2]; ds[k][3] += dz[3];
       *(uint2*)(dadd + (long long)row * d + c) = make_uint2(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]));
     }
   }
   // block reduction of the column partials, 128 columns (one k) at a time
 #pragma unroll
-  for (int which = 0; which < 2; which++) {
+  for (int which = 0; which < 3; which++) {
+    float* dst = which == 0 ? dw_out : (which == 1 ? db_out : dsum_out);
+    if (dst == nullptr) continue;
 #pragma unroll
     for (int k = 0; k < NV; k++) {
       __syncthreads();
 #pragma unroll
-      for (int e = 0; e < 4; e++) red[wp][lane * 4 + e] = which ? db[k][e] : dw[k][e];
+      for (int e = 0; e < 4; e++) red[wp][lane * 4 + e] = which == 0 ? dw[k][e] : (which == 1 ? db[k][e] : ds[k][e]);
       __syncthreads();
       if (threadIdx.x < 128) {
         float s = 0.f;
 #pragma unroll
         for (int q = 0; q < 8; q++) s += red[q][threadIdx.x];
-        atomicAdd((which ? db_out : dw_out) + k * 128 + threadIdx.x, s);
+        atomicAdd(dst + k * 128 + threadIdx.x, s);
       }
     }
   }
@@ -511,18 +514,18 @@ int train_residual_ln_fwd(float* x32, const bf16* add, const float* w, const flo
   return -2;
 }
 
-int train_ln_bwd(float* dy, const bf16* dbr, const bf16* zsave, const float2* stats, const float* w, bf16* dadd, float* dw, float* db, int rows, int d,
-                 uint32_t thresh, uint32_t seed, float scale, cudaStream_t st) {
+int train_ln_bwd(float* dy, const bf16* dbr, const bf16* zsave, const float2* stats, const float* w, bf16* dadd, float* dw, float* db,
+                 float* dsum, int rows, int d, uint32_t thresh, uint32_t seed, float scale, cudaStream_t st) {
   int nblk = (rows + 7) / 8;
   if (nblk > 148 * 2) nblk = 148 * 2;
   const dim3 grid(nblk), block(256);
   switch (d / 128) {
-    case 1: return launch_np(train_ln_bwd_kernel<1>, grid, block, 0, st, dy, dbr, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
-    case 2: return launch_np(train_ln_bwd_kernel<2>, grid, block, 0, st, dy, dbr, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
-    case 3: return launch_np(train_ln_bwd_kernel<3>, grid, block, 0, st, dy, dbr, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
-    case 4: return launch_np(train_ln_bwd_kernel<4>, grid, block, 0, st, dy, dbr, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
-    case 6: return launch_np(train_ln_bwd_kernel<6>, grid, block, 0, st, dy, dbr, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
-    case 8: return launch_np(train_ln_bwd_kernel<8>, grid, block, 0, st, dy, dbr, zsave, stats, w, dadd, dw, db, rows, thresh, seed, scale);
+    case 1: return launch_np(train_ln_bwd_kernel<1>, grid, block, 0, st, dy, dbr, zsave, stats, w, dadd, dw, db, dsum, rows, thresh, seed, scale);
+    case 2: return launch_np(train_ln_bwd_kernel<2>, grid, block, 0, st, dy, dbr, zsave, stats, w, dadd, dw, db, dsum, rows, thresh, seed, scale);
+    case 3: return launch_np(train_ln_bwd_kernel<3>, grid, block, 0, st, dy, dbr, zsave, stats, w, dadd, dw, db, dsum, rows, thresh, seed, scale);
+    case 4: return launch_np(train_ln_bwd_kernel<4>, grid, block, 0, st, dy, dbr, zsave, stats, w, dadd, dw, db, dsum, rows, thresh, seed, scale);
+    case 6: return launch_np(train_ln_bwd_kernel<6>, grid, block, 0, st, dy, dbr, zsave, stats, w, dadd, dw, db, dsum, rows, thresh, seed, scale);
+    case 8: return launch_np(train_ln_bwd_kernel<8>, grid, block, 0, st, dy, dbr, zsave, stats, w, dadd, dw, db, dsum, rows, thresh, seed, scale);
   }
   DMG_CHECK(false, "training LayerNorm backward: d_model=%d unsupported", d);
   return -2;

@@ -126,8 +126,9 @@ int train_residual_ln_fwd(float* x32, const bf16* add, const float* w, const flo
 // input-gradient GEMM produced); dy is overwritten by dz = gradient wrt z, which is also the residual-branch
 // gradient); dadd = bf16(dropout_mask * scale * dz) (gradient wrt the GEMM output that was added);
 // dw[d] / db[d] += the affine-parameter gradients (one atomic per column and block).
-int train_ln_bwd(float* dy, const bf16* dbr, const bf16* zsave, const float2* stats, const float* w, bf16* dadd, float* dw, float* db, int rows, int d,
-                 uint32_t thresh, uint32_t seed, float scale, cudaStream_t st);
+// dsum (may be NULL) += column sums of dadd: the bias gradient of the Linear whose output entered the residual sum.
+int train_ln_bwd(float* dy, const bf16* dbr, const bf16* zsave, const float2* stats, const float* w, bf16* dadd, float* dw, float* db,
+                 float* dsum, int rows, int d, uint32_t thresh, uint32_t seed, float scale, cudaStream_t st);
 int train_partial_finish(const float* partial, int nblk, int n, float* dst0, float* dst1, cudaStream_t st);   // dst += sums
 // column sums of a bf16 matrix [rows, n] (row stride ld) added into dst[n] (bias gradients)
 int train_colsum_bf16(const bf16* x, long long ld, int rows, int n, float* dst, cudaStream_t st);

@@ -191,3 +191,28 @@ def test_learner_fit_one_cycle_surface():
     logits = learn.model(base[:, :64].cuda())[0]
     acc = (logits.argmax(-1).cpu()[:, 8:] == base[:, 9:65]).float().mean().item()
     assert acc > 0.9, acc
+
+
+def test_training_memory_longer_than_segment(monkeypatch):
+    "mem_len 128 > bptt 64: the memory grows 0 -> 64 -> 128 and then slides (copy path, not the buffer swap of bptt == mem_len)"
+    cfg = small_config(mem_len=128)
+    bs, bptt = 2, 64
+    om, pm, tr = build_pair(cfg, bs, bptt, 0.)
+    om.train(); om.reset()
+    otrain.install_dropout_masks(om)
+    set_oracle_mask(monkeypatch, (1, 1))
+    opt = otrain.AdamTrueWD(otrain.unique_params(om), eps=1e-3)
+    tr.reset()
+    g = torch.Generator().manual_seed(9)
+    for s in range(4):
+        x = torch.randint(0, V, (bs, bptt), generator=g)
+        y = torch.randint(0, V, (bs, bptt), generator=g)
+        ref = otrain.train_step(om, x, y, opt, 1e-3, wd=0.01, clip=0.5)
+        tr.forward(x, y, None, mask_size=(1, 1))
+        tr.backward()
+        got = tr.losses()
+        assert abs(got['ce'] - ref['ce']) < 2e-2 * max(1., abs(ref['ce'])), (s, got, ref)
+        assert abs(got['tar'] - ref['tar']) < 3e-2 * max(1e-3, abs(ref['tar'])), (s, got, ref)
+        compare_grads(tr, om, tol=2e-2)
+        tr.optimizer_step(1e-3, betas=(0.9, 0.99), eps=1e-3, wd=0.01, clip=0.5)
+    tr.close()
