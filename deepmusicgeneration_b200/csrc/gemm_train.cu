@@ -501,10 +501,20 @@ int gemm_bf16_tc(const bf16* A, int a_mn, long long lda, const bf16* B, int b_mn
   const int CG = (!force_1cta && M > GT_BM && N > 64 && num_sms >= 2) ? 2 : 1;   // a pair stages N/2 >= 64 columns of B per CTA
   const int units = num_sms / CG;
   const int num_m = (M + GT_BM * CG - 1) / (GT_BM * CG);
-  int BN = 256;
+  // tile width: the candidate with the smallest estimated time = waves x (k-blocks x (MMA + fixed cost) + epilogue); a
+  // narrower tile only pays when it removes a (partly idle) wave
   const int groups = e.groups < 1 ? 1 : e.groups;
   const int BN_min = 64 * CG;
-  while (BN > BN_min && ((long long)num_m * ((N + BN - 1) / BN) * splitk * groups < units || N <= BN / 2)) BN >>= 1;
+  const long long kb_tile = ((K + 63) / 64 + splitk - 1) / splitk;
+  int BN = 256;
+  long long best = -1;
+  for (int cand = 256; cand >= BN_min; cand >>= 1) {
+    if (cand > 64 * CG && N <= cand / 2) continue;                       // mostly padding
+    const long long tiles = (long long)num_m * ((N + cand - 1) / cand) * splitk * groups;
+    const long long waves = (tiles + units - 1) / units;
+    const long long cost = waves * (kb_tile * (cand + 768) + 8ll * cand);   // measured: a k-block of a 128-wide tile costs ~0.85 of a 256-wide one
+    if (best < 0 || cost < best) { best = cost; BN = cand; }
+  }
   const int num_n = (N + BN - 1) / BN;
   GemmTParams p;
   p.M = M; p.N = N; p.K = K; p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;

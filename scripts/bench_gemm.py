@@ -30,6 +30,18 @@ def run(name, M, N, K, a_mn, b_mn, out_mode, splitk=1, bias=False, gelu=0, aux_m
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
     print(f'{name:28s} M={M:6d} N={N:5d} K={K:6d}  {us:8.1f} us  {2*M*N*K/us/1e6:7.1f} TFLOP/s')
+if os.environ.get('GEMM_MAJORS'):
+    for a_mn, b_mn in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        run(f'4096^3 a_mn={a_mn} b_mn={b_mn}', 4096, 4096, 4096, a_mn, b_mn, 1, reps=10)
+    run('dW2 shape, K=4096 only (no split)', 512, 2048, 4096, 1, 1, 2, splitk=1)
+    run('dW2 shape K-major operands', 512, 2048, 16384, 0, 0, 2, splitk=4)
+    for sk in (2, 4, 8, 9):
+        run(f'dW2 atomic sk{sk}', 512, 2048, rows, 1, 1, 2, splitk=sk)
+    for sk in (3, 6, 12):
+        run(f'dWqkv atomic sk{sk}', 1536, 512, rows, 1, 1, 2, splitk=sk)
+    for sk in (9, 18, 37):
+        run(f'dWo atomic sk{sk}', 512, 512, rows, 1, 1, 2, splitk=sk)
+    sys.exit(0)
 only = os.environ.get('GEMM_ONLY')
 if only:
     run('QKV fwd', rows, 1536, 512, 0, 0, 1, reps=2)
