@@ -32,9 +32,10 @@ constexpr int GT_THREADS = 64 + GT_EPI_WARPS * 32;
 // 128 rows of A and only HALF of the B tile (the pair's tensor cores read both halves), which cuts the L2 -> SM operand
 // traffic per flop by a third and is what lifts a K = 512 GEMM off the L2 bandwidth ceiling.
 __host__ __device__ constexpr int gt_stage_bytes(int BN, int CG) { return GT_BM * 64 * 2 + (BN / CG) * 64 * 2; }
-constexpr int GT_EPI_STAGE_BYTES = GT_EPI_WARPS * 32 * 128;   // fp32 32x32 transposition strip per epilogue warp
+constexpr int GT_STRIP_BYTES = 6144;                           // per epilogue warp: fp32 32x32 transposition strip, or 3 bf16 boxes
+constexpr int GT_EPI_STAGE_BYTES = GT_EPI_WARPS * GT_STRIP_BYTES;
 __host__ __device__ constexpr int gt_stages(int BN, int CG) {
-  return (192 * 1024) / gt_stage_bytes(BN, CG) > 8 ? 8 : (192 * 1024) / gt_stage_bytes(BN, CG);
+  return (176 * 1024) / gt_stage_bytes(BN, CG) > 8 ? 8 : (176 * 1024) / gt_stage_bytes(BN, CG);
 }
 __host__ __device__ constexpr int gt_smem_bytes(int BN, int CG) {
   return gt_stages(BN, CG) * gt_stage_bytes(BN, CG) + 1024 /*alignment*/ + 1024 /*barriers*/ + GT_EPI_STAGE_BYTES;
@@ -117,12 +118,14 @@ struct GemmTParams {
   uint32_t drop_thresh, drop_seed; float drop_scale;
   int groups; int a_gs, b_gs; long long c_gs;
   int tma_store;   // bf16 output(s) leave through TMA stores (tmC / tmC2)
+  int aux_tma;     // the bf16 aux operand arrives as 32x32 TMA boxes (tmX), prefetched one chunk ahead
 };
 
 template <int BN, int CG>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmTParams p) {
+                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+                  const __grid_constant__ CUtensorMap tmX, const GemmTParams p) {
   constexpr int STAGES = gt_stages(BN, CG);
   constexpr int STAGE_BYTES = gt_stage_bytes(BN, CG);
   constexpr int A_BYTES = GT_BM * 64 * 2;
@@ -135,7 +138,8 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tmem_full = empty + STAGES;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;     // [2]
   uint32_t* tmem_holder = (uint32_t*)(tmem_empty + 2);
-  float4* stage_all = (float4*)(tiles + STAGES * STAGE_BYTES + 1024);  // 8 epilogue warps x 4 KB, 1024-byte aligned (TMA-store boxes)
+  uint64_t* aux_bar = (uint64_t*)(tiles + STAGES * STAGE_BYTES + 512);  // [8 epilogue warps][2 buffers]
+  uint8_t* stage_all = tiles + STAGES * STAGE_BYTES + 1024;             // 8 epilogue warps x 6 KB, 2048-byte aligned strips
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = CG == 2 ? (int)cluster_rank() : 0;          // position in the CTA pair
@@ -150,6 +154,7 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (p.tma_store) {
       tma_prefetch_desc(&tmC);
       if (p.out2) tma_prefetch_desc(&tmC2);
+      if (p.aux_tma) tma_prefetch_desc(&tmX);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -157,6 +162,7 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
+    for (int s = 0; s < 2 * GT_EPI_WARPS; s++) mbar_init(&aux_bar[s], 1);
     for (int s = 0; s < 2; s++) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], GT_EPI_WARPS * CG);   // the leader's barrier collects the epilogue warps of both CTAs
@@ -269,7 +275,9 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int ew = warp - 2;
     const int q = warp & 3;                  // TMEM lane quarter this warp may read
     const int half = ew >> 2;                // column half of the tile
-    float4* stg = stage_all + ew * 256;
+    float4* stg = (float4*)(stage_all + ew * GT_STRIP_BYTES);
+    uint64_t* xbar = aux_bar + 2 * ew;
+    uint32_t xcnt = 0;                       // aux boxes consumed so far by this warp (buffer = xcnt & 1, parity = (xcnt >> 1) & 1)
     constexpr int HALF_COLS = BN / 2;
     uint32_t tile_i = 0;
     for (int t = unit; t < total; t += num_units, tile_i++) {
@@ -278,6 +286,10 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int m0 = (r % p.num_m) * (GT_BM * CG) + rank * GT_BM, n0 = (r / p.num_m) * BN;
       const long long c_off = (long long)grp * p.c_gs;
       const uint32_t acc = tile_i & 1, acc_ph = (tile_i >> 1) & 1;
+      if (p.aux_tma && lane == 0) {          // first aux box of the tile: in flight while the MMAs of this tile finish
+        mbar_expect_tx(&xbar[xcnt & 1], 2048);
+        tma_load_2d((uint8_t*)stg + 2048 + (xcnt & 1) * 2048, &tmX, n0 + half * HALF_COLS, m0 + q * 32, &xbar[xcnt & 1]);
+      }
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
       const bool first_split = ks == 0;
@@ -324,7 +336,25 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; j++) v[j] = gelu_tanh_fast(v[j]);
           }
-          if (p.aux_mode == GEMM_AUX_GELU_GRAD || p.aux_mode == GEMM_AUX_ADD_BF16) {
+          if (p.aux_tma) {
+            if (lane == 0 && c + 32 < HALF_COLS) {     // prefetch the next chunk's box into the other buffer
+              mbar_expect_tx(&xbar[(xcnt + 1) & 1], 2048);
+              tma_load_2d(strip + 2048 + ((xcnt + 1) & 1) * 2048, &tmX, col0 + 32, m0 + q * 32, &xbar[(xcnt + 1) & 1]);
+            }
+            mbar_wait(&xbar[xcnt & 1], (xcnt >> 1) & 1);
+            const uint8_t* xb = strip + 2048 + (xcnt & 1) * 2048 + lane * 64;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const uint4 w = *(const uint4*)(xb + ((j ^ sw) << 4));
+              const float a8[8] = {bf16lo(w.x), bf16hi(w.x), bf16lo(w.y), bf16hi(w.y), bf16lo(w.z), bf16hi(w.z), bf16lo(w.w), bf16hi(w.w)};
+#pragma unroll
+              for (int e = 0; e < 8; e++) {
+                if (p.aux_mode == GEMM_AUX_GELU_GRAD) v[8 * j + e] *= gelu_tanh_grad_fast(a8[e]);
+                else v[8 * j + e] += a8[e];
+              }
+            }
+            xcnt++;
+          } else if (p.aux_mode == GEMM_AUX_GELU_GRAD || p.aux_mode == GEMM_AUX_ADD_BF16) {
             if (row < p.M) {
               const bf16* ax = (const bf16*)p.aux + (size_t)row * p.ld_aux + col0;
 #pragma unroll
@@ -458,8 +488,8 @@ int get_tmap(const void* base, long long inner, long long rows, long long ld, in
 }
 
 template <int BN, int CG>
-int launch_gt(const TensorMap2D* ta, const TensorMap2D* tb, const TensorMap2D* tc, const TensorMap2D* tc2, const GemmTParams& p, int grid,
-              cudaStream_t st) {
+int launch_gt(const TensorMap2D* ta, const TensorMap2D* tb, const TensorMap2D* tc, const TensorMap2D* tc2, const TensorMap2D* tx,
+              const GemmTParams& p, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     DMG_CUDA_OK(cudaFuncSetAttribute(gemm_train_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, gt_smem_bytes(BN, CG)));
@@ -476,7 +506,7 @@ int launch_gt(const TensorMap2D* ta, const TensorMap2D* tb, const TensorMap2D* t
   cfg.attrs = attr;
   cfg.numAttrs = CG > 1 ? 1 : 0;
   DMG_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_train_kernel<BN, CG>, *(const CUtensorMap*)ta->bytes, *(const CUtensorMap*)tb->bytes,
-                                 *(const CUtensorMap*)tc->bytes, *(const CUtensorMap*)tc2->bytes, p));
+                                 *(const CUtensorMap*)tc->bytes, *(const CUtensorMap*)tc2->bytes, *(const CUtensorMap*)tx->bytes, p));
   g_launch_count++;
   return 0;
 }
@@ -537,21 +567,24 @@ int gemm_bf16_tc(const bf16* A, int a_mn, long long lda, const bf16* B, int b_mn
   // bf16 outputs leave through TMA stores (dense boxes; the map clips at M and N); needs N-extent columns in a group-free launch
   static const bool no_tma_store = getenv("DMG_GEMM_NO_TMA_STORE") != nullptr;
   p.tma_store = (!no_tma_store && e.out_mode == GEMM_OUT_BF16 && groups == 1 && e.aux_mode != GEMM_AUX_ADD_F32) ? 1 : 0;
-  const TensorMap2D *tc = ta, *tc2 = ta;   // placeholders when unused
+  p.aux_tma = (p.tma_store && !e.out2 && (e.aux_mode == GEMM_AUX_GELU_GRAD || e.aux_mode == GEMM_AUX_ADD_BF16) &&
+               !getenv("DMG_GEMM_NO_AUX_TMA")) ? 1 : 0;
+  const TensorMap2D *tc = ta, *tc2 = ta, *tx = ta;   // placeholders when unused
   if (p.tma_store) {
     if (get_tmap(e.out, N, M, e.ldc, -1, &tc)) return -1;
     if (e.out2 && get_tmap(e.out2, N, M, e.ld2, -1, &tc2)) return -1;
+    if (p.aux_tma && get_tmap(e.aux, N, M, e.ld_aux, -1, &tx)) return -1;
   }
   const long long total = (long long)num_m * num_n * p.splitk * groups;
   const int grid = (int)(total < units ? total : units) * CG;
   if (CG == 2) {
-    if (BN == 256) return launch_gt<256, 2>(ta, tb, tc, tc2, p, grid, st);
-    if (BN == 128) return launch_gt<128, 2>(ta, tb, tc, tc2, p, grid, st);
-    return launch_gt<64, 2>(ta, tb, tc, tc2, p, grid, st);
+    if (BN == 256) return launch_gt<256, 2>(ta, tb, tc, tc2, tx, p, grid, st);
+    if (BN == 128) return launch_gt<128, 2>(ta, tb, tc, tc2, tx, p, grid, st);
+    return launch_gt<64, 2>(ta, tb, tc, tc2, tx, p, grid, st);
   }
-  if (BN == 256) return launch_gt<256, 1>(ta, tb, tc, tc2, p, grid, st);
-  if (BN == 128) return launch_gt<128, 1>(ta, tb, tc, tc2, p, grid, st);
-  return launch_gt<64, 1>(ta, tb, tc, tc2, p, grid, st);
+  if (BN == 256) return launch_gt<256, 1>(ta, tb, tc, tc2, tx, p, grid, st);
+  if (BN == 128) return launch_gt<128, 1>(ta, tb, tc, tc2, tx, p, grid, st);
+  return launch_gt<64, 1>(ta, tb, tc, tc2, tx, p, grid, st);
 }
 
 }  // namespace dmg

@@ -53,8 +53,9 @@ run('out-proj fwd', rows, 512, 512, 0, 0, 1)
 run('FF1 fwd (bias gelu drop pre)', rows, 2048, 512, 0, 0, 1, bias=True, gelu=1, pre=True, drop=0.1)
 run('FF2 fwd (bias)', rows, 512, 2048, 0, 0, 1, bias=True)
 run('dh = dY W2 (gelu grad drop)', rows, 2048, 512, 0, 1, 1, aux_mode=1, drop=0.1)
-run('dx += dh W1 (f32 add)', rows, 512, 2048, 0, 1, 0, aux_mode=3)
-run('dx += dqkv Wqkv (f32 add)', rows, 512, 1536, 0, 1, 0, aux_mode=3)
+run('dbranch = dh W1 (bf16)', rows, 512, 2048, 0, 1, 1)
+run('dbranch = dqkv Wqkv (bf16)', rows, 512, 1536, 0, 1, 1)
+run('dattn = dY Wo (bf16)', rows, 512, 512, 0, 1, 1)
 run('dW2 = dY^T h (atomic sk4)', 512, 2048, rows, 1, 1, 2, splitk=4)
 run('dW1 = dh^T x (atomic sk4)', 2048, 512, rows, 1, 1, 2, splitk=4)
 run('dWqkv (atomic sk6)', 1536, 512, rows, 1, 1, 2, splitk=6)
