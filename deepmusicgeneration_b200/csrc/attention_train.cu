@@ -33,6 +33,13 @@ constexpr int DSK_LD = 88;     // bf16 per row of the warp-private dS strip (80 
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
+// two floats -> packed fp16 pair, saturating to +-65504 instead of overflowing to infinity (lo = first argument)
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 struct MaskP {
   int M, mem_count, win, k;
 };
@@ -84,8 +91,8 @@ __device__ __forceinline__ void scores_tile(const uint32_t (&qu)[4][4], const ui
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       const int col = 16 * p + 8 * h + 2 * t;
-      *(__half2*)(skew + g * SKEW_LD + col) = __floats2half2_rn(acc[h][0], acc[h][1]);
-      *(__half2*)(skew + (g + 8) * SKEW_LD + col) = __floats2half2_rn(acc[h][2], acc[h][3]);
+      *(uint32_t*)(skew + g * SKEW_LD + col) = pack_half2_sat(acc[h][0], acc[h][1]);
+      *(uint32_t*)(skew + (g + 8) * SKEW_LD + col) = pack_half2_sat(acc[h][2], acc[h][3]);
     }
   }
   __syncwarp();
@@ -309,7 +316,11 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
 // recompute P (normalised), dP and dS for one tile; returns ds (scaled gradient wrt AC+BD) and pd (dropped P) in s / pd
 __device__ __forceinline__ void bwd_tile_math(const AttnTrainArgs& a, const MaskP& mp, float (&s)[8][4], float (&dpd)[8][4],
                                               const int (&row_g)[2], const float (&lse2)[2], const float (&dl)[2], int j0,
-                                              const uint32_t (&drop_base)[2], int t, bool want_pd, float (&pd)[8][4]) {
+                                              const uint32_t (&drop_base)[2], int t, bool want_pd, float (&pd)[8][4],
+                                              bf16* p_row0 = nullptr, bf16* p_row1 = nullptr, bf16* ds_row0 = nullptr,
+                                              bf16* ds_row1 = nullptr) {
+  // p_row*/ds_row*: when set, the dropped probabilities and dS of this thread's two rows are also written (bf16 pairs) at
+  // column offset 8*nt + 2*t of the given row pointers - the input of the dK/dV kernel (attn_bwd_dkv_lite_kernel)
   const float c = a.scale * LOG2E;
   const bool need_mask = (j0 + 63 >= a.M) || (j0 < a.M - a.mem_count);
 #pragma unroll
@@ -331,6 +342,13 @@ __device__ __forceinline__ void bwd_tile_math(const AttnTrainArgs& a, const Mask
       const float dp = dpd[nt][e] * keep[e];
       s[nt][e] = p * (dp - dl[r]) * a.scale;
       if (want_pd) pd[nt][e] = p * keep[e];
+      if (p_row0) keep[e] *= p;                     // keep[] now holds the dropped probability
+    }
+    if (p_row0) {
+      *(uint32_t*)(p_row0 + 8 * nt + 2 * t) = pack_bf16x2(keep[0], keep[1]);
+      *(uint32_t*)(p_row1 + 8 * nt + 2 * t) = pack_bf16x2(keep[2], keep[3]);
+      *(uint32_t*)(ds_row0 + 8 * nt + 2 * t) = pack_bf16x2(s[nt][0], s[nt][1]);
+      *(uint32_t*)(ds_row1 + 8 * nt + 2 * t) = pack_bf16x2(s[nt][2], s[nt][3]);
     }
   }
 }
@@ -444,7 +462,13 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnTrainBwdArgs
         mma_bf16(dpd[2 * np + 1], dof[ks], r[2], r[3]);
       }
     }
-    bwd_tile_math(a, mp, s, dpd, row_g, lse2, dl, j0, drop_base, t, false, unused);   // s := dS
+    if (ba.p_buf) {                                   // spill P (dropped) and dS for the dK/dV kernel: [b*H+h][T][S] bf16
+      const long long o0 = (bhT + row_g[0]) * S + j0, o1 = (bhT + row_g[1]) * S + j0;
+      bwd_tile_math(a, mp, s, dpd, row_g, lse2, dl, j0, drop_base, t, false, unused, ba.p_buf + o0, ba.p_buf + o1, ba.ds_buf + o0,
+                    ba.ds_buf + o1);
+    } else {
+      bwd_tile_math(a, mp, s, dpd, row_g, lse2, dl, j0, drop_base, t, false, unused);   // s := dS
+    }
 
     // dS into the skewed strip (bf16): strip[row][64 + row - jl]
 #pragma unroll
@@ -704,6 +728,109 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnTrainBwdArg
   }
 }
 
+// dK / dV from the spilled P and dS tiles (no recomputation of the scores): key-tile owner, loops over the query tiles that
+// see it; per iteration four 64x64 tiles (P, dS, dO, Q) arrive through a double-buffered cp.async ring.
+constexpr int LITE_SMEM = 2 * 4 * TILE_BYTES;
+
+__global__ void __launch_bounds__(128) attn_bwd_dkv_lite_kernel(const AttnTrainBwdArgs ba) {
+  const AttnTrainArgs& a = ba.f;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  LaneOff L;
+  lane_off_init(L, lane, w);
+  const int nS = (a.M + a.T) / 64;
+  const int jt = blockIdx.x % nS;
+  const int bh = blockIdx.x / nS, b = bh / a.H, h = bh % a.H;
+  const int j0 = jt * 64, HD = a.H * 64, S = a.M + a.T;
+  const long long bhT = (long long)bh * a.T;
+  bf16 *dk_dst, *dv_dst;
+  long long ldd;
+  if (j0 < a.M) {
+    ldd = a.ldm;
+    dk_dst = ba.dkv_m + ((long long)b * a.M + j0) * a.ldm + h * 64;
+    dv_dst = dk_dst + HD;
+  } else {
+    ldd = a.ldx;
+    dk_dst = ba.dqkv_x + ((long long)b * a.T + (j0 - a.M)) * a.ldx + HD + h * 64;
+    dv_dst = dk_dst + HD;
+  }
+  if (j0 < a.M - a.mem_count) {
+    for (int i = tid; i < 64 * 32; i += 128) {
+      const int r = i >> 5, cidx = (i & 31) * 2;
+      *(uint32_t*)(dk_dst + (long long)r * ldd + cidx) = 0u;
+      *(uint32_t*)(dv_dst + (long long)r * ldd + cidx) = 0u;
+    }
+    return;
+  }
+  const int nT = a.T / 64;
+  const int it_lo = j0 < a.M ? 0 : (j0 - a.M) / 64;
+  auto load_stage = [&](int it) {
+    if (it < nT) {
+      uint8_t* st = smem + ((it - it_lo) & 1) * 4 * TILE_BYTES;
+      const int i0 = it * 64;
+      tile_load_async(st, ba.p_buf + (bhT + i0) * S + j0, S, tid, 128);
+      tile_load_async(st + TILE_BYTES, ba.ds_buf + (bhT + i0) * S + j0, S, tid, 128);
+      tile_load_async(st + 2 * TILE_BYTES, ba.dout + ((long long)b * a.T + i0) * HD + h * 64, HD, tid, 128);
+      tile_load_async(st + 3 * TILE_BYTES, a.qkv_x + ((long long)b * a.T + i0) * a.ldx + h * 64, a.ldx, tid, 128);
+    }
+    cp_async_commit();
+  };
+  load_stage(it_lo);
+  float dk[8][4], dv[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+    for (int e = 0; e < 4; e++) { dk[nt][e] = 0.f; dv[nt][e] = 0.f; }
+  const float* ub = a.u + h * 64;
+  for (int it = it_lo; it < nT; it++) {
+    cp_async_wait<0>();
+    __syncthreads();
+    load_stage(it + 1);
+    uint8_t* st = smem + ((it - it_lo) & 1) * 4 * TILE_BYTES;
+    uint8_t* sQ = st + 3 * TILE_BYTES;
+    // q -> q + u in place, each warp its own 16 query rows (the B operand of the dK contraction)
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+      const int c0 = 16 * ks + 2 * t;
+#pragma unroll
+      for (int hh = 0; hh < 2; hh++) {
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+          uint32_t* ptr = (uint32_t*)(sQ + tile_off(16 * w + g + 8 * rr, 2 * ks + hh) + 4 * t);
+          *ptr = pack_bf16x2(bf16lo(*ptr) + ub[c0 + 8 * hh], bf16hi(*ptr) + ub[c0 + 8 * hh + 1]);
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t sPa = smem_u32(st), sdSa = smem_u32(st + TILE_BYTES), sdOa = smem_u32(st + 2 * TILE_BYTES), sQua = smem_u32(sQ);
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+      uint32_t ap[4], as[4];
+      frag_a_t(sPa, 16 * ks, L, ap);
+      frag_a_t(sdSa, 16 * ks, L, as);
+#pragma unroll
+      for (int np = 0; np < 4; np++) {
+        uint32_t r[4];
+        frag_b_t(sdOa, np, 16 * ks, L, r);
+        mma_bf16(dv[2 * np], ap, r[0], r[1]);
+        mma_bf16(dv[2 * np + 1], ap, r[2], r[3]);
+        frag_b_t(sQua, np, 16 * ks, L, r);
+        mma_bf16(dk[2 * np], as, r[0], r[1]);
+        mma_bf16(dk[2 * np + 1], as, r[2], r[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    const long long ro = (long long)(16 * w + g + 8 * r) * ldd;
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+      *(uint32_t*)(dk_dst + ro + 8 * nt + 2 * t) = pack_bf16x2(dk[nt][2 * r], dk[nt][2 * r + 1]);
+      *(uint32_t*)(dv_dst + ro + 8 * nt + 2 * t) = pack_bf16x2(dv[nt][2 * r], dv[nt][2 * r + 1]);
+    }
+  }
+}
+
 int check_args(const AttnTrainArgs& a) {
   DMG_CHECK(a.T > 0 && a.T % 64 == 0 && a.M % 64 == 0 && a.mem_count % 64 == 0 && a.mem_count <= a.M,
             "training attention: T=%d, M=%d, mem_count=%d must be multiples of 64", a.T, a.M, a.mem_count);
@@ -734,12 +861,15 @@ int attn_train_bwd(const AttnTrainBwdArgs& ba, int num_sms, cudaStream_t st) {
   if (!configured) {
     DMG_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
     DMG_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    DMG_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_lite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LITE_SMEM));
     configured = true;
   }
   const int rows = a.B * a.T;
   if (launch_np(attn_delta_kernel, dim3((rows * 32 + 255) / 256), dim3(256), 0, st, (const bf16*)a.out, ba.dout, ba.delta, rows, a.T, a.H))
     return -1;
   if (launch_np(attn_bwd_dq_kernel, dim3(a.B * a.H * (a.T / 64)), dim3(128), (size_t)DQ_SMEM, st, ba)) return -1;
+  if (ba.p_buf && ba.ds_buf)   // P and dS were spilled by the dQ kernel: no second recomputation of the scores
+    return launch_np(attn_bwd_dkv_lite_kernel, dim3(a.B * a.H * ((a.M + a.T) / 64)), dim3(128), (size_t)LITE_SMEM, st, ba);
   return launch_np(attn_bwd_dkv_kernel, dim3(a.B * a.H * ((a.M + a.T) / 64)), dim3(128), (size_t)DKV_SMEM, st, ba);
 }
 

@@ -57,7 +57,7 @@ struct dmg_train {
   // workspaces
   float *x32 = nullptr, *dx32 = nullptr, *logits = nullptr, *delta = nullptr, *drk32 = nullptr, *partial = nullptr, *acc = nullptr;
   bf16 *proj = nullptr, *dadd = nullptr, *dh = nullptr, *dattn = nullptr, *dqkv_x = nullptr, *dkv_m = nullptr, *ds_dist = nullptr,
-       *qv = nullptr, *drk16 = nullptr, *dlogits = nullptr, *xdrop = nullptr, *dbr = nullptr;
+       *qv = nullptr, *drk16 = nullptr, *dlogits = nullptr, *xdrop = nullptr, *dbr = nullptr, *p_buf = nullptr, *ds_buf = nullptr;
   bool dbr_valid = false;                    // dbr holds a branch gradient still to be added to dx32
   const long long *ids = nullptr, *pos = nullptr;     // of the latest forward (caller-owned, must stay alive until backward ends)
   int win = 1, k = 1, training = 1;
@@ -181,7 +181,8 @@ int apply_mem_update(dmg_model* m, dmg_train* t, cudaStream_t st, int level_lo, 
   const int M = c.mem_len;
   if (M <= 0) return 0;
   for (int l = level_lo; l <= level_hi; l++) {
-    if (t->T == M) {   // the whole memory is replaced: trade buffers instead of copying (the old memory becomes next step's scratch)
+    static const bool no_swap = getenv("DMG_TRAIN_NO_SWAP") != nullptr;
+    if (t->T == M && !no_swap) {   // the whole memory is replaced: trade buffers instead of copying (the old memory becomes next step's scratch)
       std::swap(t->mem[l], l < c.n_layers ? t->act[l].xa_in : t->xa_last);
       continue;
     }
@@ -353,6 +354,7 @@ int backward_layer(dmg_model* m, dmg_train* t, int l, cudaStream_t st) {
     ba.f = attn_args(m, t, l);
     ba.dout = t->dattn; ba.delta = t->delta; ba.dqkv_x = t->dqkv_x; ba.dkv_m = t->dkv_m; ba.ds_dist = t->ds_dist; ba.qv = t->qv;
     ba.du = t->G + t->g_u; ba.dv = t->G + t->g_v;
+    ba.p_buf = t->p_buf; ba.ds_buf = t->ds_buf;
     if (attn_train_bwd(ba, ns, st)) return -1;
     // dRk[h] = dS_dist[:, h]^T (q + v)[:, h]  ->  dWr = dRk^T PE
     if (train_q_plus_bias(A.qkv_x, 3 * HD, m->v, t->qv, rows, HD, st)) return -1;
@@ -491,6 +493,10 @@ int dmg_train_create(dmg_model* m, const dmg_train_config* cfg, float* grad_flat
   TRY(talloc(t, &t->dkv_m, BM * 2 * HD));
   TRY(talloc(t, &t->ds_dist, (size_t)rows * c.n_heads * S));
   TRY(talloc(t, &t->qv, (size_t)rows * HD));
+  if (!getenv("DMG_ATTN_BWD_RECOMPUTE")) {   // spill P / dS from the dQ kernel instead of recomputing them for dK / dV
+    TRY(talloc(t, &t->p_buf, (size_t)rows * c.n_heads * S));
+    TRY(talloc(t, &t->ds_buf, (size_t)rows * c.n_heads * S));
+  }
   {   // multi-tensor Adam tables
     std::vector<AdamTensor> ht;
     std::vector<AdamChunk> hc;
@@ -692,7 +698,16 @@ int dmg_attn_train_bwd(const void* qkv_x, int64_t ldx, const void* kv_m, int64_t
                         k, drop_p, drop_seed_v);
   ba.dout = (const bf16*)dout; ba.delta = delta; ba.dqkv_x = (bf16*)dqkv_x; ba.dkv_m = (bf16*)dkv_m; ba.ds_dist = (bf16*)ds_dist;
   ba.qv = nullptr; ba.du = du; ba.dv = dv;
-  return attn_train_bwd(ba, 148, (cudaStream_t)stream);
+  static const bool recompute = getenv("DMG_ATTN_BWD_RECOMPUTE") != nullptr;
+  bf16* ws = nullptr;
+  const size_t n = (size_t)B * H * T * (M + T);
+  if (!recompute) {
+    DMG_CUDA_OK(cudaMalloc(&ws, 2 * n * sizeof(bf16)));
+    ba.p_buf = ws; ba.ds_buf = ws + n;
+  }
+  const int rc = attn_train_bwd(ba, 148, (cudaStream_t)stream);
+  if (ws) { cudaStreamSynchronize((cudaStream_t)stream); cudaFree(ws); }
+  return rc;
 }
 
 }  // extern "C"

@@ -111,6 +111,8 @@ struct AttnTrainBwdArgs {
   bf16* qv;              // [B*T, HD] bf16: q + v (operand of the dRk GEMM)
   float* du;             // [HD] accumulated (atomics)
   float* dv;             // [HD]
+  bf16* p_buf = nullptr;   // optional workspaces [B*H, T, M+T] bf16: when both are set the dQ kernel spills the dropped
+  bf16* ds_buf = nullptr;  // probabilities and dS there and dK/dV come from a kernel that does not recompute the scores
 };
 int attn_train_bwd(const AttnTrainBwdArgs& a, int num_sms, cudaStream_t st);
 

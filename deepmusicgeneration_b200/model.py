@@ -176,7 +176,7 @@ def init_state_dict(engine, seed=None):
             w[0] = 0
         elif name.endswith('.bias'):
             w = torch.zeros(shape)
-        elif '.ln.' in name or 'layers.6.' in name:
+        elif '.ln.' in name or '.ff.layers.6.' in name:          # LayerNorms: mhra.ln / mha1.ln and SequentialEx index 6 of the FFN
             w = torch.randn(shape, generator=g) * 0.02 + 1.0
         else:
             w = torch.randn(shape, generator=g) * 0.02

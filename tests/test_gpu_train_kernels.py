@@ -109,6 +109,31 @@ def test_gemm_train_epilogues():
     assert rel_err(out[kept], plain[kept] / 0.75) < 2e-3
 
 
+def test_gemm_train_persistent_many_tiles_per_cta():
+    "more tiles than CTA pairs: the persistent loop, both TMEM stages, the TMA-store strips and the aux-box prefetch wrap around"
+    torch.manual_seed(4)
+    M, N, K = 8192, 2048, 192
+    A = (torch.randn(M, K, device='cuda') * 0.5).bfloat16()
+    W = (torch.randn(N, K, device='cuda') * 0.1).bfloat16()
+    bias = torch.randn(N, device='cuda')
+    acc = A.float() @ W.float().t()
+    out, pre = gemm_train(A, 0, W, 0, M, N, K, bias=bias, gelu=1, out_mode=1, want_pre=True)
+    assert rel_err(pre, acc + bias) < 5e-3 and rel_err(out, gelu_tanh(acc + bias)) < 5e-3
+    aux = torch.randn(M, N, device='cuda').bfloat16()
+    x = aux.float().requires_grad_(True)
+    gelu_tanh(x).sum().backward()
+    out = gemm_train(A, 0, W, 0, M, N, K, aux=aux, aux_mode=1, out_mode=1)
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out, acc * x.grad) < 5e-3
+    out = gemm_train(A, 0, W, 0, M, N, K, aux=aux, aux_mode=2, out_mode=1)
+    assert rel_err(out, acc + aux.float()) < 5e-3
+    out = gemm_train(A, 0, W, 0, M, N, K, out_mode=0)
+    assert rel_err(out, acc) < 2e-3
+    Wm = W.t().contiguous()                                   # [K, N]: MN-major B
+    out = gemm_train(A, 0, Wm, 1, M, N, K, out_mode=1)
+    assert rel_err(out, acc) < 5e-3
+
+
 def test_gemm_train_grouped_heads():
     "the dRk contraction: one launch, group h reads A columns [h*S,(h+1)*S) and B columns [h*64,(h+1)*64)"
     torch.manual_seed(3)
