@@ -845,6 +845,7 @@ int check_args(const AttnTrainArgs& a) {
 
 int attn_train_fwd(const AttnTrainArgs& a, cudaStream_t st) {
   if (check_args(a)) return -2;
+  if (attn_train_fwd_tc_supported(a)) return attn_train_fwd_tc(a, st);
   static bool configured = false;
   if (!configured) {
     DMG_CUDA_OK(cudaFuncSetAttribute(attn_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));

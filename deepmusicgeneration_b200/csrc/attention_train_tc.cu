@@ -1,0 +1,398 @@
+// Training attention FORWARD on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+//
+// Same contract as attn_train_fwd_kernel (attention_train.cu; fastai MultiHeadRelativeAttention._apply_attention, SURVEY.md
+// App. A.3/A.4): out = dropout(softmax(((q+u) K^T + _line_shift((q+v) Rk^T)) / sqrt(Dh) + mask)) V, plus the row
+// log-sum-exp for the backward.  Used when T, M and mem_count are multiples of 128 (the mma.sync kernel serves the rest).
+//
+// One CTA = one (stream, head, 128-query tile); 12 warps (the auxiliary warpgroup gives its registers away: setmaxnreg):
+//   warps 0-7  softmax: warp w owns TMEM lanes 32*(w%4).. (= query rows) and the key half w/4 of every 128-key tile, so a
+//              thread owns ONE query row x 64 keys - row max / row sum need no shuffles; the two halves keep independent
+//              online-softmax states (m, l, O[64]) that are merged once at the end
+//   warp 8     TMA producer: Q once; per key tile K (2 stages), V, one new 128-distance block of Rk (2 slots)
+//   warp 9     one thread issues every tcgen05.mma
+// TMEM (512 columns): [0,128) AC = (q+u) K^T | [128,384) position strip (q+v) Rk[D0-128 .. D0+127]^T | [384,448) and
+//   [448,512) P_half V of the current tile (the running O lives in registers: o = o * alpha + PV).
+// _line_shift is index arithmetic: BD[r, j] = strip[r][128 + r - j] (D0 = M + i0 - j0 is a multiple of 128, so a window is
+// two aligned 128-row blocks of Rk and consecutive key tiles share one).  A thread needs 64 consecutive strip columns of
+// ITS OWN row at a lane-dependent offset; TMEM loads take warp-uniform column addresses, so the row passes through a
+// thread-private shared-memory line (written with 16-byte stores, read back at offset `lane` - no synchronisation at all).
+// P goes to shared memory as bf16 in the canonical K-major 128B-swizzled layout and is the A operand of the PV MMA; V is
+// used as it lies (MN-major B operand).  The softmax of tile n overlaps the score MMAs of tile n+1 (issued as soon as every
+// softmax warp has copied tile n out of TMEM) and the PV MMA of tile n-1.
+#include <cuda.h>
+#include "kernels.cuh"
+#include "launch.cuh"
+#include "mma_sync.cuh"
+#include "train_kernels.cuh"
+
+namespace dmg {
+
+namespace {
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+constexpr int TC_SOFT_WARPS = 8;
+constexpr int TC_THREADS = (TC_SOFT_WARPS + 4) * 32;   // + one auxiliary warpgroup: TMA warp, MMA warp, two idle warps
+constexpr int T16K = 128 * 64 * 2;                 // one [128 rows][64 bf16] tile, 128B swizzle
+constexpr int STRIP_LD = 68;                        // floats per thread-private strip line (64 used; 68: conflict-free v4 stores)
+constexpr int OFF_QU = 0;
+constexpr int OFF_QV = OFF_QU + T16K;
+constexpr int OFF_K = OFF_QV + T16K;                // 2 stages
+constexpr int OFF_V = OFF_K + 2 * T16K;
+constexpr int OFF_R = OFF_V + T16K;                 // 2 slots (slot = block & 1)
+constexpr int OFF_P = OFF_R + 2 * T16K;             // 2 key halves; half 0 doubles as the raw-Q landing buffer
+constexpr int OFF_STRIP = OFF_P + 2 * T16K;
+constexpr int OFF_BAR = OFF_STRIP + TC_SOFT_WARPS * 32 * STRIP_LD * 4;
+constexpr int TC_SMEM = OFF_BAR + 256 + 1024 /*alignment slack*/;
+static_assert(TC_SMEM <= 227 * 1024, "shared memory budget");
+
+enum { B_QFULL = 0, B_QREADY, B_KFULL0, B_KFULL1, B_KEMPTY0, B_KEMPTY1, B_RFULL0, B_RFULL1, B_REMPTY0, B_REMPTY1, B_VFULL, B_VEMPTY,
+       B_SFULL, B_SFREE, B_PFULL0, B_PFULL1, B_OFULL0, B_OFULL1, B_OFREE0, B_OFREE1, B_COUNT };
+
+constexpr uint32_t TM_AC = 0, TM_STRIP = 128, TM_O = 384;
+
+// shared-memory matrix descriptors (sm_100 version bit 46, SWIZZLE_128B)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {          // rows of 128 B, 8-row groups 1024 B apart
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t addr) {         // [k rows][64 mn] boxes: LBO 8192 (next mn block), SBO 1024 (next 8 k rows)
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(8192u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmM,
+                         const __grid_constant__ CUtensorMap tmR, const AttnTrainArgs a) {
+  extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
+  uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
+  uint64_t* bar = (uint64_t*)(smem + OFF_BAR);
+  uint32_t* tmem_holder = (uint32_t*)(bar + B_COUNT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nT = a.T / 128;
+  const int it = nT - 1 - (blockIdx.x % nT);        // heavy (late) query tiles first
+  const int bh = blockIdx.x / nT, b = bh / a.H, h = bh % a.H;
+  const int i0 = it * 128, HD = a.H * 64, S = a.M + a.T;
+  const int jt_lo = (a.M - a.mem_count) / 128, jt_hi = (a.M + i0) / 128;
+  const int NT = jt_hi - jt_lo + 1;                 // key tiles of this CTA
+  const int blk0 = (a.M + i0) / 128 - jt_lo;        // upper Rk block of the first tile (block = distance / 128)
+
+  if (warp == TC_SOFT_WARPS && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmM);
+    tma_prefetch_desc(&tmR);
+    for (int i = 0; i < B_COUNT; i++) {
+      uint32_t cnt = 1;
+      if (i == B_QREADY || i == B_SFREE) cnt = TC_SOFT_WARPS;
+      if (i == B_PFULL0 || i == B_PFULL1 || i == B_OFREE0 || i == B_OFREE1) cnt = TC_SOFT_WARPS / 2;
+      mbar_init(&bar[i], cnt);
+    }
+    mbar_fence_init();
+  }
+  if (warp == TC_SOFT_WARPS + 1) tmem_alloc<512>(tmem_holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  // register budget: 384 threads start with 168 registers each; the auxiliary warpgroup hands its share to the softmax warpgroups
+  if (warp >= TC_SOFT_WARPS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == TC_SOFT_WARPS) {
+    // =========================================== TMA producer ===========================================
+    if (lane == 0) {
+      mbar_expect_tx(&bar[B_QFULL], T16K);
+      tma_load_2d(smem + OFF_P, &tmX, h * 64, b * a.T + i0, &bar[B_QFULL]);
+      auto load_k = [&](int n) {
+        const int s = n & 1, j0 = (jt_lo + n) * 128;
+        mbar_wait(&bar[B_KEMPTY0 + s], ((n >> 1) & 1) ^ 1);
+        mbar_expect_tx(&bar[B_KFULL0 + s], T16K);
+        if (j0 < a.M) tma_load_2d(smem + OFF_K + s * T16K, &tmM, h * 64, b * a.M + j0, &bar[B_KFULL0 + s]);
+        else tma_load_2d(smem + OFF_K + s * T16K, &tmX, HD + h * 64, b * a.T + (j0 - a.M), &bar[B_KFULL0 + s]);
+      };
+      auto load_r = [&](int k) {                    // k-th block load: block blk0 - k (may be -1: all rows out of bounds -> zeros)
+        const int blk = blk0 - k, s = blk & 1;
+        mbar_wait(&bar[B_REMPTY0 + s], ((k >> 1) & 1) ^ 1);
+        mbar_expect_tx(&bar[B_RFULL0 + s], T16K);
+        tma_load_2d(smem + OFF_R + s * T16K, &tmR, h * 64, blk * 128, &bar[B_RFULL0 + s]);
+      };
+      auto load_v = [&](int n) {
+        const int j0 = (jt_lo + n) * 128;
+        mbar_wait(&bar[B_VEMPTY], (n & 1) ^ 1);
+        mbar_expect_tx(&bar[B_VFULL], T16K);
+        if (j0 < a.M) tma_load_2d(smem + OFF_V, &tmM, HD + h * 64, b * a.M + j0, &bar[B_VFULL]);
+        else tma_load_2d(smem + OFF_V, &tmX, 2 * HD + h * 64, b * a.T + (j0 - a.M), &bar[B_VFULL]);
+      };
+      load_k(0);
+      load_r(0);
+      load_r(1);
+      if (NT > 1) load_k(1);
+      load_v(0);
+      for (int n = 1; n < NT; n++) {                // waits in the order the MMAs retire: S(n-1), then PV(n-1)
+        load_r(n + 1);
+        if (n + 1 < NT) load_k(n + 1);
+        load_v(n);
+      }
+    }
+  } else if (warp == TC_SOFT_WARPS + 1) {
+    // =========================================== MMA issuer ===========================================
+    if (lane == 0) {
+      // instruction descriptors: D fp32, A/B bf16, N>>3 @17, M>>4 @24; bit 16: B is MN-major
+      constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      constexpr uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t qu = smem_u32(smem + OFF_QU), qv = smem_u32(smem + OFF_QV), kk = smem_u32(smem + OFF_K),
+                     vv = smem_u32(smem + OFF_V), rr = smem_u32(smem + OFF_R), pp = smem_u32(smem + OFF_P);
+      auto issue_pv = [&](int m) {
+        mbar_wait(&bar[B_VFULL], m & 1);
+#pragma unroll
+        for (int hf = 0; hf < 2; hf++) {
+          mbar_wait(&bar[B_PFULL0 + hf], m & 1);
+          if (m > 0) mbar_wait(&bar[B_OFREE0 + hf], (m - 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            umma_bf16(tmem_base + TM_O + 64 * hf, desc_kmajor(pp + hf * T16K + k * 32), desc_mnmajor(vv + hf * 8192 + k * 2048), idesc_pv,
+                      (uint32_t)(k > 0));
+          umma_commit(&bar[B_OFULL0 + hf]);
+        }
+        umma_commit(&bar[B_VEMPTY]);
+      };
+      mbar_wait(&bar[B_QREADY], 0);
+      for (int n = 0; n < NT; n++) {
+        const int s = n & 1, blkU = blk0 - n, blkL = blkU - 1;
+        mbar_wait(&bar[B_KFULL0 + s], (n >> 1) & 1);
+        mbar_wait(&bar[B_RFULL0 + (blkU & 1)], (n >> 1) & 1);
+        mbar_wait(&bar[B_RFULL0 + (blkL & 1)], ((n + 1) >> 1) & 1);
+        if (n > 0) mbar_wait(&bar[B_SFREE], (n - 1) & 1);
+        tc_fence_after();
+        const uint32_t ks = kk + s * T16K, rl = rr + (blkL & 1) * T16K, ru = rr + (blkU & 1) * T16K;
+#pragma unroll
+        for (int k = 0; k < 4; k++) umma_bf16(tmem_base + TM_AC, desc_kmajor(qu + k * 32), desc_kmajor(ks + k * 32), idesc_s, (uint32_t)(k > 0));
+#pragma unroll
+        for (int k = 0; k < 4; k++) umma_bf16(tmem_base + TM_STRIP, desc_kmajor(qv + k * 32), desc_kmajor(rl + k * 32), idesc_s, (uint32_t)(k > 0));
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          umma_bf16(tmem_base + TM_STRIP + 128, desc_kmajor(qv + k * 32), desc_kmajor(ru + k * 32), idesc_s, (uint32_t)(k > 0));
+        umma_commit(&bar[B_SFULL]);
+        umma_commit(&bar[B_KEMPTY0 + s]);
+        umma_commit(&bar[B_REMPTY0 + (blkU & 1)]);   // the upper block is dead after this tile; the lower one serves the next
+        if (n > 0) issue_pv(n - 1);
+      }
+      issue_pv(NT - 1);
+    }
+    }
+  } else {
+    // =========================================== softmax warps ===========================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int hf = warp >> 2, q4 = warp & 3;
+    const int r = q4 * 32 + lane;                   // query row of this thread inside the tile
+    const int row = i0 + r;                         // ... inside the segment
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    float* strip = (float*)(smem + OFF_STRIP) + (size_t)(warp * 32 + lane) * STRIP_LD;
+    const int vis_lim = a.k == 1 ? row + 1 : max((row / a.win) * a.win, 1);
+    const float c = a.scale * LOG2E;
+
+    // ---- q + u and q + v in the canonical swizzled layout (thread: row tid%128, four of its eight 16-byte chunks)
+    {
+      const int tid = threadIdx.x, qr = tid & 127, part = tid >> 7;
+      const uint32_t roff = (uint32_t)((qr >> 3) * 1024 + (qr & 7) * 128);
+      const float* ub = a.u + h * 64;
+      const float* vb = a.v + h * 64;
+      mbar_wait(&bar[B_QFULL], 0);
+#pragma unroll
+      for (int pc = 4 * part; pc < 4 * part + 4; pc++) {
+        const uint4 raw = *(const uint4*)(smem + OFF_P + roff + pc * 16);
+        const int col = 8 * (pc ^ (qr & 7));
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+        uint32_t ou[4], ov[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const float lo = bf16lo(w[e]), hi = bf16hi(w[e]);
+          ou[e] = pack_bf16x2(lo + ub[col + 2 * e], hi + ub[col + 2 * e + 1]);
+          ov[e] = pack_bf16x2(lo + vb[col + 2 * e], hi + vb[col + 2 * e + 1]);
+        }
+        *(uint4*)(smem + OFF_QU + roff + pc * 16) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+        *(uint4*)(smem + OFF_QV + roff + pc * 16) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[B_QREADY]);
+    }
+
+    float o[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++) o[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+    // dropout pair index of (row, key j) = ((bh*T + row)*S + j) / 2 (S and this thread's first key of a tile are even)
+    const uint32_t drop_base = (uint32_t)((((long long)bh * a.T + row) * S) >> 1);
+    uint8_t* prow = smem + OFF_P + hf * T16K + (r >> 3) * 1024 + (r & 7) * 128;
+
+    for (int n = 0; n < NT; n++) {
+      const int j0 = (jt_lo + n) * 128 + 64 * hf;    // full-context index of this thread's first key
+      float s[64];
+      mbar_wait(&bar[B_SFULL], n & 1);
+      tc_fence_after();
+      {   // content term (both loads in flight before the wait)
+        uint32_t x0[32], x1[32];
+        tmem_ld_32x32(t_lane + TM_AC + 64 * hf, x0);
+        tmem_ld_32x32(t_lane + TM_AC + 64 * hf + 32, x1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++) { s[i] = __uint_as_float(x0[i]); s[32 + i] = __uint_as_float(x1[i]); }
+      }
+      // position term: keys 32*sp .. 32*sp+31 of this half need strip columns base + (32 + lane - jj), base warp-uniform
+#pragma unroll
+      for (int sp = 0; sp < 2; sp++) {
+        const uint32_t base = (uint32_t)(96 - 64 * hf - 32 * sp + 32 * q4);
+        {
+          uint32_t x0[32], x1[32];
+          tmem_ld_32x32(t_lane + TM_STRIP + base, x0);
+          tmem_ld_32x32(t_lane + TM_STRIP + base + 32, x1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            *(float4*)(strip + 4 * k) = make_float4(__uint_as_float(x0[4 * k]), __uint_as_float(x0[4 * k + 1]),
+                                                    __uint_as_float(x0[4 * k + 2]), __uint_as_float(x0[4 * k + 3]));
+            *(float4*)(strip + 32 + 4 * k) = make_float4(__uint_as_float(x1[4 * k]), __uint_as_float(x1[4 * k + 1]),
+                                                         __uint_as_float(x1[4 * k + 2]), __uint_as_float(x1[4 * k + 3]));
+          }
+        }
+        const float* sk = strip + 32 + lane;
+#pragma unroll
+        for (int jj = 0; jj < 32; jj++) s[32 * sp + jj] += sk[-jj];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[B_SFREE]);     // the score MMAs of the next tile may overwrite TMEM
+
+      if (n > 0) {                                   // fold the previous tile's P V into the running output
+        mbar_wait(&bar[B_OFULL0 + hf], (n - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) {
+          uint32_t x[32];
+          tmem_ld_32x32(t_lane + TM_O + 64 * hf + 32 * ch, x);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) o[32 * ch + i] = fmaf(o[32 * ch + i], alpha_prev, __uint_as_float(x[i]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar[B_OFREE0 + hf]);
+      }
+
+      // mask: x-region tiles only; causal (1,1) tiles strictly below the diagonal are fully visible.  Key jx (segment
+      // coordinates) is visible from this row iff jx < vis_lim (window_mask: (1,1) -> jx <= row; (w,0) -> jx < (row/w)*w or jx == 0)
+      const int jx0 = j0 - a.M;
+      const bool need_mask = jx0 + 63 >= 1 && !(a.k == 1 && jx0 + 63 <= i0);
+      if (need_mask) {
+        const int lim = vis_lim - jx0;              // local keys jj < lim stay
+#pragma unroll
+        for (int jj = 0; jj < 64; jj++) s[jj] = jj < lim ? s[jj] : -INFINITY;
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < 64; jj++) mx = fmaxf(mx, s[jj]);
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = (m_new == -INFINITY) ? 1.f : ex2_fast((m_run - m_new) * c);
+      const float neg_mc = (m_new == -INFINITY) ? 0.f : -m_new * c;
+      m_run = m_new;
+      float rs = 0.f;
+      // P (unscaled dropout: the 1/(1-p) factor is applied to the output) -> canonical K-major swizzled bf16 tile
+#pragma unroll
+      for (int ck = 0; ck < 8; ck++) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int pp = 4 * ck + e;
+          float p0 = ex2_fast(fmaf(s[2 * pp], c, neg_mc)), p1 = ex2_fast(fmaf(s[2 * pp + 1], c, neg_mc));
+          rs += p0 + p1;
+          if (a.drop_thresh) {
+            const uint32_t hb = drop_pair_bits(a.drop_seed, drop_base + (uint32_t)(j0 >> 1) + pp);
+            p0 = ((hb & 0xFFFFu) >= a.drop_thresh) ? p0 : 0.f;
+            p1 = ((hb >> 16) >= a.drop_thresh) ? p1 : 0.f;
+          }
+          pk[e] = pack_bf16x2(p0, p1);
+        }
+        *(uint4*)(prow + ((ck ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      l_run = l_run * alpha + rs;
+      alpha_prev = alpha;
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[B_PFULL0 + hf]);
+    }
+    // last tile's P V
+    mbar_wait(&bar[B_OFULL0 + hf], (NT - 1) & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int ch = 0; ch < 2; ch++) {
+      uint32_t x[32];
+      tmem_ld_32x32(t_lane + TM_O + 64 * hf + 32 * ch, x);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i++) o[32 * ch + i] = fmaf(o[32 * ch + i], alpha_prev, __uint_as_float(x[i]));
+    }
+    tc_fence_before();
+
+    // ---- merge the two key halves of every row (half 1 hands its state over through its strip line), write out / lse
+    if (hf == 1) {
+#pragma unroll
+      for (int k = 0; k < 16; k++) *(float4*)(strip + 4 * k) = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+      strip[64] = m_run;
+      strip[65] = l_run;
+    }
+    softmax_bar_sync();
+    if (hf == 0) {
+      const float* other = strip + (size_t)4 * 32 * STRIP_LD;       // same lane of warp + 4
+      const float m1 = other[64], l1 = other[65];
+      const float m = fmaxf(m_run, m1);
+      const float w0 = (m_run == -INFINITY) ? 0.f : ex2_fast((m_run - m) * c);
+      const float w1 = (m1 == -INFINITY) ? 0.f : ex2_fast((m1 - m) * c);
+      const float l = l_run * w0 + l1 * w1;
+      const float inv = l > 0.f ? (a.drop_thresh ? a.drop_scale : 1.f) / l : 0.f;
+      bf16* orow = a.out + ((long long)b * a.T + row) * HD + h * 64;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int d0 = 8 * k + 2 * e;
+          w[e] = pack_bf16x2((o[d0] * w0 + other[d0] * w1) * inv, (o[d0 + 1] * w0 + other[d0 + 1] * w1) * inv);
+        }
+        *(uint4*)(orow + 8 * k) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      a.lse[(long long)bh * a.T + row] = (m * c + log2f(l)) * LN2;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_SOFT_WARPS + 1) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace
+
+bool attn_train_fwd_tc_supported(const AttnTrainArgs& a) {
+  static const bool off = getenv("DMG_ATTN_FWD_MMA_SYNC") != nullptr;
+  return !off && a.T % 128 == 0 && a.M % 128 == 0 && a.mem_count % 128 == 0 && a.ldx % 8 == 0 && (a.M == 0 || a.ldm % 8 == 0);
+}
+
+int attn_train_fwd_tc(const AttnTrainArgs& a, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    DMG_CUDA_OK(cudaFuncSetAttribute(attn_train_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    configured = true;
+  }
+  const int HD = a.H * 64;
+  const TensorMap2D *tx = nullptr, *tm = nullptr, *tr = nullptr;
+  if (train_get_tmap(a.qkv_x, 3 * HD, (long long)a.B * a.T, a.ldx, 128, &tx)) return -1;
+  if (a.M > 0) { if (train_get_tmap(a.kv_m, 2 * HD, (long long)a.B * a.M, a.ldm, 128, &tm)) return -1; }
+  else tm = tx;
+  if (train_get_tmap(a.rk, HD, (long long)a.M + a.T, HD, 128, &tr)) return -1;
+  return launch_np(attn_train_fwd_tc_kernel, dim3(a.B * a.H * (a.T / 128)), dim3(TC_THREADS), (size_t)TC_SMEM, st,
+                   *(const CUtensorMap*)tx->bytes, *(const CUtensorMap*)tm->bytes, *(const CUtensorMap*)tr->bytes, a);
+}
+
+}  // namespace dmg

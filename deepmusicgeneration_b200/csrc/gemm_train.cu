@@ -513,6 +513,11 @@ int launch_gt(const TensorMap2D* ta, const TensorMap2D* tb, const TensorMap2D* t
 
 }  // namespace
 
+// tensor-map cache for the other training kernels (attention_train_tc.cu): [rows, inner] bf16, 64-column x box_rows boxes
+int train_get_tmap(const void* base, long long inner, long long rows, long long ld, int box_rows, const TensorMap2D** out) {
+  return get_tmap(base, inner, rows, ld, box_rows, out);
+}
+
 int gemm_bf16_tc(const bf16* A, int a_mn, long long lda, const bf16* B, int b_mn, long long ldb, int M, int N, int K,
                  int splitk, const GemmEpi& e, int num_sms, cudaStream_t st) {
   if (M <= 0 || N <= 0) return 0;

@@ -100,6 +100,11 @@ struct AttnTrainArgs {
   uint32_t drop_thresh, drop_seed; float drop_scale;   // attention dropout (on the probabilities)
 };
 int attn_train_fwd(const AttnTrainArgs& a, cudaStream_t st);
+// tcgen05 / TMEM / TMA forward (attention_train_tc.cu): T, M, mem_count multiples of 128; attn_train_fwd dispatches to it
+bool attn_train_fwd_tc_supported(const AttnTrainArgs& a);
+int attn_train_fwd_tc(const AttnTrainArgs& a, cudaStream_t st);
+struct TensorMap2D;
+int train_get_tmap(const void* base, long long inner, long long rows, long long ld, int box_rows, const TensorMap2D** out);
 
 struct AttnTrainBwdArgs {
   AttnTrainArgs f;       // the forward arguments (out = the saved forward output)

@@ -219,6 +219,11 @@ def attn_mask_from_device(B, H, T, S, M, mem_count, p, seed):
     (1, 192, 1, 128, 64, 1, 0, 0.0),
     (2, 128, 2, 64, 64, 3, 0, 0.0),
     (2, 128, 2, 128, 128, 1, 1, 0.1),
+    # shapes served by the tcgen05 forward (attention_train_tc.cu: T, M, mem_count multiples of 128)
+    (1, 384, 2, 0, 0, 1, 1, 0.0),          # no memory: the diagonal tile's lower Rk block lies at negative distances
+    (1, 256, 2, 256, 128, 1, 1, 0.1),      # partly filled memory
+    (2, 256, 1, 128, 128, 3, 0, 0.0),      # window mask (3, 0)
+    (1, 512, 2, 512, 512, 1, 1, 0.1),      # C3 geometry
 ])
 def test_attention_train_forward_backward(B, T, H, M, mem_count, win, kk, p):
     lib = _lib.load()
