@@ -356,30 +356,36 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
   return v;
 }
 
-constexpr int SK_BN = 32;
 constexpr int SK_MAXKB = 8;                       // k-blocks (of 64) per CTA
-constexpr int SK_RED_LD = SK_BN + 4;              // padded row stride of the partial tile (floats)
-constexpr int SK_STAGE = 128 * 64 * 2 + SK_BN * 64 * 2;
-__host__ __device__ constexpr int sk_smem_bytes(int num_kb) {
-  return num_kb * SK_STAGE + 128 * SK_RED_LD * 4 + 1024 + 256;
+// BN = tile width (32, 64 or 128 output columns).  Every CTA of a wide GEMM re-reads its 128 x K/KSPLIT slice of the
+// ACTIVATIONS for each column tile (16 KB per k-block against 4 KB of weights at BN = 32): measured at C2 the four
+// per-layer GEMMs cost ~5 us + 2.5 us per 512 output columns, the slope being that redundant L2 -> SM traffic.  Wider
+// tiles for the wide GEMMs cut it 1.7x (BN 64) / 2.5x (BN 128) and still leave >= 96 CTAs.
+__host__ __device__ constexpr int sk_stage_bytes(int BN) { return 128 * 64 * 2 + BN * 64 * 2; }
+__host__ __device__ constexpr int sk_red_ld(int BN) { return BN + 4; }   // padded row stride of the partial tile (floats)
+// The fp32 partial tile reuses the operand stages when it fits (it is written only after the last MMA has retired);
+// 2 k-blocks at BN = 32 -> 42 KB per CTA -> five CTAs per SM.
+__host__ __device__ constexpr int sk_smem_bytes(int BN, int num_kb) {
+  return (num_kb * sk_stage_bytes(BN) > 128 * sk_red_ld(BN) * 4 ? num_kb * sk_stage_bytes(BN) : 128 * sk_red_ld(BN) * 4) + 1024 + 256;
 }
 
-template <int KSPLIT>
+template <int KSPLIT, int BN>
 __global__ void __launch_bounds__(192)
 gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                       const float* __restrict__ bias, void* __restrict__ C, int ldc, int M, int N, int K, int gelu,
                       int out_bf16) {
+  constexpr int STAGE = sk_stage_bytes(BN), RED_LD = sk_red_ld(BN);
   extern __shared__ __align__(1024) uint8_t sk_smem[];
   uint8_t* tiles = sk_smem + ((1024u - (smem_u32(sk_smem) & 1023u)) & 1023u);
   const int num_kb = K / 64 / KSPLIT;            // k-blocks of this CTA (<= SK_MAXKB)
-  float* red = (float*)(tiles + num_kb * SK_STAGE);
-  uint64_t* full = (uint64_t*)(red + 128 * SK_RED_LD);
+  float* red = (float*)tiles;                     // aliases the operand stages (free once tmem_full has fired)
+  uint64_t* full = (uint64_t*)(tiles + sk_smem_bytes(BN, num_kb) - 1024 - 256);
   uint64_t* tmem_full = full + SK_MAXKB;
   uint32_t* tmem_holder = (uint32_t*)(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t krank = cluster_ctarank();
-  const int n0 = (blockIdx.x / KSPLIT) * SK_BN, m0 = blockIdx.y * 128;
+  const int n0 = (blockIdx.x / KSPLIT) * BN, m0 = blockIdx.y * 128;
   const int kb0 = krank * num_kb;
   pdl_launch_dependents();
 
@@ -392,7 +398,7 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     mbar_init(tmem_full, 1);
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<32>(tmem_holder);
+  if (warp == 2) tmem_alloc<BN>(tmem_holder);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -402,19 +408,21 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0) {   // every stage is used once: issue all loads up front - the WEIGHT tiles even before the
                        // predecessor kernel has finished (they never change), the activation tiles after pdl_wait
       for (int kb = 0; kb < num_kb; kb++) {
-        mbar_expect_tx(&full[kb], SK_STAGE);
-        tma_load_2d(tiles + kb * SK_STAGE + 128 * 64 * 2, &tmW, (kb0 + kb) * 64, n0, &full[kb]);
+        mbar_expect_tx(&full[kb], STAGE);
+#pragma unroll
+        for (int j = 0; j < BN / 32; j++)          // the weight map has 32-row boxes; consecutive boxes form one K-major tile
+          tma_load_2d(tiles + kb * STAGE + 128 * 64 * 2 + j * 32 * 128, &tmW, (kb0 + kb) * 64, n0 + 32 * j, &full[kb]);
       }
       pdl_wait();
-      for (int kb = 0; kb < num_kb; kb++) tma_load_2d(tiles + kb * SK_STAGE, &tmA, (kb0 + kb) * 64, m0, &full[kb]);
+      for (int kb = 0; kb < num_kb; kb++) tma_load_2d(tiles + kb * STAGE, &tmA, (kb0 + kb) * 64, m0, &full[kb]);
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SK_BN >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
     for (int kb = 0; kb < num_kb; kb++) {
       mbar_wait(&full[kb], 0);
       tc_fence_after();
       if (lane == 0) {
-        const uint32_t a_addr = smem_u32(tiles + kb * SK_STAGE);
+        const uint32_t a_addr = smem_u32(tiles + kb * STAGE);
         const uint32_t b_addr = a_addr + 128 * 64 * 2;
 #pragma unroll
         for (int k = 0; k < 4; k++)
@@ -429,14 +437,17 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const int q = warp & 3;
-    uint32_t r[32];
-    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16), r);
-    tmem_ld_wait();
-    float4* dst = (float4*)(red + (q * 32 + lane) * SK_RED_LD);
 #pragma unroll
-    for (int j = 0; j < 8; j++)
-      dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                           __uint_as_float(r[4 * j + 3]));
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+      tmem_ld_wait();
+      float4* dst = (float4*)(red + (q * 32 + lane) * RED_LD + c);
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                             __uint_as_float(r[4 * j + 3]));
+    }
   }
   tc_fence_before();
   __syncwarp();
@@ -445,37 +456,33 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   if (warp >= 2) {
     constexpr int ROWS = 128 / KSPLIT;          // rows finalised by this CTA
+    constexpr int TPR = 128 / ROWS;             // threads per row (4 or 8)
+    constexpr int CPT = BN / TPR;               // columns per thread (a multiple of 4)
     const int te = threadIdx.x - 64;            // 0..127
-    const int rr = te >> 2, cg = (te & 3) * 8;  // 4 threads per row, 8 columns each
-    if (rr < ROWS) {
-      const int row_l = krank * ROWS + rr;
-      const uint32_t laddr = smem_u32(red + row_l * SK_RED_LD + cg);
-      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int rr = te / TPR, cg = (te % TPR) * CPT;
+    const int row_l = krank * ROWS + rr;
+    const int row = m0 + row_l;
+#pragma unroll
+    for (int c4 = 0; c4 < CPT; c4 += 4) {
+      const uint32_t laddr = smem_u32(red + row_l * RED_LD + cg + c4);
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int r2 = 0; r2 < KSPLIT; r2++) {
-        const uint32_t ra = mapa_shared(laddr, (uint32_t)r2);
-        const float4 x = ld_dsmem_f4(ra), y = ld_dsmem_f4(ra + 16);
+        const float4 x = ld_dsmem_f4(mapa_shared(laddr, (uint32_t)r2));
         v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w;
-        v[4] += y.x; v[5] += y.y; v[6] += y.z; v[7] += y.w;
       }
-      const int row = m0 + row_l, col0 = n0 + cg;
+      const int col0 = n0 + cg + c4;
       if (row < M && col0 < N) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < 4; j++) {
           if (bias && col0 + j < N) v[j] += bias[col0 + j];
           if (gelu) v[j] = gelu_tanh(v[j]);
         }
-        if (col0 + 8 <= N) {
-          if (out_bf16) {
-            *(uint4*)((bf16*)C + (size_t)row * ldc + col0) =
-                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-          } else {
-            float4* o = (float4*)((float*)C + (size_t)row * ldc + col0);
-            o[0] = make_float4(v[0], v[1], v[2], v[3]);
-            o[1] = make_float4(v[4], v[5], v[6], v[7]);
-          }
+        if (col0 + 4 <= N) {
+          if (out_bf16) *(uint2*)((bf16*)C + (size_t)row * ldc + col0) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+          else *(float4*)((float*)C + (size_t)row * ldc + col0) = make_float4(v[0], v[1], v[2], v[3]);
         } else {
-          for (int j = 0; j < 8; j++)
+          for (int j = 0; j < 4; j++)
             if (col0 + j < N) {
               if (out_bf16) ((bf16*)C)[(size_t)row * ldc + col0 + j] = __float2bfloat16_rn(v[j]);
               else ((float*)C)[(size_t)row * ldc + col0 + j] = v[j];
@@ -486,20 +493,20 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
   __syncwarp();
   cluster_sync_all();          // nobody may exit while a peer still reads its shared memory
-  if (warp == 2) tmem_dealloc<32>(tmem_base);
+  if (warp == 2) tmem_dealloc<BN>(tmem_base);
 }
 
-template <int KSPLIT>
+template <int KSPLIT, int BN>
 static int launch_splitk(const TensorMap2D* tmA, const TensorMap2D* tmW, const float* bias, void* C, int ldc, int M, int N,
                          int K, int gelu, int out_bf16, cudaStream_t st) {
   const int num_kb = K / 64 / KSPLIT;
-  const int smem = sk_smem_bytes(num_kb);
+  const int smem = sk_smem_bytes(BN, num_kb);
   static int configured = 0;
   if (configured < smem) {
-    DMG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_splitk_kernel<KSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DMG_CUDA_OK(cudaFuncSetAttribute(gemm_tc_splitk_kernel<KSPLIT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  return launch_k(gemm_tc_splitk_kernel<KSPLIT>, dim3(((N + SK_BN - 1) / SK_BN) * KSPLIT, (M + 127) / 128, 1), dim3(192), smem, st,
+  return launch_k(gemm_tc_splitk_kernel<KSPLIT, BN>, dim3(((N + BN - 1) / BN) * KSPLIT, (M + 127) / 128, 1), dim3(192), smem, st,
                   KSPLIT, *(const CUtensorMap*)tmA->bytes, *(const CUtensorMap*)tmW->bytes, bias, C, ldc, M, N, K, gelu, out_bf16);
 }
 
@@ -508,7 +515,8 @@ static int launch_splitk(const TensorMap2D* tmA, const TensorMap2D* tmW, const f
 int gemm_tc_splitk_ways(int K) {
   if (K % 64) return 0;
   const int kb = K / 64;
-  if (kb % 8 == 0 && kb / 8 >= 2 && kb / 8 <= SK_MAXKB) return 8;
+  static const int min8 = getenv("DMG_SPLITK_8") ? 1 : 2;   // DMG_SPLITK_8: 8-way split already at K = 512 (timing experiments)
+  if (kb % 8 == 0 && kb / 8 >= min8 && kb / 8 <= SK_MAXKB) return 8;
   if (kb % 4 == 0 && kb / 4 >= 1 && kb / 4 <= SK_MAXKB) return 4;
   return 0;
 }
@@ -520,8 +528,16 @@ int gemm_tc_splitk(const TensorMap2D* tmA, const TensorMap2D* tmW32, const float
   if (M <= 0 || N <= 0) return 0;
   if (out_bf16) DMG_CHECK(ldc % 8 == 0, "gemm_tc_splitk: bf16 output needs ldc %% 8 == 0 (ldc=%d)", ldc);
   else DMG_CHECK(ldc % 4 == 0, "gemm_tc_splitk: fp32 output needs ldc %% 4 == 0 (ldc=%d)", ldc);
-  return ways == 8 ? launch_splitk<8>(tmA, tmW32, bias, C, ldc, M, N, K, gelu, out_bf16, st)
-                   : launch_splitk<4>(tmA, tmW32, bias, C, ldc, M, N, K, gelu, out_bf16, st);
+  // tile width: measured at C2 (256 rows; ms per decode step): BN 32 -> 1.401, BN 64 -> 1.474, BN 128 -> 1.790 - the
+  // GEMMs of the one-token step are bound by the per-CTA latency chain (TMA -> MMA -> TMEM -> DSMEM reduction), not by L2
+  // traffic, so many small CTAs (five resident per SM) win.  DMG_SPLITK_BN overrides (timing experiments).
+  static const int force_bn = getenv("DMG_SPLITK_BN") ? atoi(getenv("DMG_SPLITK_BN")) : 0;
+  int BN = 32;
+  if (force_bn == 64 || force_bn == 128) BN = (N % force_bn == 0) ? force_bn : 32;
+#define DMG_SK(W_, B_) launch_splitk<W_, B_>(tmA, tmW32, bias, C, ldc, M, N, K, gelu, out_bf16, st)
+  if (ways == 8) return BN == 128 ? DMG_SK(8, 128) : BN == 64 ? DMG_SK(8, 64) : DMG_SK(8, 32);
+  return BN == 128 ? DMG_SK(4, 128) : BN == 64 ? DMG_SK(4, 64) : DMG_SK(4, 32);
+#undef DMG_SK
 }
 
 }  // namespace dmg
