@@ -104,6 +104,8 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
       } else {
         if (attn_decode(a, st)) return -1;
       }
+      if (m->lane_mode && l == 0 && m->lane_idx + 1 < m->lane_count)   // the next lane may start (staggered lanes)
+        DMG_CUDA_OK(cudaEventRecord(m->ev_stagger[m->lane_idx], st));
     } else {
       AttnGeneralArgs a;
       a.qkv = m->qkv; a.kring = L.kring; a.vring = L.vring; a.rd = L.rd; a.u = m->u; a.v = m->v; a.out = m->attn;
@@ -184,6 +186,8 @@ static int ensure_lanes(dmg_model* m, int n_lanes, int rows_per_lane) {
     if (!rc && cudaEventCreateWithFlags(&ln.ev, cudaEventDisableTiming) != cudaSuccess) { set_error("lane event creation failed"); rc = -1; }
   }
   if (!rc && !m->ev_fork && cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess) { set_error("fork event creation failed"); rc = -1; }
+  for (int i = 0; i < 4 && !rc; i++)
+    if (!m->ev_stagger[i] && cudaEventCreateWithFlags(&m->ev_stagger[i], cudaEventDisableTiming) != cudaSuccess) { set_error("stagger event creation failed"); rc = -1; }
 #undef TRY
   if (rc) return rc;
   m->lane_rows = (int)R;
@@ -229,10 +233,13 @@ static int forward_impl(dmg_model* m, const long long* ids, const long long* pos
       const int b0 = i * per, nb = bs - b0 < per ? bs - b0 : per;
       if (nb <= 0) break;
       cudaStream_t s_i = i == 0 ? st : m->lanes[i - 1].st;
+      static const bool no_stagger = getenv("DMG_LANE_NO_STAGGER") != nullptr;
       if (i > 0) {
-        if (cudaStreamWaitEvent(s_i, m->ev_fork, 0) != cudaSuccess) { set_error("lane fork failed"); rc = -1; break; }
+        // fork: from the previous lane's "first attention issued" event (staggered), else from the common fork point
+        if (cudaStreamWaitEvent(s_i, no_stagger ? m->ev_fork : m->ev_stagger[i - 1], 0) != cudaSuccess) { set_error("lane fork failed"); rc = -1; break; }
         lane_swap(m, m->lanes[i - 1]);
       }
+      m->lane_idx = i; m->lane_count = no_stagger ? 1 : n_lanes;
       rc = forward_chunk<bf16>(m, ids + (size_t)b0, pos ? pos + (size_t)b0 : nullptr, b0, nb, 1, win, k, logits_mode, logits, core_out, s_i);
       if (i > 0) {
         lane_swap(m, m->lanes[i - 1]);
@@ -371,6 +378,7 @@ void dmg_destroy(dmg_model* m) {
     if (ln.ev) cudaEventDestroy(ln.ev);
   }
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  for (int i = 0; i < 4; i++) if (m->ev_stagger[i]) cudaEventDestroy(m->ev_stagger[i]);
   if (m->step_graph) cudaGraphExecDestroy(m->step_graph);
   if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
   for (void* p : m->allocs) cudaFree(p);

@@ -93,6 +93,10 @@ struct dmg_model {
   int lane_rows = 0;
   int lane_stages = 4;          // K/V tile ring depth of the decode-attention kernel while lanes overlap (DMG_LANE_STAGES)
   bool lane_mode = false;       // set while a laned decode step is being issued
+  // staggered start: lane i+1 starts once lane i has issued the attention of its first layer, so that one lane's HBM-bound
+  // attention runs under the other lane's latency-bound GEMM chain instead of both lanes marching in lockstep
+  cudaEvent_t ev_stagger[4] = {nullptr, nullptr, nullptr, nullptr};
+  int lane_idx = 0, lane_count = 1;
   dmg_train* train = nullptr;   // training state (train.cu), created by dmg_train_create
 };
 

@@ -45,7 +45,7 @@ if os.environ.get('GEMM_MAJORS'):
 only = os.environ.get('GEMM_ONLY')
 if only:
     run('QKV fwd', rows, 1536, 512, 0, 0, 1, reps=2)
-    run('dh = dY W2 (gelu grad drop)', rows, 2048, 512, 0, 1, 1, aux_mode=1, drop=0.1, reps=2)
+    run('FF1 fwd (bias gelu drop pre)', rows, 2048, 512, 0, 0, 1, bias=True, gelu=1, pre=True, drop=0.1, reps=2)
     sys.exit(0)
 run('QKV fwd', rows, 1536, 512, 0, 0, 1)
 run('KVmem fwd', rows, 1024, 512, 0, 0, 1)
