@@ -353,16 +353,58 @@ __device__ __forceinline__ void bwd_tile_math(const AttnTrainArgs& a, const Mask
   }
 }
 
+// Same with the probabilities SAVED by the tcgen05 forward (AttnTrainArgs::p_save / m_save): pw[nt][r] holds the bf16 pair
+// (row r of this thread, keys 8*nt + 2*t, +1) relative to the block maximum; fac[r] = exp(m_save*scale - lse) rescales it.
+// Masked keys were saved as zeros, so no visibility test is needed.
+__device__ __forceinline__ void bwd_tile_math_saved(const AttnTrainArgs& a, const uint32_t (&pw)[8][2], const float (&fac)[2],
+                                                    float (&s)[8][4], float (&dpd)[8][4], const float (&dl)[2], int j0,
+                                                    const uint32_t (&drop_base)[2], int t, bf16* p_row0, bf16* p_row1, bf16* ds_row0,
+                                                    bf16* ds_row1) {
+#pragma unroll
+  for (int nt = 0; nt < 8; nt++) {
+    float keep[4] = {1.f, 1.f, 1.f, 1.f};
+    if (a.drop_thresh) {
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const uint32_t hb = drop_pair_bits(a.drop_seed, drop_base[r] + (uint32_t)(j0 >> 1) + 4 * nt);
+        keep[2 * r] = ((hb & 0xFFFFu) >= a.drop_thresh) ? a.drop_scale : 0.f;
+        keep[2 * r + 1] = ((hb >> 16) >= a.drop_thresh) ? a.drop_scale : 0.f;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int r = e >> 1;
+      const float p = ((e & 1) ? bf16hi(pw[nt][r]) : bf16lo(pw[nt][r])) * fac[r];
+      const float dp = dpd[nt][e] * keep[e];
+      s[nt][e] = p * (dp - dl[r]) * a.scale;
+      keep[e] *= p;                                 // keep[] now holds the dropped probability
+    }
+    if (p_row0) {
+      *(uint32_t*)(p_row0 + 8 * nt + 2 * t) = pack_bf16x2(keep[0], keep[1]);
+      *(uint32_t*)(p_row1 + 8 * nt + 2 * t) = pack_bf16x2(keep[2], keep[3]);
+      *(uint32_t*)(ds_row0 + 8 * nt + 2 * t) = pack_bf16x2(s[nt][0], s[nt][1]);
+      *(uint32_t*)(ds_row1 + 8 * nt + 2 * t) = pack_bf16x2(s[nt][2], s[nt][3]);
+    }
+  }
+}
+
 constexpr int DQ_SMEM = 2 * ATT_NST * TILE_BYTES /*K,V ring (Q and dO are staged in its last stage first)*/ + ATT_NR * TILE_BYTES /*R*/ +
                         4 * 16 * SKEW_LD * (int)sizeof(skew_t) + 4 * 16 * DSK_LD * 2;
 
-__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnTrainBwdArgs ba) {
+// PS = true: the probabilities come from the forward's p_save / m_save (no AC / BD / skew / exp recomputation, no (q+u),
+// (q+v) fragments, no skew strip): 2 ring stages, <= 168 registers -> three CTAs per SM instead of two.
+constexpr int DQ_PS_NST = 2;
+constexpr int DQ_PS_SMEM = 2 * DQ_PS_NST * TILE_BYTES + (DQ_PS_NST + 1) * TILE_BYTES + 4 * 16 * DSK_LD * 2;
+
+template <bool PS>
+__global__ void __launch_bounds__(128, PS ? 3 : 1) attn_bwd_dq_kernel(const AttnTrainBwdArgs ba) {
+  constexpr int NST = PS ? DQ_PS_NST : ATT_NST, NR = NST + 1;
   const AttnTrainArgs& a = ba.f;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sKV = smem;
-  uint8_t* sR = sKV + 2 * ATT_NST * TILE_BYTES;
-  skew_t* skew_all = (skew_t*)(sR + ATT_NR * TILE_BYTES);
-  bf16* dsk_all = (bf16*)(skew_all + 4 * 16 * SKEW_LD);
+  uint8_t* sR = sKV + 2 * NST * TILE_BYTES;
+  skew_t* skew_all = (skew_t*)(sR + NR * TILE_BYTES);
+  bf16* dsk_all = PS ? (bf16*)skew_all : (bf16*)(skew_all + 4 * 16 * SKEW_LD);
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   skew_t* skew = skew_all + w * 16 * SKEW_LD;
   LaneOff L;
@@ -380,32 +422,32 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnTrainBwdArgs
 
   auto load_stage = [&](int jt) {
     if (jt <= jt_hi) {
-      const int st = (jt - jt_lo) % ATT_NST;
+      const int st = (jt - jt_lo) % NST;
       long long ld;
       const bf16* kp = kv_tile_ptr(a, b, h, jt, 0, &ld);
       tile_load_async(sKV + 2 * st * TILE_BYTES, kp, ld, tid, 128);
       const bf16* vp = kv_tile_ptr(a, b, h, jt, 1, &ld);
       tile_load_async(sKV + (2 * st + 1) * TILE_BYTES, vp, ld, tid, 128);
       const int rt_hi = rt_top - jt;
-      if (jt == jt_lo) tile_load_async(sR + (rt_hi % ATT_NR) * TILE_BYTES, a.rk + (long long)rt_hi * 64 * HD + h * 64, HD, tid, 128);
-      if (rt_hi > 0) tile_load_async(sR + ((rt_hi - 1) % ATT_NR) * TILE_BYTES, a.rk + (long long)(rt_hi - 1) * 64 * HD + h * 64, HD, tid, 128);
+      if (jt == jt_lo) tile_load_async(sR + (rt_hi % NR) * TILE_BYTES, a.rk + (long long)rt_hi * 64 * HD + h * 64, HD, tid, 128);
+      if (rt_hi > 0) tile_load_async(sR + ((rt_hi - 1) % NR) * TILE_BYTES, a.rk + (long long)(rt_hi - 1) * 64 * HD + h * 64, HD, tid, 128);
     }
     cp_async_commit();
   };
 
   // stage Q and dO through the LAST ring stage (the prologue fills stages 0 .. NST-2) to build the A fragments
-  uint8_t* sQst = sKV + 2 * (ATT_NST - 1) * TILE_BYTES;
+  uint8_t* sQst = sKV + 2 * (NST - 1) * TILE_BYTES;
   uint8_t* sdOst = sQst + TILE_BYTES;
-  tile_load_async(sQst, a.qkv_x + ((long long)b * a.T + i0) * a.ldx + h * 64, a.ldx, tid, 128);
+  if (!PS) tile_load_async(sQst, a.qkv_x + ((long long)b * a.T + i0) * a.ldx + h * 64, a.ldx, tid, 128);
   tile_load_async(sdOst, ba.dout + ((long long)b * a.T + i0) * HD + h * 64, HD, tid, 128);
   cp_async_commit();
 #pragma unroll
-  for (int s2 = 0; s2 < ATT_NST - 1; s2++) load_stage(jt_lo + s2);
+  for (int s2 = 0; s2 < NST - 1; s2++) load_stage(jt_lo + s2);
   for (int i = lane; i < 16 * DSK_LD; i += 32) dsk[i] = __float2bfloat16_rn(0.f);   // off-band entries stay zero
-  cp_async_wait<ATT_NST - 1>();
+  cp_async_wait<NST - 1>();
   __syncthreads();
   uint32_t qu[4][4], qv[4][4], dof[4][4];
-  q_frags(smem_u32(sQst), w, lane, L, a.u + h * 64, a.v + h * 64, qu, qv);
+  if (!PS) q_frags(smem_u32(sQst), w, lane, L, a.u + h * 64, a.v + h * 64, qu, qv);
 #pragma unroll
   for (int ks = 0; ks < 4; ks++) frag_a(smem_u32(sdOst), 16 * w, ks, L, dof[ks]);
 
@@ -416,6 +458,19 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnTrainBwdArgs
   for (int r = 0; r < 2; r++) {
     lse2[r] = a.lse[bhT + row_g[r]] * LOG2E;
     dl[r] = ba.delta[bhT + row_g[r]];
+  }
+  // saved probabilities: this thread's 16 words of a tile (2 rows x 8 n-tiles) are requested at the top of an iteration and
+  // used after the dP contraction; the next tile's lines are pulled into L2 meanwhile (holding them in registers a whole
+  // tile ahead made ptxas spill them right behind the loads, which serialised everything on the load latency)
+  const int nblk = S >> 6;
+  const uint32_t* psrc[2] = {nullptr, nullptr};
+  const float* msrc[2] = {nullptr, nullptr};
+  if (PS) {
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      psrc[r] = (const uint32_t*)(a.p_save + (bhT + row_g[r]) * S) + t;
+      msrc[r] = a.m_save + (bhT + row_g[r]) * nblk;
+    }
   }
   float dq_ac[8][4], dq_bd[8][4];
 #pragma unroll
@@ -434,20 +489,37 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnTrainBwdArgs
     }
   }
 
+  const long long HS = (long long)a.H * S;
+  bf16* const ds_row_base = ba.ds_dist + ((long long)b * a.T + i0 + 16 * w) * HS + (long long)h * S;
   for (int jt = jt_lo; jt <= jt_hi; jt++) {
     const int j0 = jt * 64;
     const int D0 = a.M + i0 - j0;
     const int rt_hi = D0 / 64, rt_lo = rt_hi > 0 ? rt_hi - 1 : 0;
-    cp_async_wait<ATT_NST - 2>();
+    cp_async_wait<NST - 2>();
     __syncthreads();                                 // tile jt visible to all; tile jt-1 (and the Q/dO staging) released
-    load_stage(jt + ATT_NST - 1);
-    const int st = (jt - jt_lo) % ATT_NST;
+    load_stage(jt + NST - 1);
+    const int st = (jt - jt_lo) % NST;
     uint8_t* sK = sKV + 2 * st * TILE_BYTES;
     uint8_t* sV = sK + TILE_BYTES;
-    const uint32_t sR0 = smem_u32(sR + (rt_lo % ATT_NR) * TILE_BYTES), sR1 = smem_u32(sR + (rt_hi % ATT_NR) * TILE_BYTES);
+    const uint32_t sR0 = smem_u32(sR + (rt_lo % NR) * TILE_BYTES), sR1 = smem_u32(sR + (rt_hi % NR) * TILE_BYTES);
 
     float s[8][4], dpd[8][4], unused[8][4];
-    scores_tile(qu, qv, smem_u32(sK), sR0, sR1, skew, w, lane, L, s);
+    uint32_t pw[8][2];
+    float mblk[2] = {0.f, 0.f};
+    if (PS) {
+#pragma unroll
+      for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) pw[nt][r] = __ldg(psrc[r] + (j0 >> 1) + 4 * nt);
+#pragma unroll
+      for (int r = 0; r < 2; r++) mblk[r] = __ldg(msrc[r] + jt);
+      if (jt < jt_hi && t == 0) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(psrc[r] + ((j0 + 64) >> 1)));
+      }
+    } else {
+      scores_tile(qu, qv, smem_u32(sK), sR0, sR1, skew, w, lane, L, s);
+    }
     // dPd = dO V^T
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) { dpd[nt][0] = 0.f; dpd[nt][1] = 0.f; dpd[nt][2] = 0.f; dpd[nt][3] = 0.f; }
@@ -462,7 +534,14 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnTrainBwdArgs
         mma_bf16(dpd[2 * np + 1], dof[ks], r[2], r[3]);
       }
     }
-    if (ba.p_buf) {                                   // spill P (dropped) and dS for the dK/dV kernel: [b*H+h][T][S] bf16
+    if (PS) {
+      float fac[2];
+#pragma unroll
+      for (int r = 0; r < 2; r++) fac[r] = ex2_fast(mblk[r] * (a.scale * LOG2E) - lse2[r]);
+      const long long o0 = (bhT + row_g[0]) * S + j0, o1 = (bhT + row_g[1]) * S + j0;
+      bwd_tile_math_saved(a, pw, fac, s, dpd, dl, j0, drop_base, t, ba.p_buf ? ba.p_buf + o0 : nullptr, ba.p_buf ? ba.p_buf + o1 : nullptr,
+                          ba.p_buf ? ba.ds_buf + o0 : nullptr, ba.p_buf ? ba.ds_buf + o1 : nullptr);
+    } else if (ba.p_buf) {                            // spill P (dropped) and dS for the dK/dV kernel: [b*H+h][T][S] bf16
       const long long o0 = (bhT + row_g[0]) * S + j0, o1 = (bhT + row_g[1]) * S + j0;
       bwd_tile_math(a, mp, s, dpd, row_g, lse2, dl, j0, drop_base, t, false, unused, ba.p_buf + o0, ba.p_buf + o1, ba.ds_buf + o0,
                     ba.ds_buf + o1);
@@ -517,13 +596,23 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnTrainBwdArgs
     }
     // dS in (row, distance) coordinates: strip column col <-> distance D0 - 64 + 16w + col; valid band [1+r, 64+r]
     {
-      const long long HS = (long long)a.H * S;
-      for (int r = 0; r < 16; r++) {
-        bf16* drow = ba.ds_dist + ((long long)b * a.T + i0 + 16 * w + r) * HS + (long long)h * S + (D0 - 64 + 16 * w);
+      bf16* drow = ds_row_base + (D0 - 64 + 16 * w) + 1 + lane;      // row 16w of this tile, band start of r = 0
+      const bf16* srow = dsk + 1 + lane;
+      if (D0 - 64 + 16 * w + 1 >= 0) {                                 // every distance of the band is >= 0 (all but the diagonal tiles)
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
-          const int col = 1 + r + lane + 32 * half;
-          if (D0 - 64 + 16 * w + col >= 0) drow[col] = dsk[r * DSK_LD + col];
+        for (int r = 0; r < 16; r++) {
+          drow[r] = srow[r * DSK_LD + r];
+          drow[r + 32] = srow[r * DSK_LD + r + 32];
+          drow += HS;
+        }
+      } else {
+        for (int r = 0; r < 16; r++) {
+#pragma unroll
+          for (int half = 0; half < 2; half++) {
+            const int col = 1 + r + lane + 32 * half;
+            if (D0 - 64 + 16 * w + col >= 0) drow[r + 32 * half] = srow[r * DSK_LD + r + 32 * half];
+          }
+          drow += HS;
         }
       }
     }
@@ -860,7 +949,8 @@ int attn_train_bwd(const AttnTrainBwdArgs& ba, int num_sms, cudaStream_t st) {
   if (check_args(a)) return -2;
   static bool configured = false;
   if (!configured) {
-    DMG_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    DMG_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM));
+    DMG_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_PS_SMEM));
     DMG_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
     DMG_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_lite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LITE_SMEM));
     configured = true;
@@ -868,7 +958,11 @@ int attn_train_bwd(const AttnTrainBwdArgs& ba, int num_sms, cudaStream_t st) {
   const int rows = a.B * a.T;
   if (launch_np(attn_delta_kernel, dim3((rows * 32 + 255) / 256), dim3(256), 0, st, (const bf16*)a.out, ba.dout, ba.delta, rows, a.T, a.H))
     return -1;
-  if (launch_np(attn_bwd_dq_kernel, dim3(a.B * a.H * (a.T / 64)), dim3(128), (size_t)DQ_SMEM, st, ba)) return -1;
+  if (a.p_save && a.m_save) {   // the tcgen05 forward saved the probabilities: no score recomputation
+    if (launch_np(attn_bwd_dq_kernel<true>, dim3(a.B * a.H * (a.T / 64)), dim3(128), (size_t)DQ_PS_SMEM, st, ba)) return -1;
+  } else if (launch_np(attn_bwd_dq_kernel<false>, dim3(a.B * a.H * (a.T / 64)), dim3(128), (size_t)DQ_SMEM, st, ba)) {
+    return -1;
+  }
   if (ba.p_buf && ba.ds_buf)   // P and dS were spilled by the dQ kernel: no second recomputation of the scores
     return launch_np(attn_bwd_dkv_lite_kernel, dim3(a.B * a.H * ((a.M + a.T) / 64)), dim3(128), (size_t)LITE_SMEM, st, ba);
   return launch_np(attn_bwd_dkv_kernel, dim3(a.B * a.H * ((a.M + a.T) / 64)), dim3(128), (size_t)DKV_SMEM, st, ba);

@@ -43,7 +43,10 @@ constexpr int OFF_V = OFF_K + 2 * T16K;
 constexpr int OFF_R = OFF_V + T16K;                 // 2 slots (slot = block & 1)
 constexpr int OFF_P = OFF_R + 2 * T16K;             // 2 key halves; half 0 doubles as the raw-Q landing buffer
 constexpr int OFF_STRIP = OFF_P + 2 * T16K;
-constexpr int OFF_BAR = OFF_STRIP + TC_SOFT_WARPS * 32 * STRIP_LD * 4;
+constexpr int STRIP_WARP_BYTES = 9 * 1024;          // 32 lines of 272 B, padded to a 1024-byte multiple: the region doubles as a swizzled
+                                                    // [32 rows][128 B] tile for the TMA store of the saved probabilities
+static_assert(32 * STRIP_LD * 4 <= STRIP_WARP_BYTES, "strip lines must fit");
+constexpr int OFF_BAR = OFF_STRIP + TC_SOFT_WARPS * STRIP_WARP_BYTES;
 constexpr int TC_SMEM = OFF_BAR + 256 + 1024 /*alignment slack*/;
 static_assert(TC_SMEM <= 227 * 1024, "shared memory budget");
 
@@ -62,9 +65,11 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t addr) {         // [k 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// SAVE: also write the undropped probabilities / block maxima for the backward (AttnTrainArgs::p_save, m_save)
+template <bool SAVE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmM,
-                         const __grid_constant__ CUtensorMap tmR, const AttnTrainArgs a) {
+                         const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmP, const AttnTrainArgs a) {
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
   uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
   uint64_t* bar = (uint64_t*)(smem + OFF_BAR);
@@ -83,6 +88,7 @@ attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmM);
     tma_prefetch_desc(&tmR);
+    if (SAVE) tma_prefetch_desc(&tmP);
     for (int i = 0; i < B_COUNT; i++) {
       uint32_t cnt = 1;
       if (i == B_QREADY || i == B_SFREE) cnt = TC_SOFT_WARPS;
@@ -190,7 +196,9 @@ attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     const int r = q4 * 32 + lane;                   // query row of this thread inside the tile
     const int row = i0 + r;                         // ... inside the segment
     const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16);
-    float* strip = (float*)(smem + OFF_STRIP) + (size_t)(warp * 32 + lane) * STRIP_LD;
+    uint8_t* strip_warp = smem + OFF_STRIP + warp * STRIP_WARP_BYTES;
+    float* strip = (float*)strip_warp + (size_t)lane * STRIP_LD;
+    uint8_t* psave_row = strip_warp + (lane >> 3) * 1024 + (lane & 7) * 128;   // this lane's row of the warp's [32][128 B] swizzled tile
     const int vis_lim = a.k == 1 ? row + 1 : max((row / a.win) * a.win, 1);
     const float c = a.scale * LOG2E;
 
@@ -241,6 +249,10 @@ attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i++) { s[i] = __uint_as_float(x0[i]); s[32 + i] = __uint_as_float(x1[i]); }
+      }
+      if (SAVE) {                                    // last tile's saved-P tile has left the strip region
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
       }
       // position term: keys 32*sp .. 32*sp+31 of this half need strip columns base + (32 + lane - jj), base warp-uniform
 #pragma unroll
@@ -303,26 +315,41 @@ attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
       // P (unscaled dropout: the 1/(1-p) factor is applied to the output) -> canonical K-major swizzled bf16 tile
 #pragma unroll
       for (int ck = 0; ck < 8; ck++) {
-        uint32_t pk[4];
+        uint32_t pk[4], pu[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const int pp = 4 * ck + e;
           float p0 = ex2_fast(fmaf(s[2 * pp], c, neg_mc)), p1 = ex2_fast(fmaf(s[2 * pp + 1], c, neg_mc));
           rs += p0 + p1;
+          if (SAVE) pu[e] = pack_bf16x2(p0, p1);
           if (a.drop_thresh) {
             const uint32_t hb = drop_pair_bits(a.drop_seed, drop_base + (uint32_t)(j0 >> 1) + pp);
             p0 = ((hb & 0xFFFFu) >= a.drop_thresh) ? p0 : 0.f;
             p1 = ((hb >> 16) >= a.drop_thresh) ? p1 : 0.f;
           }
-          pk[e] = pack_bf16x2(p0, p1);
+          pk[e] = (a.drop_thresh || !SAVE) ? pack_bf16x2(p0, p1) : pu[e];
         }
         *(uint4*)(prow + ((ck ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (SAVE) *(uint4*)(psave_row + ((ck ^ (lane & 7)) << 4)) = make_uint4(pu[0], pu[1], pu[2], pu[3]);   // the strip lines are free after the skew
       }
       l_run = l_run * alpha + rs;
       alpha_prev = alpha;
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[B_PFULL0 + hf]);
+      if (SAVE) {   // the warp's 32 rows x 64 undropped probabilities leave through one TMA store
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmP), "r"(smem_u32(strip_warp)),
+                       "r"(j0), "r"(bh * a.T + i0 + q4 * 32)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        a.m_save[((long long)bh * a.T + row) * (S >> 6) + (j0 >> 6)] = m_new;
+      }
+    }
+    if (SAVE) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
     }
     // last tile's P V
     mbar_wait(&bar[B_OFULL0 + hf], (NT - 1) & 1);
@@ -346,7 +373,7 @@ attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     }
     softmax_bar_sync();
     if (hf == 0) {
-      const float* other = strip + (size_t)4 * 32 * STRIP_LD;       // same lane of warp + 4
+      const float* other = (const float*)(strip_warp + 4 * STRIP_WARP_BYTES) + (size_t)lane * STRIP_LD;   // same lane of warp + 4
       const float m1 = other[64], l1 = other[65];
       const float m = fmaxf(m_run, m1);
       const float w0 = (m_run == -INFINITY) ? 0.f : ex2_fast((m_run - m) * c);
@@ -382,17 +409,26 @@ bool attn_train_fwd_tc_supported(const AttnTrainArgs& a) {
 int attn_train_fwd_tc(const AttnTrainArgs& a, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    DMG_CUDA_OK(cudaFuncSetAttribute(attn_train_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    DMG_CUDA_OK(cudaFuncSetAttribute(attn_train_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    DMG_CUDA_OK(cudaFuncSetAttribute(attn_train_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     configured = true;
   }
+  DMG_CHECK((a.p_save == nullptr) == (a.m_save == nullptr), "training attention: p_save and m_save go together");
   const int HD = a.H * 64;
   const TensorMap2D *tx = nullptr, *tm = nullptr, *tr = nullptr;
   if (train_get_tmap(a.qkv_x, 3 * HD, (long long)a.B * a.T, a.ldx, 128, &tx)) return -1;
   if (a.M > 0) { if (train_get_tmap(a.kv_m, 2 * HD, (long long)a.B * a.M, a.ldm, 128, &tm)) return -1; }
   else tm = tx;
   if (train_get_tmap(a.rk, HD, (long long)a.M + a.T, HD, 128, &tr)) return -1;
-  return launch_np(attn_train_fwd_tc_kernel, dim3(a.B * a.H * (a.T / 128)), dim3(TC_THREADS), (size_t)TC_SMEM, st,
-                   *(const CUtensorMap*)tx->bytes, *(const CUtensorMap*)tm->bytes, *(const CUtensorMap*)tr->bytes, a);
+  const dim3 grid(a.B * a.H * (a.T / 128)), block(TC_THREADS);
+  if (a.p_save) {
+    const TensorMap2D* tp = nullptr;   // p_save as [B*H*T rows, S columns], 64 x 32 boxes
+    if (train_get_tmap(a.p_save, (long long)a.M + a.T, (long long)a.B * a.H * a.T, (long long)a.M + a.T, 32, &tp)) return -1;
+    return launch_np(attn_train_fwd_tc_kernel<true>, grid, block, (size_t)TC_SMEM, st, *(const CUtensorMap*)tx->bytes,
+                     *(const CUtensorMap*)tm->bytes, *(const CUtensorMap*)tr->bytes, *(const CUtensorMap*)tp->bytes, a);
+  }
+  return launch_np(attn_train_fwd_tc_kernel<false>, grid, block, (size_t)TC_SMEM, st, *(const CUtensorMap*)tx->bytes,
+                   *(const CUtensorMap*)tm->bytes, *(const CUtensorMap*)tr->bytes, *(const CUtensorMap*)tx->bytes, a);
 }
 
 }  // namespace dmg

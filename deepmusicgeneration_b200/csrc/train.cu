@@ -29,6 +29,8 @@ struct LayerAct {
   bf16 *xa_in = nullptr, *qkv_x = nullptr, *kv_m = nullptr, *attn = nullptr, *z1 = nullptr, *xa1 = nullptr, *hpre = nullptr,
        *hact = nullptr, *z2 = nullptr, *rk = nullptr;
   float* lse = nullptr;
+  bf16* p_save = nullptr;    // [B*H, T, S] undropped attention probabilities saved by the tcgen05 forward (AttnTrainArgs::p_save)
+  float* m_save = nullptr;   // [B*H, T, S/64] their reference maxima
   float2 *st1 = nullptr, *st2 = nullptr;
 };
 
@@ -231,6 +233,7 @@ AttnTrainArgs attn_args(dmg_model* m, dmg_train* t, int l) {
   a.scale = 1.f / sqrtf((float)c.d_head);
   const Drop dr = make_drop(t, t->cfg.attn_p, SITE_ATTN, l);
   a.drop_thresh = dr.thresh; a.drop_seed = dr.seed; a.drop_scale = dr.scale;
+  if (A.p_save && attn_train_fwd_tc_supported(a)) { a.p_save = A.p_save; a.m_save = A.m_save; }   // same predicate as the forward dispatch
   return a;
 }
 
@@ -461,6 +464,10 @@ int dmg_train_create(dmg_model* m, const dmg_train_config* cfg, float* grad_flat
     TRY(talloc(t, &A.z2, (size_t)rows * d));
     TRY(talloc(t, &A.rk, (size_t)S * HD));
     TRY(talloc(t, &A.lse, (size_t)t->B * c.n_heads * t->T));
+    if (t->T % 128 == 0 && c.mem_len % 128 == 0 && !getenv("DMG_ATTN_NO_PSAVE")) {   // geometry the tcgen05 forward serves
+      TRY(talloc(t, &A.p_save, (size_t)t->B * c.n_heads * t->T * S));
+      TRY(talloc(t, &A.m_save, (size_t)t->B * c.n_heads * t->T * (S / 64)));
+    }
     TRY(talloc(t, &A.st1, (size_t)rows));
     TRY(talloc(t, &A.st2, (size_t)rows));
   }
@@ -682,32 +689,40 @@ static AttnTrainArgs make_attn_args(const void* qkv_x, int64_t ldx, const void* 
 
 int dmg_attn_train_fwd(const void* qkv_x, int64_t ldx, const void* kv_m, int64_t ldm, const void* rk, const float* u, const float* v,
                        void* out, float* lse, int B, int T, int H, int M, int mem_count, int win, int k, float drop_p,
-                       uint32_t drop_seed_v, void* stream) {
+                       uint32_t drop_seed_v, void* p_save, float* m_save, void* stream) {
   DMG_CHECK(qkv_x && rk && u && v && out && lse, "dmg_attn_train_fwd: null argument");
-  const AttnTrainArgs a = make_attn_args(qkv_x, ldx, kv_m, ldm, rk, u, v, out, lse, B, T, H, M, mem_count, win, k, drop_p, drop_seed_v);
+  AttnTrainArgs a = make_attn_args(qkv_x, ldx, kv_m, ldm, rk, u, v, out, lse, B, T, H, M, mem_count, win, k, drop_p, drop_seed_v);
+  if (p_save && m_save) {
+    DMG_CHECK(attn_train_fwd_tc_supported(a), "dmg_attn_train_fwd: p_save needs the tcgen05 forward (T, M, mem_count multiples of 128)");
+    a.p_save = (bf16*)p_save; a.m_save = m_save;
+  }
   return attn_train_fwd(a, (cudaStream_t)stream);
 }
 
 int dmg_attn_train_bwd(const void* qkv_x, int64_t ldx, const void* kv_m, int64_t ldm, const void* rk, const float* u, const float* v,
                        const void* out, const float* lse, const void* dout, int B, int T, int H, int M, int mem_count, int win, int k,
                        float drop_p, uint32_t drop_seed_v, float* delta, void* dqkv_x, void* dkv_m, void* ds_dist, float* du,
-                       float* dv, void* stream) {
+                       float* dv, const void* p_save, const float* m_save, void* stream) {
   DMG_CHECK(qkv_x && rk && u && v && out && lse && dout && delta && dqkv_x && ds_dist && du && dv, "dmg_attn_train_bwd: null argument");
   AttnTrainBwdArgs ba;
   ba.f = make_attn_args(qkv_x, ldx, kv_m, ldm, rk, u, v, const_cast<void*>(out), const_cast<float*>(lse), B, T, H, M, mem_count, win,
                         k, drop_p, drop_seed_v);
   ba.dout = (const bf16*)dout; ba.delta = delta; ba.dqkv_x = (bf16*)dqkv_x; ba.dkv_m = (bf16*)dkv_m; ba.ds_dist = (bf16*)ds_dist;
   ba.qv = nullptr; ba.du = du; ba.dv = dv;
+  if (p_save && m_save) { ba.f.p_save = (bf16*)const_cast<void*>(p_save); ba.f.m_save = const_cast<float*>(m_save); }
   static const bool recompute = getenv("DMG_ATTN_BWD_RECOMPUTE") != nullptr;
-  bf16* ws = nullptr;
+  static bf16* ws = nullptr;          // spill workspace of this test hook: kept between calls, regrown on demand
+  static size_t ws_elems = 0;
   const size_t n = (size_t)B * H * T * (M + T);
   if (!recompute) {
-    DMG_CUDA_OK(cudaMalloc(&ws, 2 * n * sizeof(bf16)));
+    if (ws_elems < 2 * n) {
+      if (ws) { DMG_CUDA_OK(cudaDeviceSynchronize()); cudaFree(ws); ws = nullptr; ws_elems = 0; }
+      DMG_CUDA_OK(cudaMalloc(&ws, 2 * n * sizeof(bf16)));
+      ws_elems = 2 * n;
+    }
     ba.p_buf = ws; ba.ds_buf = ws + n;
   }
-  const int rc = attn_train_bwd(ba, 148, (cudaStream_t)stream);
-  if (ws) { cudaStreamSynchronize((cudaStream_t)stream); cudaFree(ws); }
-  return rc;
+  return attn_train_bwd(ba, 148, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -98,6 +98,12 @@ struct AttnTrainArgs {
   int win, k;            // window_mask (win_size, k)
   float scale;
   uint32_t drop_thresh, drop_seed; float drop_scale;   // attention dropout (on the probabilities)
+  // Optional (tcgen05 forward only; both or neither): the forward saves the UNdropped probabilities of every visited tile,
+  // p_save[b*H+h][i][j] = exp((score - m)*scale) in bf16 relative to the running row maximum m of its 64-key column block
+  // at that time, m_save[b*H+h][i][j/64] = that maximum (raw score units).  The backward then rebuilds
+  // P = p_save * exp(m_save*scale - lse) instead of recomputing AC, BD, the skew and the exponentials.
+  bf16* p_save = nullptr;   // [B*H, T, M+T]
+  float* m_save = nullptr;  // [B*H, T, (M+T)/64]
 };
 int attn_train_fwd(const AttnTrainArgs& a, cudaStream_t st);
 // tcgen05 / TMEM / TMA forward (attention_train_tc.cu): T, M, mem_count multiples of 128; attn_train_fwd dispatches to it

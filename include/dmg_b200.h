@@ -205,14 +205,17 @@ float* dmg_train_grad_buffer(dmg_model* m);
 int dmg_gemm_train(const void* a_dev, int a_mn, int64_t lda, const void* b_dev, int b_mn, int64_t ldb, int M, int N, int K,
                    int splitk, const float* bias_dev, int gelu, const void* aux_dev, int64_t ld_aux, int aux_mode, void* out_dev,
                    int64_t ldc, int out_mode, void* out2_dev, int64_t ld2, float drop_p, uint32_t drop_seed, void* stream);
-/* Unit-test entries of the training attention kernels (attention_train.cu): see AttnTrainArgs for the layouts. */
+/* Unit-test entries of the training attention kernels (attention_train.cu, attention_train_tc.cu): see AttnTrainArgs for
+ * the layouts.  p_save [B*H, T, M+T] bf16 and m_save [B*H, T, (M+T)/64] fp32 are optional (both or neither, tcgen05
+ * forward only = T, M, mem_count multiples of 128): the forward saves the undropped probabilities there and the backward,
+ * given the same pair, rebuilds P from them instead of recomputing the scores. */
 int dmg_attn_train_fwd(const void* qkv_x, int64_t ldx, const void* kv_m, int64_t ldm, const void* rk, const float* u,
                        const float* v, void* out, float* lse, int B, int T, int H, int M, int mem_count, int win, int k,
-                       float drop_p, uint32_t drop_seed, void* stream);
+                       float drop_p, uint32_t drop_seed, void* p_save, float* m_save, void* stream);
 int dmg_attn_train_bwd(const void* qkv_x, int64_t ldx, const void* kv_m, int64_t ldm, const void* rk, const float* u,
                        const float* v, const void* out, const float* lse, const void* dout, int B, int T, int H, int M,
                        int mem_count, int win, int k, float drop_p, uint32_t drop_seed, float* delta, void* dqkv_x, void* dkv_m,
-                       void* ds_dist, float* du, float* dv, void* stream);
+                       void* ds_dist, float* du, float* dv, const void* p_save, const float* m_save, void* stream);
 
 #ifdef __cplusplus
 }

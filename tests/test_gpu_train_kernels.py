@@ -225,15 +225,22 @@ def attn_mask_from_device(B, H, T, S, M, mem_count, p, seed):
     (2, 256, 1, 128, 128, 3, 0, 0.0),      # window mask (3, 0)
     (1, 512, 2, 512, 512, 1, 1, 0.1),      # C3 geometry
 ])
-def test_attention_train_forward_backward(B, T, H, M, mem_count, win, kk, p):
+@pytest.mark.parametrize('save_p', [False, True])
+def test_attention_train_forward_backward(B, T, H, M, mem_count, win, kk, p, save_p):
+    if save_p and not (T % 128 == 0 and M % 128 == 0 and mem_count % 128 == 0):
+        pytest.skip('p_save needs the tcgen05 forward')
     lib = _lib.load()
     HD, S = H * 64, M + T
     seed = 99
     qkv_x, kv_m, rk, u, v = make_attn_inputs(B, T, H, M, seed=B * 1000 + T + M)
     out = torch.zeros(B * T, HD, device='cuda', dtype=torch.bfloat16)
     lse = torch.zeros(B, H, T, device='cuda')
+    # shapes the tcgen05 forward serves also save the undropped probabilities for the backward (p_save / m_save)
+    saved = T % 128 == 0 and M % 128 == 0 and mem_count % 128 == 0 and save_p
+    p_save = torch.full((B * H, T, S), float('nan'), device='cuda', dtype=torch.bfloat16) if saved else None
+    m_save = torch.full((B * H, T, S // 64), float('nan'), device='cuda') if saved else None
     check(lib.dmg_attn_train_fwd(_p(qkv_x), 3 * HD, _p(kv_m), 2 * HD, _p(rk), _p(u), _p(v), _p(out), _p(lse), B, T, H, M, mem_count,
-                                 win, kk, p, seed, _st()), 'fwd')
+                                 win, kk, p, seed, _p(p_save), _p(m_save), _st()), 'fwd')
     torch.cuda.synchronize()
     drop = attn_mask_from_device(B, H, T, S, M, mem_count, p, seed) if p > 0 else None
     q, k, vv, r = split_ref_inputs(qkv_x, kv_m, rk, B, T, H, M, mem_count)
@@ -251,7 +258,8 @@ def test_attention_train_forward_backward(B, T, H, M, mem_count, win, kk, p):
     ds_dist = torch.full((B * T, H * S), 3.0, device='cuda', dtype=torch.bfloat16)
     du = torch.zeros(HD, device='cuda'); dv = torch.zeros(HD, device='cuda')
     check(lib.dmg_attn_train_bwd(_p(qkv_x), 3 * HD, _p(kv_m), 2 * HD, _p(rk), _p(u), _p(v), _p(out), _p(lse), _p(dout), B, T, H, M,
-                                 mem_count, win, kk, p, seed, _p(delta), _p(dqkv_x), _p(dkv_m), _p(ds_dist), _p(du), _p(dv), _st()),
+                                 mem_count, win, kk, p, seed, _p(delta), _p(dqkv_x), _p(dkv_m), _p(ds_dist), _p(du), _p(dv), _p(p_save),
+                                 _p(m_save), _st()),
           'bwd')
     torch.cuda.synchronize()
     d = dqkv_x.float().view(B, T, 3, H, 64)
