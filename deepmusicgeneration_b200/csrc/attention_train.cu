@@ -393,11 +393,12 @@ constexpr int DQ_SMEM = 2 * ATT_NST * TILE_BYTES /*K,V ring (Q and dO are staged
 
 // PS = true: the probabilities come from the forward's p_save / m_save (no AC / BD / skew / exp recomputation, no (q+u),
 // (q+v) fragments, no skew strip): 2 ring stages, <= 168 registers -> three CTAs per SM instead of two.
-constexpr int DQ_PS_NST = 2;
+constexpr int DQ_PS_NST = 3;
+constexpr int DQ_PS_MINB = 2;
 constexpr int DQ_PS_SMEM = 2 * DQ_PS_NST * TILE_BYTES + (DQ_PS_NST + 1) * TILE_BYTES + 4 * 16 * DSK_LD * 2;
 
 template <bool PS>
-__global__ void __launch_bounds__(128, PS ? 3 : 1) attn_bwd_dq_kernel(const AttnTrainBwdArgs ba) {
+__global__ void __launch_bounds__(128, PS ? DQ_PS_MINB : 1) attn_bwd_dq_kernel(const AttnTrainBwdArgs ba) {
   constexpr int NST = PS ? DQ_PS_NST : ATT_NST, NR = NST + 1;
   const AttnTrainArgs& a = ba.f;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -459,18 +460,26 @@ __global__ void __launch_bounds__(128, PS ? 3 : 1) attn_bwd_dq_kernel(const Attn
     lse2[r] = a.lse[bhT + row_g[r]] * LOG2E;
     dl[r] = ba.delta[bhT + row_g[r]];
   }
-  // saved probabilities: this thread's 16 words of a tile (2 rows x 8 n-tiles) are requested at the top of an iteration and
-  // used after the dP contraction; the next tile's lines are pulled into L2 meanwhile (holding them in registers a whole
-  // tile ahead made ptxas spill them right behind the loads, which serialised everything on the load latency)
+  // saved probabilities: this thread's 16 words of a tile (2 rows x 8 n-tiles).  They are consumed by the tile math in the
+  // first half of an iteration, and the next tile's words are requested right behind it, so the loads fly during the second
+  // half (strip, dQ contractions, dS_dist copy) without a second set of registers.
   const int nblk = S >> 6;
   const uint32_t* psrc[2] = {nullptr, nullptr};
   const float* msrc[2] = {nullptr, nullptr};
+  uint32_t pw[8][2];
+  float mblk[2] = {0.f, 0.f};
   if (PS) {
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       psrc[r] = (const uint32_t*)(a.p_save + (bhT + row_g[r]) * S) + t;
       msrc[r] = a.m_save + (bhT + row_g[r]) * nblk;
     }
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+      for (int r = 0; r < 2; r++) pw[nt][r] = __ldg(psrc[r] + ((jt_lo * 64) >> 1) + 4 * nt);
+#pragma unroll
+    for (int r = 0; r < 2; r++) mblk[r] = __ldg(msrc[r] + jt_lo);
   }
   float dq_ac[8][4], dq_bd[8][4];
 #pragma unroll
@@ -504,22 +513,7 @@ __global__ void __launch_bounds__(128, PS ? 3 : 1) attn_bwd_dq_kernel(const Attn
     const uint32_t sR0 = smem_u32(sR + (rt_lo % NR) * TILE_BYTES), sR1 = smem_u32(sR + (rt_hi % NR) * TILE_BYTES);
 
     float s[8][4], dpd[8][4], unused[8][4];
-    uint32_t pw[8][2];
-    float mblk[2] = {0.f, 0.f};
-    if (PS) {
-#pragma unroll
-      for (int nt = 0; nt < 8; nt++)
-#pragma unroll
-        for (int r = 0; r < 2; r++) pw[nt][r] = __ldg(psrc[r] + (j0 >> 1) + 4 * nt);
-#pragma unroll
-      for (int r = 0; r < 2; r++) mblk[r] = __ldg(msrc[r] + jt);
-      if (jt < jt_hi && t == 0) {
-#pragma unroll
-        for (int r = 0; r < 2; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(psrc[r] + ((j0 + 64) >> 1)));
-      }
-    } else {
-      scores_tile(qu, qv, smem_u32(sK), sR0, sR1, skew, w, lane, L, s);
-    }
+    if (!PS) scores_tile(qu, qv, smem_u32(sK), sR0, sR1, skew, w, lane, L, s);
     // dPd = dO V^T
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) { dpd[nt][0] = 0.f; dpd[nt][1] = 0.f; dpd[nt][2] = 0.f; dpd[nt][3] = 0.f; }
@@ -541,6 +535,14 @@ __global__ void __launch_bounds__(128, PS ? 3 : 1) attn_bwd_dq_kernel(const Attn
       const long long o0 = (bhT + row_g[0]) * S + j0, o1 = (bhT + row_g[1]) * S + j0;
       bwd_tile_math_saved(a, pw, fac, s, dpd, dl, j0, drop_base, t, ba.p_buf ? ba.p_buf + o0 : nullptr, ba.p_buf ? ba.p_buf + o1 : nullptr,
                           ba.p_buf ? ba.ds_buf + o0 : nullptr, ba.p_buf ? ba.ds_buf + o1 : nullptr);
+      if (jt < jt_hi) {                              // next tile's words and maxima
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+          for (int r = 0; r < 2; r++) pw[nt][r] = __ldg(psrc[r] + ((j0 + 64) >> 1) + 4 * nt);
+#pragma unroll
+        for (int r = 0; r < 2; r++) mblk[r] = __ldg(msrc[r] + jt + 1);
+      }
     } else if (ba.p_buf) {                            // spill P (dropped) and dS for the dK/dV kernel: [b*H+h][T][S] bf16
       const long long o0 = (bhT + row_g[0]) * S + j0, o1 = (bhT + row_g[1]) * S + j0;
       bwd_tile_math(a, mp, s, dpd, row_g, lse2, dl, j0, drop_base, t, false, unused, ba.p_buf + o0, ba.p_buf + o1, ba.ds_buf + o0,
