@@ -263,6 +263,11 @@ attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
           tmem_ld_32x32(t_lane + TM_STRIP + base, x0);
           tmem_ld_32x32(t_lane + TM_STRIP + base + 32, x1);
           tmem_ld_wait();
+          if (sp == 1) {                             // last TMEM read of this tile: the score MMAs of the next tile may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar[B_SFREE]);
+          }
 #pragma unroll
           for (int k = 0; k < 8; k++) {
             *(float4*)(strip + 4 * k) = make_float4(__uint_as_float(x0[4 * k]), __uint_as_float(x0[4 * k + 1]),
@@ -275,9 +280,7 @@ attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
 #pragma unroll
         for (int jj = 0; jj < 32; jj++) s[32 * sp + jj] += sk[-jj];
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar[B_SFREE]);     // the score MMAs of the next tile may overwrite TMEM
+      __syncwarp();                                  // every lane is done with its strip line (the SAVE tile reuses the region)
 
       if (n > 0) {                                   // fold the previous tile's P V into the running output
         mbar_wait(&bar[B_OFULL0 + hf], (n - 1) & 1);
