@@ -345,6 +345,11 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// split-phase exit barrier without memory ordering: it only has to keep a CTA's shared memory alive until every peer has
+// finished READING it (the release form costs an ERRBAR that waits for this CTA's global stores: 29 % of the stall samples
+// of a decode GEMM, profiles/README.md round 1d)
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_only() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
@@ -462,37 +467,48 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int rr = te / TPR, cg = (te % TPR) * CPT;
     const int row_l = krank * ROWS + rr;
     const int row = m0 + row_l;
+    float v[CPT];
 #pragma unroll
-    for (int c4 = 0; c4 < CPT; c4 += 4) {
+    for (int c4 = 0; c4 < CPT; c4 += 4) {            // all remote reads first ...
       const uint32_t laddr = smem_u32(red + row_l * RED_LD + cg + c4);
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      v[c4] = 0.f; v[c4 + 1] = 0.f; v[c4 + 2] = 0.f; v[c4 + 3] = 0.f;
 #pragma unroll
       for (int r2 = 0; r2 < KSPLIT; r2++) {
         const float4 x = ld_dsmem_f4(mapa_shared(laddr, (uint32_t)r2));
-        v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w;
+        v[c4] += x.x; v[c4 + 1] += x.y; v[c4 + 2] += x.z; v[c4 + 3] += x.w;
       }
+    }
+    // the sums must be complete (= every remote load has returned) before the arrival is issued: pin them in front of it
+#pragma unroll
+    for (int c = 0; c < CPT; c++) asm volatile("" ::"f"(v[c]) : "memory");
+    __syncwarp();
+    cluster_arrive_relaxed();                        // ... then this warp is done with the peers' shared memory
+#pragma unroll
+    for (int c4 = 0; c4 < CPT; c4 += 4) {
       const int col0 = n0 + cg + c4;
       if (row < M && col0 < N) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          if (bias && col0 + j < N) v[j] += bias[col0 + j];
-          if (gelu) v[j] = gelu_tanh(v[j]);
+          if (bias && col0 + j < N) v[c4 + j] += bias[col0 + j];
+          if (gelu) v[c4 + j] = gelu_tanh(v[c4 + j]);
         }
         if (col0 + 4 <= N) {
-          if (out_bf16) *(uint2*)((bf16*)C + (size_t)row * ldc + col0) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
-          else *(float4*)((float*)C + (size_t)row * ldc + col0) = make_float4(v[0], v[1], v[2], v[3]);
+          if (out_bf16) *(uint2*)((bf16*)C + (size_t)row * ldc + col0) = make_uint2(pack_bf16x2(v[c4], v[c4 + 1]), pack_bf16x2(v[c4 + 2], v[c4 + 3]));
+          else *(float4*)((float*)C + (size_t)row * ldc + col0) = make_float4(v[c4], v[c4 + 1], v[c4 + 2], v[c4 + 3]);
         } else {
           for (int j = 0; j < 4; j++)
             if (col0 + j < N) {
-              if (out_bf16) ((bf16*)C)[(size_t)row * ldc + col0 + j] = __float2bfloat16_rn(v[j]);
-              else ((float*)C)[(size_t)row * ldc + col0 + j] = v[j];
+              if (out_bf16) ((bf16*)C)[(size_t)row * ldc + col0 + j] = __float2bfloat16_rn(v[c4 + j]);
+              else ((float*)C)[(size_t)row * ldc + col0 + j] = v[c4 + j];
             }
         }
       }
     }
+  } else {
+    __syncwarp();
+    cluster_arrive_relaxed();
   }
-  __syncwarp();
-  cluster_sync_all();          // nobody may exit while a peer still reads its shared memory
+  cluster_wait_only();         // nobody may exit while a peer still reads its shared memory
   if (warp == 2) tmem_dealloc<BN>(tmem_base);
 }
 
