@@ -168,6 +168,7 @@ def ref_attention(q, k, v, rk, u, vb, win, kk, mem_count, drop_mask=None):
     score = score.masked_fill(mask, -float('inf'))
     p = torch.softmax(score, dim=-1)
     lse = torch.logsumexp(score, dim=-1)
+    ref_attention.last_probs = p.detach()                  # undropped probabilities [B, H, T, Sc] (saved-P format test)
     if drop_mask is not None:
         p = p * drop_mask
     o = torch.matmul(p, wv)
@@ -248,6 +249,13 @@ def test_attention_train_forward_backward(B, T, H, M, mem_count, win, kk, p, sav
     ref, ref_lse = ref_attention(*leaves, win, kk, mem_count, drop)
     assert rel_err(lse, ref_lse) < 2e-3
     assert rel_err(out.view(B, T, HD), ref) < 1e-2
+    if saved:
+        # the saved format: P = p_save * exp(m_save * scale - lse) wherever the forward visited a tile (bf16 rounding only);
+        # tiles above the diagonal are never written (still NaN) and hold no probability mass
+        fac = torch.exp(m_save.view(B, H, T, S // 64) * 0.125 - lse.view(B, H, T, 1))
+        rebuilt = p_save.float().view(B, H, T, S // 64, 64) * fac.unsqueeze(-1)
+        rebuilt = torch.nan_to_num(rebuilt, nan=0.0).view(B, H, T, S)[..., M - mem_count:]
+        assert rel_err(rebuilt, ref_attention.last_probs) < 1e-2
 
     dout = (torch.randn(B * T, HD, device='cuda') * 0.5).bfloat16()
     ref.backward(dout.float().view(B, T, HD))
