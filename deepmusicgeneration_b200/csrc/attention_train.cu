@@ -965,6 +965,7 @@ int attn_train_bwd(const AttnTrainBwdArgs& ba, int num_sms, cudaStream_t st) {
   } else if (launch_np(attn_bwd_dq_kernel<false>, dim3(a.B * a.H * (a.T / 64)), dim3(128), (size_t)DQ_SMEM, st, ba)) {
     return -1;
   }
+  if (attn_bwd_dkv_tc_supported(ba)) return attn_bwd_dkv_tc(ba, st);   // spilled tiles + (q+u): tcgen05 contraction
   if (ba.p_buf && ba.ds_buf)   // P and dS were spilled by the dQ kernel: no second recomputation of the scores
     return launch_np(attn_bwd_dkv_lite_kernel, dim3(a.B * a.H * ((a.M + a.T) / 64)), dim3(128), (size_t)LITE_SMEM, st, ba);
   return launch_np(attn_bwd_dkv_kernel, dim3(a.B * a.H * ((a.M + a.T) / 64)), dim3(128), (size_t)DKV_SMEM, st, ba);

@@ -69,7 +69,8 @@ __device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 2
 template <bool SAVE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmM,
-                         const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmP, const AttnTrainArgs a) {
+                         const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmP,
+                         const __grid_constant__ CUtensorMap tmQU, const __grid_constant__ CUtensorMap tmQV, const AttnTrainArgs a) {
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
   uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
   uint64_t* bar = (uint64_t*)(smem + OFF_BAR);
@@ -166,6 +167,15 @@ attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         umma_commit(&bar[B_VEMPTY]);
       };
       mbar_wait(&bar[B_QREADY], 0);
+      if (SAVE && a.qu_save) {                       // the biased query tiles are the backward's operands as well: store them as they lie
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmQU), "r"(qu), "r"(h * 64),
+                     "r"(b * a.T + i0)
+                     : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmQV), "r"(qv), "r"(h * 64),
+                     "r"(b * a.T + i0)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
       for (int n = 0; n < NT; n++) {
         const int s = n & 1, blkU = blk0 - n, blkL = blkU - 1;
         mbar_wait(&bar[B_KFULL0 + s], (n >> 1) & 1);
@@ -187,6 +197,7 @@ attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         if (n > 0) issue_pv(n - 1);
       }
       issue_pv(NT - 1);
+      if (SAVE && a.qu_save) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     }
   } else {
@@ -402,6 +413,175 @@ attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
   if (warp == TC_SOFT_WARPS + 1) tmem_dealloc<512>(tmem_base);
 }
 
+// =============================================================================================
+// dK / dV on tcgen05 from the tiles the dQ kernel spilled (no softmax work left: a pure contraction, HBM-bound):
+//   dV[keys, :] = sum_i Pd[i, keys]^T dO[i, :]        dK[keys, :] = sum_i dS[i, keys]^T (q_i + u)
+// One CTA = (stream, head, 128-key tile); the reduction runs over the query rows that see the tile, 64 per pipeline stage.
+// Pd / dS lie row-major [query][key], i.e. with the reduction index as the slow one: they are MN-major A operands (64 x 64
+// TMA boxes, LBO 8192 / SBO 1024, as in gemm_train.cu), dO and (q+u) are MN-major B operands.  Accumulators: TMEM columns
+// [0,64) dV, [64,128) dK.  Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue.
+// The dQ kernel works on 64 x 64 tiles and never touches tiles above the diagonal, so for a key tile inside the current
+// segment the upper key half of the FIRST stage was never written: it is not loaded, its shared-memory boxes are zero-filled.
+// =============================================================================================
+constexpr int DKV_STAGES = 2;                                      // 2 x 48 KB -> two CTAs per SM: one CTA's prologue / epilogue hides under the other's stream
+constexpr int DKV_BOX = 64 * 64 * 2;                                  // one 64 x 64 bf16 box
+constexpr int DKV_STAGE_BYTES = 6 * DKV_BOX;                          // Pd (2 key halves), dS (2), dO, q+u
+constexpr int DKV_SMEM = DKV_STAGES * DKV_STAGE_BYTES + 1024 + 256;
+enum { DB_FULL0 = 0, DB_EMPTY0 = DKV_STAGES, DB_ACC = 2 * DKV_STAGES, DB_ZERO, DB_COUNT };
+
+__device__ __forceinline__ uint64_t desc_mn64(uint32_t addr) { return desc_mnmajor(addr); }   // LBO 8192 (next 64-wide block), SBO 1024
+
+__global__ void __launch_bounds__(192)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmPd, const __grid_constant__ CUtensorMap tmdS,
+                       const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmQu, const AttnTrainBwdArgs ba) {
+  const AttnTrainArgs& a = ba.f;
+  extern __shared__ __align__(1024) uint8_t dk_smem_raw[];
+  uint8_t* smem = dk_smem_raw + ((1024u - (smem_u32(dk_smem_raw) & 1023u)) & 1023u);
+  uint64_t* bar = (uint64_t*)(smem + DKV_STAGES * DKV_STAGE_BYTES);
+  uint32_t* tmem_holder = (uint32_t*)(bar + DB_COUNT);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nS = (a.M + a.T) / 128;
+  const int jt = (int)(blockIdx.x % nS);            // memory tiles (most query rows) first
+  const int bh = blockIdx.x / nS, b = bh / a.H, h = bh % a.H;
+  const int j0 = jt * 128, HD = a.H * 64;
+  const bool in_x = j0 >= a.M;
+  bf16 *dk_dst, *dv_dst;
+  long long ldd;
+  if (!in_x) {
+    ldd = a.ldm;
+    dk_dst = ba.dkv_m + ((long long)b * a.M + j0) * a.ldm + h * 64;
+    dv_dst = dk_dst + HD;
+  } else {
+    ldd = a.ldx;
+    dk_dst = ba.dqkv_x + ((long long)b * a.T + (j0 - a.M)) * a.ldx + HD + h * 64;
+    dv_dst = dk_dst + HD;
+  }
+  if (j0 < a.M - a.mem_count) {                     // memory rows that hold nothing yet: zero gradient
+    for (int i = threadIdx.x; i < 128 * 8; i += 192) {
+      const int r = i >> 3, c8 = (i & 7) * 8;
+      *(uint4*)(dk_dst + (long long)r * ldd + c8) = make_uint4(0u, 0u, 0u, 0u);
+      *(uint4*)(dv_dst + (long long)r * ldd + c8) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    return;
+  }
+  const int it_lo = in_x ? (j0 - a.M) / 64 : 0;    // first 64-row query chunk that sees the tile's first key half
+  const int NI = a.T / 64 - it_lo;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmPd); tma_prefetch_desc(&tmdS); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmQu);
+    for (int i = 0; i < DB_COUNT; i++) mbar_init(&bar[i], i == DB_ZERO ? 4u : 1u);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<128>(tmem_holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int n = 0; n < NI; n++) {
+        const int s = n % DKV_STAGES, i0 = (it_lo + n) * 64;
+        mbar_wait(&bar[DB_EMPTY0 + s], ((n / DKV_STAGES) & 1) ^ 1);
+        const bool half_only = in_x && n == 0;       // the upper key half of the diagonal chunk was never written
+        uint8_t* st = smem + s * DKV_STAGE_BYTES;
+        mbar_expect_tx(&bar[DB_FULL0 + s], (half_only ? 4 : 6) * DKV_BOX);
+        tma_load_2d(st, &tmPd, j0, bh * a.T + i0, &bar[DB_FULL0 + s]);
+        tma_load_2d(st + 2 * DKV_BOX, &tmdS, j0, bh * a.T + i0, &bar[DB_FULL0 + s]);
+        if (!half_only) {
+          tma_load_2d(st + DKV_BOX, &tmPd, j0 + 64, bh * a.T + i0, &bar[DB_FULL0 + s]);
+          tma_load_2d(st + 3 * DKV_BOX, &tmdS, j0 + 64, bh * a.T + i0, &bar[DB_FULL0 + s]);
+        }
+        tma_load_2d(st + 4 * DKV_BOX, &tmdO, h * 64, b * a.T + i0, &bar[DB_FULL0 + s]);
+        tma_load_2d(st + 5 * DKV_BOX, &tmQu, h * 64, b * a.T + i0, &bar[DB_FULL0 + s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D fp32, A / B bf16, both MN-major (bits 15, 16), N = 64, M = 128
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+      if (in_x) mbar_wait(&bar[DB_ZERO], 0);
+      for (int n = 0; n < NI; n++) {
+        const int s = n % DKV_STAGES;
+        mbar_wait(&bar[DB_FULL0 + s], (n / DKV_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * DKV_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          umma_bf16(tmem_base, desc_mn64(st + k * 2048), desc_mn64(st + 4 * DKV_BOX + k * 2048), idesc, (uint32_t)(n > 0 || k > 0));
+          umma_bf16(tmem_base + 64, desc_mn64(st + 2 * DKV_BOX + k * 2048), desc_mn64(st + 5 * DKV_BOX + k * 2048), idesc,
+                    (uint32_t)(n > 0 || k > 0));
+        }
+        umma_commit(&bar[DB_EMPTY0 + s]);
+      }
+      umma_commit(&bar[DB_ACC]);
+    }
+  } else {
+    const int q4 = warp & 3;
+    if (in_x) {                                      // zero the never-written upper key half of the first stage (Pd and dS boxes)
+      for (int i = (warp - 2) * 32 + lane; i < DKV_BOX / 16; i += 128) {
+        *(uint4*)(smem + DKV_BOX + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+        *(uint4*)(smem + 3 * DKV_BOX + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[DB_ZERO]);
+    }
+    mbar_wait(&bar[DB_ACC], 0);
+    tc_fence_after();
+    const int key = q4 * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16);
+#pragma unroll
+    for (int which = 0; which < 2; which++) {
+      bf16* dst = (which == 0 ? dv_dst : dk_dst) + (long long)key * ldd;
+#pragma unroll
+      for (int ch = 0; ch < 2; ch++) {
+        uint32_t x[32];
+        tmem_ld_32x32(t_lane + 64 * which + 32 * ch, x);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          *(uint4*)(dst + 32 * ch + 8 * k) =
+              make_uint4(pack_bf16x2(__uint_as_float(x[8 * k]), __uint_as_float(x[8 * k + 1])),
+                         pack_bf16x2(__uint_as_float(x[8 * k + 2]), __uint_as_float(x[8 * k + 3])),
+                         pack_bf16x2(__uint_as_float(x[8 * k + 4]), __uint_as_float(x[8 * k + 5])),
+                         pack_bf16x2(__uint_as_float(x[8 * k + 6]), __uint_as_float(x[8 * k + 7])));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<128>(tmem_base);
+}
+
+}  // namespace
+
+bool attn_bwd_dkv_tc_supported(const AttnTrainBwdArgs& ba) {
+  static const bool off = getenv("DMG_ATTN_DKV_MMA_SYNC") != nullptr;
+  const AttnTrainArgs& a = ba.f;
+  return !off && ba.p_buf && ba.ds_buf && ba.qu && a.T % 128 == 0 && a.M % 128 == 0 && a.mem_count % 128 == 0 && a.ldx % 8 == 0 &&
+         (a.M == 0 || a.ldm % 8 == 0);
+}
+
+int attn_bwd_dkv_tc(const AttnTrainBwdArgs& ba, cudaStream_t st) {
+  const AttnTrainArgs& a = ba.f;
+  static bool configured = false;
+  if (!configured) {
+    DMG_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM));
+    configured = true;
+  }
+  const int HD = a.H * 64;
+  const long long S = (long long)a.M + a.T;
+  const TensorMap2D *tp = nullptr, *ts = nullptr, *td = nullptr, *tq = nullptr;
+  if (train_get_tmap(ba.p_buf, S, (long long)a.B * a.H * a.T, S, 64, &tp)) return -1;
+  if (train_get_tmap(ba.ds_buf, S, (long long)a.B * a.H * a.T, S, 64, &ts)) return -1;
+  if (train_get_tmap(ba.dout, HD, (long long)a.B * a.T, HD, 64, &td)) return -1;
+  if (train_get_tmap(ba.qu, HD, (long long)a.B * a.T, HD, 64, &tq)) return -1;
+  return launch_np(attn_bwd_dkv_tc_kernel, dim3(a.B * a.H * (int)(S / 128)), dim3(192), (size_t)DKV_SMEM, st, *(const CUtensorMap*)tp->bytes,
+                   *(const CUtensorMap*)ts->bytes, *(const CUtensorMap*)td->bytes, *(const CUtensorMap*)tq->bytes, ba);
+}
+
+namespace {
 }  // namespace
 
 bool attn_train_fwd_tc_supported(const AttnTrainArgs& a) {
@@ -425,13 +605,20 @@ int attn_train_fwd_tc(const AttnTrainArgs& a, cudaStream_t st) {
   if (train_get_tmap(a.rk, HD, (long long)a.M + a.T, HD, 128, &tr)) return -1;
   const dim3 grid(a.B * a.H * (a.T / 128)), block(TC_THREADS);
   if (a.p_save) {
-    const TensorMap2D* tp = nullptr;   // p_save as [B*H*T rows, S columns], 64 x 32 boxes
+    const TensorMap2D *tp = nullptr, *tqu = tx, *tqv = tx;   // p_save as [B*H*T rows, S columns], 64 x 32 boxes
     if (train_get_tmap(a.p_save, (long long)a.M + a.T, (long long)a.B * a.H * a.T, (long long)a.M + a.T, 32, &tp)) return -1;
+    DMG_CHECK((a.qu_save == nullptr) == (a.qv_save == nullptr), "training attention: qu_save and qv_save go together");
+    if (a.qu_save) {
+      if (train_get_tmap(a.qu_save, HD, (long long)a.B * a.T, HD, 128, &tqu)) return -1;
+      if (train_get_tmap(a.qv_save, HD, (long long)a.B * a.T, HD, 128, &tqv)) return -1;
+    }
     return launch_np(attn_train_fwd_tc_kernel<true>, grid, block, (size_t)TC_SMEM, st, *(const CUtensorMap*)tx->bytes,
-                     *(const CUtensorMap*)tm->bytes, *(const CUtensorMap*)tr->bytes, *(const CUtensorMap*)tp->bytes, a);
+                     *(const CUtensorMap*)tm->bytes, *(const CUtensorMap*)tr->bytes, *(const CUtensorMap*)tp->bytes,
+                     *(const CUtensorMap*)tqu->bytes, *(const CUtensorMap*)tqv->bytes, a);
   }
   return launch_np(attn_train_fwd_tc_kernel<false>, grid, block, (size_t)TC_SMEM, st, *(const CUtensorMap*)tx->bytes,
-                   *(const CUtensorMap*)tm->bytes, *(const CUtensorMap*)tr->bytes, *(const CUtensorMap*)tx->bytes, a);
+                   *(const CUtensorMap*)tm->bytes, *(const CUtensorMap*)tr->bytes, *(const CUtensorMap*)tx->bytes,
+                   *(const CUtensorMap*)tx->bytes, *(const CUtensorMap*)tx->bytes, a);
 }
 
 }  // namespace dmg

@@ -31,6 +31,7 @@ struct LayerAct {
   float* lse = nullptr;
   bf16* p_save = nullptr;    // [B*H, T, S] undropped attention probabilities saved by the tcgen05 forward (AttnTrainArgs::p_save)
   float* m_save = nullptr;   // [B*H, T, S/64] their reference maxima
+  bf16 *qu_save = nullptr, *qv_save = nullptr;   // [rows, HD] q + u / q + v tiles stored by the tcgen05 forward
   float2 *st1 = nullptr, *st2 = nullptr;
 };
 
@@ -233,7 +234,9 @@ AttnTrainArgs attn_args(dmg_model* m, dmg_train* t, int l) {
   a.scale = 1.f / sqrtf((float)c.d_head);
   const Drop dr = make_drop(t, t->cfg.attn_p, SITE_ATTN, l);
   a.drop_thresh = dr.thresh; a.drop_seed = dr.seed; a.drop_scale = dr.scale;
-  if (A.p_save && attn_train_fwd_tc_supported(a)) { a.p_save = A.p_save; a.m_save = A.m_save; }   // same predicate as the forward dispatch
+  if (A.p_save && attn_train_fwd_tc_supported(a)) {   // same predicate as the forward dispatch
+    a.p_save = A.p_save; a.m_save = A.m_save; a.qu_save = A.qu_save; a.qv_save = A.qv_save;
+  }
   return a;
 }
 
@@ -358,9 +361,12 @@ int backward_layer(dmg_model* m, dmg_train* t, int l, cudaStream_t st) {
     ba.dout = t->dattn; ba.delta = t->delta; ba.dqkv_x = t->dqkv_x; ba.dkv_m = t->dkv_m; ba.ds_dist = t->ds_dist; ba.qv = t->qv;
     ba.du = t->G + t->g_u; ba.dv = t->G + t->g_v;
     ba.p_buf = t->p_buf; ba.ds_buf = t->ds_buf;
+    const bool q_saved = ba.f.qu_save != nullptr;    // the tcgen05 forward stored q + u and q + v
+    if (q_saved) ba.qu = ba.f.qu_save;
     if (attn_train_bwd(ba, ns, st)) return -1;
     // dRk[h] = dS_dist[:, h]^T (q + v)[:, h]  ->  dWr = dRk^T PE
-    if (train_q_plus_bias(A.qkv_x, 3 * HD, m->v, t->qv, rows, HD, st)) return -1;
+    const bf16* qv_op = q_saved ? ba.f.qv_save : t->qv;
+    if (!q_saved && train_q_plus_bias(A.qkv_x, 3 * HD, m->v, t->qv, rows, HD, st)) return -1;
     DMG_CUDA_OK(cudaMemsetAsync(t->drk32, 0, (size_t)S * HD * sizeof(float), st));
     {   // one grouped launch: group h reads dS_dist columns [h*S, (h+1)*S) and (q+v) columns [h*64, (h+1)*64)
       GemmEpi er; er.out = t->drk32; er.ldc = HD; er.out_mode = GEMM_OUT_ATOMIC;
@@ -368,7 +374,7 @@ int backward_layer(dmg_model* m, dmg_train* t, int l, cudaStream_t st) {
       int sk = (2 * ns) / (c.n_heads * ((S + 127) / 128));
       if (sk < 1) sk = 1;
       if (sk > rows / 512) sk = rows / 512 > 0 ? rows / 512 : 1;
-      if (gemm_bf16_tc(t->ds_dist, 1, (long long)c.n_heads * S, t->qv, 1, HD, S, 64, rows, sk, er, ns, st)) return -1;
+      if (gemm_bf16_tc(t->ds_dist, 1, (long long)c.n_heads * S, qv_op, 1, HD, S, 64, rows, sk, er, ns, st)) return -1;
     }
     if (train_cast_bf16(t->drk32, t->drk16, (long long)S * HD, st)) return -1;
     if (grad_w(m, t, t->drk16, HD, t->pe, d, HD, d, S, g.wr, st)) return -1;
@@ -467,6 +473,8 @@ int dmg_train_create(dmg_model* m, const dmg_train_config* cfg, float* grad_flat
     if (t->T % 128 == 0 && c.mem_len % 128 == 0 && !getenv("DMG_ATTN_NO_PSAVE")) {   // geometry the tcgen05 forward serves
       TRY(talloc(t, &A.p_save, (size_t)t->B * c.n_heads * t->T * S));
       TRY(talloc(t, &A.m_save, (size_t)t->B * c.n_heads * t->T * (S / 64)));
+      TRY(talloc(t, &A.qu_save, (size_t)rows * HD));
+      TRY(talloc(t, &A.qv_save, (size_t)rows * HD));
     }
     TRY(talloc(t, &A.st1, (size_t)rows));
     TRY(talloc(t, &A.st2, (size_t)rows));
@@ -721,6 +729,17 @@ int dmg_attn_train_bwd(const void* qkv_x, int64_t ldx, const void* kv_m, int64_t
       ws_elems = 2 * n;
     }
     ba.p_buf = ws; ba.ds_buf = ws + n;
+    // (q + u) operand of the tcgen05 dK/dV kernel (in the trainer the tcgen05 forward stores it)
+    static bf16* qu_ws = nullptr;
+    static size_t qu_elems = 0;
+    const size_t nq = (size_t)B * T * H * 64;
+    if (qu_elems < nq) {
+      if (qu_ws) { DMG_CUDA_OK(cudaDeviceSynchronize()); cudaFree(qu_ws); qu_ws = nullptr; qu_elems = 0; }
+      DMG_CUDA_OK(cudaMalloc(&qu_ws, nq * sizeof(bf16)));
+      qu_elems = nq;
+    }
+    if (train_q_plus_bias((const bf16*)qkv_x, ldx, u, qu_ws, B * T, H * 64, (cudaStream_t)stream)) return -1;
+    ba.qu = qu_ws;
   }
   return attn_train_bwd(ba, 148, (cudaStream_t)stream);
 }

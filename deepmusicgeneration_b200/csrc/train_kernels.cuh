@@ -104,11 +104,18 @@ struct AttnTrainArgs {
   // P = p_save * exp(m_save*scale - lse) instead of recomputing AC, BD, the skew and the exponentials.
   bf16* p_save = nullptr;   // [B*H, T, M+T]
   float* m_save = nullptr;  // [B*H, T, (M+T)/64]
+  // Optional, with p_save: the forward also stores its (q+u) and (q+v) tiles, [B*T, HD] bf16 each - the operands of the
+  // dK contraction (tcgen05 dK/dV kernel) and of the dRk GEMM in the backward
+  bf16* qu_save = nullptr;
+  bf16* qv_save = nullptr;
 };
 int attn_train_fwd(const AttnTrainArgs& a, cudaStream_t st);
 // tcgen05 / TMEM / TMA forward (attention_train_tc.cu): T, M, mem_count multiples of 128; attn_train_fwd dispatches to it
 bool attn_train_fwd_tc_supported(const AttnTrainArgs& a);
 int attn_train_fwd_tc(const AttnTrainArgs& a, cudaStream_t st);
+struct AttnTrainBwdArgs;
+bool attn_bwd_dkv_tc_supported(const AttnTrainBwdArgs& ba);
+int attn_bwd_dkv_tc(const AttnTrainBwdArgs& ba, cudaStream_t st);
 struct TensorMap2D;
 int train_get_tmap(const void* base, long long inner, long long rows, long long ld, int box_rows, const TensorMap2D** out);
 
@@ -122,6 +129,8 @@ struct AttnTrainBwdArgs {
   bf16* qv;              // [B*T, HD] bf16: q + v (operand of the dRk GEMM)
   float* du;             // [HD] accumulated (atomics)
   float* dv;             // [HD]
+  const bf16* qu = nullptr; // optional [B*T, HD] bf16: q + u; with p_buf / ds_buf and T, M, mem_count multiples of 128 it selects the
+                            // tcgen05 dK/dV kernel (attention_train_tc.cu)
   bf16* p_buf = nullptr;   // optional workspaces [B*H, T, M+T] bf16: when both are set the dQ kernel spills the dropped
   bf16* ds_buf = nullptr;  // probabilities and dS there and dK/dV come from a kernel that does not recompute the scores
 };
