@@ -72,16 +72,23 @@ class MusicLearner:
 
     def fit_one_cycle(self, cyc_len, max_lr, batches, bs=None, bptt=None, wd=0.01, clip=0.5, moms=(0.95, 0.85), drop_mult=1.,
                       callback=None):
-        """learner.fit_one_cycle(epochs, lr) over `batches`, a list of (x, y[, pos]) LongTensors [bs, bptt] (the
-        MusicPreloader's contiguous streams, deep_music_genre.py:1088-1096): one-cycle LR / momentum schedule over all
-        cyc_len passes, memory reset at every epoch start (RNNTrainer.on_epoch_begin), Adam(true_wd), gradient clipping."""
+        """learner.fit_one_cycle(epochs, lr) over `batches`: a list of (x, y[, pos]) LongTensors [bs, bptt], or a
+        deepmusicgeneration_b200.preloader.MusicPreloader (the reference's contiguous streams with per-item random transpose,
+        deep_music_genre.py:1001-1125, assembled on the GPU; every pass is a new epoch = new shuffle / transposes, like the
+        reference's DataLoader): one-cycle LR / momentum schedule over all cyc_len passes, memory reset at every epoch start
+        (RNNTrainer.on_epoch_begin), Adam(true_wd), gradient clipping."""
         from .training import one_cycle_lr
-        x0 = batches[0][0]
-        tr = self.trainer(bs or x0.shape[0], bptt or x0.shape[1], drop_mult=drop_mult)
-        total, i = cyc_len * len(batches), 0
+        from .preloader import MusicPreloader
+        is_pl = isinstance(batches, MusicPreloader)
+        n_b = batches.n_batches if is_pl else len(batches)
+        tr = self.trainer(bs or (batches.local_bs if is_pl else batches[0][0].shape[0]),
+                          bptt or (batches.bptt if is_pl else batches[0][0].shape[1]), drop_mult=drop_mult)
+        total, i = cyc_len * n_b, 0
         for _ in range(cyc_len):
             tr.reset()
             for b in batches:
+                if is_pl:                           # (x, y) or ({'x', 'pos'}, y)
+                    b = (b[0]['x'], b[1], b[0]['pos']) if isinstance(b[0], dict) else b
                 lr, mom = one_cycle_lr(i, total, max_lr, moms=moms)
                 tr.step(b[0], b[1], b[2] if len(b) > 2 else None, lr=lr, betas=(mom, 0.99), wd=wd, clip=clip)
                 if callback is not None:

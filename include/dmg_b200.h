@@ -217,6 +217,22 @@ int dmg_attn_train_bwd(const void* qkv_x, int64_t ldx, const void* kv_m, int64_t
                        int mem_count, int win, int k, float drop_p, uint32_t drop_seed, float* delta, void* dqkv_x, void* dkv_m,
                        void* ds_dist, float* du, float* dv, const void* p_save, const float* m_save, void* stream);
 
+/* ---- training data feed ------------------------------------------------------------------------
+ * dmg_preload_fill = MusicPreloader.__getitem__ / fill_row (deep_music_genre.py:1088-1125) for all `bs` rows of one batch.
+ * Everything is device memory: `tokens` / `positions` the flat ragged corpus (int32), `offsets` [n_items+1] (int64), `perm` the
+ * CircularIndex permutation (:1005-1014, int64), `transpose` the per-item semitone shift or NULL (MusicItem.transpose :1247,
+ * applied to ids in [note_lo, note_hi)), `ro` / `ri` [bs] the row cursors (in/out), `x` / `y` [bs, bptt] int64 (y = the stream
+ * shifted by y_offset), `xpos` [bs, bptt] the positions of x or NULL (batch_position_tfm :1129-1136).  forward = !backwards. */
+int dmg_preload_fill(const int32_t* tokens, const int32_t* positions, const int64_t* offsets, const int64_t* perm, int n_items,
+                     int forward, const int32_t* transpose, int note_lo, int note_hi, int64_t* ro, int64_t* ri, int bs, int bptt,
+                     int y_offset, int64_t* x, int64_t* y, int64_t* xpos, void* stream);
+/* mask_tfm (deep_music_remix.py:1208-1223) in place on device tensors of n elements: tokens inside [mask_lo, mask_hi) are
+ * masked with probability 0.8 p, replaced by a random token of the range with 0.1 p, left with 0.1 p; y becomes pad_idx where
+ * nothing was selected.  rand_out / wrong_out (nullable, n elements) export the uniform draw and the replacement candidate of
+ * every element (test hooks: the oracle replays them). */
+int dmg_mask_tfm(int64_t* x, int64_t* y, int64_t n, int mask_lo, int mask_hi, int mask_idx, int pad_idx, double p, uint32_t seed,
+                 float* rand_out, int64_t* wrong_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
