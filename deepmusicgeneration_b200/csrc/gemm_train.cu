@@ -325,14 +325,25 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t sw = (uint32_t)((lane >> 1) & 3);
           if (lane == 0) tma_store_wait_read<0>();     // the boxes of the previous chunk have been read out
           __syncwarp();
-          if (p.out2) {
+          float g2[32];                               // act = 2: the saved backward factor gelu'(pre) (dropout applied below)
+          if (p.out2 && p.act != GEMM_ACT_GELU_GRADSAVE) {
 #pragma unroll
             for (int j = 0; j < 4; j++)
               *(uint4*)(strip + 2048 + lane * 64 + ((j ^ sw) << 4)) =
                   make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                              pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
           }
-          if (p.act) {
+          if (p.act == GEMM_ACT_GELU_GRADSAVE) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              const float x = v[j], kk = 0.7978845608028654f, cc = 0.044715f;
+              const float x2 = x * x;
+              const float t = tanh_fast(x * fmaf(kk * cc, x2, kk));
+              const float hx = 0.5f * x;
+              v[j] = fmaf(hx, t, hx);
+              g2[j] = fmaf(hx * (1.f - t * t), fmaf(3.f * kk * cc, x2, kk), fmaf(0.5f, t, 0.5f));
+            }
+          } else if (p.act) {
 #pragma unroll
             for (int j = 0; j < 32; j++) v[j] = gelu_tanh_fast(v[j]);
           }
@@ -350,11 +361,12 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int e = 0; e < 8; e++) {
                 if (p.aux_mode == GEMM_AUX_GELU_GRAD) v[8 * j + e] *= gelu_tanh_grad_fast(a8[e]);
+                else if (p.aux_mode == GEMM_AUX_MUL_BF16) v[8 * j + e] *= a8[e];
                 else v[8 * j + e] += a8[e];
               }
             }
             xcnt++;
-          } else if (p.aux_mode == GEMM_AUX_GELU_GRAD || p.aux_mode == GEMM_AUX_ADD_BF16) {
+          } else if (p.aux_mode == GEMM_AUX_GELU_GRAD || p.aux_mode == GEMM_AUX_ADD_BF16 || p.aux_mode == GEMM_AUX_MUL_BF16) {
             if (row < p.M) {
               const bf16* ax = (const bf16*)p.aux + (size_t)row * p.ld_aux + col0;
 #pragma unroll
@@ -365,6 +377,7 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                   for (int e = 0; e < 8; e++) {
                     if (p.aux_mode == GEMM_AUX_GELU_GRAD) v[8 * j + e] *= gelu_tanh_grad_fast(a8[e]);
+                    else if (p.aux_mode == GEMM_AUX_MUL_BF16) v[8 * j + e] *= a8[e];
                     else v[8 * j + e] += a8[e];
                   }
                 }
@@ -378,7 +391,18 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const uint32_t h = drop_pair_bits(p.drop_seed, e0 + (j >> 1));
               v[j] = ((h & 0xFFFFu) >= p.drop_thresh) ? v[j] * p.drop_scale : 0.f;
               v[j + 1] = ((h >> 16) >= p.drop_thresh) ? v[j + 1] * p.drop_scale : 0.f;
+              if (p.act == GEMM_ACT_GELU_GRADSAVE) {
+                g2[j] = ((h & 0xFFFFu) >= p.drop_thresh) ? g2[j] * p.drop_scale : 0.f;
+                g2[j + 1] = ((h >> 16) >= p.drop_thresh) ? g2[j + 1] * p.drop_scale : 0.f;
+              }
             }
+          }
+          if (p.out2 && p.act == GEMM_ACT_GELU_GRADSAVE) {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              *(uint4*)(strip + 2048 + lane * 64 + ((j ^ sw) << 4)) =
+                  make_uint4(pack_bf16x2(g2[8 * j], g2[8 * j + 1]), pack_bf16x2(g2[8 * j + 2], g2[8 * j + 3]),
+                             pack_bf16x2(g2[8 * j + 4], g2[8 * j + 5]), pack_bf16x2(g2[8 * j + 6], g2[8 * j + 7]));
           }
 #pragma unroll
           for (int j = 0; j < 4; j++)
@@ -572,8 +596,9 @@ int gemm_bf16_tc(const bf16* A, int a_mn, long long lda, const bf16* B, int b_mn
   // bf16 outputs leave through TMA stores (dense boxes; the map clips at M and N); needs N-extent columns in a group-free launch
   static const bool no_tma_store = getenv("DMG_GEMM_NO_TMA_STORE") != nullptr;
   p.tma_store = (!no_tma_store && e.out_mode == GEMM_OUT_BF16 && groups == 1 && e.aux_mode != GEMM_AUX_ADD_F32) ? 1 : 0;
-  p.aux_tma = (p.tma_store && !e.out2 && (e.aux_mode == GEMM_AUX_GELU_GRAD || e.aux_mode == GEMM_AUX_ADD_BF16) &&
+  p.aux_tma = (p.tma_store && !e.out2 && (e.aux_mode == GEMM_AUX_GELU_GRAD || e.aux_mode == GEMM_AUX_ADD_BF16 || e.aux_mode == GEMM_AUX_MUL_BF16) &&
                !getenv("DMG_GEMM_NO_AUX_TMA")) ? 1 : 0;
+  DMG_CHECK(e.act != GEMM_ACT_GELU_GRADSAVE || (p.tma_store && e.out2), "gemm_bf16_tc: the gradient-saving GeLU epilogue needs bf16 TMA-store outputs and a second output");
   const TensorMap2D *tc = ta, *tc2 = ta, *tx = ta;   // placeholders when unused
   if (p.tma_store) {
     if (get_tmap(e.out, N, M, e.ldc, -1, &tc)) return -1;

@@ -279,7 +279,9 @@ int train_forward(dmg_model* m, dmg_train* t, const long long* ids, const long l
     }
     {   // FFN
       const Drop d3 = make_drop(t, t->cfg.ff_p, SITE_FF, l);
-      GemmEpi e; e.bias = W.b1; e.act = 1; e.out = A.hact; e.ldc = c.d_inner; e.out_mode = GEMM_OUT_BF16;
+      // hpre receives the backward factor gelu'(pre) * dropout instead of the pre-activation (GEMM_ACT_GELU_GRADSAVE)
+      static const bool old_epi = getenv("DMG_FFN_SAVE_PRE") != nullptr;
+      GemmEpi e; e.bias = W.b1; e.act = old_epi ? GEMM_ACT_GELU : GEMM_ACT_GELU_GRADSAVE; e.out = A.hact; e.ldc = c.d_inner; e.out_mode = GEMM_OUT_BF16;
       e.out2 = A.hpre; e.ld2 = c.d_inner; e.drop_thresh = d3.thresh; e.drop_seed = d3.seed; e.drop_scale = d3.scale;
       if (gemm_bf16_tc(A.xa1, 0, d, W.w1.b16, 0, d, rows, c.d_inner, d, 1, e, ns, st)) return -1;
       GemmEpi e2; e2.bias = W.b2; e2.out = t->proj; e2.ldc = d; e2.out_mode = GEMM_OUT_BF16;
@@ -338,8 +340,13 @@ int backward_layer(dmg_model* m, dmg_train* t, int l, cudaStream_t st) {
                      d4.thresh, d4.seed, d4.scale, st)) return -1;   // also the FFN-down bias gradient
     if (grad_w(m, t, t->dadd, d, A.hact, di, d, di, rows, g.w2, st)) return -1;
     const Drop d3 = make_drop(t, t->cfg.ff_p, SITE_FF, l);
-    GemmEpi e; e.aux = A.hpre; e.ld_aux = di; e.aux_mode = GEMM_AUX_GELU_GRAD; e.out = t->dh; e.ldc = di; e.out_mode = GEMM_OUT_BF16;
-    e.drop_thresh = d3.thresh; e.drop_seed = d3.seed; e.drop_scale = d3.scale;
+    static const bool old_epi = getenv("DMG_FFN_SAVE_PRE") != nullptr;
+    GemmEpi e; e.aux = A.hpre; e.ld_aux = di; e.out = t->dh; e.ldc = di; e.out_mode = GEMM_OUT_BF16;
+    if (old_epi) {   // hpre = pre-activation: recompute gelu' and the dropout mask here
+      e.aux_mode = GEMM_AUX_GELU_GRAD; e.drop_thresh = d3.thresh; e.drop_seed = d3.seed; e.drop_scale = d3.scale;
+    } else {         // hpre = gelu'(pre) * keep * scale, stored by the forward: one multiply
+      e.aux_mode = GEMM_AUX_MUL_BF16;
+    }
     if (gemm_bf16_tc(t->dadd, 0, d, W.w2.b16, 1, di, rows, di, d, 1, e, ns, st)) return -1;
     if (grad_w(m, t, t->dh, di, A.xa1, d, di, d, rows, g.w1, st)) return -1;
     if (train_colsum_bf16(t->dh, di, rows, di, t->G + g.b1, st)) return -1;

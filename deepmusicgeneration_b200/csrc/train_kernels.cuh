@@ -57,10 +57,15 @@ __device__ __forceinline__ float gelu_tanh_grad_fast(float x) {
 //   b_mn = 0: B is [N, K] row-major (nn.Linear weight layout)      b_mn = 1: B is [K, N] row-major
 // lda / ldb are row strides in elements (multiples of 8).  splitk > 1 requires out_mode = GEMM_OUT_ATOMIC.
 enum { GEMM_OUT_F32 = 0, GEMM_OUT_BF16 = 1, GEMM_OUT_ATOMIC = 2 };
+// act = 2 (GEMM_ACT_GELU_GRADSAVE): tanh-GeLU after the bias like act = 1, but the second output receives the BACKWARD
+// factor gelu'(pre) * keep * drop_scale instead of the pre-activation (it is the only thing the backward needs the
+// pre-activation for), so that the input-gradient GEMM's epilogue is one multiply (GEMM_AUX_MUL_BF16): no tanh, no dropout hash.
+enum { GEMM_ACT_NONE = 0, GEMM_ACT_GELU = 1, GEMM_ACT_GELU_GRADSAVE = 2 };
 enum { GEMM_AUX_NONE = 0,
        GEMM_AUX_GELU_GRAD = 1,   // value *= gelu'(aux[m,n])                 (aux bf16: the saved pre-activation)
        GEMM_AUX_ADD_BF16 = 2,    // value += aux[m,n]                        (bf16 residual)
-       GEMM_AUX_ADD_F32 = 3 };   // value += aux[m,n]                        (fp32 residual)
+       GEMM_AUX_ADD_F32 = 3,     // value += aux[m,n]                        (fp32 residual)
+       GEMM_AUX_MUL_BF16 = 4 };  // value *= aux[m,n]                        (bf16: a saved gradient factor)
 struct GemmEpi {
   const float* bias = nullptr;   // [N]
   int act = 0;                   // 1: tanh-GeLU after the bias

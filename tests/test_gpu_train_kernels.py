@@ -109,6 +109,29 @@ def test_gemm_train_epilogues():
     assert rel_err(out[kept], plain[kept] / 0.75) < 2e-3
 
 
+def test_gemm_train_gradient_saving_gelu_epilogue():
+    "act = 2: out = dropout(gelu(acc + bias)), second output = gelu'(acc + bias) * the same dropout factor; aux_mode 4 multiplies by it"
+    torch.manual_seed(6)
+    M, N, K = 1024, 2048, 512
+    A = (torch.randn(M, K, device='cuda') * 0.5).bfloat16()
+    W = (torch.randn(N, K, device='cuda') * 0.1).bfloat16()
+    bias = torch.randn(N, device='cuda') * 0.3
+    x = (A.float() @ W.float().t() + bias).requires_grad_(True)
+    gelu_tanh(x).sum().backward()
+    out, gfac = gemm_train(A, 0, W, 0, M, N, K, bias=bias, gelu=2, out_mode=1, want_pre=True)
+    assert rel_err(out, gelu_tanh(x.detach())) < 5e-3 and rel_err(gfac, x.grad) < 5e-3
+    out, gfac = gemm_train(A, 0, W, 0, M, N, K, bias=bias, gelu=2, out_mode=1, want_pre=True, drop_p=0.25, seed=11)
+    plain = gemm_train(A, 0, W, 0, M, N, K, bias=bias, gelu=1, out_mode=1, drop_p=0.25, seed=11)
+    kept = plain != 0
+    assert torch.equal(out != 0, kept) and rel_err(out, plain) < 2e-3  # same mask as the act = 1 epilogue (the GeLU is factored differently)
+    assert (gfac[~kept] == 0).all()
+    assert rel_err(gfac[kept], (x.grad / 0.75)[kept]) < 5e-3
+    dy = (torch.randn(M, K, device='cuda') * 0.5).bfloat16()          # dh = (dY W2) * factor with W2 [K, N] MN-major
+    W2 = (torch.randn(K, N, device='cuda') * 0.1).bfloat16()
+    dh = gemm_train(dy, 0, W2, 1, M, N, K, aux=gfac, aux_mode=4, out_mode=1)
+    assert rel_err(dh, (dy.float() @ W2.float()) * gfac.float()) < 5e-3
+
+
 def test_gemm_train_persistent_many_tiles_per_cta():
     "more tiles than CTA pairs: the persistent loop, both TMEM stages, the TMA-store strips and the aux-box prefetch wrap around"
     torch.manual_seed(4)
