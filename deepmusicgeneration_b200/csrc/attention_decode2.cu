@@ -144,6 +144,25 @@ attn_decode2_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         mbar_expect_tx(r_full, (uint32_t)(L.r_boxes * 8192));
         for (int bx = 0; bx < L.r_boxes; bx++) tma_load_2d(Rres + bx * 8192, &tmR, 0, cur_h * a.Dcap + bx * 64, r_full);
       }
+      // The K/V ring of this layer was last written by this layer's attention kernel of the PREVIOUS step (116 launches
+      // back: long retired - at most a handful of kernels of the chain can be resident at once), so the first item's tiles
+      // do not depend on the predecessor kernel either: fill the stage ring while the QKV GEMM drains (the HBM pipe is idle
+      // then), and only the current token's q / k / v wait for it.
+      int pre = 0;                                   // tiles of the first item already requested
+      if (lo < hi && !a.no_early_kv) {
+        const int h = lo / B, b = lo - h * B;
+        const int row0 = ((b0 + b) * H + h) * M;
+        const int npre = min(n_stages, 2 * nT);
+        for (int t = 0; t < npre; ++t, ++tile_cnt, ++pre) {
+          const int s = tile_cnt & smask;
+          mbar_expect_tx(&full[s], (uint32_t)L.tile_bytes);
+          uint8_t* dst = stages + s * L.tile_bytes;
+          const CUtensorMap* tm = t < nT ? &tmK : &tmV;
+          const int r0 = row0 + (t < nT ? t : t - nT) * TR;
+#pragma unroll
+          for (int gq = 0; gq < G; gq++) tma_load_2d(dst + gq * 8192, tm, 0, r0 + gq * 64, &full[s]);
+        }
+      }
       pdl_wait();
       for (int it = lo, n = 0; it < hi; ++it, ++n) {
         const int h = it / B, b = it - h * B;
@@ -161,7 +180,7 @@ attn_decode2_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         bulk_g2s(qbuf + qs * 192 + 64, qrow + HD, 256, &q_full[qs]);
         bulk_g2s(qbuf + qs * 192 + 128, qrow + 2 * HD, 256, &q_full[qs]);
         const int row0 = ((b0 + b) * H + h) * M;
-        for (int t = 0; t < 2 * nT; ++t, ++tile_cnt) {
+        for (int t = (it == lo ? pre : 0); t < 2 * nT; ++t, ++tile_cnt) {
           const int s = tile_cnt & smask;
           const uint32_t ph = (tile_cnt >> sshift) & 1;
           mbar_wait(&empty[s], ph ^ 1);
@@ -349,8 +368,11 @@ static int launch_d2(const TensorMap2D* tmK, const TensorMap2D* tmV, const Tenso
                   *(const CUtensorMap*)tmV->bytes, *(const CUtensorMap*)tmR->bytes, a, ns, b0);
 }
 
-int attn_decode2(const TensorMap2D* tmK, const TensorMap2D* tmV, const TensorMap2D* tmR, const AttnDecodeArgs& a, int b0,
+int attn_decode2(const TensorMap2D* tmK, const TensorMap2D* tmV, const TensorMap2D* tmR, const AttnDecodeArgs& a_in, int b0,
                  int num_sms, int max_stages, cudaStream_t st) {
+  static const int no_early = getenv("DMG_NO_EARLY_KV") ? 1 : 0;
+  AttnDecodeArgs a = a_in;
+  a.no_early_kv = no_early;
   DMG_CHECK(a.Dcap >= a.M + 1, "attn_decode2: rel-pos cache too small (%d < %d)", a.Dcap, a.M + 1);
   const int G = d2_pick_groups(a.M);
   DMG_CHECK(G > 0, "attn_decode2: mem_len %d not supported", a.M);

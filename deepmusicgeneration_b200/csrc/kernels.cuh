@@ -112,6 +112,7 @@ struct AttnDecodeArgs {
   const int* dev_state; // [0] pos_total, [1] mem_count
   int B, H, M, Dcap;
   float scale;
+  int no_early_kv = 0;  // v2 kernel: 1 = request the first K/V tiles only after the predecessor kernel has finished (DMG_NO_EARLY_KV)
 };
 int attn_decode(const AttnDecodeArgs& a, cudaStream_t st);
 bool attn_decode_supported(int Dh, int M);
