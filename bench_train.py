@@ -148,7 +148,7 @@ def run_b200(args):
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, n, threads, dt = cpu_reference(2, 1, budget_s=60.0)
+        v, n, threads, dt = cpu_reference(2, 8, budget_s=15.0)                  # a bounded sample: about 15 s of host work
         cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                'sample': f'{n} training step(s) of 2 sequences x 512 tokens over a full memory, fp32 eager-PyTorch oracle, {dt:.1f} s'}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': step_ms,
