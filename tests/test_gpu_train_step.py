@@ -76,11 +76,12 @@ def install_masks(tr, sites, cfg, bs, bptt, m_len, step):
         sites['res2'][l].mask = tr.dropout_mask(4, l, (bs, bptt, d), step).cpu()
 
 
+@pytest.mark.parametrize('bptt', [64, 128])      # 128 (with mem_len 128): the tcgen05 forward / saved-probability dQ / tcgen05 dK-dV path
 @pytest.mark.parametrize('drop_mult,encode_position,mask_size', [(0., False, (1, 1)), (0., True, (1, 0)), (1., False, (1, 1)),
                                                                  (1., True, (2, 0))])
-def test_training_step_matches_oracle(monkeypatch, drop_mult, encode_position, mask_size):
-    cfg = small_config(encode_position=encode_position, mask_steps=2)
-    bs, bptt, steps = 3, 64, 3
+def test_training_step_matches_oracle(monkeypatch, drop_mult, encode_position, mask_size, bptt):
+    cfg = small_config(encode_position=encode_position, mask_steps=2, mem_len=bptt, ctx_len=bptt)
+    bs, steps = 3, 3
     om, pm, tr = build_pair(cfg, bs, bptt, drop_mult)
     om.train(); om.reset()
     sites = otrain.install_dropout_masks(om)
