@@ -9,6 +9,7 @@
 
 #include "model.cuh"
 #include "launch.cuh"
+#include "train_kernels.cuh"
 
 namespace dmg {
 
@@ -48,6 +49,16 @@ static int linear(dmg_model* m, int abuf, const void* A, const Weight& w, const 
   if (!m->is_bf16) return gemm_simt<float>((const float*)A, K, w.f32, K, bias, C, ldc, M, N, K, gelu, out_bf16, st);
   if (m->use_tc && w.has_tm && K % 64 == 0) {
     const bool skinny = M <= 512;
+    // many rows (prefill segments, the BERT encoder): the persistent CTA-pair kernel of the training path (gemm_train.cu) -
+    // 256-row tiles, TMA-store epilogue.  Measured at C4 (32768 rows, QKV 512 -> 1536): 307 us with gemm_tc_kernel<128> = 168
+    // TFLOP/s; the same shape runs at ~800 TFLOP/s there.
+    static const bool no_big = getenv("DMG_NO_BIG_GEMM") != nullptr;
+    if (!no_big && M >= 1024 && N % 4 == 0 && (out_bf16 ? ldc % 8 == 0 : ldc % 4 == 0)) {
+      GemmEpi e;
+      e.bias = bias; e.act = gelu ? GEMM_ACT_GELU : GEMM_ACT_NONE; e.out = C; e.ldc = ldc;
+      e.out_mode = out_bf16 ? GEMM_OUT_BF16 : GEMM_OUT_F32;
+      return gemm_bf16_tc((const bf16*)A, 0, K, w.b16, 0, K, M, N, K, 1, e, m->num_sms, st);
+    }
     if (skinny && gemm_tc_splitk_ways(K) && !getenv("DMG_NO_SPLITK"))
       return gemm_tc_splitk(&m->tmA[abuf], &w.tm32, bias, C, ldc, M, N, K, gelu, out_bf16, st);
     return gemm_tc(&m->tmA[abuf], skinny ? &w.tm32 : &w.tm128, skinny ? 32 : 128, bias, C, ldc, M, N, K, gelu, out_bf16, st);
