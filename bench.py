@@ -301,10 +301,12 @@ def main():
     ap.add_argument('--steps', type=int, default=None)
     ap.add_argument('--warmup', type=int, default=None)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=['c2', 'c3', 'c5'],
-                    help='c2 (default, the headline): batched incremental generation; c3: data-parallel training step')
+    ap.add_argument('--workload', default='c2', choices=['c2', 'c3', 'c4', 'c5'],
+                    help='c2 (default, the headline): batched incremental generation; c3: data-parallel training step; '
+                         'c4: remix (masked-BERT) encoder forward; c5: the scaled generation model')
     ap.add_argument('--batch', type=int, default=B_PER_GPU, help='c2: streams per GPU')
     ap.add_argument('--train-batch', type=int, default=32, help='c3: sequences per GPU and step')
+    ap.add_argument('--bert-batch', type=int, default=512, help='c4: sequences per GPU and forward')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.workload == 'c3':
@@ -312,6 +314,11 @@ def main():
         args.steps = args.steps if args.steps is not None else 30
         args.warmup = args.warmup if args.warmup is not None else 5
         return bench_train.run_reference(args) if args.impl == 'reference' else bench_train.run_b200(args)
+    if args.workload == 'c4':
+        import bench_bert
+        args.steps = args.steps if args.steps is not None else 10
+        args.warmup = args.warmup if args.warmup is not None else 3
+        return bench_bert.run_reference(args) if args.impl == 'reference' else bench_bert.run_b200(args)
     args.steps = args.steps if args.steps is not None else 2048
     args.warmup = args.warmup if args.warmup is not None else 32
     if args.impl == 'reference':
