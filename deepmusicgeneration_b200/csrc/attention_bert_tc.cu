@@ -1,0 +1,372 @@
+// Attention of the masked-BERT remix encoder on tcgen05 / TMEM / TMA (inference, bf16), for sequences that are multiples of 128.
+//
+// Replaces MemMultiHeadRelativeAttentionKV._apply_attention (deep_music_remix.py:2078-2104; a14-a18 of SURVEY.md section 8):
+//   softmax(((q+u) K^T + _line_shift((q+v) Rk^T, mask=False)) / sqrt(Dh)) V        - no mask, no dropout, no out-projection
+// where the unmasked _line_shift keeps all three "lines" of the padded reshape alive:
+//   j <= i   : BD[i, j] = (q_i + v)     . Rk[i - j]                (line 1)
+//   j == i+1 : BD[i, j] = 0                                        (line 2, the zero pad)
+//   j >  i+1 : BD[i, j] = (q_{i+1} + v) . Rk[T + 1 + i - j]        (line 3: the NEXT query row, wrapped distance)
+// Same scheme as attn_train_fwd_tc_kernel (attention_train_tc.cu): one CTA per (stream, head, 128-query tile), row-per-thread
+// softmax warps, AC and a 256-column position strip in TMEM, skew through thread-private shared-memory lines, P as the A operand
+// of the PV MMA.  The strip is strip[r][c] = BD[r, jj] with c = 128 + r - jj; below the diagonal both 128-column halves come from
+// (q+v) and two consecutive 128-row blocks of Rk, above it from (q_next+v) and blocks of Rk3[x] = Rk[x+1], and ON the diagonal tile
+// line 1 only ever reads the upper half (r - jj >= 0) and line 3 only the lower half (r - jj <= -2), so one half of each fits the
+// same 256 columns.  Consecutive key tiles share a block (upper half of tile n+1 = lower half of tile n), also across the diagonal.
+#include <cuda.h>
+#include "kernels.cuh"
+#include "launch.cuh"
+#include "mma_sync.cuh"
+#include "train_kernels.cuh"
+
+namespace dmg {
+
+namespace {
+
+constexpr float BT_LOG2E = 1.4426950408889634f;
+constexpr int BT_SOFT_WARPS = 8;
+constexpr int BT_THREADS = (BT_SOFT_WARPS + 4) * 32;   // + one auxiliary warpgroup: TMA warp, MMA warp, two idle warps
+constexpr int BT16K = 128 * 64 * 2;
+constexpr int BT_STRIP_LD = 68;
+constexpr int BO_QU = 0;
+constexpr int BO_QV = BO_QU + BT16K;
+constexpr int BO_QVN = BO_QV + BT16K;
+constexpr int BO_K = BO_QVN + BT16K;                   // one stage
+constexpr int BO_V = BO_K + BT16K;
+constexpr int BO_R = BO_V + BT16K;                     // 2 slots (slot = load index & 1)
+constexpr int BO_P = BO_R + 2 * BT16K;                 // 2 key halves; the raw q / q_next tiles land here first
+constexpr int BO_STRIP = BO_P + 2 * BT16K;
+constexpr int BO_BAR = BO_STRIP + BT_SOFT_WARPS * 32 * BT_STRIP_LD * 4;
+constexpr int BT_SMEM = BO_BAR + 256 + 1024;
+static_assert(BT_SMEM <= 227 * 1024, "shared memory budget");
+
+enum { Q_QFULL = 0, Q_QREADY, Q_KFULL, Q_KEMPTY, Q_RFULL0, Q_RFULL1, Q_REMPTY0, Q_REMPTY1, Q_VFULL, Q_VEMPTY, Q_SFULL, Q_SFREE,
+       Q_PFULL0, Q_PFULL1, Q_OFULL0, Q_OFULL1, Q_OFREE0, Q_OFREE1, Q_COUNT };
+constexpr uint32_t BTM_AC = 0, BTM_STRIP = 128, BTM_O = 384;
+
+__device__ __forceinline__ uint64_t bt_desc_k(uint32_t addr) {          // K-major, 128B swizzle: rows of 128 B, 8-row groups 1024 B apart
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t bt_desc_mn(uint32_t addr) {         // MN-major: LBO 8192, SBO 1024
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(8192u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void bt_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct BertTcArgs {
+  const float* u; const float* v;   // [H*64]
+  bf16* out;                        // [B*T, H*64]
+  int B, T, H, Dcap;
+  float scale;
+};
+
+__global__ void __launch_bounds__(BT_THREADS, 1)
+attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmR, const BertTcArgs a) {
+  extern __shared__ __align__(1024) uint8_t bt_smem_raw[];
+  uint8_t* smem = bt_smem_raw + ((1024u - (smem_u32(bt_smem_raw) & 1023u)) & 1023u);
+  uint64_t* bar = (uint64_t*)(smem + BO_BAR);
+  uint32_t* tmem_holder = (uint32_t*)(bar + Q_COUNT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nT = a.T / 128;
+  const int it = blockIdx.x % nT;                   // every query tile sees all nT key tiles: uniform work
+  const int bh = blockIdx.x / nT, b = bh / a.H, h = bh % a.H;
+  const int i0 = it * 128, HD = a.H * 64;
+  const int NT = nT;
+
+  if (warp == BT_SOFT_WARPS && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmR);
+    for (int i = 0; i < Q_COUNT; i++) {
+      uint32_t cnt = 1;
+      if (i == Q_QREADY || i == Q_SFREE) cnt = BT_SOFT_WARPS;
+      if (i == Q_PFULL0 || i == Q_PFULL1 || i == Q_OFREE0 || i == Q_OFREE1) cnt = BT_SOFT_WARPS / 2;
+      mbar_init(&bar[i], cnt);
+    }
+    mbar_fence_init();
+  }
+  if (warp == BT_SOFT_WARPS + 1) tmem_alloc<512>(tmem_holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  pdl_launch_dependents();
+
+  if (warp >= BT_SOFT_WARPS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == BT_SOFT_WARPS) {
+      // =========================================== TMA producer ===========================================
+      if (lane == 0) {
+        pdl_wait();                                  // q | k | v come from the predecessor kernel (the QKV GEMM)
+        mbar_expect_tx(&bar[Q_QFULL], 2 * BT16K);
+        tma_load_2d(smem + BO_P, &tmX, h * 64, b * a.T + i0, &bar[Q_QFULL]);
+        tma_load_2d(smem + BO_P + BT16K, &tmX, h * 64, b * a.T + i0 + 1, &bar[Q_QFULL]);   // rows i+1 (the last row of the last tile is never used)
+        auto load_k = [&](int n) {
+          mbar_wait(&bar[Q_KEMPTY], (n & 1) ^ 1);
+          mbar_expect_tx(&bar[Q_KFULL], BT16K);
+          tma_load_2d(smem + BO_K, &tmX, HD + h * 64, b * a.T + n * 128, &bar[Q_KFULL]);
+        };
+        auto load_r = [&](int k) {                  // load 0 = upper block of tile 0; load k >= 1 = lower block of tile k-1
+          const int s = k & 1;
+          const int row = k <= it ? (it - k) * 128 : (nT + it - k) * 128 + 1;   // Rk block it-k, or Rk3 block nT+it-k (Rk3[x] = Rk[x+1])
+          mbar_wait(&bar[Q_REMPTY0 + s], ((k >> 1) & 1) ^ 1);
+          mbar_expect_tx(&bar[Q_RFULL0 + s], BT16K);
+          tma_load_2d(smem + BO_R + s * BT16K, &tmR, 0, h * a.Dcap + row, &bar[Q_RFULL0 + s]);
+        };
+        auto load_v = [&](int n) {
+          mbar_wait(&bar[Q_VEMPTY], (n & 1) ^ 1);
+          mbar_expect_tx(&bar[Q_VFULL], BT16K);
+          tma_load_2d(smem + BO_V, &tmX, 2 * HD + h * 64, b * a.T + n * 128, &bar[Q_VFULL]);
+        };
+        load_k(0);
+        load_r(0);
+        load_r(1);
+        load_v(0);
+        for (int n = 1; n < NT; n++) {              // waits in the order the MMAs retire: S(n-1), then PV(n-1)
+          load_k(n);
+          load_r(n + 1);
+          load_v(n);
+        }
+      }
+    } else if (warp == BT_SOFT_WARPS + 1) {
+      // =========================================== MMA issuer ===========================================
+      if (lane == 0) {
+        constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+        constexpr uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t qu = smem_u32(smem + BO_QU), qv = smem_u32(smem + BO_QV), qvn = smem_u32(smem + BO_QVN), kk = smem_u32(smem + BO_K),
+                       vv = smem_u32(smem + BO_V), rr = smem_u32(smem + BO_R), pp = smem_u32(smem + BO_P);
+        auto issue_pv = [&](int m) {
+          mbar_wait(&bar[Q_VFULL], m & 1);
+#pragma unroll
+          for (int hf = 0; hf < 2; hf++) {
+            mbar_wait(&bar[Q_PFULL0 + hf], m & 1);
+            if (m > 0) mbar_wait(&bar[Q_OFREE0 + hf], (m - 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              umma_bf16(tmem_base + BTM_O + 64 * hf, bt_desc_k(pp + hf * BT16K + k * 32), bt_desc_mn(vv + hf * 8192 + k * 2048), idesc_pv,
+                        (uint32_t)(k > 0));
+            umma_commit(&bar[Q_OFULL0 + hf]);
+          }
+          umma_commit(&bar[Q_VEMPTY]);
+        };
+        mbar_wait(&bar[Q_QREADY], 0);
+        for (int n = 0; n < NT; n++) {
+          mbar_wait(&bar[Q_KFULL], n & 1);
+          mbar_wait(&bar[Q_RFULL0 + (n & 1)], (n >> 1) & 1);                 // load n   = this tile's upper block
+          mbar_wait(&bar[Q_RFULL0 + ((n + 1) & 1)], ((n + 1) >> 1) & 1);     // load n+1 = this tile's lower block
+          if (n > 0) mbar_wait(&bar[Q_SFREE], (n - 1) & 1);
+          tc_fence_after();
+          const uint32_t ru = rr + (n & 1) * BT16K, rl = rr + ((n + 1) & 1) * BT16K;
+          const uint32_t au = n <= it ? qv : qvn, al = (n + 1) <= it ? qv : qvn;     // line 1 below / on the diagonal, line 3 above
+#pragma unroll
+          for (int k = 0; k < 4; k++) umma_bf16(tmem_base + BTM_AC, bt_desc_k(qu + k * 32), bt_desc_k(kk + k * 32), idesc_s, (uint32_t)(k > 0));
+#pragma unroll
+          for (int k = 0; k < 4; k++) umma_bf16(tmem_base + BTM_STRIP, bt_desc_k(al + k * 32), bt_desc_k(rl + k * 32), idesc_s, (uint32_t)(k > 0));
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            umma_bf16(tmem_base + BTM_STRIP + 128, bt_desc_k(au + k * 32), bt_desc_k(ru + k * 32), idesc_s, (uint32_t)(k > 0));
+          umma_commit(&bar[Q_SFULL]);
+          umma_commit(&bar[Q_KEMPTY]);
+          umma_commit(&bar[Q_REMPTY0 + (n & 1)]);   // the upper block is dead after this tile; the lower one serves the next
+          if (n > 0) issue_pv(n - 1);
+        }
+        issue_pv(NT - 1);
+      }
+    }
+  } else {
+    // =========================================== softmax warps ===========================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int hf = warp >> 2, q4 = warp & 3;
+    const int r = q4 * 32 + lane;                   // query row of this thread inside the tile
+    const int row = i0 + r;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    float* strip = (float*)(smem + BO_STRIP) + (size_t)(warp * 32 + lane) * BT_STRIP_LD;
+    const float c = a.scale * BT_LOG2E;
+
+    {   // q + u, q + v and q_next + v in the canonical swizzled layout (thread: row tid%128, four of its eight 16-byte chunks)
+      const int tid = threadIdx.x, qr = tid & 127, part = tid >> 7;
+      const uint32_t roff = (uint32_t)((qr >> 3) * 1024 + (qr & 7) * 128);
+      const float* ub = a.u + h * 64;
+      const float* vb = a.v + h * 64;
+      mbar_wait(&bar[Q_QFULL], 0);
+#pragma unroll
+      for (int pc = 4 * part; pc < 4 * part + 4; pc++) {
+        const uint4 raw = *(const uint4*)(smem + BO_P + roff + pc * 16);
+        const uint4 rawn = *(const uint4*)(smem + BO_P + BT16K + roff + pc * 16);
+        const int col = 8 * (pc ^ (qr & 7));
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w}, wn[4] = {rawn.x, rawn.y, rawn.z, rawn.w};
+        uint32_t ou[4], ov[4], on[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const float u0 = ub[col + 2 * e], u1 = ub[col + 2 * e + 1], v0 = vb[col + 2 * e], v1 = vb[col + 2 * e + 1];
+          ou[e] = pack_bf16x2(bf16lo(w[e]) + u0, bf16hi(w[e]) + u1);
+          ov[e] = pack_bf16x2(bf16lo(w[e]) + v0, bf16hi(w[e]) + v1);
+          on[e] = pack_bf16x2(bf16lo(wn[e]) + v0, bf16hi(wn[e]) + v1);
+        }
+        *(uint4*)(smem + BO_QU + roff + pc * 16) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+        *(uint4*)(smem + BO_QV + roff + pc * 16) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+        *(uint4*)(smem + BO_QVN + roff + pc * 16) = make_uint4(on[0], on[1], on[2], on[3]);
+      }
+      bt_fence_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[Q_QREADY]);
+    }
+
+    float o[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++) o[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
+    uint8_t* prow = smem + BO_P + hf * BT16K + (r >> 3) * 1024 + (r & 7) * 128;
+    // the zero pad of _line_shift: key j = i + 1 (tile (row+1)/128, local key (row+1)%128; for the last row of a tile that is key 0
+    // of the NEXT tile)
+    const int zero_tile = (row + 1) >> 7, zero_jj = ((((row + 1) & 127) >> 6) == hf) ? ((row + 1) & 63) : -1000;
+
+    for (int n = 0; n < NT; n++) {
+      float s[64];
+      mbar_wait(&bar[Q_SFULL], n & 1);
+      tc_fence_after();
+      {
+        uint32_t x0[32], x1[32];
+        tmem_ld_32x32(t_lane + BTM_AC + 64 * hf, x0);
+        tmem_ld_32x32(t_lane + BTM_AC + 64 * hf + 32, x1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++) { s[i] = __uint_as_float(x0[i]); s[32 + i] = __uint_as_float(x1[i]); }
+      }
+      const int zj = n == zero_tile ? zero_jj : -1000;
+#pragma unroll
+      for (int sp = 0; sp < 2; sp++) {
+        const uint32_t base = (uint32_t)(96 - 64 * hf - 32 * sp + 32 * q4);
+        {
+          uint32_t x0[32], x1[32];
+          tmem_ld_32x32(t_lane + BTM_STRIP + base, x0);
+          tmem_ld_32x32(t_lane + BTM_STRIP + base + 32, x1);
+          tmem_ld_wait();
+          if (sp == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar[Q_SFREE]);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            *(float4*)(strip + 4 * k) = make_float4(__uint_as_float(x0[4 * k]), __uint_as_float(x0[4 * k + 1]),
+                                                    __uint_as_float(x0[4 * k + 2]), __uint_as_float(x0[4 * k + 3]));
+            *(float4*)(strip + 32 + 4 * k) = make_float4(__uint_as_float(x1[4 * k]), __uint_as_float(x1[4 * k + 1]),
+                                                         __uint_as_float(x1[4 * k + 2]), __uint_as_float(x1[4 * k + 3]));
+          }
+        }
+        const float* sk = strip + 32 + lane;
+#pragma unroll
+        for (int jj = 0; jj < 32; jj++) s[32 * sp + jj] += (32 * sp + jj == zj) ? 0.f : sk[-jj];
+      }
+
+      if (n > 0) {                                   // fold the previous tile's P V into the running output
+        mbar_wait(&bar[Q_OFULL0 + hf], (n - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) {
+          uint32_t x[32];
+          tmem_ld_32x32(t_lane + BTM_O + 64 * hf + 32 * ch, x);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) o[32 * ch + i] = fmaf(o[32 * ch + i], alpha_prev, __uint_as_float(x[i]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar[Q_OFREE0 + hf]);
+      }
+
+      float mx = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < 64; jj++) mx = fmaxf(mx, s[jj]);
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = ex2_fast((m_run - m_new) * c);        // exp2(-inf) = 0 on the first tile
+      const float neg_mc = -m_new * c;
+      m_run = m_new;
+      float rs = 0.f;
+#pragma unroll
+      for (int ck = 0; ck < 8; ck++) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int pp = 4 * ck + e;
+          const float p0 = ex2_fast(fmaf(s[2 * pp], c, neg_mc)), p1 = ex2_fast(fmaf(s[2 * pp + 1], c, neg_mc));
+          rs += p0 + p1;
+          pk[e] = pack_bf16x2(p0, p1);
+        }
+        *(uint4*)(prow + ((ck ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      l_run = l_run * alpha + rs;
+      alpha_prev = alpha;
+      bt_fence_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[Q_PFULL0 + hf]);
+    }
+    mbar_wait(&bar[Q_OFULL0 + hf], (NT - 1) & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int ch = 0; ch < 2; ch++) {
+      uint32_t x[32];
+      tmem_ld_32x32(t_lane + BTM_O + 64 * hf + 32 * ch, x);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i++) o[32 * ch + i] = fmaf(o[32 * ch + i], alpha_prev, __uint_as_float(x[i]));
+    }
+    tc_fence_before();
+
+    if (hf == 1) {                                   // merge the two key halves of every row
+#pragma unroll
+      for (int k = 0; k < 16; k++) *(float4*)(strip + 4 * k) = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+      strip[64] = m_run;
+      strip[65] = l_run;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (hf == 0) {
+      const float* other = strip + (size_t)4 * 32 * BT_STRIP_LD;       // same lane of warp + 4
+      const float m1 = other[64], l1 = other[65];
+      const float m = fmaxf(m_run, m1);
+      const float w0 = ex2_fast((m_run - m) * c), w1 = ex2_fast((m1 - m) * c);
+      const float inv = 1.f / (l_run * w0 + l1 * w1);
+      bf16* orow = a.out + ((long long)b * a.T + row) * HD + h * 64;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int d0 = 8 * k + 2 * e;
+          w[e] = pack_bf16x2((o[d0] * w0 + other[d0] * w1) * inv, (o[d0 + 1] * w0 + other[d0 + 1] * w1) * inv);
+        }
+        *(uint4*)(orow + 8 * k) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == BT_SOFT_WARPS + 1) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace
+
+bool attn_bert_tc_supported(int T, int H, int Dcap) {
+  static const bool off = getenv("DMG_BERT_ATTN_MMA_SYNC") != nullptr;
+  return !off && T >= 128 && T % 128 == 0 && Dcap >= T && H >= 1;
+}
+
+// qkv: bf16 [B*T, 3*H*64] (q | k | v); rd: the inference rel-pos key cache [H][Dcap][64] (bf16, row = distance); out: bf16 [B*T, H*64]
+int attn_bert_tc(const bf16* qkv, const bf16* rd, int Dcap, const float* u, const float* v, bf16* out, int B, int T, int H, float scale,
+                 cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    DMG_CUDA_OK(cudaFuncSetAttribute(attn_bert_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
+    configured = true;
+  }
+  const int HD = H * 64;
+  const TensorMap2D *tx = nullptr, *tr = nullptr;
+  if (train_get_tmap(qkv, 3 * HD, (long long)B * T, 3 * HD, 128, &tx)) return -1;
+  if (train_get_tmap(rd, 64, (long long)H * Dcap, 64, 128, &tr)) return -1;
+  BertTcArgs a;
+  a.u = u; a.v = v; a.out = out; a.B = B; a.T = T; a.H = H; a.Dcap = Dcap; a.scale = scale;
+  return launch_k(attn_bert_tc_kernel, dim3(B * H * (T / 128)), dim3(BT_THREADS), (size_t)BT_SMEM, st, 1, *(const CUtensorMap*)tx->bytes,
+                  *(const CUtensorMap*)tr->bytes, a);
+}
+
+}  // namespace dmg
