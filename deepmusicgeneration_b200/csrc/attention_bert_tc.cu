@@ -182,29 +182,33 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     float* strip = (float*)(smem + BO_STRIP) + (size_t)(warp * 32 + lane) * BT_STRIP_LD;
     const float c = a.scale * BT_LOG2E;
 
-    {   // q + u, q + v and q_next + v in the canonical swizzled layout (thread: row tid%128, four of its eight 16-byte chunks)
-      const int tid = threadIdx.x, qr = tid & 127, part = tid >> 7;
-      const uint32_t roff = (uint32_t)((qr >> 3) * 1024 + (qr & 7) * 128);
-      const float* ub = a.u + h * 64;
-      const float* vb = a.v + h * 64;
+    {   // q + u, q + v and q_next + v in the canonical swizzled layout.  Eight consecutive threads take the eight 16-byte chunks of
+        // one row (128 contiguous bytes: no bank conflicts); a thread's rows are 32 apart, so its physical chunk maps to the same
+        // logical columns in all of them and it needs one 8-wide slice of u and v only (requested before the wait for q).
+      const int tid = threadIdx.x, pc = tid & 7, rb = tid >> 3;
+      const int col = 8 * (pc ^ (rb & 7));
+      const float4 ua = __ldg((const float4*)(a.u + h * 64 + col)), ub = __ldg((const float4*)(a.u + h * 64 + col + 4));
+      const float4 va = __ldg((const float4*)(a.v + h * 64 + col)), vb = __ldg((const float4*)(a.v + h * 64 + col + 4));
+      const float uu[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w}, vv8[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
       mbar_wait(&bar[Q_QFULL], 0);
 #pragma unroll
-      for (int pc = 4 * part; pc < 4 * part + 4; pc++) {
-        const uint4 raw = *(const uint4*)(smem + BO_P + roff + pc * 16);
-        const uint4 rawn = *(const uint4*)(smem + BO_P + BT16K + roff + pc * 16);
-        const int col = 8 * (pc ^ (qr & 7));
+      for (int k = 0; k < 4; k++) {
+        const int qr = rb + 32 * k;
+        const uint32_t off = (uint32_t)((qr >> 3) * 1024 + (qr & 7) * 128 + pc * 16);
+        const uint4 raw = *(const uint4*)(smem + BO_P + off);
+        const uint4 rawn = *(const uint4*)(smem + BO_P + BT16K + off);
         const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w}, wn[4] = {rawn.x, rawn.y, rawn.z, rawn.w};
         uint32_t ou[4], ov[4], on[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-          const float u0 = ub[col + 2 * e], u1 = ub[col + 2 * e + 1], v0 = vb[col + 2 * e], v1 = vb[col + 2 * e + 1];
+          const float u0 = uu[2 * e], u1 = uu[2 * e + 1], v0 = vv8[2 * e], v1 = vv8[2 * e + 1];
           ou[e] = pack_bf16x2(bf16lo(w[e]) + u0, bf16hi(w[e]) + u1);
           ov[e] = pack_bf16x2(bf16lo(w[e]) + v0, bf16hi(w[e]) + v1);
           on[e] = pack_bf16x2(bf16lo(wn[e]) + v0, bf16hi(wn[e]) + v1);
         }
-        *(uint4*)(smem + BO_QU + roff + pc * 16) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
-        *(uint4*)(smem + BO_QV + roff + pc * 16) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
-        *(uint4*)(smem + BO_QVN + roff + pc * 16) = make_uint4(on[0], on[1], on[2], on[3]);
+        *(uint4*)(smem + BO_QU + off) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+        *(uint4*)(smem + BO_QV + off) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+        *(uint4*)(smem + BO_QVN + off) = make_uint4(on[0], on[1], on[2], on[3]);
       }
       bt_fence_async();
       __syncwarp();

@@ -213,27 +213,31 @@ attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     const int vis_lim = a.k == 1 ? row + 1 : max((row / a.win) * a.win, 1);
     const float c = a.scale * LOG2E;
 
-    // ---- q + u and q + v in the canonical swizzled layout (thread: row tid%128, four of its eight 16-byte chunks)
+    // ---- q + u and q + v in the canonical swizzled layout.  Eight consecutive threads take the eight 16-byte chunks of one row (128
+    // contiguous bytes: no bank conflicts); a thread's rows are 32 apart, so its physical chunk maps to the same logical columns in all
+    // of them and it needs one 8-wide slice of u and v only (requested before the wait for q).
     {
-      const int tid = threadIdx.x, qr = tid & 127, part = tid >> 7;
-      const uint32_t roff = (uint32_t)((qr >> 3) * 1024 + (qr & 7) * 128);
-      const float* ub = a.u + h * 64;
-      const float* vb = a.v + h * 64;
+      const int tid = threadIdx.x, pc = tid & 7, rb = tid >> 3;
+      const int col = 8 * (pc ^ (rb & 7));
+      const float4 ua = __ldg((const float4*)(a.u + h * 64 + col)), ub = __ldg((const float4*)(a.u + h * 64 + col + 4));
+      const float4 va = __ldg((const float4*)(a.v + h * 64 + col)), vb = __ldg((const float4*)(a.v + h * 64 + col + 4));
+      const float uu[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w}, vv8[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
       mbar_wait(&bar[B_QFULL], 0);
 #pragma unroll
-      for (int pc = 4 * part; pc < 4 * part + 4; pc++) {
-        const uint4 raw = *(const uint4*)(smem + OFF_P + roff + pc * 16);
-        const int col = 8 * (pc ^ (qr & 7));
+      for (int k = 0; k < 4; k++) {
+        const int qr = rb + 32 * k;
+        const uint32_t off = (uint32_t)((qr >> 3) * 1024 + (qr & 7) * 128 + pc * 16);
+        const uint4 raw = *(const uint4*)(smem + OFF_P + off);
         const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
         uint32_t ou[4], ov[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const float lo = bf16lo(w[e]), hi = bf16hi(w[e]);
-          ou[e] = pack_bf16x2(lo + ub[col + 2 * e], hi + ub[col + 2 * e + 1]);
-          ov[e] = pack_bf16x2(lo + vb[col + 2 * e], hi + vb[col + 2 * e + 1]);
+          ou[e] = pack_bf16x2(lo + uu[2 * e], hi + uu[2 * e + 1]);
+          ov[e] = pack_bf16x2(lo + vv8[2 * e], hi + vv8[2 * e + 1]);
         }
-        *(uint4*)(smem + OFF_QU + roff + pc * 16) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
-        *(uint4*)(smem + OFF_QV + roff + pc * 16) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+        *(uint4*)(smem + OFF_QU + off) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+        *(uint4*)(smem + OFF_QV + off) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
       }
       fence_proxy_async();
       __syncwarp();
