@@ -137,11 +137,14 @@ attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
       load_r(1);
       if (NT > 1) load_k(1);
       load_v(0);
-      for (int n = 1; n < NT; n++) {                // waits in the order the MMAs retire: S(n-1), then PV(n-1)
+      // waits in the order the MMAs retire: S(n-1) is issued half a tile before PV(n-2), so the V requests trail the K / R requests by
+      // one tile (a V request waiting for PV(n-1) in front of them would hold the operands of S(n+1) back until half a tile before use)
+      for (int n = 1; n < NT; n++) {
         load_r(n + 1);
         if (n + 1 < NT) load_k(n + 1);
-        load_v(n);
+        if (n >= 2) load_v(n - 1);
       }
+      if (NT >= 2) load_v(NT - 1);
     }
   } else if (warp == TC_SOFT_WARPS + 1) {
     // =========================================== MMA issuer ===========================================
