@@ -1,4 +1,4 @@
-// Attention of the masked-BERT remix encoder on tcgen05 / TMEM / TMA (inference, bf16), for sequences that are multiples of 128.
+// Attention of the masked-BERT remix encoder on tcgen05 / TMEM / TMA (inference, bf16), for sequences of at least 128 tokens.
 //
 // Replaces MemMultiHeadRelativeAttentionKV._apply_attention (deep_music_remix.py:2078-2104; a14-a18 of SURVEY.md section 8):
 //   softmax(((q+u) K^T + _line_shift((q+v) Rk^T, mask=False)) / sqrt(Dh)) V        - no mask, no dropout, no out-projection
@@ -9,9 +9,11 @@
 // Same scheme as attn_train_fwd_tc_kernel (attention_train_tc.cu): one CTA per (stream, head, 128-query tile), row-per-thread
 // softmax warps, AC and a 256-column position strip in TMEM, skew through thread-private shared-memory lines, P as the A operand
 // of the PV MMA.  The strip is strip[r][c] = BD[r, jj] with c = 128 + r - jj; below the diagonal both 128-column halves come from
-// (q+v) and two consecutive 128-row blocks of Rk, above it from (q_next+v) and blocks of Rk3[x] = Rk[x+1], and ON the diagonal tile
-// line 1 only ever reads the upper half (r - jj >= 0) and line 3 only the lower half (r - jj <= -2), so one half of each fits the
-// same 256 columns.  Consecutive key tiles share a block (upper half of tile n+1 = lower half of tile n), also across the diagonal.
+// (q+v) and two consecutive 128-row blocks of Rk, above it from (q_next+v) and blocks of Rk3[x] = Rk[x + T + 1 - 128 nT] (nT key tiles;
+// a TMA box may start at any row), and ON the diagonal tile line 1 only ever reads the upper half (r - jj >= 0) and line 3 only the
+// lower half (r - jj <= -2), so one half of each fits the same 256 columns.  Consecutive key tiles share a block (upper half of tile
+// n+1 = lower half of tile n), also across the diagonal.  A ragged last tile (T not a multiple of 128) masks its keys >= T and does
+// not store its rows >= T; the boxes that reach past the sequence bring finite rows of the neighbouring sequence / head or zeros.
 #include <cuda.h>
 #include "kernels.cuh"
 #include "launch.cuh"
@@ -66,7 +68,7 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint32_t* tmem_holder = (uint32_t*)(bar + Q_COUNT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nT = a.T / 128;
+  const int nT = (a.T + 127) / 128;                  // a ragged last tile: keys >= T are masked, rows >= T are not stored
   const int it = blockIdx.x % nT;                   // every query tile sees all nT key tiles: uniform work
   const int bh = blockIdx.x / nT, b = bh / a.H, h = bh % a.H;
   const int i0 = it * 128, HD = a.H * 64;
@@ -106,7 +108,9 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         };
         auto load_r = [&](int k) {                  // load 0 = upper block of tile 0; load k >= 1 = lower block of tile k-1
           const int s = k & 1;
-          const int row = k <= it ? (it - k) * 128 : (nT + it - k) * 128 + 1;   // Rk block it-k, or Rk3 block nT+it-k (Rk3[x] = Rk[x+1])
+          // line 1: Rk rows (it-k)*128 ...; line 3: Rk rows T + 1 + (it-k)*128 ... (distance T + 1 + i - j; rows below 0 or past T - 1
+          // only meet masked keys or the zero pad)
+          const int row = k <= it ? (it - k) * 128 : a.T + 1 + (it - k) * 128;
           mbar_wait(&bar[Q_REMPTY0 + s], ((k >> 1) & 1) ^ 1);
           mbar_expect_tx(&bar[Q_RFULL0 + s], BT16K);
           tma_load_2d(smem + BO_R + s * BT16K, &tmR, 0, h * a.Dcap + row, &bar[Q_RFULL0 + s]);
@@ -161,6 +165,8 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           tc_fence_after();
           const uint32_t ru = rr + (n & 1) * BT16K, rl = rr + ((n + 1) & 1) * BT16K;
           const uint32_t au = n <= it ? qv : qvn, al = (n + 1) <= it ? qv : qvn;     // line 1 below / on the diagonal, line 3 above
+          // (separate ready / free barriers for AC and the strip - AC(n+1) issued right after the AC reads of tile n - were measured
+          // slower: 68.4 vs 64.4 ms per C4 forward; the extra arrive sits in the softmax warps' critical path)
 #pragma unroll
           for (int k = 0; k < 4; k++) umma_bf16(tmem_base + BTM_AC, bt_desc_k(qu + k * 32), bt_desc_k(kk + k * 32), idesc_s, (uint32_t)(k > 0));
 #pragma unroll
@@ -267,6 +273,12 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         for (int jj = 0; jj < 32; jj++) s[32 * sp + jj] += (32 * sp + jj == zj) ? 0.f : sk[-jj];
       }
 
+      if (n == NT - 1 && (a.T & 127)) {              // ragged last tile: keys past the sequence end
+        const int jlim = a.T - n * 128 - 64 * hf;
+#pragma unroll
+        for (int jj = 0; jj < 64; jj++) s[jj] = jj < jlim ? s[jj] : -INFINITY;
+      }
+
       if (n > 0) {                                   // fold the previous tile's P V into the running output
         mbar_wait(&bar[Q_OFULL0 + hf], (n - 1) & 1);
         tc_fence_after();
@@ -328,7 +340,7 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       strip[65] = l_run;
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (hf == 0) {
+    if (hf == 0 && row < a.T) {
       const float* other = strip + (size_t)4 * 32 * BT_STRIP_LD;       // same lane of warp + 4
       const float m1 = other[64], l1 = other[65];
       const float m = fmaxf(m_run, m1);
@@ -355,8 +367,8 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 }  // namespace
 
 bool attn_bert_tc_supported(int T, int H, int Dcap) {
-  static const bool off = getenv("DMG_BERT_ATTN_MMA_SYNC") != nullptr;
-  return !off && T >= 128 && T % 128 == 0 && Dcap >= T && H >= 1;
+  const bool off = getenv("DMG_BERT_ATTN_MMA_SYNC") != nullptr;   // read per call: the tests switch kernels inside one process
+  return !off && T >= 128 && Dcap >= T && H >= 1;   // T >= 128: every row has seen a full tile before the ragged one (finite running maximum)
 }
 
 // qkv: bf16 [B*T, 3*H*64] (q | k | v); rd: the inference rel-pos key cache [H][Dcap][64] (bf16, row = distance); out: bf16 [B*T, H*64]
@@ -373,7 +385,7 @@ int attn_bert_tc(const bf16* qkv, const bf16* rd, int Dcap, const float* u, cons
   if (train_get_tmap(rd, 64, (long long)H * Dcap, 64, 128, &tr)) return -1;
   BertTcArgs a;
   a.u = u; a.v = v; a.out = out; a.B = B; a.T = T; a.H = H; a.Dcap = Dcap; a.scale = scale;
-  return launch_k(attn_bert_tc_kernel, dim3(B * H * (T / 128)), dim3(BT_THREADS), (size_t)BT_SMEM, st, 1, *(const CUtensorMap*)tx->bytes,
+  return launch_k(attn_bert_tc_kernel, dim3(B * H * ((T + 127) / 128)), dim3(BT_THREADS), (size_t)BT_SMEM, st, 1, *(const CUtensorMap*)tx->bytes,
                   *(const CUtensorMap*)tr->bytes, a);
 }
 

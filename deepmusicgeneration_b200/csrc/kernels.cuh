@@ -115,7 +115,7 @@ struct AttnDecodeArgs {
   int no_early_kv = 0;  // v2 kernel: 1 = request the first K/V tiles only after the predecessor kernel has finished (DMG_NO_EARLY_KV)
 };
 int attn_decode(const AttnDecodeArgs& a, cudaStream_t st);
-// BERT-encoder attention on tcgen05 (attention_bert_tc.cu): T a multiple of 128; same contract as attn_flash(..., bert = 1, ...)
+// BERT-encoder attention on tcgen05 (attention_bert_tc.cu): T >= 128; same contract as attn_flash(..., bert = 1, ...)
 bool attn_bert_tc_supported(int T, int H, int Dcap);
 int attn_bert_tc(const bf16* qkv, const bf16* rd, int Dcap, const float* u, const float* v, bf16* out, int B, int T, int H, float scale,
                  cudaStream_t st);

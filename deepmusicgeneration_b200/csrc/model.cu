@@ -91,7 +91,7 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
     if (flash) {
       // memory-less segment: bf16 q|k|v straight from the GEMM epilogue, tensor-core flash attention (attention_flash.cu)
       if (linear(m, A_XA, xa, L.wqkv, L.bqkv, m->qkv16, 3 * HD, rows, 0, 1, st)) return -1;
-      if (bert && attn_bert_tc_supported(T_len, c.n_heads, m->Dcap)) {   // tcgen05 / TMEM / TMA kernel (sequences of n x 128 tokens)
+      if (bert && attn_bert_tc_supported(T_len, c.n_heads, m->Dcap)) {   // tcgen05 / TMEM / TMA kernel (sequences of at least 128 tokens)
         if (attn_bert_tc(m->qkv16, (const bf16*)L.rd, m->Dcap, m->u, m->v, (bf16*)m->attn, nb, T_len, c.n_heads,
                          1.f / sqrtf((float)c.d_head), st)) return -1;
       } else if (attn_flash(m->qkv16, (const bf16*)L.rd, m->Dcap, m->u, m->v, (bf16*)m->attn, nb, T_len, c.n_heads, bert ? 1 : 0,

@@ -332,20 +332,23 @@ def test_bert_flash_attention_bf16_ragged_lengths(T):
     with torch.no_grad():
         ol = om({'msk': {'x': x, 'pos': pos.clone()}})['msk']
     os.environ.pop('DMG_NO_FLASH', None)
-    pl = pm({'msk': {'x': x.cuda(), 'pos': pos.cuda()}})['msk'].cpu()
     try:
+        os.environ['DMG_BERT_ATTN_MMA_SYNC'] = '1'       # sequences of 128 tokens and more default to attention_bert_tc.cu
+        pl = pm({'msk': {'x': x.cuda(), 'pos': pos.cuda()}})['msk'].cpu()
         os.environ['DMG_NO_FLASH'] = '1'
         pg = pm({'msk': {'x': x.cuda(), 'pos': pos.cuda()}})['msk'].cpu()
     finally:
         os.environ.pop('DMG_NO_FLASH', None)
+        os.environ.pop('DMG_BERT_ATTN_MMA_SYNC', None)
     print(f'T={T}: flash vs oracle {_rel(pl, ol):.3e}, general vs oracle {_rel(pg, ol):.3e}, flash vs general {(pl - pg).abs().max():.3e}')
     assert _rel(pl, ol) <= 2e-2 and (pl - pg).abs().max() < 3e-2
 
 
-@pytest.mark.parametrize('T', [128, 256, 384, 1024])
+@pytest.mark.parametrize('T', [128, 129, 191, 256, 257, 320, 384, 1000, 1024])
 def test_bert_tcgen05_attention_bf16(T):
-    """attention_bert_tc.cu (tcgen05 / TMEM / TMA; sequences of n x 128 tokens): all three _line_shift lines, the zero pad at
-    j = i + 1 (also across a tile boundary) and the wrapped line-3 distances, against the oracle and the FFMA general kernel"""
+    """attention_bert_tc.cu (tcgen05 / TMEM / TMA; sequences of 128 tokens and more): all three _line_shift lines, the zero pad at
+    j = i + 1 (also across a tile boundary), the wrapped line-3 distances and a ragged last tile (masked keys, one or both key
+    halves), against the oracle and the FFMA general kernel"""
     cfg = dict(obert.multitask_config(), enc_layers=2, d_model=128, n_heads=2, d_head=64, d_inner=256)
     om, pm = _bert_pair(cfg, 'bf16', 3, 1024)
     g = torch.Generator().manual_seed(T)
