@@ -269,8 +269,9 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           }
         }
         const float* sk = strip + 32 + lane;
+        if ((unsigned)(zj - 32 * sp) < 32u) strip[32 + lane - (zj - 32 * sp)] = 0.f;   // the zero pad: one slot of the line, no select per key
 #pragma unroll
-        for (int jj = 0; jj < 32; jj++) s[32 * sp + jj] += (32 * sp + jj == zj) ? 0.f : sk[-jj];
+        for (int jj = 0; jj < 32; jj++) s[32 * sp + jj] += sk[-jj];
       }
 
       if (n == NT - 1 && (a.T & 127)) {              // ragged last tile: keys past the sequence end
@@ -374,6 +375,7 @@ bool attn_bert_tc_supported(int T, int H, int Dcap) {
 // qkv: bf16 [B*T, 3*H*64] (q | k | v); rd: the inference rel-pos key cache [H][Dcap][64] (bf16, row = distance); out: bf16 [B*T, H*64]
 int attn_bert_tc(const bf16* qkv, const bf16* rd, int Dcap, const float* u, const float* v, bf16* out, int B, int T, int H, float scale,
                  cudaStream_t st) {
+  if (getenv("DMG_BERT_TC16")) return attn_bert_tc16(qkv, rd, Dcap, u, v, out, B, T, H, scale, st);   // sixteen softmax warps (attention_bert_tc16.cu)
   static bool configured = false;
   if (!configured) {
     DMG_CUDA_OK(cudaFuncSetAttribute(attn_bert_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));

@@ -119,6 +119,8 @@ int attn_decode(const AttnDecodeArgs& a, cudaStream_t st);
 bool attn_bert_tc_supported(int T, int H, int Dcap);
 int attn_bert_tc(const bf16* qkv, const bf16* rd, int Dcap, const float* u, const float* v, bf16* out, int B, int T, int H, float scale,
                  cudaStream_t st);
+int attn_bert_tc16(const bf16* qkv, const bf16* rd, int Dcap, const float* u, const float* v, bf16* out, int B, int T, int H, float scale,
+                   cudaStream_t st);   // sixteen softmax warps (attention_bert_tc16.cu)
 bool attn_decode_supported(int Dh, int M);
 // v2: persistent, TMA-2D swizzled K/V tiles, resident rel-pos keys, mma.sync dot products (attention_decode2.cu).
 // tmK/tmV: ring viewed as [max_batch*H*M rows, 64 cols]; tmR: Rd viewed as [H*Dcap rows, 64 cols]; 64-row boxes.
