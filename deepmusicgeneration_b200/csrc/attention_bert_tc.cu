@@ -15,6 +15,7 @@
 // n+1 = lower half of tile n), also across the diagonal.  A ragged last tile (T not a multiple of 128) masks its keys >= T and does
 // not store its rows >= T; the boxes that reach past the sequence bring finite rows of the neighbouring sequence / head or zeros.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "kernels.cuh"
 #include "launch.cuh"
 #include "mma_sync.cuh"
@@ -40,6 +41,7 @@ constexpr int BO_STRIP = BO_P + 2 * BT16K;
 constexpr int BO_BAR = BO_STRIP + BT_SOFT_WARPS * 32 * BT_STRIP_LD * 4;
 constexpr int BT_SMEM = BO_BAR + 256 + 1024;
 static_assert(BT_SMEM <= 227 * 1024, "shared memory budget");
+static_assert(BT_SOFT_WARPS * 32 * 208 <= BT_SOFT_WARPS * 32 * BT_STRIP_LD * 4 && 128 * 68 * 4 <= 3 * BT16K, "fp16 lines / merge buffer fit");
 
 enum { Q_QFULL = 0, Q_QREADY, Q_KFULL, Q_KEMPTY, Q_RFULL0, Q_RFULL1, Q_REMPTY0, Q_REMPTY1, Q_VFULL, Q_VEMPTY, Q_SFULL, Q_SFREE,
        Q_PFULL0, Q_PFULL1, Q_OFULL0, Q_OFULL1, Q_OFREE0, Q_OFREE1, Q_COUNT };
@@ -52,6 +54,13 @@ __device__ __forceinline__ uint64_t bt_desc_mn(uint32_t addr) {         // MN-ma
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(8192u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 __device__ __forceinline__ void bt_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t bt_f16x2_sat(float lo, float hi) {
+  uint32_t w;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi), "f"(lo));
+  return w;
+}
+constexpr int BT_LINE16 = 208;                         // bytes of an fp16 strip line: 96 halves + 16 (16-byte stores of 8 lanes hit 8 bank groups)
+constexpr int BT_MROW = 68;                            // floats per row of the final merge buffer of the fp16-strip kernel (in the dead q tiles)
 
 struct BertTcArgs {
   const float* u; const float* v;   // [H*64]
@@ -60,6 +69,11 @@ struct BertTcArgs {
   float scale;
 };
 
+// H16: the position strip goes through shared memory as fp16 (|BD| < 65504 saturates; 11 bits of mantissa against the 8 of the bf16
+// operands): the thread's two 64-column windows overlap in 32 columns, so it reads 96 distinct columns once (three tcgen05.ld.x32
+// instead of four), stores 12 instead of 32 16-byte chunks and reads its 64 scores back as 33 aligned words + funnel shifts - 40 % of
+// the shared-memory wavefronts of the fp32 line (the kernel sits on the shared-memory pipe, profiles/r1g_attn_bert_tc_ncu.txt).
+template <bool H16>
 __global__ void __launch_bounds__(BT_THREADS, 1)
 attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmR, const BertTcArgs a) {
   extern __shared__ __align__(1024) uint8_t bt_smem_raw[];
@@ -238,6 +252,61 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       float s[64];
       mbar_wait(&bar[Q_SFULL], n & 1);
       tc_fence_after();
+      const int zj = n == zero_tile ? zero_jj : -1000;
+      if constexpr (H16) {
+        // strip columns [wbase, wbase + 96) -> fp16 -> this thread's line; score of local key jj (0..63) = line[64 + lane - jj]
+        const uint32_t wbase = (uint32_t)(64 - 64 * hf + 32 * q4);
+        uint8_t* line = smem + BO_STRIP + (size_t)(warp * 32 + lane) * BT_LINE16;
+        {
+          uint32_t x0[32], x1[32];
+          tmem_ld_32x32(t_lane + BTM_STRIP + wbase, x0);
+          tmem_ld_32x32(t_lane + BTM_STRIP + wbase + 32, x1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            *(uint4*)(line + 16 * k) = make_uint4(bt_f16x2_sat(__uint_as_float(x0[8 * k]), __uint_as_float(x0[8 * k + 1])),
+                                                  bt_f16x2_sat(__uint_as_float(x0[8 * k + 2]), __uint_as_float(x0[8 * k + 3])),
+                                                  bt_f16x2_sat(__uint_as_float(x0[8 * k + 4]), __uint_as_float(x0[8 * k + 5])),
+                                                  bt_f16x2_sat(__uint_as_float(x0[8 * k + 6]), __uint_as_float(x0[8 * k + 7])));
+          tmem_ld_32x32(t_lane + BTM_STRIP + wbase + 64, x0);
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            *(uint4*)(line + 64 + 16 * k) = make_uint4(bt_f16x2_sat(__uint_as_float(x1[8 * k]), __uint_as_float(x1[8 * k + 1])),
+                                                       bt_f16x2_sat(__uint_as_float(x1[8 * k + 2]), __uint_as_float(x1[8 * k + 3])),
+                                                       bt_f16x2_sat(__uint_as_float(x1[8 * k + 4]), __uint_as_float(x1[8 * k + 5])),
+                                                       bt_f16x2_sat(__uint_as_float(x1[8 * k + 6]), __uint_as_float(x1[8 * k + 7])));
+          tmem_ld_32x32(t_lane + BTM_AC + 64 * hf, x1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            *(uint4*)(line + 128 + 16 * k) = make_uint4(bt_f16x2_sat(__uint_as_float(x0[8 * k]), __uint_as_float(x0[8 * k + 1])),
+                                                        bt_f16x2_sat(__uint_as_float(x0[8 * k + 2]), __uint_as_float(x0[8 * k + 3])),
+                                                        bt_f16x2_sat(__uint_as_float(x0[8 * k + 4]), __uint_as_float(x0[8 * k + 5])),
+                                                        bt_f16x2_sat(__uint_as_float(x0[8 * k + 6]), __uint_as_float(x0[8 * k + 7])));
+          tmem_ld_32x32(t_lane + BTM_AC + 64 * hf + 32, x0);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar[Q_SFREE]);
+#pragma unroll
+          for (int i = 0; i < 32; i++) { s[i] = __uint_as_float(x1[i]); s[32 + i] = __uint_as_float(x0[i]); }
+        }
+        const int S_h = 64 + lane;                   // half index of local key 0
+        if ((unsigned)zj < 64u) ((__half*)line)[S_h - zj] = __float2half(0.f);   // the zero pad: one slot of the line
+        asm volatile("" ::: "memory");              // the word reads below alias the stores above
+        const uint32_t* rdw = (const uint32_t*)line + (S_h >> 1);   // word k back holds halves S' - 2k - 1 (low), S' - 2k (high), S' = S_h | 1
+        const uint32_t sh = (S_h & 1) ? 0u : 16u;   // lanes with an even S_h shift the word chain by one half
+        uint32_t wprev = rdw[0];
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+          const uint32_t wnext = rdw[-(k + 1)];
+          const uint32_t x = __funnelshift_l(wnext, wprev, sh);
+          const __half2 h2 = *reinterpret_cast<const __half2*>(&x);
+          s[2 * k] += __high2float(h2);
+          s[2 * k + 1] += __low2float(h2);
+          wprev = wnext;
+        }
+      } else {
       {
         uint32_t x0[32], x1[32];
         tmem_ld_32x32(t_lane + BTM_AC + 64 * hf, x0);
@@ -246,7 +315,6 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
         for (int i = 0; i < 32; i++) { s[i] = __uint_as_float(x0[i]); s[32 + i] = __uint_as_float(x1[i]); }
       }
-      const int zj = n == zero_tile ? zero_jj : -1000;
 #pragma unroll
       for (int sp = 0; sp < 2; sp++) {
         const uint32_t base = (uint32_t)(96 - 64 * hf - 32 * sp + 32 * q4);
@@ -272,6 +340,8 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if ((unsigned)(zj - 32 * sp) < 32u) strip[32 + lane - (zj - 32 * sp)] = 0.f;   // the zero pad: one slot of the line, no select per key
 #pragma unroll
         for (int jj = 0; jj < 32; jj++) s[32 * sp + jj] += sk[-jj];
+      }
+
       }
 
       if (n == NT - 1 && (a.T & 127)) {              // ragged last tile: keys past the sequence end
@@ -334,15 +404,18 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
     tc_fence_before();
 
-    if (hf == 1) {                                   // merge the two key halves of every row
+    // merge the two key halves of every row: half 1 leaves its output, maximum and row sum in its strip line (fp32 strip) or in the q
+    // tiles (fp16 strip: the lines are too short; every MMA that reads the q tiles has completed once the last P V has)
+    float* mine = H16 ? (float*)(smem + BO_QU) + (size_t)r * BT_MROW : strip;
+    if (hf == 1) {
 #pragma unroll
-      for (int k = 0; k < 16; k++) *(float4*)(strip + 4 * k) = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
-      strip[64] = m_run;
-      strip[65] = l_run;
+      for (int k = 0; k < 16; k++) *(float4*)(mine + 4 * k) = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+      mine[64] = m_run;
+      mine[65] = l_run;
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (hf == 0 && row < a.T) {
-      const float* other = strip + (size_t)4 * 32 * BT_STRIP_LD;       // same lane of warp + 4
+      const float* other = H16 ? mine : strip + (size_t)4 * 32 * BT_STRIP_LD;       // same row: same lane of warp + 4
       const float m1 = other[64], l1 = other[65];
       const float m = fmaxf(m_run, m1);
       const float w0 = ex2_fast((m_run - m) * c), w1 = ex2_fast((m1 - m) * c);
@@ -378,16 +451,22 @@ int attn_bert_tc(const bf16* qkv, const bf16* rd, int Dcap, const float* u, cons
   if (getenv("DMG_BERT_TC16")) return attn_bert_tc16(qkv, rd, Dcap, u, v, out, B, T, H, scale, st);   // sixteen softmax warps (attention_bert_tc16.cu)
   static bool configured = false;
   if (!configured) {
-    DMG_CUDA_OK(cudaFuncSetAttribute(attn_bert_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
+    DMG_CUDA_OK(cudaFuncSetAttribute(attn_bert_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
+    DMG_CUDA_OK(cudaFuncSetAttribute(attn_bert_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
     configured = true;
   }
+  const bool fp32_strip = getenv("DMG_BERT_TC_FP32_STRIP") != nullptr;   // the first version: fp32 strip lines (2.5 x the shared-memory wavefronts)
   const int HD = H * 64;
   const TensorMap2D *tx = nullptr, *tr = nullptr;
   if (train_get_tmap(qkv, 3 * HD, (long long)B * T, 3 * HD, 128, &tx)) return -1;
   if (train_get_tmap(rd, 64, (long long)H * Dcap, 64, 128, &tr)) return -1;
   BertTcArgs a;
   a.u = u; a.v = v; a.out = out; a.B = B; a.T = T; a.H = H; a.Dcap = Dcap; a.scale = scale;
-  return launch_k(attn_bert_tc_kernel, dim3(B * H * ((T + 127) / 128)), dim3(BT_THREADS), (size_t)BT_SMEM, st, 1, *(const CUtensorMap*)tx->bytes,
+  const dim3 grid(B * H * ((T + 127) / 128));
+  if (fp32_strip)
+    return launch_k(attn_bert_tc_kernel<false>, grid, dim3(BT_THREADS), (size_t)BT_SMEM, st, 1, *(const CUtensorMap*)tx->bytes,
+                    *(const CUtensorMap*)tr->bytes, a);
+  return launch_k(attn_bert_tc_kernel<true>, grid, dim3(BT_THREADS), (size_t)BT_SMEM, st, 1, *(const CUtensorMap*)tx->bytes,
                   *(const CUtensorMap*)tr->bytes, a);
 }
 

@@ -344,12 +344,13 @@ def test_bert_flash_attention_bf16_ragged_lengths(T):
     assert _rel(pl, ol) <= 2e-2 and (pl - pg).abs().max() < 3e-2
 
 
-@pytest.mark.parametrize('warps16', [False, True])
+@pytest.mark.parametrize('variant', ['default', 'DMG_BERT_TC_FP32_STRIP', 'DMG_BERT_TC16'])
 @pytest.mark.parametrize('T', [128, 129, 191, 256, 257, 320, 384, 1000, 1024])
-def test_bert_tcgen05_attention_bf16(T, warps16):
+def test_bert_tcgen05_attention_bf16(T, variant):
     """attention_bert_tc.cu (tcgen05 / TMEM / TMA; sequences of 128 tokens and more): all three _line_shift lines, the zero pad at
     j = i + 1 (also across a tile boundary), the wrapped line-3 distances and a ragged last tile (masked keys, one or both key
-    halves), against the oracle and the FFMA general kernel; warps16: the sixteen-softmax-warp variant (attention_bert_tc16.cu, DMG_BERT_TC16)"""
+    halves), against the oracle and the FFMA general kernel.  Variants: the default (fp16 strip line), the fp32 strip line
+    (DMG_BERT_TC_FP32_STRIP) and the sixteen-softmax-warp kernel (attention_bert_tc16.cu, DMG_BERT_TC16)"""
     cfg = dict(obert.multitask_config(), enc_layers=2, d_model=128, n_heads=2, d_head=64, d_inner=256)
     om, pm = _bert_pair(cfg, 'bf16', 3, 1024)
     g = torch.Generator().manual_seed(T)
@@ -359,14 +360,14 @@ def test_bert_tcgen05_attention_bf16(T, warps16):
         ol = om({'msk': {'x': x, 'pos': pos.clone()}})['msk']
     os.environ.pop('DMG_NO_FLASH', None)
     try:
-        if warps16:
-            os.environ['DMG_BERT_TC16'] = '1'
+        if variant != 'default':
+            os.environ[variant] = '1'
         pl = pm({'msk': {'x': x.cuda(), 'pos': pos.cuda()}})['msk'].cpu()
         os.environ['DMG_NO_FLASH'] = '1'
         pg = pm({'msk': {'x': x.cuda(), 'pos': pos.cuda()}})['msk'].cpu()
     finally:
         os.environ.pop('DMG_NO_FLASH', None)
-        os.environ.pop('DMG_BERT_TC16', None)
+        os.environ.pop(variant, None)
     print(f'T={T}: tcgen05 vs oracle {_rel(pl, ol):.3e}, general vs oracle {_rel(pg, ol):.3e}, tcgen05 vs general {(pl - pg).abs().max():.3e}')
     assert _rel(pl, ol) <= 2e-2 and (pl - pg).abs().max() < 3e-2
 
