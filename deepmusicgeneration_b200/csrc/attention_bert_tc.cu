@@ -14,60 +14,22 @@
 // lower half (r - jj <= -2), so one half of each fits the same 256 columns.  Consecutive key tiles share a block (upper half of tile
 // n+1 = lower half of tile n), also across the diagonal.  A ragged last tile (T not a multiple of 128) masks its keys >= T and does
 // not store its rows >= T; the boxes that reach past the sequence bring finite rows of the neighbouring sequence / head or zeros.
-#include <cuda.h>
-#include <cuda_fp16.h>
-#include "kernels.cuh"
-#include "launch.cuh"
-#include "mma_sync.cuh"
-#include "train_kernels.cuh"
+#include "attention_bert_tc_common.cuh"
 
 namespace dmg {
 
 namespace {
 
-constexpr float BT_LOG2E = 1.4426950408889634f;
+using namespace bert_tc;
+
 constexpr int BT_SOFT_WARPS = 8;
 constexpr int BT_THREADS = (BT_SOFT_WARPS + 4) * 32;   // + one auxiliary warpgroup: TMA warp, MMA warp, two idle warps
-constexpr int BT16K = 128 * 64 * 2;
 constexpr int BT_STRIP_LD = 68;
-constexpr int BO_QU = 0;
-constexpr int BO_QV = BO_QU + BT16K;
-constexpr int BO_QVN = BO_QV + BT16K;
-constexpr int BO_K = BO_QVN + BT16K;                   // one stage
-constexpr int BO_V = BO_K + BT16K;
-constexpr int BO_R = BO_V + BT16K;                     // 2 slots (slot = load index & 1)
-constexpr int BO_P = BO_R + 2 * BT16K;                 // 2 key halves; the raw q / q_next tiles land here first
-constexpr int BO_STRIP = BO_P + 2 * BT16K;
 constexpr int BO_BAR = BO_STRIP + BT_SOFT_WARPS * 32 * BT_STRIP_LD * 4;
 constexpr int BT_SMEM = BO_BAR + 256 + 1024;
 static_assert(BT_SMEM <= 227 * 1024, "shared memory budget");
-static_assert(BT_SOFT_WARPS * 32 * 208 <= BT_SOFT_WARPS * 32 * BT_STRIP_LD * 4 && 128 * 68 * 4 <= 3 * BT16K, "fp16 lines / merge buffer fit");
-
-enum { Q_QFULL = 0, Q_QREADY, Q_KFULL, Q_KEMPTY, Q_RFULL0, Q_RFULL1, Q_REMPTY0, Q_REMPTY1, Q_VFULL, Q_VEMPTY, Q_SFULL, Q_SFREE,
-       Q_PFULL0, Q_PFULL1, Q_OFULL0, Q_OFULL1, Q_OFREE0, Q_OFREE1, Q_COUNT };
-constexpr uint32_t BTM_AC = 0, BTM_STRIP = 128, BTM_O = 384;
-
-__device__ __forceinline__ uint64_t bt_desc_k(uint32_t addr) {          // K-major, 128B swizzle: rows of 128 B, 8-row groups 1024 B apart
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ uint64_t bt_desc_mn(uint32_t addr) {         // MN-major: LBO 8192, SBO 1024
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(8192u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void bt_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ uint32_t bt_f16x2_sat(float lo, float hi) {
-  uint32_t w;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi), "f"(lo));
-  return w;
-}
-constexpr int BT_LINE16 = 208;                         // bytes of an fp16 strip line: 96 halves + 16 (16-byte stores of 8 lanes hit 8 bank groups)
+static_assert(BT_SOFT_WARPS * 32 * BT_LINE16 <= BT_SOFT_WARPS * 32 * BT_STRIP_LD * 4 && 128 * 68 * 4 <= 3 * BT16K, "fp16 lines / merge buffer fit");
 constexpr int BT_MROW = 68;                            // floats per row of the final merge buffer of the fp16-strip kernel (in the dead q tiles)
-
-struct BertTcArgs {
-  const float* u; const float* v;   // [H*64]
-  bf16* out;                        // [B*T, H*64]
-  int B, T, H, Dcap;
-  float scale;
-};
 
 // H16: the position strip goes through shared memory as fp16 (|BD| < 65504 saturates; 11 bits of mantissa against the 8 of the bf16
 // operands): the thread's two 64-column windows overlap in 32 columns, so it reads 96 distinct columns once (three tcgen05.ld.x32
@@ -91,13 +53,7 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   if (warp == BT_SOFT_WARPS && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmR);
-    for (int i = 0; i < Q_COUNT; i++) {
-      uint32_t cnt = 1;
-      if (i == Q_QREADY || i == Q_SFREE) cnt = BT_SOFT_WARPS;
-      if (i == Q_PFULL0 || i == Q_PFULL1 || i == Q_OFREE0 || i == Q_OFREE1) cnt = BT_SOFT_WARPS / 2;
-      mbar_init(&bar[i], cnt);
-    }
-    mbar_fence_init();
+    bt_init_barriers(bar, BT_SOFT_WARPS);
   }
   if (warp == BT_SOFT_WARPS + 1) tmem_alloc<512>(tmem_holder);
   tc_fence_before();
@@ -110,91 +66,10 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == BT_SOFT_WARPS) {
       // =========================================== TMA producer ===========================================
-      if (lane == 0) {
-        pdl_wait();                                  // q | k | v come from the predecessor kernel (the QKV GEMM)
-        mbar_expect_tx(&bar[Q_QFULL], 2 * BT16K);
-        tma_load_2d(smem + BO_P, &tmX, h * 64, b * a.T + i0, &bar[Q_QFULL]);
-        tma_load_2d(smem + BO_P + BT16K, &tmX, h * 64, b * a.T + i0 + 1, &bar[Q_QFULL]);   // rows i+1 (the last row of the last tile is never used)
-        auto load_k = [&](int n) {
-          mbar_wait(&bar[Q_KEMPTY], (n & 1) ^ 1);
-          mbar_expect_tx(&bar[Q_KFULL], BT16K);
-          tma_load_2d(smem + BO_K, &tmX, HD + h * 64, b * a.T + n * 128, &bar[Q_KFULL]);
-        };
-        auto load_r = [&](int k) {                  // load 0 = upper block of tile 0; load k >= 1 = lower block of tile k-1
-          const int s = k & 1;
-          // line 1: Rk rows (it-k)*128 ...; line 3: Rk rows T + 1 + (it-k)*128 ... (distance T + 1 + i - j; rows below 0 or past T - 1
-          // only meet masked keys or the zero pad)
-          const int row = k <= it ? (it - k) * 128 : a.T + 1 + (it - k) * 128;
-          mbar_wait(&bar[Q_REMPTY0 + s], ((k >> 1) & 1) ^ 1);
-          mbar_expect_tx(&bar[Q_RFULL0 + s], BT16K);
-          tma_load_2d(smem + BO_R + s * BT16K, &tmR, 0, h * a.Dcap + row, &bar[Q_RFULL0 + s]);
-        };
-        auto load_v = [&](int n) {
-          mbar_wait(&bar[Q_VEMPTY], (n & 1) ^ 1);
-          mbar_expect_tx(&bar[Q_VFULL], BT16K);
-          tma_load_2d(smem + BO_V, &tmX, 2 * HD + h * 64, b * a.T + n * 128, &bar[Q_VFULL]);
-        };
-        load_k(0);
-        load_r(0);
-        load_r(1);
-        load_v(0);
-        // waits in the order the MMAs retire: S(n-1) is issued half a tile before PV(n-2), so the V requests trail the K / R requests
-        // by one tile (a V request waiting for PV(n-1) in front of them would hold the operands of S(n+1) back until half a tile before
-        // use: measured 70.8 -> 64.5 ms per C4 forward)
-        for (int n = 1; n < NT; n++) {
-          load_k(n);
-          load_r(n + 1);
-          if (n >= 2) load_v(n - 1);
-        }
-        if (NT >= 2) load_v(NT - 1);
-      }
+      if (lane == 0) bt_producer(smem, bar, tmX, tmR, a, b, h, it, NT);
     } else if (warp == BT_SOFT_WARPS + 1) {
       // =========================================== MMA issuer ===========================================
-      if (lane == 0) {
-        constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-        constexpr uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t qu = smem_u32(smem + BO_QU), qv = smem_u32(smem + BO_QV), qvn = smem_u32(smem + BO_QVN), kk = smem_u32(smem + BO_K),
-                       vv = smem_u32(smem + BO_V), rr = smem_u32(smem + BO_R), pp = smem_u32(smem + BO_P);
-        auto issue_pv = [&](int m) {
-          mbar_wait(&bar[Q_VFULL], m & 1);
-#pragma unroll
-          for (int hf = 0; hf < 2; hf++) {
-            mbar_wait(&bar[Q_PFULL0 + hf], m & 1);
-            if (m > 0) mbar_wait(&bar[Q_OFREE0 + hf], (m - 1) & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-              umma_bf16(tmem_base + BTM_O + 64 * hf, bt_desc_k(pp + hf * BT16K + k * 32), bt_desc_mn(vv + hf * 8192 + k * 2048), idesc_pv,
-                        (uint32_t)(k > 0));
-            umma_commit(&bar[Q_OFULL0 + hf]);
-          }
-          umma_commit(&bar[Q_VEMPTY]);
-        };
-        mbar_wait(&bar[Q_QREADY], 0);
-        for (int n = 0; n < NT; n++) {
-          mbar_wait(&bar[Q_KFULL], n & 1);
-          mbar_wait(&bar[Q_RFULL0 + (n & 1)], (n >> 1) & 1);                 // load n   = this tile's upper block
-          mbar_wait(&bar[Q_RFULL0 + ((n + 1) & 1)], ((n + 1) >> 1) & 1);     // load n+1 = this tile's lower block
-          if (n > 0) mbar_wait(&bar[Q_SFREE], (n - 1) & 1);
-          tc_fence_after();
-          const uint32_t ru = rr + (n & 1) * BT16K, rl = rr + ((n + 1) & 1) * BT16K;
-          const uint32_t au = n <= it ? qv : qvn, al = (n + 1) <= it ? qv : qvn;     // line 1 below / on the diagonal, line 3 above
-          // (separate ready / free barriers for AC and the strip - AC(n+1) issued right after the AC reads of tile n - were measured
-          // slower: 68.4 vs 64.4 ms per C4 forward; the extra arrive sits in the softmax warps' critical path)
-#pragma unroll
-          for (int k = 0; k < 4; k++) umma_bf16(tmem_base + BTM_AC, bt_desc_k(qu + k * 32), bt_desc_k(kk + k * 32), idesc_s, (uint32_t)(k > 0));
-#pragma unroll
-          for (int k = 0; k < 4; k++) umma_bf16(tmem_base + BTM_STRIP, bt_desc_k(al + k * 32), bt_desc_k(rl + k * 32), idesc_s, (uint32_t)(k > 0));
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            umma_bf16(tmem_base + BTM_STRIP + 128, bt_desc_k(au + k * 32), bt_desc_k(ru + k * 32), idesc_s, (uint32_t)(k > 0));
-          umma_commit(&bar[Q_SFULL]);
-          umma_commit(&bar[Q_KEMPTY]);
-          umma_commit(&bar[Q_REMPTY0 + (n & 1)]);   // the upper block is dead after this tile; the lower one serves the next
-          if (n > 0) issue_pv(n - 1);
-        }
-        issue_pv(NT - 1);
-      }
+      if (lane == 0) bt_mma_issuer(smem, bar, tmem_base, it, NT);
     }
   } else {
     // =========================================== softmax warps ===========================================

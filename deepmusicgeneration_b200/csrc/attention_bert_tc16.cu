@@ -9,48 +9,23 @@
 // memory (64-thread named barrier), writes its 2 x 32 probabilities into the same swizzled P row, and splits the fold of the
 // P V partial by d_head halves (32 accumulator registers per thread instead of 64).  Registers: 104 per softmax thread (640 threads x 96 at launch; setmaxnreg only moves registers inside the CTA).
 // fp16 strip: |BD| < 65504 saturates, 11 bits of mantissa against the 8 of the bf16 operands.
-#include <cuda.h>
-#include <cuda_fp16.h>
-#include "kernels.cuh"
-#include "launch.cuh"
-#include "mma_sync.cuh"
-#include "train_kernels.cuh"
+#include "attention_bert_tc_common.cuh"
 
 namespace dmg {
 
 namespace {
 
-constexpr float B6_LOG2E = 1.4426950408889634f;
+using namespace bert_tc;
+
 constexpr int B6_SOFT_WARPS = 16;
 constexpr int B6_THREADS = (B6_SOFT_WARPS + 4) * 32;   // + one auxiliary warpgroup: TMA warp, MMA warp, two idle warps
-constexpr int B616K = 128 * 64 * 2;
-constexpr int B6_LINE = 208;                           // bytes per pair line: 96 halves + 16 (16-byte stores of 8 lanes hit 8 bank groups)
 constexpr int B6_MROW = 76;                            // floats per row of the final merge buffer: 2 x (32 + m + l + pad) + 4
-constexpr int C_QU = 0;
-constexpr int C_QV = C_QU + B616K;
-constexpr int C_QVN = C_QV + B616K;
-constexpr int C_K = C_QVN + B616K;                     // one stage
-constexpr int C_V = C_K + B616K;
-constexpr int C_R = C_V + B616K;                       // 2 slots (slot = load index & 1)
-constexpr int C_P = C_R + 2 * B616K;                   // 2 key halves; the raw q / q_next tiles land here first
-constexpr int C_STRIP = C_P + 2 * B616K;               // 256 pair lines
-constexpr int C_XCH = C_STRIP + 256 * B6_LINE;         // 256 pairs x 2 floats (local maxima)
+constexpr int C_XCH = BO_STRIP + 256 * BT_LINE16;      // after the 256 pair lines: 256 pairs x 2 floats (local maxima)
 constexpr int C_BAR = C_XCH + 256 * 2 * 4;
 constexpr int B6_SMEM = C_BAR + 256 + 1024;
 static_assert(B6_SMEM <= 227 * 1024, "shared memory budget");
-static_assert(128 * B6_MROW * 4 <= 3 * B616K, "merge buffer aliases the three q tiles");
+static_assert(128 * B6_MROW * 4 <= 3 * BT16K, "merge buffer aliases the three q tiles");
 
-enum { G_QFULL = 0, G_QREADY, G_KFULL, G_KEMPTY, G_RFULL0, G_RFULL1, G_REMPTY0, G_REMPTY1, G_VFULL, G_VEMPTY, G_SFULL, G_SFREE,
-       G_PFULL0, G_PFULL1, G_OFULL0, G_OFULL1, G_OFREE0, G_OFREE1, G_COUNT };
-constexpr uint32_t B6M_AC = 0, B6M_STRIP = 128, B6M_O = 384;
-
-__device__ __forceinline__ uint64_t b6_desc_k(uint32_t addr) {          // K-major, 128B swizzle: rows of 128 B, 8-row groups 1024 B apart
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ uint64_t b6_desc_mn(uint32_t addr) {         // MN-major: LBO 8192, SBO 1024
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(8192u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void b6_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void b6_pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -60,25 +35,13 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
-  uint32_t w;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi), "f"(lo));
-  return w;
-}
-
-struct BertTc16Args {
-  const float* u; const float* v;   // [H*64]
-  bf16* out;                        // [B*T, H*64]
-  int B, T, H, Dcap;
-  float scale;
-};
 
 __global__ void __launch_bounds__(B6_THREADS, 1)
-attn_bert_tc16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmR, const BertTc16Args a) {
+attn_bert_tc16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmR, const BertTcArgs a) {
   extern __shared__ __align__(1024) uint8_t b6_smem_raw[];
   uint8_t* smem = b6_smem_raw + ((1024u - (smem_u32(b6_smem_raw) & 1023u)) & 1023u);
   uint64_t* bar = (uint64_t*)(smem + C_BAR);
-  uint32_t* tmem_holder = (uint32_t*)(bar + G_COUNT);
+  uint32_t* tmem_holder = (uint32_t*)(bar + Q_COUNT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nT = (a.T + 127) / 128;                  // a ragged last tile: keys >= T are masked, rows >= T are not stored
@@ -90,13 +53,7 @@ attn_bert_tc16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   if (warp == B6_SOFT_WARPS && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmR);
-    for (int i = 0; i < G_COUNT; i++) {
-      uint32_t cnt = 1;
-      if (i == G_QREADY || i == G_SFREE) cnt = B6_SOFT_WARPS;
-      if (i == G_PFULL0 || i == G_PFULL1 || i == G_OFREE0 || i == G_OFREE1) cnt = B6_SOFT_WARPS / 2;
-      mbar_init(&bar[i], cnt);
-    }
-    mbar_fence_init();
+    bt_init_barriers(bar, B6_SOFT_WARPS);
   }
   if (warp == B6_SOFT_WARPS + 1) tmem_alloc<512>(tmem_holder);
   tc_fence_before();
@@ -109,84 +66,10 @@ attn_bert_tc16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == B6_SOFT_WARPS) {
       // =========================================== TMA producer ===========================================
-      if (lane == 0) {
-        pdl_wait();                                  // q | k | v come from the predecessor kernel (the QKV GEMM)
-        mbar_expect_tx(&bar[G_QFULL], 2 * B616K);
-        tma_load_2d(smem + C_P, &tmX, h * 64, b * a.T + i0, &bar[G_QFULL]);
-        tma_load_2d(smem + C_P + B616K, &tmX, h * 64, b * a.T + i0 + 1, &bar[G_QFULL]);
-        auto load_k = [&](int n) {
-          mbar_wait(&bar[G_KEMPTY], (n & 1) ^ 1);
-          mbar_expect_tx(&bar[G_KFULL], B616K);
-          tma_load_2d(smem + C_K, &tmX, HD + h * 64, b * a.T + n * 128, &bar[G_KFULL]);
-        };
-        auto load_r = [&](int k) {                  // load 0 = upper block of tile 0; load k >= 1 = lower block of tile k-1
-          const int s = k & 1;
-          const int row = k <= it ? (it - k) * 128 : a.T + 1 + (it - k) * 128;   // line 1 / line 3 (distance T + 1 + i - j)
-          mbar_wait(&bar[G_REMPTY0 + s], ((k >> 1) & 1) ^ 1);
-          mbar_expect_tx(&bar[G_RFULL0 + s], B616K);
-          tma_load_2d(smem + C_R + s * B616K, &tmR, 0, h * a.Dcap + row, &bar[G_RFULL0 + s]);
-        };
-        auto load_v = [&](int n) {
-          mbar_wait(&bar[G_VEMPTY], (n & 1) ^ 1);
-          mbar_expect_tx(&bar[G_VFULL], B616K);
-          tma_load_2d(smem + C_V, &tmX, 2 * HD + h * 64, b * a.T + n * 128, &bar[G_VFULL]);
-        };
-        load_k(0);
-        load_r(0);
-        load_r(1);
-        load_v(0);
-        for (int n = 1; n < NT; n++) {              // V requests trail the K / R requests by one tile (see attention_bert_tc.cu)
-          load_k(n);
-          load_r(n + 1);
-          if (n >= 2) load_v(n - 1);
-        }
-        if (NT >= 2) load_v(NT - 1);
-      }
+      if (lane == 0) bt_producer(smem, bar, tmX, tmR, a, b, h, it, NT);
     } else if (warp == B6_SOFT_WARPS + 1) {
       // =========================================== MMA issuer ===========================================
-      if (lane == 0) {
-        constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-        constexpr uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t qu = smem_u32(smem + C_QU), qv = smem_u32(smem + C_QV), qvn = smem_u32(smem + C_QVN), kk = smem_u32(smem + C_K),
-                       vv = smem_u32(smem + C_V), rr = smem_u32(smem + C_R), pp = smem_u32(smem + C_P);
-        auto issue_pv = [&](int m) {
-          mbar_wait(&bar[G_VFULL], m & 1);
-#pragma unroll
-          for (int hf = 0; hf < 2; hf++) {
-            mbar_wait(&bar[G_PFULL0 + hf], m & 1);
-            if (m > 0) mbar_wait(&bar[G_OFREE0 + hf], (m - 1) & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-              umma_bf16(tmem_base + B6M_O + 64 * hf, b6_desc_k(pp + hf * B616K + k * 32), b6_desc_mn(vv + hf * 8192 + k * 2048), idesc_pv,
-                        (uint32_t)(k > 0));
-            umma_commit(&bar[G_OFULL0 + hf]);
-          }
-          umma_commit(&bar[G_VEMPTY]);
-        };
-        mbar_wait(&bar[G_QREADY], 0);
-        for (int n = 0; n < NT; n++) {
-          mbar_wait(&bar[G_KFULL], n & 1);
-          mbar_wait(&bar[G_RFULL0 + (n & 1)], (n >> 1) & 1);                 // load n   = this tile's upper block
-          mbar_wait(&bar[G_RFULL0 + ((n + 1) & 1)], ((n + 1) >> 1) & 1);     // load n+1 = this tile's lower block
-          if (n > 0) mbar_wait(&bar[G_SFREE], (n - 1) & 1);
-          tc_fence_after();
-          const uint32_t ru = rr + (n & 1) * B616K, rl = rr + ((n + 1) & 1) * B616K;
-          const uint32_t au = n <= it ? qv : qvn, al = (n + 1) <= it ? qv : qvn;     // line 1 below / on the diagonal, line 3 above
-#pragma unroll
-          for (int k = 0; k < 4; k++) umma_bf16(tmem_base + B6M_AC, b6_desc_k(qu + k * 32), b6_desc_k(kk + k * 32), idesc_s, (uint32_t)(k > 0));
-#pragma unroll
-          for (int k = 0; k < 4; k++) umma_bf16(tmem_base + B6M_STRIP, b6_desc_k(al + k * 32), b6_desc_k(rl + k * 32), idesc_s, (uint32_t)(k > 0));
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            umma_bf16(tmem_base + B6M_STRIP + 128, b6_desc_k(au + k * 32), b6_desc_k(ru + k * 32), idesc_s, (uint32_t)(k > 0));
-          umma_commit(&bar[G_SFULL]);
-          umma_commit(&bar[G_KEMPTY]);
-          umma_commit(&bar[G_REMPTY0 + (n & 1)]);
-          if (n > 0) issue_pv(n - 1);
-        }
-        issue_pv(NT - 1);
-      }
+      if (lane == 0) bt_mma_issuer(smem, bar, tmem_base, it, NT);
     }
   } else {
     // =========================================== softmax warps ===========================================
@@ -197,9 +80,9 @@ attn_bert_tc16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16);
     const int pair = (hf * 4 + q4) * 32 + lane;
     const int pair_bar = 1 + hf * 4 + q4;           // named barriers 1..8: the two warps of a pair
-    uint8_t* line = smem + C_STRIP + (size_t)pair * B6_LINE;
+    uint8_t* line = smem + BO_STRIP + (size_t)pair * BT_LINE16;
     float* xch = (float*)(smem + C_XCH) + pair * 2;
-    const float c = a.scale * B6_LOG2E;
+    const float c = a.scale * BT_LOG2E;
 
     {   // q + u, q + v and q_next + v in the canonical swizzled layout: eight consecutive threads take the eight 16-byte chunks of a row
       const int tid = threadIdx.x, pc = tid & 7, rb = tid >> 3;       // rb 0..63
@@ -207,13 +90,13 @@ attn_bert_tc16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       const float4 ua = __ldg((const float4*)(a.u + h * 64 + col)), ub = __ldg((const float4*)(a.u + h * 64 + col + 4));
       const float4 va = __ldg((const float4*)(a.v + h * 64 + col)), vb = __ldg((const float4*)(a.v + h * 64 + col + 4));
       const float uu[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w}, vv8[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-      mbar_wait(&bar[G_QFULL], 0);
+      mbar_wait(&bar[Q_QFULL], 0);
 #pragma unroll
       for (int k = 0; k < 2; k++) {
         const int qr = rb + 64 * k;
         const uint32_t off = (uint32_t)((qr >> 3) * 1024 + (qr & 7) * 128 + pc * 16);
-        const uint4 raw = *(const uint4*)(smem + C_P + off);
-        const uint4 rawn = *(const uint4*)(smem + C_P + B616K + off);
+        const uint4 raw = *(const uint4*)(smem + BO_P + off);
+        const uint4 rawn = *(const uint4*)(smem + BO_P + BT16K + off);
         const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w}, wn[4] = {rawn.x, rawn.y, rawn.z, rawn.w};
         uint32_t ou[4], ov[4], on[4];
 #pragma unroll
@@ -223,20 +106,20 @@ attn_bert_tc16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           ov[e] = pack_bf16x2(bf16lo(w[e]) + v0, bf16hi(w[e]) + v1);
           on[e] = pack_bf16x2(bf16lo(wn[e]) + v0, bf16hi(wn[e]) + v1);
         }
-        *(uint4*)(smem + C_QU + off) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
-        *(uint4*)(smem + C_QV + off) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
-        *(uint4*)(smem + C_QVN + off) = make_uint4(on[0], on[1], on[2], on[3]);
+        *(uint4*)(smem + BO_QU + off) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+        *(uint4*)(smem + BO_QV + off) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+        *(uint4*)(smem + BO_QVN + off) = make_uint4(on[0], on[1], on[2], on[3]);
       }
-      b6_fence_async();
+      bt_fence_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar[G_QREADY]);
+      if (lane == 0) mbar_arrive(&bar[Q_QREADY]);
     }
 
     float o[32];                                     // running output, d_head columns [32 sub, 32 sub + 32) of key half hf
 #pragma unroll
     for (int i = 0; i < 32; i++) o[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
-    uint8_t* prow = smem + C_P + hf * B616K + (r >> 3) * 1024 + (r & 7) * 128;
+    uint8_t* prow = smem + BO_P + hf * BT16K + (r >> 3) * 1024 + (r & 7) * 128;
     // this thread's keys inside a tile: kbase + jj, jj = 0..31
     const int kbase = 64 * hf + 32 * sub;
     // the zero pad of _line_shift: key j = i + 1 (tile (row+1)/128, local key (row+1)%128)
@@ -252,34 +135,34 @@ attn_bert_tc16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 
     for (int n = 0; n < NT; n++) {
       float s[32];
-      mbar_wait(&bar[G_SFULL], n & 1);
+      mbar_wait(&bar[Q_SFULL], n & 1);
       tc_fence_after();
       {   // 48 strip columns -> fp16 -> the pair's line
         uint32_t x0[32], x1[16];
-        tmem_ld_32x32(t_lane + B6M_STRIP + wbase + ld_off, x0);
-        tmem_ld_32x16(t_lane + B6M_STRIP + wbase + ld_off + 32, x1);
+        tmem_ld_32x32(t_lane + BTM_STRIP + wbase + ld_off, x0);
+        tmem_ld_32x16(t_lane + BTM_STRIP + wbase + ld_off + 32, x1);
         tmem_ld_wait();
         uint8_t* dst = line + 2 * ld_off;
 #pragma unroll
         for (int k = 0; k < 4; k++)
-          *(uint4*)(dst + 16 * k) = make_uint4(pack_f16x2_sat(__uint_as_float(x0[8 * k]), __uint_as_float(x0[8 * k + 1])),
-                                               pack_f16x2_sat(__uint_as_float(x0[8 * k + 2]), __uint_as_float(x0[8 * k + 3])),
-                                               pack_f16x2_sat(__uint_as_float(x0[8 * k + 4]), __uint_as_float(x0[8 * k + 5])),
-                                               pack_f16x2_sat(__uint_as_float(x0[8 * k + 6]), __uint_as_float(x0[8 * k + 7])));
+          *(uint4*)(dst + 16 * k) = make_uint4(bt_f16x2_sat(__uint_as_float(x0[8 * k]), __uint_as_float(x0[8 * k + 1])),
+                                               bt_f16x2_sat(__uint_as_float(x0[8 * k + 2]), __uint_as_float(x0[8 * k + 3])),
+                                               bt_f16x2_sat(__uint_as_float(x0[8 * k + 4]), __uint_as_float(x0[8 * k + 5])),
+                                               bt_f16x2_sat(__uint_as_float(x0[8 * k + 6]), __uint_as_float(x0[8 * k + 7])));
 #pragma unroll
         for (int k = 0; k < 2; k++)
-          *(uint4*)(dst + 64 + 16 * k) = make_uint4(pack_f16x2_sat(__uint_as_float(x1[8 * k]), __uint_as_float(x1[8 * k + 1])),
-                                                    pack_f16x2_sat(__uint_as_float(x1[8 * k + 2]), __uint_as_float(x1[8 * k + 3])),
-                                                    pack_f16x2_sat(__uint_as_float(x1[8 * k + 4]), __uint_as_float(x1[8 * k + 5])),
-                                                    pack_f16x2_sat(__uint_as_float(x1[8 * k + 6]), __uint_as_float(x1[8 * k + 7])));
+          *(uint4*)(dst + 64 + 16 * k) = make_uint4(bt_f16x2_sat(__uint_as_float(x1[8 * k]), __uint_as_float(x1[8 * k + 1])),
+                                                    bt_f16x2_sat(__uint_as_float(x1[8 * k + 2]), __uint_as_float(x1[8 * k + 3])),
+                                                    bt_f16x2_sat(__uint_as_float(x1[8 * k + 4]), __uint_as_float(x1[8 * k + 5])),
+                                                    bt_f16x2_sat(__uint_as_float(x1[8 * k + 6]), __uint_as_float(x1[8 * k + 7])));
       }
       {   // content term of this thread's 32 keys
         uint32_t x[32];
-        tmem_ld_32x32(t_lane + B6M_AC + kbase, x);
+        tmem_ld_32x32(t_lane + BTM_AC + kbase, x);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar[G_SFREE]);
+        if (lane == 0) mbar_arrive(&bar[Q_SFREE]);
 #pragma unroll
         for (int i = 0; i < 32; i++) s[i] = __uint_as_float(x[i]);
       }
@@ -312,16 +195,16 @@ attn_bert_tc16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       xch[sub] = mx;
 
       if (n > 0) {                                   // fold the previous tile's P V into the running output (this thread's d_head half)
-        mbar_wait(&bar[G_OFULL0 + hf], (n - 1) & 1);
+        mbar_wait(&bar[Q_OFULL0 + hf], (n - 1) & 1);
         tc_fence_after();
         uint32_t x[32];
-        tmem_ld_32x32(t_lane + B6M_O + 64 * hf + 32 * sub, x);
+        tmem_ld_32x32(t_lane + BTM_O + 64 * hf + 32 * sub, x);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i++) o[i] = fmaf(o[i], alpha_prev, __uint_as_float(x[i]));
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar[G_OFREE0 + hf]);
+        if (lane == 0) mbar_arrive(&bar[Q_OFREE0 + hf]);
       }
 
       b6_pair_sync(pair_bar);                        // local maxima exchanged; the partner is done with the strip line
@@ -344,15 +227,15 @@ attn_bert_tc16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       }
       l_run = l_run * alpha + rs;
       alpha_prev = alpha;
-      b6_fence_async();
+      bt_fence_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar[G_PFULL0 + hf]);
+      if (lane == 0) mbar_arrive(&bar[Q_PFULL0 + hf]);
     }
-    mbar_wait(&bar[G_OFULL0 + hf], (NT - 1) & 1);
+    mbar_wait(&bar[Q_OFULL0 + hf], (NT - 1) & 1);
     tc_fence_after();
     {
       uint32_t x[32];
-      tmem_ld_32x32(t_lane + B6M_O + 64 * hf + 32 * sub, x);
+      tmem_ld_32x32(t_lane + BTM_O + 64 * hf + 32 * sub, x);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; i++) o[i] = fmaf(o[i], alpha_prev, __uint_as_float(x[i]));
@@ -360,7 +243,7 @@ attn_bert_tc16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     tc_fence_before();
 
     // merge the two key halves of every row: half 1 leaves its output slice, maximum and row sums in the (dead) q tiles
-    float* mrow = (float*)(smem + C_QU) + (size_t)r * B6_MROW;
+    float* mrow = (float*)(smem + BO_QU) + (size_t)r * B6_MROW;
     if (hf == 1) {
 #pragma unroll
       for (int k = 0; k < 8; k++) *(float4*)(mrow + 36 * sub + 4 * k) = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
@@ -409,7 +292,7 @@ int attn_bert_tc16(const bf16* qkv, const bf16* rd, int Dcap, const float* u, co
   const TensorMap2D *tx = nullptr, *tr = nullptr;
   if (train_get_tmap(qkv, 3 * HD, (long long)B * T, 3 * HD, 128, &tx)) return -1;
   if (train_get_tmap(rd, 64, (long long)H * Dcap, 64, 128, &tr)) return -1;
-  BertTc16Args a;
+  BertTcArgs a;
   a.u = u; a.v = v; a.out = out; a.B = B; a.T = T; a.H = H; a.Dcap = Dcap; a.scale = scale;
   return launch_k(attn_bert_tc16_kernel, dim3(B * H * ((T + 127) / 128)), dim3(B6_THREADS), (size_t)B6_SMEM, st, 1,
                   *(const CUtensorMap*)tx->bytes, *(const CUtensorMap*)tr->bytes, a);
