@@ -59,6 +59,8 @@ SYMBOLS = {
     'dmg_generate_step_host': (c_i32, [c_vp, c_vp, c_vp, c_vp]),
     'dmg_sample_logits': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, C.POINTER(VocabLayout), C.POINTER(SamplerParams),
                                   c_u64, c_vp, c_vp, c_vp]),
+    'dmg_sample_probs': (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, C.POINTER(VocabLayout), C.POINTER(SamplerParams),
+                                 c_u64, c_vp, c_vp, c_vp, c_vp]),
     'dmg_device_bytes': (c_i64, [c_vp]),
     'dmg_launch_count': (c_i64, []),
     'dmg_uses_tcgen05': (c_i32, [c_vp]),

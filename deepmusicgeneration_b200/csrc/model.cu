@@ -748,6 +748,31 @@ int dmg_sample_logits(dmg_model* m, const float* logits_dev, const int32_t* prev
   return sample_launch(a, n, (cudaStream_t)stream);
 }
 
+int dmg_sample_probs(dmg_model* m, int predict_loop, const float* logits_dev, const int32_t* prev_idx_dev,
+                     const int32_t* repeat_count_dev, const int32_t* last_xxsep_dev, const int64_t* pos_since_start_dev, int n,
+                     const dmg_vocab_layout* vocab, const dmg_sampler_params* params, uint64_t offset, int32_t* out_dev,
+                     int32_t* num_choices_dev, float* probs_dev, void* stream) {
+  DMG_CHECK(m && logits_dev && prev_idx_dev && repeat_count_dev && vocab && params && out_dev, "dmg_sample_probs: null argument");
+  DMG_CHECK(!predict_loop || (last_xxsep_dev && pos_since_start_dev), "dmg_sample_probs: the predict loop needs last_xxsep and positions");
+  DMG_CUDA_OK(cudaSetDevice(m->device));
+  SampleArgs a;
+  memset(&a, 0, sizeof(a));
+  a.logits = logits_dev;
+  a.V = m->cfg.vocab;
+  a.vocab = *vocab;
+  a.params = *params;
+  a.loop_mode = predict_loop ? 2 : 0;
+  a.offset = offset;
+  a.prev_idx = const_cast<int*>(prev_idx_dev);
+  a.repeat_count = const_cast<int*>(repeat_count_dev);
+  a.last_xxsep = const_cast<int*>(last_xxsep_dev);
+  a.last_pos = (long long*)const_cast<int64_t*>(pos_since_start_dev);     // start_pos = 0: last_pos - start_pos = the given distance
+  a.out_tokens = out_dev;
+  a.num_choices = num_choices_dev;
+  a.probs = probs_dev;
+  return sample_launch(a, n, (cudaStream_t)stream);
+}
+
 int dmg_attn_decode_layer(dmg_model* m, int layer, void* stream) {
   DMG_CHECK(m, "dmg_attn_decode_layer: null model");
   const dmg_config& c = m->cfg;

@@ -105,7 +105,12 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(SampleArgs a) {
   // ---------------- per-stream scalar state ----------------
   int prev, repeat_count, last_xxsep = 0, status = 0, step = 0;
   long long last_pos = 0, start_pos = 0;
-  if (a.loop_mode) {
+  if (a.loop_mode == 2) {   // one step of the predict loop on caller-provided state (nothing is written back)
+    prev = a.prev_idx[sidx];
+    repeat_count = a.repeat_count[sidx];
+    last_xxsep = a.last_xxsep[sidx];
+    last_pos = a.last_pos[sidx];
+  } else if (a.loop_mode) {
     status = a.status[sidx];
     prev = a.prev_idx[sidx];
     repeat_count = a.repeat_count[sidx];
@@ -139,10 +144,12 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(SampleArgs a) {
     else if (prev_ins || prev == vl.pad) temperature = sp.temperatures[0];
     else {   // reference: `assert temperature is not None` -> AssertionError (deep_music_genre.py:1920-1925)
       if (tid == 0) {
-        a.status[sidx] = 2;
         if (a.out_tokens) a.out_tokens[sidx] = -2;
-        a.next_ids[sidx] = vl.pad;
-        if (a.next_pos) a.next_pos[sidx] = last_pos;
+        if (a.loop_mode == 1) {
+          a.status[sidx] = 2;
+          a.next_ids[sidx] = vl.pad;
+          if (a.next_pos) a.next_pos[sidx] = last_pos;
+        }
       }
       return;
     }
@@ -262,6 +269,7 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(SampleArgs a) {
   for (int i = tid; i < V; i += SAMP_THREADS) {
     const float p = pr[i] / tot;
     pr[i] = p;
+    if (a.probs) a.probs[(size_t)sidx * V + i] = p;
     nz += p > 0.f ? 1 : 0;
   }
   const int num_choices = (int)(block_sum((float)nz, scratch) + 0.5f);
@@ -293,7 +301,7 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(SampleArgs a) {
   // ---------------- bookkeeping ----------------
   if (tid != 0) return;
   if (a.num_choices) a.num_choices[sidx] = num_choices;
-  if (!a.loop_mode) {
+  if (a.loop_mode != 1) {
     a.out_tokens[sidx] = idx;
     return;
   }

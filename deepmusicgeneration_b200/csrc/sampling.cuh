@@ -9,7 +9,8 @@ struct SampleArgs {
   int V;
   dmg_vocab_layout vocab;
   dmg_sampler_params params;
-  int loop_mode;              // 1: MusicLearner.predict loop state below; 0: stateless (predict_mask)
+  int loop_mode;              // 1: MusicLearner.predict loop state below; 0: stateless (predict_mask);
+                              // 2: one stateless step of the predict loop (test hook: state is read, never written)
   unsigned long long offset;  // Philox counter base
   // loop state, one entry per stream
   int* prev_idx;
@@ -24,6 +25,7 @@ struct SampleArgs {
   long long* next_ids;        // [n] input ids of the next one-token forward (loop mode)
   long long* next_pos;        // [n] beat position of the next token (loop mode, may be NULL)
   int* num_choices;           // [n] optional
+  float* probs;               // [n, V] optional: the final probabilities (after filter / top-k / top-p / softmax)
 };
 
 int sample_launch(const SampleArgs& a, int n, cudaStream_t st);

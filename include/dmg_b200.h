@@ -135,6 +135,16 @@ int dmg_sample_logits(dmg_model* m, const float* logits_dev, const int32_t* prev
                       const dmg_sampler_params* params, uint64_t offset, int32_t* out_dev, int32_t* num_choices_dev,
                       void* stream);
 
+/* Test hook: ONE sampling step for n independent rows that also returns the final probabilities probs_dev fp32 [n, V] (may be
+ * NULL) - their support is the set kept by the grammar filter, top-k and top-p.  predict_loop = 0: predict_mask's step (as
+ * dmg_sample_logits; last_xxsep_dev / pos_since_start_dev ignored).  predict_loop = 1: the step of MusicLearner.predict
+ * (deep_music_genre.py:1895-1944) on caller-provided loop state: prev_idx, repeat_count, last_xxsep as they are BEFORE the update
+ * of :1897-1901, and last_pos - start_pos (for the min_bars rule :1937); nothing is written back. */
+int dmg_sample_probs(dmg_model* m, int predict_loop, const float* logits_dev, const int32_t* prev_idx_dev,
+                     const int32_t* repeat_count_dev, const int32_t* last_xxsep_dev, const int64_t* pos_since_start_dev, int n,
+                     const dmg_vocab_layout* vocab, const dmg_sampler_params* params, uint64_t offset, int32_t* out_dev,
+                     int32_t* num_choices_dev, float* probs_dev, void* stream);
+
 /* Introspection for tests / bench. */
 int64_t dmg_device_bytes(dmg_model* m);          /* bytes of HBM owned by the model */
 int64_t dmg_launch_count(void);                  /* kernels launched by this library so far (process-wide) */
