@@ -17,12 +17,15 @@ F32, BF16 = 0, 1
 GEMM_AUTO, GEMM_SIMT, GEMM_TC_TILE = 0, 1, 2
 LOGITS_NONE, LOGITS_ALL, LOGITS_LAST = 0, 1, 2
 SAMPLE_EARLY_STOP, SAMPLE_MASK_UNUSED, SAMPLE_REMIX_FILTER = 1, 2, 4
+# dmg_config.kernel_flags (DMG_KF_*): non-default kernels for parity tests / reproducing measurements; 0 = the product path
+(KF_NO_DECODE_KERNEL, KF_NO_FLASH, KF_NO_GRAPH, KF_BERT_MMA_SYNC, KF_BERT_FP32_STRIP, KF_NO_SPLITK, KF_NO_BIG_GEMM, KF_GEMM_SIMT,
+ KF_NO_FUSED_DECODE) = (1, 2, 4, 8, 16, 32, 64, 128, 256)
 
 
 class Config(C.Structure):
     _fields_ = [(n, c_i32) for n in ('arch', 'dtype', 'vocab', 'd_model', 'n_layers', 'n_heads', 'd_head', 'd_inner',
                                      'mem_len', 'attn_bias', 'encode_position', 'max_batch', 'max_seq', 'max_rows',
-                                     'keep_hidden', 'gemm_backend')] + [('reserved', c_i32 * 4)]
+                                     'keep_hidden', 'gemm_backend', 'kernel_flags')] + [('reserved', c_i32 * 3)]
 
 
 class VocabLayout(C.Structure):

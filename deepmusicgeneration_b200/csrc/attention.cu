@@ -9,10 +9,7 @@
 //     j >  M+i+1 : BD[i,j] = (q_{i+1}+v) . Rd[S+1+i-j]           (the live wrap-around of the unmasked encoder)
 // (SURVEY.md App. A.4).  K/V of past tokens live in a per-(stream, head) ring in HBM, slot = token index mod M.
 //
-//  * attn_decode_kernel  - x_len == 1, bf16 ring: the HBM-bound kernel of batched generation.  One CTA per
-//    (stream, head); K, R and V tiles stream through a 4-stage shared-memory ring filled by the TMA engine
-//    (cp.async.bulk + mbarrier complete_tx); exact two-pass softmax over the M+1 scores held in shared memory;
-//    the new token's K/V are appended to the ring by the same CTA after its last read of the oldest slot.
+//  * x_len == 1 over the bf16 ring (the HBM-bound kernel of batched generation) lives in attention_decode2.cu.
 //  * attn_general_kernel - any x_len (prefill, training-shape forward, BERT encoder), fp32 or bf16 ring,
 //    flash-style online softmax over 32x32 tiles on the FFMA pipe.
 #include "kernels.cuh"
@@ -20,219 +17,7 @@
 
 namespace dmg {
 
-// =============================================================================================
-// decode kernel
-// =============================================================================================
-constexpr int DEC_STAGES = 4;
-constexpr int DEC_STAGE_BYTES = 16384;   // K item: 64 keys K + 64 rows R;  V item: 128 keys
 constexpr float LOG2E = 1.4426950408889634f;
-
-__host__ __device__ inline int dec_smem_bytes(int M) {
-  return DEC_STAGES * DEC_STAGE_BYTES + (M + 8) * 4 /*scores*/ + 16 * 64 * 4 /*group partials*/ + 128 * 4 /*qu,qv*/ +
-         64 /*reduction scratch*/ + DEC_STAGES * 8 /*mbarriers*/ + 128 /*alignment*/;
-}
-
-__global__ void __launch_bounds__(128) attn_decode_kernel(AttnDecodeArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-  uint8_t* stages = base;
-  float* sc = (float*)(stages + DEC_STAGES * DEC_STAGE_BYTES);
-  const int M = a.M;
-  float* red = sc + (M + 8);
-  float* qu = red + 16 * 64;
-  float* qv = qu + 64;
-  float* scratch = qv + 64;                    // 16 floats
-  uint64_t* full = (uint64_t*)(scratch + 16);
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int h = blockIdx.x, b = blockIdx.y;
-  const int H = a.H, HD = H * 64;
-  pdl_launch_dependents();
-  pdl_wait();
-  const int pos_total = a.dev_state[0], mc = a.dev_state[1];
-  const int head = pos_total % M;
-  const int nK = M / 64, nV = M / 128, nItems = nK + nV;
-
-  const bf16* kbase = a.kring + ((size_t)b * H + h) * M * 64;
-  const bf16* vbase = a.vring + ((size_t)b * H + h) * M * 64;
-  const bf16* rbase = a.rd + (size_t)h * a.Dcap * 64;
-  const float* qrow = a.qkv + (size_t)b * 3 * HD + h * 64;
-
-  if (tid == 0) {
-    for (int s = 0; s < DEC_STAGES; s++) mbar_init(&full[s], 1);
-    mbar_fence_init();
-  }
-  if (tid < 64) {
-    const float q = qrow[tid];
-    qu[tid] = q + a.u[h * 64 + tid];
-    qv[tid] = q + a.v[h * 64 + tid];
-  }
-  __syncthreads();
-
-  auto issue = [&](int item) {
-    const int s = item % DEC_STAGES;
-    uint8_t* dst = stages + s * DEC_STAGE_BYTES;
-    mbar_expect_tx(&full[s], DEC_STAGE_BYTES);
-    if (item < nK) {
-      const int p0 = item * 64;
-      bulk_g2s(dst, kbase + (size_t)p0 * 64, 8192, &full[s]);
-      uint8_t* rdst = dst + 8192;
-      // slot p0+r holds the key at distance (p<head ? head-p : M+head-p); shared row 63-r <-> slot p0+r
-      if (p0 + 64 <= head) {
-        bulk_g2s(rdst, rbase + (size_t)(head - p0 - 63) * 64, 8192, &full[s]);
-      } else if (p0 >= head) {
-        bulk_g2s(rdst, rbase + (size_t)(M + head - p0 - 63) * 64, 8192, &full[s]);
-      } else {
-        const int n1 = head - p0;   // slots below head: distances n1..1 -> rows 64-n1..63
-        bulk_g2s(rdst + (64 - n1) * 128, rbase + (size_t)1 * 64, n1 * 128, &full[s]);
-        bulk_g2s(rdst, rbase + (size_t)(M + n1 - 63) * 64, (64 - n1) * 128, &full[s]);
-      }
-    } else {
-      const int p0 = (item - nK) * 128;
-      bulk_g2s(dst, vbase + (size_t)p0 * 64, 16384, &full[s]);
-    }
-  };
-  if (tid == 0) {
-    for (int it = 0; it < DEC_STAGES && it < nItems; it++) issue(it);
-  }
-
-  const int g = tid >> 3, c = tid & 7;
-  float quf[8], qvf[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    quf[j] = qu[c * 8 + j];
-    qvf[j] = qv[c * 8 + j];
-  }
-  const float sscale = a.scale * LOG2E;
-
-  // ---------------- phase 1: scores over the ring ----------------
-  for (int it = 0; it < nK; it++) {
-    const int s = it % DEC_STAGES;
-    mbar_wait(&full[s], (it / DEC_STAGES) & 1);
-    const uint8_t* st = stages + s * DEC_STAGE_BYTES;
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-      const int r = g + 16 * t;
-      const uint4 kw = *(const uint4*)(st + r * 128 + c * 16);
-      const uint4 rw = *(const uint4*)(st + 8192 + (63 - r) * 128 + c * 16);
-      float acc = quf[0] * bf16lo(kw.x);
-      acc = fmaf(quf[1], bf16hi(kw.x), acc);
-      acc = fmaf(quf[2], bf16lo(kw.y), acc);
-      acc = fmaf(quf[3], bf16hi(kw.y), acc);
-      acc = fmaf(quf[4], bf16lo(kw.z), acc);
-      acc = fmaf(quf[5], bf16hi(kw.z), acc);
-      acc = fmaf(quf[6], bf16lo(kw.w), acc);
-      acc = fmaf(quf[7], bf16hi(kw.w), acc);
-      float acc2 = qvf[0] * bf16lo(rw.x);
-      acc2 = fmaf(qvf[1], bf16hi(rw.x), acc2);
-      acc2 = fmaf(qvf[2], bf16lo(rw.y), acc2);
-      acc2 = fmaf(qvf[3], bf16hi(rw.y), acc2);
-      acc2 = fmaf(qvf[4], bf16lo(rw.z), acc2);
-      acc2 = fmaf(qvf[5], bf16hi(rw.z), acc2);
-      acc2 = fmaf(qvf[6], bf16lo(rw.w), acc2);
-      acc2 = fmaf(qvf[7], bf16hi(rw.w), acc2);
-      acc += acc2;
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-      if (c == 0) {
-        const int p = it * 64 + r;
-        const int dist = p < head ? head - p : M + head - p;
-        sc[p] = dist <= mc ? acc * sscale : -INFINITY;
-      }
-    }
-    __syncthreads();
-    if (tid == 0 && it + DEC_STAGES < nItems) issue(it + DEC_STAGES);
-  }
-
-  // the new token itself (distance 0, always visible); its K/V are still fp32 in the qkv buffer
-  if (warp == 0) {
-    const float k0 = qrow[HD + lane], k1 = qrow[HD + lane + 32];
-    const float r0 = __bfloat162float(rbase[lane]), r1 = __bfloat162float(rbase[lane + 32]);
-    float acc = qu[lane] * k0 + qu[lane + 32] * k1 + qv[lane] * r0 + qv[lane + 32] * r1;
-    acc = warp_sum(acc);
-    if (lane == 0) sc[M] = acc * sscale;
-  }
-  __syncthreads();
-
-  // ---------------- exact softmax over M+1 scores (kept un-normalised; 1/sum applied at the end) ----------------
-  float mx = -INFINITY;
-  for (int j = tid; j <= M; j += 128) mx = fmaxf(mx, sc[j]);
-  mx = warp_max(mx);
-  if (lane == 0) scratch[warp] = mx;
-  __syncthreads();
-  mx = fmaxf(fmaxf(scratch[0], scratch[1]), fmaxf(scratch[2], scratch[3]));
-  float sum = 0.f;
-  for (int j = tid; j <= M; j += 128) {
-    const float p = exp2f(sc[j] - mx);
-    sc[j] = p;
-    sum += p;
-  }
-  sum = warp_sum(sum);
-  if (lane == 0) scratch[4 + warp] = sum;
-  __syncthreads();
-  sum = scratch[4] + scratch[5] + scratch[6] + scratch[7];
-
-  // ---------------- phase 2: P.V ----------------
-  float o[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) o[j] = 0.f;
-  for (int iv = 0; iv < nV; iv++) {
-    const int it = nK + iv;
-    const int s = it % DEC_STAGES;
-    mbar_wait(&full[s], (it / DEC_STAGES) & 1);
-    const uint8_t* st = stages + s * DEC_STAGE_BYTES;
-#pragma unroll
-    for (int t = 0; t < 8; t++) {
-      const int r = g + 16 * t;
-      const float p = sc[iv * 128 + r];
-      const uint4 vw = *(const uint4*)(st + r * 128 + c * 16);
-      o[0] = fmaf(p, bf16lo(vw.x), o[0]);
-      o[1] = fmaf(p, bf16hi(vw.x), o[1]);
-      o[2] = fmaf(p, bf16lo(vw.y), o[2]);
-      o[3] = fmaf(p, bf16hi(vw.y), o[3]);
-      o[4] = fmaf(p, bf16lo(vw.z), o[4]);
-      o[5] = fmaf(p, bf16hi(vw.z), o[5]);
-      o[6] = fmaf(p, bf16lo(vw.w), o[6]);
-      o[7] = fmaf(p, bf16hi(vw.w), o[7]);
-    }
-    __syncthreads();
-    if (tid == 0 && it + DEC_STAGES < nItems) issue(it + DEC_STAGES);
-  }
-  if (g == 0) {
-    const float p = sc[M];
-#pragma unroll
-    for (int j = 0; j < 8; j++) o[j] = fmaf(p, qrow[2 * HD + c * 8 + j], o[j]);
-  }
-#pragma unroll
-  for (int j = 0; j < 8; j++) red[g * 64 + c * 8 + j] = o[j];
-  __syncthreads();
-  if (tid < 64) {
-    float tot = 0.f;
-#pragma unroll
-    for (int gg = 0; gg < 16; gg++) tot += red[gg * 64 + tid];
-    a.out[(size_t)b * HD + h * 64 + tid] = __float2bfloat16_rn(tot / sum);
-  } else {
-    // ring append (K13): this CTA is the only reader of the (stream, head) ring and has finished with slot `head`
-    const int e = tid - 64;
-    const size_t o_ = ((size_t)b * H + h) * M * 64 + (size_t)head * 64 + e;
-    a.kring[o_] = __float2bfloat16_rn(qrow[HD + e]);
-    a.vring[o_] = __float2bfloat16_rn(qrow[2 * HD + e]);
-  }
-}
-
-bool attn_decode_supported(int Dh, int M) { return Dh == 64 && M >= 128 && M % 128 == 0 && dec_smem_bytes(M) <= 227 * 1024; }
-
-int attn_decode(const AttnDecodeArgs& a, cudaStream_t st) {
-  DMG_CHECK(a.Dcap >= a.M + 1, "attn_decode: rel-pos cache too small (%d < %d)", a.Dcap, a.M + 1);
-  const int smem = dec_smem_bytes(a.M);
-  static int configured = 0;
-  if (configured < smem) {
-    DMG_CUDA_OK(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
-  return launch_k(attn_decode_kernel, dim3(a.H, a.B), dim3(128), smem, st, 1, a);
-}
 
 // =============================================================================================
 // general kernel

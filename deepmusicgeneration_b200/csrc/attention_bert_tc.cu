@@ -316,21 +316,18 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 }  // namespace
 
 bool attn_bert_tc_supported(int T, int H, int Dcap) {
-  const bool off = getenv("DMG_BERT_ATTN_MMA_SYNC") != nullptr;   // read per call: the tests switch kernels inside one process
-  return !off && T >= 128 && Dcap >= T && H >= 1;   // T >= 128: every row has seen a full tile before the ragged one (finite running maximum)
+  return T >= 128 && Dcap >= T && H >= 1;   // T >= 128: every row has seen a full tile before the ragged one (finite running maximum)
 }
 
 // qkv: bf16 [B*T, 3*H*64] (q | k | v); rd: the inference rel-pos key cache [H][Dcap][64] (bf16, row = distance); out: bf16 [B*T, H*64]
 int attn_bert_tc(const bf16* qkv, const bf16* rd, int Dcap, const float* u, const float* v, bf16* out, int B, int T, int H, float scale,
-                 cudaStream_t st) {
-  if (getenv("DMG_BERT_TC16")) return attn_bert_tc16(qkv, rd, Dcap, u, v, out, B, T, H, scale, st);   // sixteen softmax warps (attention_bert_tc16.cu)
+                 int fp32_strip, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     DMG_CUDA_OK(cudaFuncSetAttribute(attn_bert_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
     DMG_CUDA_OK(cudaFuncSetAttribute(attn_bert_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM));
     configured = true;
   }
-  const bool fp32_strip = getenv("DMG_BERT_TC_FP32_STRIP") != nullptr;   // the first version: fp32 strip lines (2.5 x the shared-memory wavefronts)
   const int HD = H * 64;
   const TensorMap2D *tx = nullptr, *tr = nullptr;
   if (train_get_tmap(qkv, 3 * HD, (long long)B * T, 3 * HD, 128, &tx)) return -1;

@@ -50,14 +50,13 @@ __host__ __device__ inline D2Layout d2_layout(int M, int G, int n_stages) {
   return L;
 }
 
-static int d2_pick_stages(int M, int G, int max_stages = 16) {
+static int d2_pick_stages(int M, int G) {
   for (int s = 16; s >= 2; s >>= 1)
-    if (s <= max_stages && d2_layout(M, G, s).total <= 227 * 1024) return s;
+    if (d2_layout(M, G, s).total <= 227 * 1024) return s;
   return 0;
 }
 static int d2_pick_groups(int M) {
-  const char* e = getenv("DMG_DECODE_GROUPS");
-  int want = e ? atoi(e) : 2;
+  static const int want = getenv("DMG_DECODE_GROUPS") ? atoi(getenv("DMG_DECODE_GROUPS")) : 2;   // timing experiments; read once
   for (int G = want; G >= 1; G >>= 1)
     if ((G == 1 || G == 2 || G == 4) && M % (64 * G) == 0 && d2_pick_stages(M, G) >= 2) return G;
   return 0;
@@ -352,8 +351,8 @@ attn_decode2_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 
 template <int G>
 static int launch_d2(const TensorMap2D* tmK, const TensorMap2D* tmV, const TensorMap2D* tmR, const AttnDecodeArgs& a, int b0,
-                     int num_sms, int max_stages, cudaStream_t st) {
-  const int ns = d2_pick_stages(a.M, G, max_stages > 0 ? max_stages : 16);
+                     int num_sms, cudaStream_t st) {
+  const int ns = d2_pick_stages(a.M, G);
   const D2Layout L = d2_layout(a.M, G, ns);
   static int configured = 0;
   if (configured < L.total) {
@@ -369,16 +368,16 @@ static int launch_d2(const TensorMap2D* tmK, const TensorMap2D* tmV, const Tenso
 }
 
 int attn_decode2(const TensorMap2D* tmK, const TensorMap2D* tmV, const TensorMap2D* tmR, const AttnDecodeArgs& a_in, int b0,
-                 int num_sms, int max_stages, cudaStream_t st) {
+                 int num_sms, cudaStream_t st) {
   static const int no_early = getenv("DMG_NO_EARLY_KV") ? 1 : 0;
   AttnDecodeArgs a = a_in;
   a.no_early_kv = no_early;
   DMG_CHECK(a.Dcap >= a.M + 1, "attn_decode2: rel-pos cache too small (%d < %d)", a.Dcap, a.M + 1);
   const int G = d2_pick_groups(a.M);
   DMG_CHECK(G > 0, "attn_decode2: mem_len %d not supported", a.M);
-  if (G == 4) return launch_d2<4>(tmK, tmV, tmR, a, b0, num_sms, max_stages, st);
-  if (G == 2) return launch_d2<2>(tmK, tmV, tmR, a, b0, num_sms, max_stages, st);
-  return launch_d2<1>(tmK, tmV, tmR, a, b0, num_sms, max_stages, st);
+  if (G == 4) return launch_d2<4>(tmK, tmV, tmR, a, b0, num_sms, st);
+  if (G == 2) return launch_d2<2>(tmK, tmV, tmR, a, b0, num_sms, st);
+  return launch_d2<1>(tmK, tmV, tmR, a, b0, num_sms, st);
 }
 
 }  // namespace dmg

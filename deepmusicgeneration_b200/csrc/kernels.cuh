@@ -31,12 +31,6 @@ int gemm_tc_splitk_ways(int K);
 int gemm_tc_splitk(const TensorMap2D* tmA, const TensorMap2D* tmW32, const float* bias, void* C, int ldc, int M, int N,
                    int K, int gelu, int out_bf16, cudaStream_t st);
 
-// Decode-step fusion (gemm_ln.cu): x32 = LayerNorm(x32 + A W^T + bias), xa = bf16(x32) in one 8-CTA-cluster kernel.
-// tmA16: activation map with 16-row boxes; tmW: weight map with (d/8)-row boxes.
-bool gemm_ln_supported(int d, int K);
-int gemm_ln(const TensorMap2D* tmA16, const TensorMap2D* tmW, const float* bias, float* x32, const float* ln_w, const float* ln_b,
-            bf16* xa, int M, int d, int K, cudaStream_t st);
-
 // ------------------------------------------------------------------ elementwise / small kernels
 // x32[row] = emb[id] (+ beat[pos%32] + bar[min(pos/32 % 1024, 1023)]); xa = T(x32)
 template <class T>
@@ -114,20 +108,16 @@ struct AttnDecodeArgs {
   float scale;
   int no_early_kv = 0;  // v2 kernel: 1 = request the first K/V tiles only after the predecessor kernel has finished (DMG_NO_EARLY_KV)
 };
-int attn_decode(const AttnDecodeArgs& a, cudaStream_t st);
 // BERT-encoder attention on tcgen05 (attention_bert_tc.cu): T >= 128; same contract as attn_flash(..., bert = 1, ...)
 bool attn_bert_tc_supported(int T, int H, int Dcap);
+// fp32_strip = 1: the first version of the strip skew (fp32 lines, 2.5 x the shared-memory wavefronts); kept for the parity tests
 int attn_bert_tc(const bf16* qkv, const bf16* rd, int Dcap, const float* u, const float* v, bf16* out, int B, int T, int H, float scale,
-                 cudaStream_t st);
-int attn_bert_tc16(const bf16* qkv, const bf16* rd, int Dcap, const float* u, const float* v, bf16* out, int B, int T, int H, float scale,
-                   cudaStream_t st);   // sixteen softmax warps (attention_bert_tc16.cu)
-bool attn_decode_supported(int Dh, int M);
-// v2: persistent, TMA-2D swizzled K/V tiles, resident rel-pos keys, mma.sync dot products (attention_decode2.cu).
-// tmK/tmV: ring viewed as [max_batch*H*M rows, 64 cols]; tmR: Rd viewed as [H*Dcap rows, 64 cols]; 64-row boxes.
-// max_stages > 0 caps the K/V tile ring (and with it the shared memory of the persistent CTA) so that the small GEMM kernels
-// of ANOTHER group of streams can share the SM while this kernel streams its rings (decode lanes, model.cu).
+                 int fp32_strip, cudaStream_t st);
+// x_len == 1 over the bf16 ring: persistent, TMA-2D swizzled K/V tiles, resident rel-pos keys, mma.sync dot products
+// (attention_decode2.cu).  tmK/tmV: ring viewed as [max_batch*H*M rows, 64 cols]; tmR: Rd viewed as [H*Dcap rows, 64 cols];
+// 64-row boxes.
 int attn_decode2(const TensorMap2D* tmK, const TensorMap2D* tmV, const TensorMap2D* tmR, const AttnDecodeArgs& a, int b0,
-                 int num_sms, int max_stages, cudaStream_t st);
+                 int num_sms, cudaStream_t st);
 bool attn_decode2_supported(int Dh, int M);
 
 }  // namespace dmg

@@ -52,14 +52,13 @@ static int linear(dmg_model* m, int abuf, const void* A, const Weight& w, const 
     // many rows (prefill segments, the BERT encoder): the persistent CTA-pair kernel of the training path (gemm_train.cu) -
     // 256-row tiles, TMA-store epilogue.  Measured at C4 (32768 rows, QKV 512 -> 1536): 307 us with gemm_tc_kernel<128> = 168
     // TFLOP/s; the same shape runs at ~800 TFLOP/s there.
-    static const bool no_big = getenv("DMG_NO_BIG_GEMM") != nullptr;
-    if (!no_big && M >= 1024 && N % 4 == 0 && (out_bf16 ? ldc % 8 == 0 : ldc % 4 == 0)) {
+    if (!(m->kflags & DMG_KF_NO_BIG_GEMM) && M >= 1024 && N % 4 == 0 && (out_bf16 ? ldc % 8 == 0 : ldc % 4 == 0)) {
       GemmEpi e;
       e.bias = bias; e.act = gelu ? GEMM_ACT_GELU : GEMM_ACT_NONE; e.out = C; e.ldc = ldc;
       e.out_mode = out_bf16 ? GEMM_OUT_BF16 : GEMM_OUT_F32;
       return gemm_bf16_tc((const bf16*)A, 0, K, w.b16, 0, K, M, N, K, 1, e, m->num_sms, st);
     }
-    if (skinny && gemm_tc_splitk_ways(K) && !getenv("DMG_NO_SPLITK"))
+    if (skinny && gemm_tc_splitk_ways(K) && !(m->kflags & DMG_KF_NO_SPLITK))
       return gemm_tc_splitk(&m->tmA[abuf], &w.tm32, bias, C, ldc, M, N, K, gelu, out_bf16, st);
     return gemm_tc(&m->tmA[abuf], skinny ? &w.tm32 : &w.tm128, skinny ? 32 : 128, bias, C, ldc, M, N, K, gelu, out_bf16, st);
   }
@@ -75,35 +74,30 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
   T* xa = (T*)m->xa;
   if (embed<T>(ids, c.encode_position ? pos : nullptr, m->emb.f32, m->beat, m->bar, m->x32, xa, rows, d, c.vocab, st)) return -1;
   if (c.keep_hidden && M > 0 && ring_append_hidden(m->x32, m->hrings[0], nb, T_len, d, M, m->pos_total, b0, st)) return -1;
-  static const int skip = getenv("DMG_DEBUG_SKIP") ? atoi(getenv("DMG_DEBUG_SKIP")) : 0;   // timing experiments only
-  const bool v2_ok = !bert && M > 0 && m->layers[0].has_ring_tm && attn_decode2_supported(c.d_head, M) && !getenv("DMG_DECODE_V1");
-  const bool fast_decode = m->is_bf16 && !bert && T_len == 1 && (v2_ok || attn_decode_supported(c.d_head, M)) &&
-                           !getenv("DMG_NO_DECODE_KERNEL");
+  const bool fast_decode = m->is_bf16 && !bert && T_len == 1 && M > 0 && m->layers[0].has_ring_tm &&
+                           attn_decode2_supported(c.d_head, M) && !(m->kflags & DMG_KF_NO_DECODE_KERNEL);
   // segments without memory (prefill after reset(), every BERT forward) in bf16: flash attention on the tensor cores
   const bool flash = m->is_bf16 && m->use_tc && T_len > 1 && (bert || (m->mem_count == 0 && win == 1 && k == 1)) &&
-                     m->Dcap >= T_len && !getenv("DMG_NO_FLASH");
-  // Measured and rejected as the default (profiles/README.md, r1c): the 8-CTA-cluster GEMM + LayerNorm kernel is exact but
-  // slower than the split-K GEMM + LayerNorm pair at 256 rows (16 CTAs stream the whole K: 1.58 vs 1.46 ms/step at C2).
-  const bool want_gemm_ln = getenv("DMG_GEMM_LN") != nullptr;
-  const bool fuse_ln = want_gemm_ln && m->is_bf16 && m->use_tc && !bert && rows <= 512;
+                     m->Dcap >= T_len && !(m->kflags & DMG_KF_NO_FLASH);
   for (int l = 0; l < c.n_layers; l++) {
     LayerW& L = m->layers[l];
     if (flash) {
       // memory-less segment: bf16 q|k|v straight from the GEMM epilogue, tensor-core flash attention (attention_flash.cu)
       if (linear(m, A_XA, xa, L.wqkv, L.bqkv, m->qkv16, 3 * HD, rows, 0, 1, st)) return -1;
-      if (bert && attn_bert_tc_supported(T_len, c.n_heads, m->Dcap)) {   // tcgen05 / TMEM / TMA kernel (sequences of at least 128 tokens)
+      if (bert && !(m->kflags & DMG_KF_BERT_MMA_SYNC) && attn_bert_tc_supported(T_len, c.n_heads, m->Dcap)) {
+        // tcgen05 / TMEM / TMA kernel (sequences of at least 128 tokens)
         if (attn_bert_tc(m->qkv16, (const bf16*)L.rd, m->Dcap, m->u, m->v, (bf16*)m->attn, nb, T_len, c.n_heads,
-                         1.f / sqrtf((float)c.d_head), st)) return -1;
+                         1.f / sqrtf((float)c.d_head), (m->kflags & DMG_KF_BERT_FP32_STRIP) ? 1 : 0, st)) return -1;
       } else if (attn_flash(m->qkv16, (const bf16*)L.rd, m->Dcap, m->u, m->v, (bf16*)m->attn, nb, T_len, c.n_heads, bert ? 1 : 0,
                             1.f / sqrtf((float)c.d_head), st)) {
         return -1;
       }
       if (M > 0 && ring_append_kv<bf16, bf16>(m->qkv16, (bf16*)L.kring, (bf16*)L.vring, nb, T_len, c.n_heads, c.d_head, M,
                                                m->pos_total, b0, c.max_batch, st)) return -1;
-    } else if (!(skip & 1) && linear(m, A_XA, xa, L.wqkv, L.bqkv, m->qkv, 3 * HD, rows, 0, 0, st)) {
+    } else if (linear(m, A_XA, xa, L.wqkv, L.bqkv, m->qkv, 3 * HD, rows, 0, 0, st)) {
       return -1;
     }
-    if (flash || (skip & 2)) {
+    if (flash) {
     } else if (fast_decode) {
       AttnDecodeArgs a;
       a.qkv = m->qkv;
@@ -115,13 +109,7 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
       a.dev_state = m->dev_state;
       a.B = nb; a.H = c.n_heads; a.M = M; a.Dcap = m->Dcap;
       a.scale = 1.f / sqrtf((float)c.d_head);
-      if (v2_ok) {
-        if (attn_decode2(&L.tmK, &L.tmV, &L.tmR, a, b0, m->num_sms, m->lane_mode ? m->lane_stages : 0, st)) return -1;
-      } else {
-        if (attn_decode(a, st)) return -1;
-      }
-      if (m->lane_mode && l == 0 && m->lane_idx + 1 < m->lane_count)   // the next lane may start (staggered lanes)
-        DMG_CUDA_OK(cudaEventRecord(m->ev_stagger[m->lane_idx], st));
+      if (attn_decode2(&L.tmK, &L.tmV, &L.tmR, a, b0, m->num_sms, st)) return -1;
     } else {
       AttnGeneralArgs a;
       a.qkv = m->qkv; a.kring = L.kring; a.vring = L.vring; a.rd = L.rd; a.u = m->u; a.v = m->v; a.out = m->attn;
@@ -135,21 +123,11 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
     if (bert) {
       if (residual_layernorm<T, T>(m->x32, (const T*)m->attn, L.ln1w, L.ln1b, xa, rows, d, st)) return -1;
     } else {
-      // one-token steps: projection + residual + LayerNorm in one cluster kernel (gemm_ln.cu)
-      const bool fuse1 = fuse_ln && L.wo.has_tmln && m->has_tmA16[A_ATTN], fuse2 = fuse_ln && L.w2.has_tmln && m->has_tmA16[A_H];
-      if (fuse1) {
-        if (!(skip & 4) && gemm_ln(&m->tmA16[A_ATTN], &L.wo.tmln, L.bo, m->x32, L.ln1w, L.ln1b, (bf16*)xa, rows, d, HD, st)) return -1;
-      } else {
-        if (!(skip & 4) && linear(m, A_ATTN, m->attn, L.wo, L.bo, m->proj, d, rows, 0, 0, st)) return -1;
-        if (!(skip & 8) && residual_layernorm<T, float>(m->x32, m->proj, L.ln1w, L.ln1b, xa, rows, d, st)) return -1;
-      }
-      if (!(skip & 16) && linear(m, A_XA, xa, L.w1, L.b1, m->hbuf, c.d_inner, rows, 1, m->is_bf16 ? 1 : 0, st)) return -1;
-      if (fuse2) {
-        if (!(skip & 32) && gemm_ln(&m->tmA16[A_H], &L.w2.tmln, L.b2, m->x32, L.ln2w, L.ln2b, (bf16*)xa, rows, d, c.d_inner, st)) return -1;
-      } else {
-        if (!(skip & 32) && linear(m, A_H, m->hbuf, L.w2, L.b2, m->proj, d, rows, 0, 0, st)) return -1;
-        if (!(skip & 64) && residual_layernorm<T, float>(m->x32, m->proj, L.ln2w, L.ln2b, xa, rows, d, st)) return -1;
-      }
+      if (linear(m, A_ATTN, m->attn, L.wo, L.bo, m->proj, d, rows, 0, 0, st)) return -1;
+      if (residual_layernorm<T, float>(m->x32, m->proj, L.ln1w, L.ln1b, xa, rows, d, st)) return -1;
+      if (linear(m, A_XA, xa, L.w1, L.b1, m->hbuf, c.d_inner, rows, 1, m->is_bf16 ? 1 : 0, st)) return -1;
+      if (linear(m, A_H, m->hbuf, L.w2, L.b2, m->proj, d, rows, 0, 0, st)) return -1;
+      if (residual_layernorm<T, float>(m->x32, m->proj, L.ln2w, L.ln2b, xa, rows, d, st)) return -1;
     }
     if (c.keep_hidden && M > 0 && ring_append_hidden(m->x32, m->hrings[l + 1], nb, T_len, d, M, m->pos_total, b0, st)) return -1;
   }
@@ -161,67 +139,6 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
     if (gather_rows<T>(xa, (T*)m->xlast + (size_t)b0 * d, nb, d, T_len, T_len - 1, st)) return -1;
   }
   return 0;
-}
-
-// ---- decode lanes -------------------------------------------------------------------------------------------------
-static void lane_swap(dmg_model* m, dmg_model::Lane& ln) {
-  std::swap(m->x32, ln.x32); std::swap(m->qkv, ln.qkv); std::swap(m->proj, ln.proj);
-  std::swap(m->xa, ln.xa); std::swap(m->attn, ln.attn); std::swap(m->hbuf, ln.hbuf); std::swap(m->qkv16, ln.qkv16);
-  for (int i = 0; i < A_COUNT; i++) {
-    if (i == A_XLAST) continue;                       // the gathered last-position rows are shared by all lanes
-    std::swap(m->tmA[i], ln.tmA[i]); std::swap(m->tmA16[i], ln.tmA16[i]); std::swap(m->has_tmA16[i], ln.has_tmA16[i]);
-  }
-}
-
-static int ensure_lanes(dmg_model* m, int n_lanes, int rows_per_lane) {
-  const dmg_config& c = m->cfg;
-  const int d = c.d_model, HD = m->HD;
-  if ((int)m->lanes.size() >= n_lanes - 1 && m->lane_rows >= rows_per_lane) return 0;
-  DMG_CHECK(m->lanes.empty(), "decode lanes cannot be re-sized (asked for %d x %d rows)", n_lanes, rows_per_lane);
-  const size_t R = (size_t)((rows_per_lane + 127) / 128) * 128;
-  m->lanes.resize(n_lanes - 1);
-  int rc = 0;
-#define TRY(x) do { if (!rc && (x)) rc = -1; } while (0)
-  for (auto& ln : m->lanes) {
-    TRY(dalloc(m, &ln.x32, R * d));
-    { bf16* t = nullptr; TRY(dalloc(m, &t, R * d)); ln.xa = t; }
-    TRY(dalloc(m, &ln.qkv, R * 3 * HD));
-    TRY(dalloc(m, &ln.qkv16, R * 3 * HD));
-    { bf16* t = nullptr; TRY(dalloc(m, &t, R * HD)); ln.attn = t; }
-    TRY(dalloc(m, &ln.proj, R * d));
-    { bf16* t = nullptr; TRY(dalloc(m, &t, R * c.d_inner)); ln.hbuf = t; }
-    void* bufs[A_COUNT] = {ln.xa, ln.attn, ln.hbuf, nullptr};
-    const int cols[A_COUNT] = {d, HD, c.d_inner, 0};
-    for (int i = 0; i < A_COUNT && !rc; i++) {
-      if (!bufs[i] || cols[i] % 64) continue;
-      TRY(make_tmap_bf16(&ln.tmA[i], bufs[i], cols[i], (long long)R, cols[i], 128));
-      TRY(make_tmap_bf16(&ln.tmA16[i], bufs[i], cols[i], (long long)R, cols[i], 16));
-      ln.has_tmA16[i] = !rc;
-    }
-    if (!rc && cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking) != cudaSuccess) { set_error("lane stream creation failed"); rc = -1; }
-    if (!rc && cudaEventCreateWithFlags(&ln.ev, cudaEventDisableTiming) != cudaSuccess) { set_error("lane event creation failed"); rc = -1; }
-  }
-  if (!rc && !m->ev_fork && cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess) { set_error("fork event creation failed"); rc = -1; }
-  for (int i = 0; i < 4 && !rc; i++)
-    if (!m->ev_stagger[i] && cudaEventCreateWithFlags(&m->ev_stagger[i], cudaEventDisableTiming) != cudaSuccess) { set_error("stagger event creation failed"); rc = -1; }
-#undef TRY
-  if (rc) return rc;
-  m->lane_rows = (int)R;
-  return 0;
-}
-
-static int decode_lane_count(dmg_model* m, int bs, int T_len) {
-  const dmg_config& c = m->cfg;
-  if (T_len != 1 || !m->is_bf16 || !m->use_tc || c.arch != DMG_ARCH_TXL || c.keep_hidden || c.mem_len <= 0) return 1;
-  if (!attn_decode2_supported(c.d_head, c.mem_len) || getenv("DMG_DECODE_V1") || getenv("DMG_NO_DECODE_KERNEL")) return 1;
-  // Opt-in (DMG_DECODE_LANES=2..4).  Measured at C2 (profiles/README.md, r1c): 1.480 ms/step with two lanes vs 1.461 ms
-  // with one - the "latency-bound" GEMM chain still wants every SM (256-512 CTAs per kernel), and next to a persistent
-  // attention CTA only one of its CTAs fits per SM instead of three, so the overlap buys nothing.
-  const char* e = getenv("DMG_DECODE_LANES");
-  int n = e ? atoi(e) : 1;
-  if (n > 4) n = 4;
-  while (n > 1 && bs / n < 64) n--;                    // a lane should fill at least half a 128-row GEMM tile
-  return n < 1 ? 1 : n;
 }
 
 static int forward_impl(dmg_model* m, const long long* ids, const long long* pos, int bs, int T_len, int win, int k,
@@ -236,39 +153,7 @@ static int forward_impl(dmg_model* m, const long long* ids, const long long* pos
   if (m->mem_count == 0) m->batch = bs;   // fastai: memory is (re)created by the first forward after reset()
   DMG_CHECK(bs == m->batch, "dmg_forward: batch %d does not match the %d streams held in memory", bs, m->batch);
   const int cb = m->max_rows / T_len;
-  const int n_lanes = decode_lane_count(m, bs, T_len);
-  bool laned = false;
-  if (n_lanes > 1 && cb >= bs) {
-    // one-token step in `n_lanes` groups of streams on parallel streams (graph-capturable: fork / join through events)
-    const int per = (bs + n_lanes - 1) / n_lanes;
-    if (ensure_lanes(m, n_lanes, per)) return -1;
-    DMG_CUDA_OK(cudaEventRecord(m->ev_fork, st));
-    m->lane_mode = true;
-    int rc = 0;
-    for (int i = 0; i < n_lanes && !rc; i++) {
-      const int b0 = i * per, nb = bs - b0 < per ? bs - b0 : per;
-      if (nb <= 0) break;
-      cudaStream_t s_i = i == 0 ? st : m->lanes[i - 1].st;
-      static const bool no_stagger = getenv("DMG_LANE_NO_STAGGER") != nullptr;
-      if (i > 0) {
-        // fork: from the previous lane's "first attention issued" event (staggered), else from the common fork point
-        if (cudaStreamWaitEvent(s_i, no_stagger ? m->ev_fork : m->ev_stagger[i - 1], 0) != cudaSuccess) { set_error("lane fork failed"); rc = -1; break; }
-        lane_swap(m, m->lanes[i - 1]);
-      }
-      m->lane_idx = i; m->lane_count = no_stagger ? 1 : n_lanes;
-      rc = forward_chunk<bf16>(m, ids + (size_t)b0, pos ? pos + (size_t)b0 : nullptr, b0, nb, 1, win, k, logits_mode, logits, core_out, s_i);
-      if (i > 0) {
-        lane_swap(m, m->lanes[i - 1]);
-        if (!rc && (cudaEventRecord(m->lanes[i - 1].ev, s_i) != cudaSuccess || cudaStreamWaitEvent(st, m->lanes[i - 1].ev, 0) != cudaSuccess)) {
-          set_error("lane join failed"); rc = -1;
-        }
-      }
-    }
-    m->lane_mode = false;
-    if (rc) return rc;
-    laned = true;
-  }
-  for (int b0 = 0; b0 < bs && !laned; b0 += cb) {
+  for (int b0 = 0; b0 < bs; b0 += cb) {
     const int nb = bs - b0 < cb ? bs - b0 : cb;
     const long long* p = pos ? pos + (size_t)b0 * T_len : nullptr;
     int rc = m->is_bf16 ? forward_chunk<bf16>(m, ids + (size_t)b0 * T_len, p, b0, nb, T_len, win, k, logits_mode, logits, core_out, st)
@@ -276,7 +161,7 @@ static int forward_impl(dmg_model* m, const long long* ids, const long long* pos
     if (rc) return rc;
   }
   if (logits_mode == DMG_LOGITS_LAST) {
-    const bool direct = T_len == 1 && cb >= bs && !laned;   // one-token step in a single chunk: the last rows ARE the rows
+    const bool direct = T_len == 1 && cb >= bs;   // one-token step in a single chunk: the last rows ARE the rows
     if (linear(m, direct ? A_XA : A_XLAST, direct ? m->xa : m->xlast, m->emb, m->head_b, m->logits_buf, c.vocab, bs, 0, 0, st)) return -1;
     if (logits) DMG_CUDA_OK(cudaMemcpyAsync(logits, m->logits_buf, (size_t)bs * c.vocab * 4, cudaMemcpyDeviceToDevice, st));
     m->logits_valid = true;
@@ -318,10 +203,6 @@ static int commit_weight(dmg_model* m, Weight& w) {
     if (make_tmap_bf16(&w.tm32, w.b16, w.cols, w.rows, w.cols, 32)) return -1;
     if (make_tmap_bf16(&w.tm128, w.b16, w.cols, w.rows, w.cols, 128)) return -1;
     w.has_tm = true;
-    if (w.rows == m->cfg.d_model && gemm_ln_supported(w.rows, w.cols)) {
-      if (make_tmap_bf16(&w.tmln, w.b16, w.cols, w.rows, w.cols, w.rows / 8)) return -1;
-      w.has_tmln = true;
-    }
   }
   return 0;
 }
@@ -336,9 +217,8 @@ static int decode_forward(dmg_model* m, int bs, cudaStream_t st) {
 // dev_state on the device, so replay stays valid while the memory advances).
 static int decode_forward_graphed(dmg_model* m, int bs, cudaStream_t st) {
   const bool graph_ok = m->is_bf16 && m->cfg.arch == DMG_ARCH_TXL && !m->cfg.keep_hidden && m->cfg.max_rows >= bs &&
-                        (attn_decode_supported(m->cfg.d_head, m->cfg.mem_len) ||
-                         attn_decode2_supported(m->cfg.d_head, m->cfg.mem_len)) && !getenv("DMG_NO_GRAPH") &&
-                        !getenv("DMG_NO_DECODE_KERNEL");
+                        attn_decode2_supported(m->cfg.d_head, m->cfg.mem_len) &&
+                        !(m->kflags & (DMG_KF_NO_GRAPH | DMG_KF_NO_DECODE_KERNEL));
   if (!graph_ok) return decode_forward(m, bs, st);
   if (m->step_graph == nullptr || m->graph_bs != bs) {
     // first call for this batch size: run eagerly (also performs every one-time cudaFuncSetAttribute), then capture
@@ -389,12 +269,6 @@ void dmg_destroy(dmg_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   dmg_train_destroy(m);
-  for (auto& ln : m->lanes) {
-    if (ln.st) cudaStreamDestroy(ln.st);
-    if (ln.ev) cudaEventDestroy(ln.ev);
-  }
-  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
-  for (int i = 0; i < 4; i++) if (m->ev_stagger[i]) cudaEventDestroy(m->ev_stagger[i]);
   if (m->step_graph) cudaGraphExecDestroy(m->step_graph);
   if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
   for (void* p : m->allocs) cudaFree(p);
@@ -428,9 +302,19 @@ int dmg_create(const dmg_config* cfg, int device, dmg_model** out) {
   if (c.arch == DMG_ARCH_BERT) m->cfg.encode_position = 1;   // TransformerEmbedding always adds beat + bar
   m->device = device;
   m->is_bf16 = c.dtype == DMG_BF16;
-  m->use_tc = m->is_bf16 && c.gemm_backend != DMG_GEMM_SIMT && !getenv("DMG_GEMM_SIMT");
+  // kernel selectors: the config's flags plus the environment variables of the same names, read here and nowhere else
+  m->kflags = c.kernel_flags;
+  {
+    static const struct { const char* env; int flag; } sw[] = {
+        {"DMG_NO_DECODE_KERNEL", DMG_KF_NO_DECODE_KERNEL}, {"DMG_NO_FLASH", DMG_KF_NO_FLASH}, {"DMG_NO_GRAPH", DMG_KF_NO_GRAPH},
+        {"DMG_BERT_ATTN_MMA_SYNC", DMG_KF_BERT_MMA_SYNC}, {"DMG_BERT_TC_FP32_STRIP", DMG_KF_BERT_FP32_STRIP},
+        {"DMG_NO_SPLITK", DMG_KF_NO_SPLITK}, {"DMG_NO_BIG_GEMM", DMG_KF_NO_BIG_GEMM}, {"DMG_GEMM_SIMT", DMG_KF_GEMM_SIMT},
+        {"DMG_NO_FUSED_DECODE", DMG_KF_NO_FUSED_DECODE}};
+    for (const auto& e : sw)
+      if (getenv(e.env)) m->kflags |= e.flag;
+  }
+  m->use_tc = m->is_bf16 && c.gemm_backend != DMG_GEMM_SIMT && !(m->kflags & DMG_KF_GEMM_SIMT);
   m->num_sms = prop.multiProcessorCount;
-  if (const char* ls = getenv("DMG_LANE_STAGES")) { m->lane_stages = atoi(ls); if (m->lane_stages < 2) m->lane_stages = 2; }
   m->esz = m->is_bf16 ? 2 : 4;
   m->HD = c.n_heads * c.d_head;
   m->Dcap = c.mem_len + c.max_seq + 1;
@@ -543,8 +427,6 @@ int dmg_create(const dmg_config* cfg, int device, dmg_model** out) {
     for (int i = 0; i < A_COUNT && !rc; i++) {
       if (bufs[i] == nullptr || m->a_cols[i] % 64 != 0) continue;
       TRY(make_tmap_bf16(&m->tmA[i], bufs[i], m->a_cols[i], m->a_rows[i], m->a_cols[i], 128));
-      TRY(make_tmap_bf16(&m->tmA16[i], bufs[i], m->a_cols[i], m->a_rows[i], m->a_cols[i], 16));
-      m->has_tmA16[i] = !rc;
     }
   }
   if (!rc && cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -777,9 +659,8 @@ int dmg_attn_decode_layer(dmg_model* m, int layer, void* stream) {
   DMG_CHECK(m, "dmg_attn_decode_layer: null model");
   const dmg_config& c = m->cfg;
   DMG_CHECK(layer >= 0 && layer < c.n_layers, "dmg_attn_decode_layer: layer %d out of range", layer);
-  DMG_CHECK(m->is_bf16 && c.arch == DMG_ARCH_TXL &&
-                (attn_decode_supported(c.d_head, c.mem_len) || attn_decode2_supported(c.d_head, c.mem_len)),
-            "dmg_attn_decode_layer: the fused decode kernels need bf16, d_head 64 and mem_len %% 64 == 0");
+  DMG_CHECK(m->is_bf16 && c.arch == DMG_ARCH_TXL && attn_decode2_supported(c.d_head, c.mem_len) && m->layers[layer].has_ring_tm,
+            "dmg_attn_decode_layer: the fused decode kernel needs bf16, d_head 64 and mem_len %% 64 == 0");
   DMG_CHECK(m->batch >= 1 && m->batch <= m->max_rows, "dmg_attn_decode_layer: no active streams");
   DMG_CUDA_OK(cudaSetDevice(m->device));
   LayerW& L = m->layers[layer];
@@ -788,10 +669,7 @@ int dmg_attn_decode_layer(dmg_model* m, int layer, void* stream) {
   a.u = m->u; a.v = m->v; a.out = (bf16*)m->attn; a.dev_state = m->dev_state;
   a.B = m->batch; a.H = c.n_heads; a.M = c.mem_len; a.Dcap = m->Dcap;
   a.scale = 1.f / sqrtf((float)c.d_head);
-  if (L.has_ring_tm && attn_decode2_supported(c.d_head, c.mem_len) && !getenv("DMG_DECODE_V1"))
-    return attn_decode2(&L.tmK, &L.tmV, &L.tmR, a, 0, m->num_sms, decode_lane_count(m, m->batch, 1) > 1 ? m->lane_stages : 0,
-                        (cudaStream_t)stream);   // same ring depth as inside the (laned) step
-  return attn_decode(a, (cudaStream_t)stream);
+  return attn_decode2(&L.tmK, &L.tmV, &L.tmR, a, 0, m->num_sms, (cudaStream_t)stream);
 }
 
 int dmg_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_dev, void* c_dev, int M, int N, int K, int gelu,

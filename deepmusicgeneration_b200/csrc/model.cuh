@@ -17,8 +17,7 @@ struct Weight {
   bf16* b16 = nullptr;
   int rows = 0, cols = 0;
   TensorMap2D tm32, tm128;   // TMA maps with 32- and 128-row boxes
-  TensorMap2D tmln;          // (rows/8)-row boxes: the fused GEMM + LayerNorm cluster kernel (weights with rows == d_model)
-  bool has_tm = false, has_tmln = false;
+  bool has_tm = false;
 };
 
 struct LayerW {
@@ -46,6 +45,7 @@ using dmg::Weight; using dmg::LayerW; using dmg::RegEntry; using dmg::TensorMap2
 
 struct dmg_model {
   dmg_config cfg;
+  int kflags = 0;   // DMG_KF_* kernel selectors: cfg.kernel_flags | the DMG_* environment variables, read ONCE at dmg_create
   int device = 0;
   bool is_bf16 = false, use_tc = false, committed = false;
   int HD = 0, Dcap = 0, max_rows = 0, esz = 4, num_sms = 148;
@@ -65,8 +65,6 @@ struct dmg_model {
   bf16* qkv16 = nullptr;        // bf16 q|k|v of a segment for the flash-attention path
   void *xa = nullptr, *attn = nullptr, *hbuf = nullptr, *xlast = nullptr;
   TensorMap2D tmA[A_COUNT];
-  TensorMap2D tmA16[A_COUNT];   // 16-row boxes (multicast slices of the fused GEMM + LayerNorm kernel)
-  bool has_tmA16[A_COUNT] = {false, false, false, false};
   int a_rows[A_COUNT], a_cols[A_COUNT];
   // generation loop
   bool samp_ready = false, logits_valid = false;
@@ -77,26 +75,6 @@ struct dmg_model {
   cudaGraphExec_t step_graph = nullptr;
   int graph_bs = -1;
   long long graph_launches = 0;
-  // decode lanes: extra activation workspaces + streams so that the one-token step of one group of streams (latency-bound
-  // GEMM chain) overlaps the ring-streaming attention of another group (HBM-bound); lane 0 = the buffers above
-  struct Lane {
-    float *x32 = nullptr, *qkv = nullptr, *proj = nullptr;
-    void *xa = nullptr, *attn = nullptr, *hbuf = nullptr;
-    bf16* qkv16 = nullptr;
-    TensorMap2D tmA[A_COUNT], tmA16[A_COUNT];
-    bool has_tmA16[A_COUNT] = {false, false, false, false};
-    cudaStream_t st = nullptr;
-    cudaEvent_t ev = nullptr;
-  };
-  std::vector<Lane> lanes;
-  cudaEvent_t ev_fork = nullptr;
-  int lane_rows = 0;
-  int lane_stages = 4;          // K/V tile ring depth of the decode-attention kernel while lanes overlap (DMG_LANE_STAGES)
-  bool lane_mode = false;       // set while a laned decode step is being issued
-  // staggered start: lane i+1 starts once lane i has issued the attention of its first layer, so that one lane's HBM-bound
-  // attention runs under the other lane's latency-bound GEMM chain instead of both lanes marching in lockstep
-  cudaEvent_t ev_stagger[4] = {nullptr, nullptr, nullptr, nullptr};
-  int lane_idx = 0, lane_count = 1;
   dmg_train* train = nullptr;   // training state (train.cu), created by dmg_train_create
 };
 

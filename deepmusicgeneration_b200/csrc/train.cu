@@ -477,7 +477,8 @@ int dmg_train_create(dmg_model* m, const dmg_train_config* cfg, float* grad_flat
     TRY(talloc(t, &A.z2, (size_t)rows * d));
     TRY(talloc(t, &A.rk, (size_t)S * HD));
     TRY(talloc(t, &A.lse, (size_t)t->B * c.n_heads * t->T));
-    if (t->T % 128 == 0 && c.mem_len % 128 == 0 && !getenv("DMG_ATTN_NO_PSAVE")) {   // geometry the tcgen05 forward serves
+    static const bool no_psave = getenv("DMG_ATTN_NO_PSAVE") != nullptr;   // measurement switch, read once
+    if (t->T % 128 == 0 && c.mem_len % 128 == 0 && !no_psave) {   // geometry the tcgen05 forward serves
       TRY(talloc(t, &A.p_save, (size_t)t->B * c.n_heads * t->T * S));
       TRY(talloc(t, &A.m_save, (size_t)t->B * c.n_heads * t->T * (S / 64)));
       TRY(talloc(t, &A.qu_save, (size_t)rows * HD));
@@ -515,7 +516,8 @@ int dmg_train_create(dmg_model* m, const dmg_train_config* cfg, float* grad_flat
   TRY(talloc(t, &t->dkv_m, BM * 2 * HD));
   TRY(talloc(t, &t->ds_dist, (size_t)rows * c.n_heads * S));
   TRY(talloc(t, &t->qv, (size_t)rows * HD));
-  if (!getenv("DMG_ATTN_BWD_RECOMPUTE")) {   // spill P / dS from the dQ kernel instead of recomputing them for dK / dV
+  static const bool bwd_recompute = getenv("DMG_ATTN_BWD_RECOMPUTE") != nullptr;   // measurement switch, read once
+  if (!bwd_recompute) {   // spill P / dS from the dQ kernel instead of recomputing them for dK / dV
     TRY(talloc(t, &t->p_buf, (size_t)rows * c.n_heads * S));
     TRY(talloc(t, &t->ds_buf, (size_t)rows * c.n_heads * S));
   }

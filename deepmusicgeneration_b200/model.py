@@ -38,7 +38,7 @@ def _ptr(t):
 
 class _Engine:
     "Owns one dmg_model handle."
-    def __init__(self, arch, vocab_sz, config, dtype, device, max_batch, max_seq, max_rows, keep_hidden, gemm_backend=0):
+    def __init__(self, arch, vocab_sz, config, dtype, device, max_batch, max_seq, max_rows, keep_hidden, gemm_backend=0, kernel_flags=0):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError('deepmusicgeneration_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
@@ -56,6 +56,7 @@ class _Engine:
         cfg.max_batch, cfg.max_seq, cfg.max_rows = max_batch, max_seq, max_rows
         cfg.keep_hidden = int(keep_hidden and not bert)
         cfg.gemm_backend = gemm_backend
+        cfg.kernel_flags = kernel_flags
         self.cfg, self.dtype = cfg, dtype
         h = C.c_void_p()
         check(self.lib.dmg_create(C.byref(cfg), self.device.index, C.byref(h)), 'dmg_create')
@@ -278,11 +279,11 @@ class _LazyHidden:
 
 
 def get_language_model(vocab_sz, config, drop_mult=1., dtype='bf16', device=0, max_batch=1, max_seq=None, max_rows=0,
-                       keep_hidden=True, seed=None, init=True, gemm_backend=0):
+                       keep_hidden=True, seed=None, init=True, gemm_backend=0, kernel_flags=0):
     "fastai get_language_model(MusicTransformerXL, vocab_sz, config, drop_mult) (deep_music_genre.py:1793)."
     config = dict(config)
     max_seq = max_seq or max(config.get('ctx_len', 512), config['mem_len'], 1024)
-    eng = _Engine(_lib.ARCH_TXL, vocab_sz, config, dtype, device, max_batch, max_seq, max_rows, keep_hidden, gemm_backend)
+    eng = _Engine(_lib.ARCH_TXL, vocab_sz, config, dtype, device, max_batch, max_seq, max_rows, keep_hidden, gemm_backend, kernel_flags)
     model = SequentialRNN(eng, config)
     if init:
         eng.load_state_dict(init_state_dict(eng, seed))
@@ -315,10 +316,10 @@ class MultiTransformer:
 
 
 def get_multitask_model(vocab_size, config, drop_mult=1., pad_idx=None, dtype='bf16', device=0, max_batch=1, max_seq=1024,
-                        max_rows=0, seed=None, init=True, gemm_backend=0):
+                        max_rows=0, seed=None, init=True, gemm_backend=0, kernel_flags=0):
     "deep_music_remix.py:1851-1862 (encoder + head; the decoder is not built)."
     config = dict(config)
-    eng = _Engine(_lib.ARCH_BERT, vocab_size, config, dtype, device, max_batch, max_seq, max_rows, False, gemm_backend)
+    eng = _Engine(_lib.ARCH_BERT, vocab_size, config, dtype, device, max_batch, max_seq, max_rows, False, gemm_backend, kernel_flags)
     model = MultiTransformer(eng, config)
     if init:
         eng.load_state_dict(init_state_dict(eng, seed))

@@ -30,6 +30,18 @@ enum { DMG_GEMM_AUTO = 0,  /* bf16: tcgen05/TMEM/TMA kernels (cluster split-K fo
        DMG_GEMM_SIMT = 1,  /* debugging: SIMT kernel for every dtype */
        DMG_GEMM_TC_TILE = 2 /* dmg_gemm_bf16 only: the one-CTA-per-tile tcgen05 kernel even for skinny shapes */ };
 enum { DMG_LOGITS_NONE = 0, DMG_LOGITS_ALL = 1, DMG_LOGITS_LAST = 2 };
+/* dmg_config.kernel_flags: selectors of the non-default kernels, for the parity tests (every alternative kernel is compared with the
+ * default one and with the oracle) and for reproducing the measurements in profiles/README.md.  0 = the product path.  The
+ * environment variable DMG_<NAME> sets the same bit; the environment is read once, in dmg_create. */
+enum { DMG_KF_NO_DECODE_KERNEL = 1,  /* one-token steps through the general attention kernel instead of attention_decode2.cu        */
+       DMG_KF_NO_FLASH = 2,          /* memory-less bf16 segments (prefill, BERT) through the general FFMA attention kernel           */
+       DMG_KF_NO_GRAPH = 4,          /* generation loop launched kernel by kernel instead of replaying the captured CUDA graph        */
+       DMG_KF_BERT_MMA_SYNC = 8,     /* BERT attention on the mma.sync flash kernel for every length (env DMG_BERT_ATTN_MMA_SYNC)      */
+       DMG_KF_BERT_FP32_STRIP = 16,  /* BERT tcgen05 attention with fp32 strip lines (env DMG_BERT_TC_FP32_STRIP)                      */
+       DMG_KF_NO_SPLITK = 32,        /* one-token GEMMs without cluster split-K                                                       */
+       DMG_KF_NO_BIG_GEMM = 64,      /* many-row GEMMs on gemm_tc_kernel instead of the persistent CTA-pair kernel                    */
+       DMG_KF_GEMM_SIMT = 128,       /* every GEMM on the FFMA kernel                                                                 */
+       DMG_KF_NO_FUSED_DECODE = 256  /* one-token step as separate GEMM / LayerNorm launches instead of the fused layer kernels       */ };
 
 /* Model hyper-parameters: the keys of the reference config dicts (app_utils.py:13-63, fastai tfmerXL_lm_config). */
 typedef struct dmg_config {
@@ -45,7 +57,8 @@ typedef struct dmg_config {
   int32_t max_rows;         /* activation workspace rows per chunk; 0 = max_batch*max_seq                 */
   int32_t keep_hidden;      /* also keep the reference's hidden-state mems (model[0].hidden) for export   */
   int32_t gemm_backend;     /* DMG_GEMM_*                                                                 */
-  int32_t reserved[4];
+  int32_t kernel_flags;     /* DMG_KF_* (0 = product path)                                                */
+  int32_t reserved[3];
 } dmg_config;
 
 /* Index layout of MusicVocab (deep_music_genre.py:812-890); ranges are [lo, hi). */
