@@ -106,56 +106,153 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference(batch, steps, warmup, budget_s):
-    """The reference algorithm on the host: eager PyTorch fp32, hidden-state memory re-projected to K/V every step,
-    materialised _line_shift (oracle/txl.py).  Memory is pre-filled with random hidden states (its contents do not
-    change the cost).  Returns (tokens/s, steps actually timed, threads)."""
-    from oracle import txl
-    torch.manual_seed(0)
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    model = txl.get_language_model(V, txl.baseline_config()).eval()
-    enc = model[0]
-    enc.reset(); enc.init = True
-    enc.hidden = [torch.randn(batch, CFG['mem_len'], CFG['d_model']) for _ in range(CFG['n_layers'] + 1)]
-    g = torch.Generator().manual_seed(1234)
-    x = torch.randint(0, V, (batch, 1), generator=g)
-    t_begin = time.time()
-    with torch.no_grad():
-        for _ in range(warmup):
-            x = model(x)[0][:, -1].argmax(-1, keepdim=True)
-            if time.time() - t_begin > budget_s / 3:
-                break
-        done, t0 = 0, time.time()
-        for _ in range(steps):
-            x = model(x)[0][:, -1].argmax(-1, keepdim=True)
-            done += 1
-            if time.time() - t_begin > budget_s:
-                break
-        dt = time.time() - t0
-    return batch * done / dt, done, threads, dt
+class CpuReference:
+    """The reference algorithm on the host: eager PyTorch fp32, hidden-state memory re-projected to K/V every step, materialised
+    _line_shift (oracle/txl.py).  Memory is pre-filled with random hidden states (its contents do not change the cost)."""
+    def __init__(self):
+        from oracle import txl
+        torch.manual_seed(0)
+        self.threads = os.cpu_count() or 1
+        torch.set_num_threads(self.threads)
+        self.model = txl.get_language_model(V, txl.baseline_config()).eval()
+
+    def run(self, batch, steps, warmup, budget_s):
+        "-> (tokens/s, steps timed, seconds)"
+        enc = self.model[0]
+        enc.reset(); enc.init = True
+        enc.hidden = [torch.randn(batch, CFG['mem_len'], CFG['d_model']) for _ in range(CFG['n_layers'] + 1)]
+        x = torch.randint(0, V, (batch, 1), generator=torch.Generator().manual_seed(1234))
+        t_begin = time.time()
+        with torch.no_grad():
+            for _ in range(warmup):
+                x = self.model(x)[0][:, -1].argmax(-1, keepdim=True)
+            done, t0 = 0, time.time()
+            for _ in range(steps):
+                x = self.model(x)[0][:, -1].argmax(-1, keepdim=True)
+                done += 1
+                if time.time() - t_begin > budget_s:
+                    break
+            dt = time.time() - t0
+        return batch * done / dt, done, dt
+
+    def best_batch(self, candidates=(8, 32, 64)):
+        "The CPU's own best case: the batch (of the candidates) with the highest tokens/s over three steps."
+        rates = {}
+        for b in candidates:
+            rates[b] = self.run(b, 3, 1, budget_s=60.0)[0]
+        return max(rates, key=rates.get), rates
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    batch = 8
-    value, done, threads, dt = cpu_reference(batch, args.steps, min(args.warmup, 2), budget_s=150.0)
+    if args.workload == 'c1':
+        return print(json.dumps(c1_line(args, cpu_only=True)), flush=True)
+    ref = CpuReference()
+    batch, rates = ref.best_batch()
+    warm = min(args.warmup, 2)
+    value, done, dt = ref.run(batch, args.steps, warm, budget_s=150.0)
     sample = (f'{batch} streams x {done} one-token steps over a full 512-slot memory, greedy, fp32 eager PyTorch oracle '
-              f'(reference algorithm: hidden-state mems re-projected every step), {threads} threads')
+              f'(reference algorithm: hidden-state mems re-projected every step), {ref.threads} threads; batch chosen as the '
+              f'fastest of a sweep: ' + ', '.join(f'{b}: {r:.0f} tok/s' for b, r in rates.items()))
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': done,
-            'warmup': min(args.warmup, 2), 'ms_per_step': 1e3 * dt / max(done, 1), 'higher_is_better': True,
+            'warmup': warm, 'ms_per_step': 1e3 * dt / max(done, 1), 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'cpu_batch': batch},
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+            'config': {'workload': WORKLOAD, 'cpu_batch': batch, 'cpu_batch_sweep_tok_s': rates},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': ref.threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------------------- C1: the reference's own CPU-runnable case
+def c1_line(args, cpu_only=False):
+    """BASELINE.json configs[0]: random-init Transformer-XL (C2's model), seed = the whole encoded fur_elise.mid, 512 greedy tokens,
+    fp32.  CPU: the oracle's reference loop (deep_music_genre.py:1853-1972), wall time split into prefill and decode.  GPU: the same
+    call through MusicLearner.predict in fp32 mode; the two token streams must be identical."""
+    from oracle import codec as ocodec, sampling as osamp, txl
+    mid = os.path.join(ROOT, 'tests', 'golden', 'fur_elise.mid')
+    ov = ocodec.MusicVocab.create()
+    seed = ocodec.seed_from_midi(mid, ov, strip_eos=True)
+    pos = ocodec.position_enc(seed.copy(), ov)
+    n_words = 512
+    torch.manual_seed(0)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    om = txl.get_language_model(V, txl.baseline_config()).eval()
+    with torch.no_grad():
+        om[1].decoder.bias[308:] = -50.          # mt*/dummy* ids: never filtered by the reference, never produced by a trained model
+    marks = []
+    t0 = time.time()
+    ref = osamp.predict(om, ov, seed, pos, n_words=n_words, temperatures=(1., 1., 1.), min_bars=10 ** 6, top_k=1, top_p=0.0,
+                        on_step=lambda i, lg: marks.append(time.time()))
+    t_cpu = time.time() - t0
+    prefill_cpu = marks[0] - t0
+    cpu = {'value': len(ref) / (t_cpu - prefill_cpu), 'unit': UNIT, 'cores': threads, 'kind': 'port',
+           'sample': f'the whole case: seed {len(seed)} tokens prefilled in {prefill_cpu:.1f} s, {len(ref)} greedy tokens in '
+                     f'{t_cpu - prefill_cpu:.1f} s, total wall {t_cpu:.1f} s (fp32 eager-PyTorch oracle, reference loop)',
+           'wall_s': t_cpu, 'prefill_s': prefill_cpu}
+    base = {'metric': METRIC, 'unit': UNIT, 'n_gpus': 1, 'steps': len(ref), 'warmup': 0, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'fur_elise.mid seed (tests/golden), random-init weights',
+            'config': {'workload': 'C1: Transformer-XL d_model 512, 16 layers, 8 heads x 64, mem_len 512, vocab 324, random init; '
+                                   f'generate {n_words} greedy tokens from the encoded fur_elise.mid ({len(seed)} tokens), batch 1, fp32'},
+            'cpu_baseline': cpu}
+    if cpu_only:
+        return dict(base, impl='reference', value=cpu['value'], ms_per_step=1e3 * (t_cpu - prefill_cpu) / max(len(ref), 1),
+                    e2e={'value': cpu['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, gpu_launches=0)
+    from deepmusicgeneration_b200 import _lib
+    from deepmusicgeneration_b200.codec import MusicDataBunch, MusicItem
+    from deepmusicgeneration_b200.learner import MusicLearner
+    from deepmusicgeneration_b200.model import get_language_model
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device - the CUDA path has no CPU fallback')
+    lib = _lib.load()
+    data = MusicDataBunch.empty('')
+    item = MusicItem.from_file(mid, data.vocab)
+    item = MusicItem(item.data[:-1], data.vocab) if item.data[-1] == data.vocab.stoi['xxeos'] else item
+    assert list(item.data) == list(seed), 'MIDI -> token encoding differs from the oracle'
+    pm = get_language_model(V, txl.baseline_config(), dtype='f32', device=0, max_batch=1, max_seq=len(seed), keep_hidden=False, init=False)
+    pm.load_state_dict(om.state_dict())
+    learn = MusicLearner(data, pm)
+    learn.predict(item, n_words=8, temperatures=(1., 1., 1.), min_bars=10 ** 6, top_k=1, top_p=0.0)        # warm-up
+    torch.cuda.synchronize()
+    l0 = lib.dmg_launch_count()
+    t0 = time.time()
+    pred, _ = learn.predict(item, n_words=n_words, temperatures=(1., 1., 1.), min_bars=10 ** 6, top_k=1, top_p=0.0)
+    torch.cuda.synchronize()
+    t_gpu = time.time() - t0
+    same = list(pred.data) == list(ref)
+    return dict(base, value=len(pred.data) / t_gpu, ms_per_step=1e3 * t_gpu / max(len(pred.data), 1),
+                config=dict(base['config'], token_stream_identical_to_oracle=same, gpu_wall_s=t_gpu,
+                            note='value = generated tokens / wall seconds of the whole predict() call (seed encoding excluded, '
+                                 'prefill of the seed included), host buffers in, tokens out'),
+                e2e={'value': len(pred.data) / t_gpu, 'unit': UNIT, 'h2d_bytes_per_step': 16 * len(seed) // max(len(pred.data), 1),
+                     'd2h_bytes_per_step': 4},
+                gpu_launches=int(lib.dmg_launch_count() - l0))
+
+
 # --------------------------------------------------------------------------------------------- CUDA arm
 def run_b200(args):
+    "C2 headline + (default run) the C3 training step and the C4 encoder forward as sub-records of the one JSON line."
+    line = measure_c2(args)
+    if args.workload == 'c2' and not args.no_extra_legs:
+        import argparse
+        import bench_bert
+        import bench_train
+        sub = argparse.Namespace(**vars(args))
+        sub.steps, sub.warmup = args.train_steps, 4
+        train = bench_train.measure(sub, sample_clocks=False)
+        sub.steps, sub.warmup = args.bert_steps, 3
+        bert = bench_bert.measure(sub, sample_clocks=False)
+        if line is not None:
+            line['train'], line['bert'] = train, bert
+            line['gpu_launches_all_legs'] = line['gpu_launches'] + train['gpu_launches'] + bert['gpu_launches']
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def measure_c2(args):
     from deepmusicgeneration_b200 import _lib, sharding
     from deepmusicgeneration_b200.app_utils import baseline_config
     from deepmusicgeneration_b200.codec import MusicDataBunch
@@ -268,20 +365,24 @@ def run_b200(args):
     if os.path.exists(tpath):
         try: traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
         except Exception: traffic = None
-    roofline = {'bound': 'hbm', 'kernel': 'attn_decode_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+    roofline = {'bound': 'hbm', 'kernel': 'attn_decode2_kernel<2> (attention_decode2.cu)', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': abytes, 'kernel_ms': attn_ms,
                 'kernel_share_of_step': attn_ms * L / (ms / K),
                 'step_algorithmic_bytes': sbytes, 'step_frac': sbytes / (ms / K / 1e3) / 1e9 / peak}
 
+    del learn, model, e, toks
+    torch.cuda.empty_cache()
     if rank != 0:
-        return
+        return None
     cpu = None
     if world == 1 and not args.no_cpu_baseline and not c5:
-        v, done, threads, dt = cpu_reference(8, 100000, 1, budget_s=15.0)      # a bounded sample: about 15 s of host work
-        cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-               'sample': f'8 streams x {done} one-token steps over a full 512-slot memory, fp32 eager-PyTorch oracle '
-                         f'(reference algorithm), {dt:.1f} s'}
+        ref = CpuReference()
+        cb, rates = ref.best_batch((8, 32))
+        v, done, dt = ref.run(cb, 100000, 1, budget_s=15.0)                    # a bounded sample: about 15 s of host work
+        cpu = {'value': v, 'unit': UNIT, 'cores': ref.threads, 'kind': 'port',
+               'sample': f'{cb} streams x {done} one-token steps over a full 512-slot memory, fp32 eager-PyTorch oracle '
+                         f'(reference algorithm), {dt:.1f} s; batch = the faster of ' + ', '.join(f'{b}: {r:.0f} tok/s' for b, r in rates.items())}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms_max / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
             'data': 'synthetic',
@@ -292,7 +393,7 @@ def run_b200(args):
             'roofline': roofline, 'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': B * 8, 'd2h_bytes_per_step': B * 4, 'steps': Ke},
             'gpu_launches': launches, 'clocks': clock_info}
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def main():
@@ -301,14 +402,24 @@ def main():
     ap.add_argument('--steps', type=int, default=None)
     ap.add_argument('--warmup', type=int, default=None)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=['c2', 'c3', 'c4', 'c5'],
-                    help='c2 (default, the headline): batched incremental generation; c3: data-parallel training step; '
-                         'c4: remix (masked-BERT) encoder forward; c5: the scaled generation model')
+    ap.add_argument('--workload', default='c2', choices=['c1', 'c2', 'c3', 'c4', 'c5'],
+                    help='c2 (default, the headline; its line also carries the c3 and c4 legs as `train` / `bert`): batched incremental '
+                         'generation; c1: 512 greedy tokens from fur_elise.mid, CPU oracle wall + CUDA fp32; c3: data-parallel training '
+                         'step alone; c4: remix (masked-BERT) encoder forward alone; c5: the scaled generation model')
+    ap.add_argument('--no-extra-legs', action='store_true', help='c2 only: skip the `train` (C3) and `bert` (C4) sub-records')
+    ap.add_argument('--train-steps', type=int, default=12, help='timed steps of the C3 leg inside the default run')
+    ap.add_argument('--bert-steps', type=int, default=5, help='timed forwards of the C4 leg inside the default run')
     ap.add_argument('--batch', type=int, default=B_PER_GPU, help='c2: streams per GPU')
     ap.add_argument('--train-batch', type=int, default=32, help='c3: sequences per GPU and step')
     ap.add_argument('--bert-batch', type=int, default=512, help='c4: sequences per GPU and forward')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    if args.workload == 'c1':
+        if args.impl == 'reference':
+            return run_reference(args)
+        if int(os.environ.get('RANK', '0')) == 0:
+            print(json.dumps(c1_line(args)), flush=True)
+        return
     if args.workload == 'c3':
         import bench_train
         args.steps = args.steps if args.steps is not None else 30

@@ -36,6 +36,13 @@ def synthetic(B, gen):
 
 
 def run_b200(args):
+    line = measure(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def measure(args, sample_clocks=True, cpu_leg=True):
+    "Runs the C4 leg on every rank; returns the JSON record on rank 0 (None elsewhere)."
     from bench import ClockSampler
     from deepmusicgeneration_b200 import _lib, sharding
     from deepmusicgeneration_b200.app_utils import multitask_config
@@ -62,7 +69,7 @@ def run_b200(args):
 
     # ---- timed region: K forwards, inputs resident in HBM
     sharding.barrier(); torch.cuda.synchronize()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
+    clocks = ClockSampler(local_rank) if rank == 0 and sample_clocks else None
     launches0 = lib.dmg_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
@@ -97,8 +104,10 @@ def run_b200(args):
     e2e_ms = sharding.max_over_ranks(ev0.elapsed_time(ev1), device=dev)
     e2e_value = B * T * world * Ke / (e2e_ms / 1e3)
 
+    del e, pm
+    torch.cuda.empty_cache()
     if rank != 0:
-        return
+        return None
     try:
         pk = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         peak_tf, peak_src = float(pk['bf16_tflops_sustained']), 'measured sustained (MEASURED_PEAKS.json)'
@@ -110,7 +119,7 @@ def run_b200(args):
                 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': None, 'peak_source': peak_src,
                 'flops_per_token_dense': fpt}
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and cpu_leg:
         v, n, threads, dt = cpu_reference(budget_s=15.0)
         cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                'sample': f'{n} forward(s) of 2 sequences x {T} tokens, fp32 eager-PyTorch oracle (oracle/bert.py), {dt:.1f} s'}
@@ -122,7 +131,7 @@ def run_b200(args):
             'roofline': roofline, 'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 2 * B * T * 8, 'd2h_bytes_per_step': B * V * 4, 'steps': Ke},
             'gpu_launches': launches, 'clocks': clock_info}
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def cpu_reference(budget_s, batch=2):

@@ -47,6 +47,13 @@ def lakh_shaped_tokens(bs, n, gen):
 
 
 def run_b200(args):
+    line = measure(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def measure(args, sample_clocks=True, cpu_leg=True):
+    "Runs the C3 leg on every rank; returns the JSON record on rank 0 (None elsewhere)."
     from bench import ClockSampler
     from deepmusicgeneration_b200 import _lib, sharding
     from deepmusicgeneration_b200.app_utils import baseline_config
@@ -62,7 +69,7 @@ def run_b200(args):
     lib = _lib.load()
     cfg = dict(baseline_config(), mask_steps=1)
     model = get_language_model(V, cfg, dtype='bf16', device=local_rank, max_batch=1, max_seq=64, max_rows=64, keep_hidden=False, seed=0)
-    tr = TXLTrainer(model, B, T, cfg, drop_mult=1.0, alpha=2., beta=1., seed=7 + rank, distributed=world > 1, bucket_layers=4)
+    tr = TXLTrainer(model, B, T, cfg, drop_mult=1.0, alpha=2., beta=1., seed=7, distributed=world > 1)
     np.random.seed(1234)          # rand_window_mask draws: identical on every rank, like a shared schedule
 
     n_batches = 4
@@ -79,7 +86,8 @@ def run_b200(args):
             tr.step(xd[i % n_batches], yd[i % n_batches], lr=1e-4)
         torch.cuda.synchronize()
         print('profile run done', tr.losses())
-        return
+        tr.close()
+        return None
     tr.reset()
     for i in range(W):
         tr.step(xd[i % n_batches], yd[i % n_batches], lr=1e-4)
@@ -88,7 +96,7 @@ def run_b200(args):
 
     # ---- timed region: K steps, inputs resident in HBM
     sharding.barrier(); torch.cuda.synchronize()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
+    clocks = ClockSampler(local_rank) if rank == 0 and sample_clocks else None
     launches0 = lib.dmg_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
@@ -105,6 +113,7 @@ def run_b200(args):
     ms_max = sharding.max_over_ranks(ms, device=dev)
     value = B * T * world * K / (ms_max / 1e3)
     l1 = tr.losses()
+    grad_exchange = tr.describe_exchange()
 
     # ---- end to end: every step copies its tokens/targets from pinned host memory and reads the loss back
     Ke = min(K, 20)
@@ -144,23 +153,28 @@ def run_b200(args):
                 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': None, 'peak_source': peak_src,
                 'flops_per_token_fwd_bwd_dense': fb_f, 'forward_ms': t_fwd, 'forward_backward_ms': t_fb,
                 'optimizer_and_rest_ms': step_ms - t_fb}
+    comm = tr.profile_comm(lambda: tr.step(xd[0], yd[0], lr=1e-4), reps=3) if world > 1 else None
+    tr.close()
+    del tr, model
+    torch.cuda.empty_cache()
     if rank != 0:
-        return
+        return None
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and cpu_leg:
         v, n, threads, dt = cpu_reference(2, 8, budget_s=15.0)                  # a bounded sample: about 15 s of host work
         cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                'sample': f'{n} training step(s) of 2 sequences x 512 tokens over a full memory, fp32 eager-PyTorch oracle, {dt:.1f} s'}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': step_ms,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'global_batch': B * world, 'bptt': T,
-                       'parallelism': f'dp{world}: batch sharded, flat fp32 gradient all-reduced over NCCL in 4-layer buckets overlapped with backward',
+                       'parallelism': f'dp{world}: batch sharded; ' + grad_exchange,
                        'l2': 'activations per step (>3 GB) exceed the 126 MB L2',
-                       'loss_before': l0['loss'], 'loss_after': l1['loss']},
+                       'loss_before': l0['loss'], 'loss_after': l1['loss'], 'loss_parts_before': l0, 'loss_parts_after': l1,
+                       'comm': comm},
             'roofline': roofline, 'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 2 * B * T * 8, 'd2h_bytes_per_step': 16, 'steps': Ke},
             'gpu_launches': launches, 'clocks': clock_info}
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def cpu_reference(batch, steps, budget_s):

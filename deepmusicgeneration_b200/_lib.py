@@ -77,6 +77,8 @@ SYMBOLS = {
     'dmg_train_forward': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i64, c_vp]),
     'dmg_train_backward': (c_i32, [c_vp, c_i32, c_i32, c_vp]),
     'dmg_train_grad_span': (c_i32, [c_vp, c_i32, c_i32, C.POINTER(c_i64), C.POINTER(c_i64)]),
+    'dmg_train_grad_pack': (c_i32, [c_vp, c_i64, c_i64, c_vp, c_vp]),
+    'dmg_train_grad_unpack': (c_i32, [c_vp, c_i64, c_i64, c_vp, c_vp]),
     'dmg_train_optimizer_step': (c_i32, [c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp]),
     'dmg_train_losses': (c_i32, [c_vp, c_vp, c_vp]),
     'dmg_train_get_grad': (c_i32, [c_vp, C.c_char_p, c_vp, c_i64]),

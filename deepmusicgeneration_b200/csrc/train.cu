@@ -613,6 +613,22 @@ int dmg_train_grad_span(dmg_model* m, int layer_hi, int layer_lo, int64_t* offse
   return 0;
 }
 
+int dmg_train_grad_pack(dmg_model* m, int64_t offset, int64_t count, void* wire_bf16_dev, void* stream) {
+  if (check_train(m, "dmg_train_grad_pack")) return -2;
+  dmg_train* t = m->train;
+  DMG_CHECK(wire_bf16_dev && offset >= 0 && count >= 0 && offset + count <= t->total, "dmg_train_grad_pack: bad span");
+  DMG_CUDA_OK(cudaSetDevice(m->device));
+  return train_grad_pack(t->G + offset, (bf16*)wire_bf16_dev, count, (cudaStream_t)stream);
+}
+
+int dmg_train_grad_unpack(dmg_model* m, int64_t offset, int64_t count, const void* wire_bf16_dev, void* stream) {
+  if (check_train(m, "dmg_train_grad_unpack")) return -2;
+  dmg_train* t = m->train;
+  DMG_CHECK(wire_bf16_dev && offset >= 0 && count >= 0 && offset + count <= t->total, "dmg_train_grad_unpack: bad span");
+  DMG_CUDA_OK(cudaSetDevice(m->device));
+  return train_grad_unpack((const bf16*)wire_bf16_dev, t->G + offset, count, (cudaStream_t)stream);
+}
+
 int dmg_train_optimizer_step(dmg_model* m, float lr, float beta1, float beta2, float eps, float wd, float clip, float grad_scale,
                              void* stream) {
   if (check_train(m, "dmg_train_optimizer_step")) return -2;

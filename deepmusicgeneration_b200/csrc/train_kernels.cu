@@ -389,6 +389,21 @@ __global__ void __launch_bounds__(256) train_cast_kernel(const float* __restrict
     for (long long i = n4 * 4; i < n; i++) dst[i] = __float2bfloat16_rn(src[i]);
 }
 
+// bf16 -> fp32 (the gradient bucket coming back from the bf16 all-reduce)
+__global__ void __launch_bounds__(256) train_uncast_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n, int vec) {
+  const long long n4 = vec ? (n >> 2) : 0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const uint2 v = ((const uint2*)src)[i];
+    ((float4*)dst)[i] = make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                                    __uint_as_float(v.y & 0xffff0000u));
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+    dst[i] = __bfloat162float(src[i]);
+}
+__global__ void __launch_bounds__(256) train_cast_scalar_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
 __global__ void __launch_bounds__(256) train_qpb_kernel(const bf16* __restrict__ qkv, long long ldx, const float* __restrict__ v,
                                                         bf16* __restrict__ out, int rows, int HD) {
   const int h2 = HD >> 1;
@@ -570,6 +585,17 @@ int train_tar(const bf16* h, long long bstride, int B, int n, int d, float* acc,
 
 int train_cast_bf16(const float* src, bf16* dst, long long n, cudaStream_t st) {
   return launch_np(train_cast_kernel, dim3(grid_for(n / 4)), dim3(256), 0, st, src, dst, n);
+}
+
+int train_grad_pack(const float* src, bf16* dst, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if ((((uintptr_t)src) & 15) == 0 && (((uintptr_t)dst) & 7) == 0) return train_cast_bf16(src, dst, n, st);
+  return launch_np(train_cast_scalar_kernel, dim3(grid_for(n)), dim3(256), 0, st, src, dst, n);
+}
+int train_grad_unpack(const bf16* src, float* dst, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int vec = (((uintptr_t)dst) & 15) == 0 && (((uintptr_t)src) & 7) == 0;
+  return launch_np(train_uncast_kernel, dim3(grid_for(vec ? n / 4 + 1 : n)), dim3(256), 0, st, src, dst, n, vec);
 }
 
 int train_q_plus_bias(const bf16* qkv_x, long long ldx, const float* v, bf16* out, int rows, int HD, cudaStream_t st) {

@@ -178,6 +178,9 @@ int train_embed_bwd(const long long* ids, const long long* pos, const float* dx,
                     int rows, int d, int vocab, uint32_t thresh, uint32_t seed, float scale, cudaStream_t st);
 // fp32 [rows, d] -> bf16
 int train_cast_bf16(const float* src, bf16* dst, long long n, cudaStream_t st);
+// gradient bucket <-> its bf16 wire format (any alignment)
+int train_grad_pack(const float* src, bf16* dst, long long n, cudaStream_t st);
+int train_grad_unpack(const bf16* src, float* dst, long long n, cudaStream_t st);
 // q + v -> bf16 [rows, HD]   (q = qkv_x columns [0, HD))
 int train_q_plus_bias(const bf16* qkv_x, long long ldx, const float* v, bf16* out, int rows, int HD, cudaStream_t st);
 // memory update of the training state: mem = cat(mem, x)[:, -M:]  (bf16 hidden states, right-aligned)

@@ -49,7 +49,7 @@ class TXLTrainer:
     trainer.losses()                                                    # {'ce':.., 'ar':.., 'tar':.., 'loss':.., 'grad_norm':..}
     """
     def __init__(self, model, bs, bptt, config, drop_mult=1., alpha=2., beta=1., seed=0, process_group=None, bucket_layers=4,
-                 distributed=None):
+                 distributed=None, wire='bf16', rank_seed=True):
         self.model, self.e = model, model._e
         self.lib = self.e.lib
         self.bs, self.bptt = bs, bptt
@@ -64,6 +64,11 @@ class TXLTrainer:
         self.distributed = distributed
         self.world = torch.distributed.get_world_size(process_group) if distributed else 1
         self.bucket_layers = max(1, bucket_layers)
+        self.wire = wire if distributed else 'none'
+        assert self.wire in ('bf16', 'f32', 'none')
+        if distributed and rank_seed:
+            # independent dropout masks per rank, like the reference's DDP processes (each draws from its own generator)
+            seed = (int(seed) + 0x9E3779B97F4A7C15 * torch.distributed.get_rank(process_group)) % (1 << 64)
         tc = _lib.TrainConfig()
         tc.batch, tc.bptt = bs, bptt
         for k in ('resid_p', 'attn_p', 'ff_p', 'embed_p', 'output_p'):
@@ -77,7 +82,10 @@ class TXLTrainer:
             self.grad = torch.zeros(n, device=self.e.device, dtype=torch.float32)      # torch-owned: NCCL all-reduces it
             check(self.lib.dmg_train_create(self.e.h, C.byref(tc), _ptr(self.grad)), 'dmg_train_create')
             self.comm_stream = torch.cuda.Stream(device=self.e.device) if distributed else None
+            self.wire_buf = torch.empty(n, device=self.e.device, dtype=torch.bfloat16) if self.wire == 'bf16' else None
         self._keep = None
+        self._comm_events = None
+        self.buckets = self._bucket_plan()
 
     def close(self):
         if self.e.h:
@@ -108,15 +116,49 @@ class TXLTrainer:
                                              int(self.training), self.step_count, _stream_ptr()), 'dmg_train_forward')
         return mask_size
 
+    def _bucket_plan(self):
+        """(layer_hi, layer_lo) slices of one backward pass.  One rank: a single slice.  Data parallel: the head + the two top layers
+        go out first (their all-reduce starts while almost the whole backward is still ahead), then `bucket_layers`-layer buckets,
+        and the LAST bucket - the only one whose all-reduce nothing is left to hide behind - holds at most two layers."""
+        L = self.n_layers
+        if not self.distributed:
+            return [(L, 0)]
+        cuts = [L]
+        first = min(2, L)
+        if L - first > 0:
+            cuts.append(L - first)
+        tail = min(2, cuts[-1])
+        while cuts[-1] - self.bucket_layers > tail:
+            cuts.append(cuts[-1] - self.bucket_layers)
+        if cuts[-1] > tail:
+            cuts.append(tail)
+        if cuts[-1] != 0:
+            cuts.append(0)
+        return list(zip(cuts[:-1], cuts[1:]))
+
+    def describe_exchange(self):
+        if not self.distributed:
+            return 'single rank, no gradient exchange'
+        return (f'flat gradient all-reduced over NCCL as {self.wire} in {len(self.buckets)} buckets {self.buckets} (layer slices, '
+                f'issued on a side stream as each slice of the backward pass completes), 1/{self.world} folded into Adam')
+
+    def _exchange(self, off, cnt):
+        "all-reduce (SUM) of grad[off:off+cnt] on the communication stream, in the wire format"
+        h, cs = self.e.h, C.c_void_p(self.comm_stream.cuda_stream)
+        if self.wire == 'bf16':
+            w = self.wire_buf[off:off + cnt]
+            check(self.lib.dmg_train_grad_pack(h, off, cnt, _ptr(w), cs), 'dmg_train_grad_pack')
+            torch.distributed.all_reduce(w, group=self.pg)
+            check(self.lib.dmg_train_grad_unpack(h, off, cnt, _ptr(w), cs), 'dmg_train_grad_unpack')
+        else:
+            torch.distributed.all_reduce(self.grad[off:off + cnt], group=self.pg)
+
     def backward(self):
         "loss.backward(); with >1 rank the all-reduce of each bucket of layers overlaps the backward of the next bucket."
-        L, dev = self.n_layers, self.e.device
+        dev = self.e.device
+        prof = self._comm_events
         with torch.cuda.device(dev):
-            hi = L
-            first = True
-            while first or hi > 0:
-                first = False
-                lo = max(0, hi - self.bucket_layers)
+            for hi, lo in self.buckets:
                 check(self.lib.dmg_train_backward(self.e.h, hi, lo, _stream_ptr()), 'dmg_train_backward')
                 if self.distributed:
                     off, cnt = C.c_int64(), C.c_int64()
@@ -126,10 +168,39 @@ class TXLTrainer:
                         ev.record(torch.cuda.current_stream())
                         self.comm_stream.wait_event(ev)
                         with torch.cuda.stream(self.comm_stream):
-                            torch.distributed.all_reduce(self.grad[off.value:off.value + cnt.value], group=self.pg)
-                hi = lo
+                            if prof is not None:
+                                e0 = torch.cuda.Event(enable_timing=True); e0.record()
+                            self._exchange(off.value, cnt.value)
+                            if prof is not None:
+                                e1 = torch.cuda.Event(enable_timing=True); e1.record()
+                                prof['buckets'].append((hi, lo, cnt.value, e0, e1))
             if self.distributed:
+                if prof is not None:
+                    prof['bwd_end'] = torch.cuda.Event(enable_timing=True); prof['bwd_end'].record()
                 torch.cuda.current_stream().wait_stream(self.comm_stream)
+                if prof is not None:
+                    prof['joined'] = torch.cuda.Event(enable_timing=True); prof['joined'].record()
+
+    def profile_comm(self, step_fn, reps=3):
+        """Device-timed view of the gradient exchange over `reps` steps: per bucket the all-reduce time (pack + NCCL + unpack on the
+        communication stream) and `exposed_ms` = how long the compute stream waited for the last bucket after backward ended."""
+        if not self.distributed:
+            return None
+        acc, exposed = {}, 0.
+        for _ in range(reps):
+            self._comm_events = {'buckets': []}
+            step_fn()
+            torch.cuda.synchronize(self.e.device)
+            p = self._comm_events
+            for hi, lo, cnt, e0, e1 in p['buckets']:
+                a = acc.setdefault((hi, lo), {'layers': [hi, lo], 'elements': cnt, 'ms': 0.})
+                a['ms'] += e0.elapsed_time(e1) / reps
+            exposed += p['bwd_end'].elapsed_time(p['joined']) / reps
+        self._comm_events = None
+        bytes_per = 2 if self.wire == 'bf16' else 4
+        out = {'wire': self.wire, 'exposed_ms': exposed, 'buckets': list(acc.values()),
+               'bytes_per_step': int(sum(a['elements'] for a in acc.values()) * bytes_per)}
+        return out
 
     def optimizer_step(self, lr, betas=(0.9, 0.99), eps=1e-8, wd=0.01, clip=0.5):
         with torch.cuda.device(self.e.device):

@@ -208,6 +208,11 @@ int dmg_train_forward(dmg_model* m, const int64_t* ids_dev, const int64_t* pos_d
 int dmg_train_backward(dmg_model* m, int layer_hi, int layer_lo, void* stream);
 /* Flat-gradient slice that is final once dmg_train_backward(m, layer_hi, layer_lo) has run. */
 int dmg_train_grad_span(dmg_model* m, int layer_hi, int layer_lo, int64_t* offset, int64_t* count);
+/* Wire format of the data-parallel gradient exchange: the slice [offset, offset+count) of the flat fp32 gradient packed to bf16
+ * (round to nearest even) into a caller-owned device buffer of `count` bf16 elements, and back (overwrites the fp32 slice) after
+ * the all-reduce.  Halves the bytes on NVLink (109.5 MB instead of 219 MB per step for the 16-layer model). */
+int dmg_train_grad_pack(dmg_model* m, int64_t offset, int64_t count, void* wire_bf16_dev, void* stream);
+int dmg_train_grad_unpack(dmg_model* m, int64_t offset, int64_t count, const void* wire_bf16_dev, void* stream);
 /* Adam(betas, eps) with fastai's true_wd (p *= 1 - lr*wd first), gradients scaled by grad_scale (1/world_size after a
  * SUM all-reduce) and clipped to global norm `clip` (<= 0: no clipping); refreshes the bf16 weight copies.
  * Inference entry points need dmg_commit_weights() again afterwards (the rel-pos key cache follows r_attn). */

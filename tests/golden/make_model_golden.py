@@ -124,9 +124,9 @@ tk_cases = [(1, 0.0), (20, 0.8), (40, 0.6), (0, 0.9), (5, 0.0), (0, 0.0), (400, 
 out['topk_logits'], out['topk_cases'] = tk_logits.numpy(), np.array(tk_cases, dtype=np.float64)
 out['topk_kept'] = np.stack([np.stack([torch.isfinite(G['top_k_top_p'](row, top_k=int(k), top_p=float(p))).numpy() for row in tk_logits])
                              for k, p in tk_cases])
-# the same after the grammar filter of a previous NOTE token (only durations stay finite): what the predict loop feeds top_k_top_p
-dur_only = torch.full_like(tk_logits, -float('inf'))
-dur_only[:, vocab.dur_range[0]:vocab.dur_range[1]] = tk_logits[:, vocab.dur_range[0]:vocab.dur_range[1]]
+# the same after the reference's grammar filter for a previous NOTE token (durations stay finite - and mt*/dummy*, which the
+# reference never filters): what the predict loop feeds top_k_top_p
+dur_only = torch.stack([G['filter_invalid_indexes'](row.clone(), vocab.stoi['n60'], vocab) for row in tk_logits])
 out['topk_kept_after_note'] = np.stack([np.stack([torch.isfinite(G['top_k_top_p'](row, top_k=int(k), top_p=float(p))).numpy() for row in dur_only])
                                         for k, p in tk_cases])
 prevs = ['xxpad', 'd4', 'd160', 'i0', 'i6', 'n60', 'n0', 'xxsep', 'xxni', 'xxbos', 'xxmask', 'xxpop', 'mt3']

@@ -217,3 +217,35 @@ def test_training_memory_longer_than_segment(monkeypatch):
         compare_grads(tr, om, tol=2e-2)
         tr.optimizer_step(1e-3, betas=(0.9, 0.99), eps=1e-3, wd=0.01, clip=0.5)
     tr.close()
+
+
+def test_loss_curve_50_steps_c3_geometry(monkeypatch):
+    """N-step loss-curve parity at the C3 width (d_model 512, 8 heads x 64, d_inner 2048, bptt = mem_len = 512: the tcgen05 attention
+    forward / saved-probability backward / persistent GEMMs of the benchmark), 4 layers, 2 sequences, 50 steps of the notebook's recipe
+    (Adam(0.9, 0.99), true_wd 0.01, clip 0.5, default eps) on four repeating LakhMIDI-shaped batches, dropout off so that both sides
+    are deterministic: every loss part of every step follows the oracle's fastai step, and the loss falls."""
+    import bench_train
+    cfg = dict(txl.baseline_config(), n_layers=4, mask_steps=1)
+    bs, bptt, steps = 2, 512, 50
+    om, pm, tr = build_pair(cfg, bs, bptt, 0.)
+    om.train(); om.reset()
+    set_oracle_mask(monkeypatch, (1, 1))
+    opt = otrain.AdamTrueWD(otrain.unique_params(om))
+    toks = bench_train.lakh_shaped_tokens(bs, 4 * bptt, torch.Generator().manual_seed(3))
+    tr.reset()
+    lr = 5e-4
+    curve = []
+    for s in range(steps):
+        i = s % 4
+        x, y = toks[:, i * bptt:(i + 1) * bptt], toks[:, i * bptt + 1:(i + 1) * bptt + 1]
+        ref = otrain.train_step(om, x, y, opt, lr, wd=0.01, clip=0.5)
+        tr.step(x, y, lr=lr, mask_size=(1, 1))
+        got = tr.losses()
+        curve.append((ref['ce'], got['ce'], ref['ar'], got['ar'], ref['tar'], got['tar']))
+    for s, (rce, gce, rar, gar, rtar, gtar) in enumerate(curve):
+        assert abs(gce - rce) < 3e-2 * rce + 2e-2, (s, curve[s])
+        assert abs(gar - rar) < 3e-2 * rar + 1e-3, (s, curve[s])
+        assert abs(gtar - rtar) < 5e-2 * rtar + 1e-3, (s, curve[s])
+    print('loss curve (oracle ce, cuda ce) every 10 steps:', [(round(c[0], 3), round(c[1], 3)) for c in curve[::10]], 'last', curve[-1])
+    assert curve[-1][1] < curve[0][1] - 1.0                         # the model learns the four batches
+    tr.close()

@@ -61,7 +61,7 @@ def test_top_k_top_p_kept_sets(G):
         for r, row in enumerate(logits):
             kept = torch.isfinite(osamp.top_k_top_p(row, top_k=int(k), top_p=float(p))).numpy()
             assert np.array_equal(kept, G['topk_kept'][c, r]), (k, p, r)
-            dur = torch.full_like(row, -float('inf')); dur[140:301] = row[140:301]
+            dur = osamp.filter_invalid_indexes(row.clone(), 72, ocodec.MusicVocab.create())
             assert np.array_equal(torch.isfinite(osamp.top_k_top_p(dur, top_k=int(k), top_p=float(p))).numpy(),
                                   G['topk_kept_after_note'][c, r])
 

@@ -86,3 +86,73 @@ def test_oracle_fixed_masks_replace_every_dropout():
     np.random.seed(3)
     b = m(x)[0]
     assert torch.equal(a, b)        # no other randomness left
+
+
+# ------------------------------------------------------------------------------------------------ data-parallel host logic (gloo, 2 ranks)
+def test_bucket_plan_covers_every_layer_once_and_ends_small():
+    from deepmusicgeneration_b200.training import TXLTrainer
+
+    class Plan(TXLTrainer):
+        def __init__(self, L, distributed, bucket_layers=4):
+            self.n_layers, self.distributed, self.bucket_layers = L, distributed, bucket_layers
+
+    for L in (1, 2, 3, 6, 8, 16, 24):
+        assert Plan(L, False)._bucket_plan() == [(L, 0)]
+        plan = Plan(L, True)._bucket_plan()
+        assert plan[0][0] == L and plan[-1][1] == 0
+        assert all(a[1] == b[0] for a, b in zip(plan, plan[1:])) and all(hi > lo for hi, lo in plan)
+        assert plan[-1][0] - plan[-1][1] <= 2                       # the exposed bucket
+        assert plan[0][0] - plan[0][1] <= 2                         # the first one leaves early
+
+
+def _dp_worker(rank, world, port, q):
+    import os
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from deepmusicgeneration_b200 import sharding
+    sharding.init_distributed(backend='gloo')
+    torch.set_num_threads(2)
+    cfg = dict(txl.default_config(), n_layers=2, d_model=32, n_heads=2, d_head=16, d_inner=64, mem_len=8, encode_position=False)
+    torch.manual_seed(0)                                             # same weights on every rank
+    m = txl.get_language_model(50, cfg, drop_mult=0.).train()
+    m.reset()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randint(0, 50, (4, 8), generator=g); y = torch.randint(0, 50, (4, 8), generator=g)
+    lo, hi = sharding.shard_range(4, rank, world)
+    total, *_ = otrain.rnn_trainer_loss(m(x[lo:hi]), y[lo:hi])
+    total.backward()
+    params = otrain.unique_params(m)
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    wire = flat.to(torch.bfloat16)                                   # the exchange's wire format (dmg_train_grad_pack)
+    dist.all_reduce(wire)                                            # SUM, like TXLTrainer._exchange
+    flat32 = flat.clone(); dist.all_reduce(flat32)
+    q.put((rank, (wire.float() / world).tolist(), (flat32 / world).tolist()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_average_equals_full_batch_gradient():
+    """The data-parallel contract of TXLTrainer: SUM all-reduce of the per-rank gradients, times 1/world inside Adam, is the gradient
+    of the reference step on the concatenated batch (equal shards: every loss term is a mean); the bf16 wire format keeps it within
+    the bf16 tolerance."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs: p.join(timeout=60)
+    cfg = dict(txl.default_config(), n_layers=2, d_model=32, n_heads=2, d_head=16, d_inner=64, mem_len=8, encode_position=False)
+    torch.manual_seed(0)
+    m = txl.get_language_model(50, cfg, drop_mult=0.).train()
+    m.reset()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randint(0, 50, (4, 8), generator=g); y = torch.randint(0, 50, (4, 8), generator=g)
+    total, *_ = otrain.rnn_trainer_loss(m(x), y)
+    total.backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in otrain.unique_params(m)])
+    for rank, wire_avg, f32_avg in res:
+        f32_avg, wire_avg = torch.tensor(f32_avg), torch.tensor(wire_avg)
+        assert ((f32_avg - ref).norm() / ref.norm()).item() < 1e-5
+        assert ((wire_avg - ref).norm() / ref.norm()).item() < 1e-2
