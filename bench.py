@@ -371,6 +371,7 @@ def measure_c2(args):
                 'kernel_share_of_step': attn_ms * L / (ms / K),
                 'step_algorithmic_bytes': sbytes, 'step_frac': sbytes / (ms / K / 1e3) / 1e9 / peak}
 
+    uses_tc = bool(lib.dmg_uses_tcgen05(e.h))
     del learn, model, e, toks
     torch.cuda.empty_cache()
     if rank != 0:
@@ -389,7 +390,7 @@ def measure_c2(args):
             'config': {'workload': workload, 'batch_per_gpu': B, 'global_batch': B * world, 'prefill': PREFILL,
                        'parallelism': f'streams sharded over {world} GPU(s), no collective',
                        'l2': f'inputs larger than L2: every step streams {sbytes / 1e9:.1f} GB of K/V through a 126 MB L2',
-                       'tcgen05_gemm': bool(lib.dmg_uses_tcgen05(e.h)), 'all_streams_alive': bool(good)},
+                       'tcgen05_gemm': uses_tc, 'all_streams_alive': bool(good)},
             'roofline': roofline, 'cpu_baseline': cpu,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': B * 8, 'd2h_bytes_per_step': B * 4, 'steps': Ke},
             'gpu_launches': launches, 'clocks': clock_info}
