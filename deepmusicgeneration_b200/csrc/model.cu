@@ -79,7 +79,37 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
   // segments without memory (prefill after reset(), every BERT forward) in bf16: flash attention on the tensor cores
   const bool flash = m->is_bf16 && m->use_tc && T_len > 1 && (bert || (m->mem_count == 0 && win == 1 && k == 1)) &&
                      m->Dcap >= T_len && !(m->kflags & DMG_KF_NO_FLASH);
-  for (int l = 0; l < c.n_layers; l++) {
+  // one-token step, product path: per layer ONE decode-attention launch + ONE fused layer launch (decode_layer.cu)
+  const bool fused = fast_decode && m->fused_decode && !c.keep_hidden && m->layers[0].wqkv.has_tm;
+  if (fused) {
+    DecodeLayerArgs da;
+    da.x32 = m->x32; da.qkv = m->qkv; da.P = m->dl_P; da.H = m->dl_H;
+    da.B = nb; da.d = d; da.HD = HD; da.di = c.d_inner; da.n3 = 3 * HD;
+    for (int l = 0; l <= c.n_layers; l++) {
+      const bool body = l > 0, next = l < c.n_layers;
+      LayerW& Lb = m->layers[body ? l - 1 : 0];        // the layer whose body runs
+      LayerW& Ln = m->layers[next ? l : 0];            // the layer whose q|k|v are produced
+      if (body) {
+        AttnDecodeArgs a;
+        a.qkv = m->qkv;
+        a.kring = (bf16*)Lb.kring + (size_t)b0 * c.n_heads * M * 64;
+        a.vring = (bf16*)Lb.vring + (size_t)b0 * c.n_heads * M * 64;
+        a.rd = (const bf16*)Lb.rd;
+        a.u = m->u; a.v = m->v;
+        a.out = (bf16*)m->attn;
+        a.dev_state = m->dev_state;
+        a.B = nb; a.H = c.n_heads; a.M = M; a.Dcap = m->Dcap;
+        a.scale = 1.f / sqrtf((float)c.d_head);
+        if (attn_decode2(&Lb.tmK, &Lb.tmV, &Lb.tmR, a, b0, m->num_sms, st)) return -1;
+      }
+      da.mode = (body ? 1 : 0) | (next ? 2 : 0);
+      da.xa_out = next ? nullptr : (bf16*)m->xa;
+      da.bo = Lb.bo; da.b1 = Lb.b1; da.b2 = Lb.b2; da.ln1w = Lb.ln1w; da.ln1b = Lb.ln1b; da.ln2w = Lb.ln2w; da.ln2b = Lb.ln2b;
+      da.bq = Ln.bqkv;
+      if (decode_layer(&m->tmAttn16, &m->tmH16, &Lb.wo.tm64, &Lb.w1.tm64, &Lb.w2.tm64, &Ln.wqkv.tm64, da, st)) return -1;
+    }
+  }
+  for (int l = 0; l < c.n_layers && !fused; l++) {
     LayerW& L = m->layers[l];
     if (flash) {
       // memory-less segment: bf16 q|k|v straight from the GEMM epilogue, tensor-core flash attention (attention_flash.cu)
@@ -202,6 +232,7 @@ static int commit_weight(dmg_model* m, Weight& w) {
   if (m->use_tc && w.cols % 64 == 0) {
     if (make_tmap_bf16(&w.tm32, w.b16, w.cols, w.rows, w.cols, 32)) return -1;
     if (make_tmap_bf16(&w.tm128, w.b16, w.cols, w.rows, w.cols, 128)) return -1;
+    if (make_tmap_bf16(&w.tm64, w.b16, w.cols, w.rows, w.cols, 64)) return -1;
     w.has_tm = true;
   }
   return 0;
@@ -393,7 +424,7 @@ int dmg_create(const dmg_config* cfg, int device, dmg_model** out) {
     for (int l = 0; l <= L; l++) TRY(dalloc(m, &m->hrings[l], (size_t)c.max_batch * c.mem_len * d));
   }
   // workspaces
-  const size_t R = (size_t)(m->max_rows < 128 ? 128 : m->max_rows);   // TMA boxes are 128 rows tall
+  const size_t R = ((size_t)(m->max_rows < 128 ? 128 : m->max_rows) + 127) / 128 * 128;   // TMA boxes are 128 rows tall
   const size_t RB = (size_t)(c.max_batch < 128 ? 128 : c.max_batch);
   TRY(dalloc(m, &m->x32, R * d));
   if (m->is_bf16) { bf16* t = nullptr; TRY(dalloc(m, &t, R * d)); m->xa = t; } else m->xa = m->x32;
@@ -427,6 +458,15 @@ int dmg_create(const dmg_config* cfg, int device, dmg_model** out) {
     for (int i = 0; i < A_COUNT && !rc; i++) {
       if (bufs[i] == nullptr || m->a_cols[i] % 64 != 0) continue;
       TRY(make_tmap_bf16(&m->tmA[i], bufs[i], m->a_cols[i], m->a_rows[i], m->a_cols[i], 128));
+    }
+    // fused one-token layer step: the projection / FFN-down scratch is `proj`, the GeLU(FFN-up) scratch is `hbuf` (both unused
+    // by that path otherwise); 16-row boxes over the attention output and over H
+    if (!rc && !bert && c.mem_len > 0 && !(m->kflags & DMG_KF_NO_FUSED_DECODE) && decode_layer_supported(d, HD, c.d_inner, 3 * HD)) {
+      m->dl_P = m->proj;
+      m->dl_H = (bf16*)m->hbuf;
+      TRY(make_tmap_bf16(&m->tmAttn16, m->attn, HD, (long long)R, HD, DL_ROWS));
+      TRY(make_tmap_bf16(&m->tmH16, m->hbuf, c.d_inner, (long long)R, c.d_inner, DL_ROWS));
+      m->fused_decode = !rc;
     }
   }
   if (!rc && cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {

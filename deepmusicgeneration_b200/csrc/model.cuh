@@ -17,6 +17,7 @@ struct Weight {
   bf16* b16 = nullptr;
   int rows = 0, cols = 0;
   TensorMap2D tm32, tm128;   // TMA maps with 32- and 128-row boxes
+  TensorMap2D tm64;          // 64-row boxes (fused decode layer kernel)
   bool has_tm = false;
 };
 
@@ -65,6 +66,11 @@ struct dmg_model {
   bf16* qkv16 = nullptr;        // bf16 q|k|v of a segment for the flash-attention path
   void *xa = nullptr, *attn = nullptr, *hbuf = nullptr, *xlast = nullptr;
   TensorMap2D tmA[A_COUNT];
+  // fused one-token layer step (decode_layer.cu)
+  bool fused_decode = false;
+  float* dl_P = nullptr;
+  bf16* dl_H = nullptr;
+  TensorMap2D tmAttn16, tmH16;
   int a_rows[A_COUNT], a_cols[A_COUNT];
   // generation loop
   bool samp_ready = false, logits_valid = false;

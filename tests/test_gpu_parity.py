@@ -209,6 +209,36 @@ def test_decode_kernels_equal_general_kernel_and_oracle(M):
     assert w2g < 2e-2 and wug < 2e-2 and w2o <= 2e-2
 
 
+@pytest.mark.parametrize('B', [5, 40, 256])
+def test_fused_decode_layer_kernel_matches_unfused_and_oracle(B):
+    """decode_layer.cu (out-projection + LayerNorm + FFN + LayerNorm + next q|k|v in one cluster kernel; d_model 512 geometry):
+    logits of the one-token step against the unfused launches and against the fp32 oracle; B = 5 (one ragged cluster),
+    40 (three clusters, the last one ragged), 256 (the benchmark's 16 clusters)."""
+    from deepmusicgeneration_b200 import _lib as L
+    cfg = dict(txl.baseline_config(), n_layers=3, mem_len=128)
+    om, pf = _pair(cfg, 'bf16', B, 128, keep_hidden=False, max_rows=max(B, 4 * 128))
+    _, pu = _pair(cfg, 'bf16', B, 128, keep_hidden=False, max_rows=max(B, 4 * 128), kernel_flags=L.KF_NO_FUSED_DECODE)
+    g = torch.Generator().manual_seed(17)
+    x0 = torch.randint(0, V, (B, 90), generator=g)
+    with_oracle = B <= 40
+    if with_oracle:
+        om.reset()
+        with torch.no_grad(): om(x0)
+    for pm in (pf, pu):
+        pm.reset(); pm[0].forward(x0.cuda(), logits_mode=2)
+    wfu = wfo = 0.
+    for s in range(60):                                          # crosses the wrap-around of the 128-slot ring
+        xs = torch.randint(0, V, (B, 1), generator=g)
+        lf = pf[0].forward(xs.cuda(), logits_mode=1)[0].cpu()
+        lu = pu[0].forward(xs.cuda(), logits_mode=1)[0].cpu()
+        wfu = max(wfu, (lf - lu).abs().max().item())
+        if with_oracle:
+            with torch.no_grad(): lo = om(xs)[0]
+            wfo = max(wfo, _rel(lf, lo))
+    print(f'B={B}: fused vs unfused max abs {wfu:.3e}; fused vs oracle max rel {wfo:.3e}')
+    assert wfu < 2e-2 and wfo <= 2e-2
+
+
 def test_greedy_token_stream_f32_bit_exact(golden_dir):
     "fp32 mode: the greedy stream of MusicLearner.predict equals the oracle's reference loop token for token."
     from deepmusicgeneration_b200.codec import MusicDataBunch, MusicItem
