@@ -33,7 +33,7 @@ int gemm_tc_splitk(const TensorMap2D* tmA, const TensorMap2D* tmW32, const float
 
 // Fused one-token layer step (decode_layer.cu): out-projection + residual + LayerNorm + FFN (GeLU) + residual + LayerNorm + the
 // next layer's q|k|v projection in ONE launch; a cluster of DL_CLUSTER CTAs owns DL_ROWS generation streams.
-constexpr int DL_ROWS = 16, DL_CLUSTER = 8;
+constexpr int DL_ROWS = 32, DL_CLUSTER = 8;
 struct DecodeLayerArgs {
   float* x32;            // [rows, d] fp32 residual stream, in / out
   bf16* xa_out;          // [rows, d] bf16 copy of the final rows (input of the head GEMM) or NULL
@@ -42,11 +42,13 @@ struct DecodeLayerArgs {
   bf16* H;               // scratch [rows padded to DL_ROWS, di] bf16: GeLU(FFN-up)
   const float *bo, *b1, *b2, *bq;            // biases (any may be NULL)
   const float *ln1w, *ln1b, *ln2w, *ln2b;
-  int B, d, HD, di, n3;  // streams, d_model, n_heads * d_head, d_inner, 3 * n_heads * d_head
+  int row_base, B;       // rows [row_base, B) of the buffers belong to this launch (a stream lane of the step)
+  int d, HD, di, n3;     // d_model, n_heads * d_head, d_inner, 3 * n_heads * d_head
   int mode;              // bit 0: the layer body (needs the attention output); bit 1: the next q|k|v projection
+  unsigned long long* dbg = nullptr;   // optional timeline of CTA 0 (48 slots), see decode_layer.cu dl_mark
 };
 bool decode_layer_supported(int d, int HD, int di, int n3);
-// tmAttn / tmH: 16-row boxes over the attention output [rows, HD] and the H scratch; tmWo, tmW1, tmW2, tmWq: 64-row boxes
+// tmAttn / tmH: DL_ROWS-row boxes over the attention output [rows, HD] and the H scratch; tmWo, tmW1, tmW2, tmWq: 64-row boxes
 int decode_layer(const TensorMap2D* tmAttn, const TensorMap2D* tmH, const TensorMap2D* tmWo, const TensorMap2D* tmW1,
                  const TensorMap2D* tmW2, const TensorMap2D* tmWq, const DecodeLayerArgs& a, cudaStream_t st);
 

@@ -82,9 +82,11 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
   // one-token step, product path: per layer ONE decode-attention launch + ONE fused layer launch (decode_layer.cu)
   const bool fused = fast_decode && m->fused_decode && !c.keep_hidden && m->layers[0].wqkv.has_tm;
   if (fused) {
+    // Stream lanes (groups of streams on parallel CUDA streams, the attention of one group over the fused layer kernel of
+    // another) were measured on top of this path and rejected: profiles/README.md, round 2.
     DecodeLayerArgs da;
     da.x32 = m->x32; da.qkv = m->qkv; da.P = m->dl_P; da.H = m->dl_H;
-    da.B = nb; da.d = d; da.HD = HD; da.di = c.d_inner; da.n3 = 3 * HD;
+    da.row_base = 0; da.B = nb; da.d = d; da.HD = HD; da.di = c.d_inner; da.n3 = 3 * HD;
     for (int l = 0; l <= c.n_layers; l++) {
       const bool body = l > 0, next = l < c.n_layers;
       LayerW& Lb = m->layers[body ? l - 1 : 0];        // the layer whose body runs
@@ -103,6 +105,7 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
         if (attn_decode2(&Lb.tmK, &Lb.tmV, &Lb.tmR, a, b0, m->num_sms, st)) return -1;
       }
       da.mode = (body ? 1 : 0) | (next ? 2 : 0);
+      da.dbg = l == c.n_layers / 2 ? m->dl_dbg : nullptr;      // timeline probe: one mid-stack launch
       da.xa_out = next ? nullptr : (bf16*)m->xa;
       da.bo = Lb.bo; da.b1 = Lb.b1; da.b2 = Lb.b2; da.ln1w = Lb.ln1w; da.ln1b = Lb.ln1b; da.ln2w = Lb.ln2w; da.ln2b = Lb.ln2b;
       da.bq = Ln.bqkv;
@@ -467,6 +470,7 @@ int dmg_create(const dmg_config* cfg, int device, dmg_model** out) {
       TRY(make_tmap_bf16(&m->tmAttn16, m->attn, HD, (long long)R, HD, DL_ROWS));
       TRY(make_tmap_bf16(&m->tmH16, m->hbuf, c.d_inner, (long long)R, c.d_inner, DL_ROWS));
       m->fused_decode = !rc;
+      if (!rc && getenv("DMG_DECODE_TIMELINE")) TRY(dalloc(m, &m->dl_dbg, 64));
     }
   }
   if (!rc && cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -693,6 +697,15 @@ int dmg_sample_probs(dmg_model* m, int predict_loop, const float* logits_dev, co
   a.num_choices = num_choices_dev;
   a.probs = probs_dev;
   return sample_launch(a, n, (cudaStream_t)stream);
+}
+
+int dmg_decode_timeline(dmg_model* m, uint64_t* out48_host) {
+  DMG_CHECK(m && out48_host, "dmg_decode_timeline: null argument");
+  DMG_CHECK(m->dl_dbg != nullptr, "dmg_decode_timeline: create the model with DMG_DECODE_TIMELINE=1 in the environment");
+  DMG_CUDA_OK(cudaSetDevice(m->device));
+  DMG_CUDA_OK(cudaDeviceSynchronize());
+  DMG_CUDA_OK(cudaMemcpy(out48_host, m->dl_dbg, 48 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 int dmg_attn_decode_layer(dmg_model* m, int layer, void* stream) {

@@ -71,6 +71,7 @@ struct dmg_model {
   float* dl_P = nullptr;
   bf16* dl_H = nullptr;
   TensorMap2D tmAttn16, tmH16;
+  unsigned long long* dl_dbg = nullptr;   // DMG_DECODE_TIMELINE=1: timeline of the fused kernel's CTA 0 (the LAST launch wins)
   int a_rows[A_COUNT], a_cols[A_COUNT];
   // generation loop
   bool samp_ready = false, logits_valid = false;

@@ -163,6 +163,10 @@ int64_t dmg_device_bytes(dmg_model* m);          /* bytes of HBM owned by the mo
 int64_t dmg_launch_count(void);                  /* kernels launched by this library so far (process-wide) */
 int dmg_uses_tcgen05(dmg_model* m);              /* 1 when GEMMs run on the tcgen05 kernel */
 
+/* Measurement hook: %globaltimer marks (ns) of CTA 0 of one mid-stack launch of the fused one-token layer kernel (decode_layer.cu):
+ * 3 roles (TMA producer, MMA issuer, epilogue thread) x 16 marks.  Needs DMG_DECODE_TIMELINE=1 in the environment at dmg_create. */
+int dmg_decode_timeline(dmg_model* m, uint64_t* out48_host);
+
 /* Measurement hook for bench.py's roofline: re-launch ONLY the fused decode-attention kernel of `layer` on the
  * current ring state and the q/k/v of the latest one-token forward (idempotent: the ring position is not advanced). */
 int dmg_attn_decode_layer(dmg_model* m, int layer, void* stream);
