@@ -62,6 +62,7 @@ SYMBOLS = {
     'dmg_generate_step_host': (c_i32, [c_vp, c_vp, c_vp, c_vp]),
     'dmg_sample_logits': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, C.POINTER(VocabLayout), C.POINTER(SamplerParams),
                                   c_u64, c_vp, c_vp, c_vp]),
+    'dmg_beam_step': (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     'dmg_sample_probs': (c_i32, [c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, C.POINTER(VocabLayout), C.POINTER(SamplerParams),
                                  c_u64, c_vp, c_vp, c_vp, c_vp]),
     'dmg_device_bytes': (c_i64, [c_vp]),
@@ -81,6 +82,8 @@ SYMBOLS = {
     'dmg_train_grad_pack': (c_i32, [c_vp, c_i64, c_i64, c_vp, c_vp]),
     'dmg_train_grad_unpack': (c_i32, [c_vp, c_i64, c_i64, c_vp, c_vp]),
     'dmg_train_optimizer_step': (c_i32, [c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp]),
+    'dmg_train_opt_state': (c_i32, [c_vp, C.c_char_p, c_i32, c_i32, c_vp, c_i64]),
+    'dmg_train_opt_steps': (c_i64, [c_vp, c_i64]),
     'dmg_train_losses': (c_i32, [c_vp, c_vp, c_vp]),
     'dmg_train_get_grad': (c_i32, [c_vp, C.c_char_p, c_vp, c_i64]),
     'dmg_train_dropout_mask': (c_i32, [c_vp, c_i32, c_i32, c_i64, c_vp, c_i64, c_vp]),

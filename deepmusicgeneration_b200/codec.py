@@ -373,7 +373,7 @@ def to_tensor(t, device=None):
 # ------------------------------------------------------------------------------------------ MIDI writer
 class MidiStream:
     """What ``MusicItem.to_stream(bpm)`` returns: enough of music21's Stream for ``.write('midi', fp=...)``
-    (app.py:191, 275).  One tempo track plus one track per instrument class, 1024 ticks per quarter."""
+    (app.py:191, 275).  One tempo track plus one track per instrument class, 1024 ticks per quarter (layout: ``to_bytes``)."""
     TPQ = 1024
     PROGRAMS = {0: 0, 1: 24, 2: 33, 3: 73, 4: 61, 5: 40, 6: 0}      # ACCEP_INS index -> General-MIDI program
 
@@ -401,28 +401,40 @@ class MidiStream:
             n >>= 7
         return bytes(reversed(out))
 
-    def _track(self, events):
+    NAMES = {0: 'Piano', 1: 'Guitar', 2: 'Bass', 3: 'Woodwind', 4: 'Brass', 5: 'StringInstrument', 6: 'Piano'}
+
+    def _track(self, events, end_gap):
+        "events: (tick, order, bytes); same-tick events keep `order` (note-offs before note-ons: offs by note start then pitch, ons by duration group then pitch); EOT `end_gap` ticks later"
         body, now = b'', 0
-        for tick, data in sorted(events, key=lambda e: e[0]):
+        for tick, _, data in sorted(events, key=lambda e: (e[0], e[1])):
             body += self._vl(tick - now) + data
             now = tick
-        body += b'\x00\xff\x2f\x00'
+        body += self._vl(end_gap) + b'\xff\x2f\x00'
         return b'MTrk' + struct.pack('>I', len(body)) + body
 
     def to_bytes(self):
+        """The file layout music21 gives ``full.to_stream(bpm).write('midi', fp)`` (app.py:191, 275; pinned byte for byte by the
+        reference's own outputs/genre_output.mid and outputs/remix_Notes_output.mid for the Piano-only case): format 1, 1024 ticks
+        per quarter; track 0 = tempo, key signature 0, time signature 4/4, end of track one quarter later; one track per part =
+        track name, program change, pitch-bend centre, program change again, then note-on velocity 90 / note-off velocity 0 at the
+        exact note end, the end of track one quarter after the last event."""
         per = self.TPQ // SAMPLE_FREQ
         tempo = int(round(60_000_000 / self.bpm))
-        tracks = [self._track([(0, b'\xff\x51\x03' + tempo.to_bytes(3, 'big')), (0, b'\xff\x58\x04\x04\x02\x18\x08')])]
+        conductor = [(0, 0, b'\xff\x51\x03' + tempo.to_bytes(3, 'big')), (0, 1, b'\xff\x59\x02\x00\x00'),
+                     (0, 2, b'\xff\x58\x04\x04\x02\x18\x08')]
+        tracks = [self._track(conductor, self.TPQ)]
         by_ins = {}
         for start, dur, pitch, ins in self.notes():
             by_ins.setdefault(ins, []).append((start, dur, pitch))
         for ch, (ins, notes) in enumerate(sorted(by_ins.items())):
-            ch = min(ch, 15)
-            ev = [(0, bytes([0xC0 | ch, self.PROGRAMS.get(ins, 0)]))]
+            ch = min(ch if ch < 9 else ch + 1, 15)                 # channel 10 (index 9) is percussion
+            name = self.NAMES.get(ins, 'Piano').encode()
+            prog = bytes([0xC0 | ch, self.PROGRAMS.get(ins, 0)])
+            ev = [(0, (-4,), b'\xff\x03' + self._vl(len(name)) + name), (0, (-3,), prog), (0, (-2,), bytes([0xE0 | ch, 0x00, 0x40])), (0, (-1,), prog)]
             for start, dur, pitch in notes:
-                ev.append((start * per, bytes([0x90 | ch, pitch, 90])))
-                ev.append((max(start * per + 1, (start + dur) * per - 1), bytes([0x80 | ch, pitch, 0])))
-            tracks.append(self._track(ev))
+                ev.append((start * per, (1, dur, pitch), bytes([0x90 | ch, pitch, 90])))     # group_notes_by_duration (:536-541)
+                ev.append(((start + dur) * per, (0, start, pitch), bytes([0x80 | ch, pitch, 0])))
+            tracks.append(self._track(ev, self.TPQ))
         return b'MThd' + struct.pack('>IHHH', 6, 1, len(tracks), self.TPQ) + b''.join(tracks)
 
     def write(self, fmt='midi', fp=None):

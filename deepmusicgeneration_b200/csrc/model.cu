@@ -495,6 +495,7 @@ int dmg_set_weight(dmg_model* m, const char* name, const float* data_host, int64
   DMG_CUDA_OK(cudaSetDevice(m->device));
   DMG_CUDA_OK(cudaMemcpy(it->second.dst, data_host, (size_t)numel * 4, cudaMemcpyHostToDevice));
   m->committed = false;
+  m->weights_set_externally = true;
   return 0;
 }
 
@@ -517,6 +518,8 @@ int dmg_commit_weights(dmg_model* m) {
     if (commit_weight(m, L.wqkv) || commit_weight(m, L.wo) || commit_weight(m, L.w1) || commit_weight(m, L.w2)) return -1;
   }
   if (build_rd(m)) return -1;
+  if (m->train && train_weights_reloaded(m, m->weights_set_externally)) return -1;
+  m->weights_set_externally = false;
   DMG_CUDA_OK(cudaDeviceSynchronize());
   m->committed = true;
   return 0;
@@ -672,6 +675,19 @@ int dmg_sample_logits(dmg_model* m, const float* logits_dev, const int32_t* prev
   a.out_tokens = out_dev;
   a.num_choices = num_choices_dev;
   return sample_launch(a, n, (cudaStream_t)stream);
+}
+
+int dmg_beam_step(dmg_model* m, const float* scores_dev, int n_scores, int nb, int top_k, int beam_sz, float* scores_out_dev,
+                  int32_t* parents_out_dev, int32_t* tokens_out_dev, void* stream) {
+  DMG_CHECK(m && scores_dev && scores_out_dev && parents_out_dev && tokens_out_dev, "dmg_beam_step: null argument");
+  DMG_CHECK(m->logits_valid && nb == m->batch, "dmg_beam_step: needs the logits of a DMG_LOGITS_LAST forward over %d beams (have %d streams)",
+            nb, m->batch);
+  DMG_CHECK(n_scores == 1 || n_scores == nb, "dmg_beam_step: n_scores must be 1 or nb");
+  DMG_CUDA_OK(cudaSetDevice(m->device));
+  BeamArgs a;
+  a.logits = m->logits_buf; a.V = m->cfg.vocab; a.nb = nb; a.top_k = top_k; a.beam_sz = beam_sz;
+  a.scores_in = scores_dev; a.n_scores = n_scores; a.scores_out = scores_out_dev; a.parents = parents_out_dev; a.tokens = tokens_out_dev;
+  return beam_step_launch(a, (cudaStream_t)stream);
 }
 
 int dmg_sample_probs(dmg_model* m, int predict_loop, const float* logits_dev, const int32_t* prev_idx_dev,

@@ -49,6 +49,7 @@ struct dmg_model {
   int kflags = 0;   // DMG_KF_* kernel selectors: cfg.kernel_flags | the DMG_* environment variables, read ONCE at dmg_create
   int device = 0;
   bool is_bf16 = false, use_tc = false, committed = false;
+  bool weights_set_externally = false;   // dmg_set_weight since the last commit (a checkpoint was loaded over a live trainer)
   int HD = 0, Dcap = 0, max_rows = 0, esz = 4, num_sms = 148;
   Weight emb;   // [V, d] (tied head)
   float *beat = nullptr, *bar = nullptr, *u = nullptr, *v = nullptr, *head_b = nullptr;
@@ -86,6 +87,10 @@ struct dmg_model {
 };
 
 namespace dmg {
+
+// train.cu: called by dmg_commit_weights when a trainer exists - refreshes the bf16 r_attn copies the training forward multiplies
+// with and, when the weights were replaced from outside (load_state_dict over a live trainer), restarts Adam (zero moments, step 0)
+int train_weights_reloaded(dmg_model* m, bool reset_optimizer);
 
 template <class T>
 inline int dalloc(dmg_model* m, T** p, size_t n, bool zero = true) {

@@ -330,6 +330,85 @@ __global__ void __launch_bounds__(SAMP_THREADS) sample_kernel(SampleArgs a) {
   if (a.next_pos) a.next_pos[sidx] = last_pos;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// One step of MusicLearner.beam_search (deep_music_genre.py:1834-1847) for all live beams, one CTA:
+//   out = log_softmax(logits[:, -1]); values, indices = out.topk(top_k); scores = (-values + scores[:, None]).view(-1)
+//   sort_idx = scores.argsort()[:beam_sz]  ->  new scores, parent beam (sort_idx // top_k), appended token
+// Ties are broken towards the lower candidate index (a stable argsort; torch leaves the order of exact ties unspecified - and the
+// reference creates exact ties itself by starting from top_k identical copies of the seed).
+__device__ void block_arg_best(float v, int idx, bool want_max, float* sval, int* sidx, float& best_v, int& best_i) {
+  // (value, index) reduction: larger (want_max) or smaller value wins, lower index on ties
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    const bool better = want_max ? (ov > v || (ov == v && oi < idx)) : (ov < v || (ov == v && oi < idx));
+    if (better) { v = ov; idx = oi; }
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { sval[threadIdx.x >> 5] = v; sidx[threadIdx.x >> 5] = idx; }
+  __syncthreads();
+  best_v = sval[0]; best_i = sidx[0];
+  for (int w = 1; w < SAMP_THREADS / 32; w++) {
+    const float ov = sval[w]; const int oi = sidx[w];
+    const bool better = want_max ? (ov > best_v || (ov == best_v && oi < best_i)) : (ov < best_v || (ov == best_v && oi < best_i));
+    if (better) { best_v = ov; best_i = oi; }
+  }
+}
+
+__global__ void __launch_bounds__(SAMP_THREADS) beam_step_kernel(BeamArgs a) {
+  __shared__ float lp[SAMP_MAXV];
+  __shared__ float cand_score[SAMP_MAXV];
+  __shared__ int cand_tok[SAMP_MAXV];
+  __shared__ float scratch[SAMP_THREADS / 32];
+  __shared__ float sval[SAMP_THREADS / 32];
+  __shared__ int sidx[SAMP_THREADS / 32];
+  const int tid = threadIdx.x, V = a.V, K = a.top_k;
+  const float INF = INFINITY;
+  pdl_launch_dependents();
+  pdl_wait();                                  // the logits come from the head GEMM launched just before
+  for (int row = 0; row < a.nb; row++) {
+    const float* lg = a.logits + (size_t)row * V;
+    float part = -INF;
+    for (int i = tid; i < V; i += SAMP_THREADS) { lp[i] = lg[i]; part = fmaxf(part, lg[i]); }
+    const float mx = block_max(part, scratch);
+    float ps = 0.f;
+    for (int i = tid; i < V; i += SAMP_THREADS) ps += expf(lp[i] - mx);
+    const float lse = mx + logf(block_sum(ps, scratch));
+    __syncthreads();
+    for (int i = tid; i < V; i += SAMP_THREADS) lp[i] -= lse;        // log_softmax
+    __syncthreads();
+    const float prev = a.scores_in[a.n_scores == 1 ? 0 : row];
+    for (int j = 0; j < K; j++) {                                     // topk: K passes of a block argmax
+      float v = -INF; int idx = 0x7fffffff;
+      for (int i = tid; i < V; i += SAMP_THREADS)
+        if (lp[i] > v || (lp[i] == v && i < idx)) { v = lp[i]; idx = i; }
+      float bv; int bi;
+      block_arg_best(v, idx, true, sval, sidx, bv, bi);
+      if (tid == 0) { cand_score[row * K + j] = -bv + prev; cand_tok[row * K + j] = bi; lp[bi] = -INF; }
+      __syncthreads();
+    }
+  }
+  const int NC = a.nb * K;
+  for (int j = 0; j < a.beam_sz; j++) {                               // argsort()[:beam_sz]: beam_sz passes of a block argmin
+    float v = INF; int idx = 0x7fffffff;
+    for (int i = tid; i < NC; i += SAMP_THREADS)
+      if (cand_score[i] < v || (cand_score[i] == v && i < idx)) { v = cand_score[i]; idx = i; }
+    float bv; int bi;
+    block_arg_best(v, idx, false, sval, sidx, bv, bi);
+    if (tid == 0) {
+      if (j < NC) { a.scores_out[j] = bv; a.parents[j] = bi / K; a.tokens[j] = cand_tok[bi]; cand_score[bi] = INF; }
+    }
+    __syncthreads();
+  }
+}
+
+int beam_step_launch(const BeamArgs& a, cudaStream_t st) {
+  DMG_CHECK(a.V <= SAMP_MAXV && a.nb >= 1 && a.top_k >= 1 && a.top_k <= a.V && a.nb * a.top_k <= SAMP_MAXV && a.beam_sz >= 1 &&
+                a.beam_sz <= a.nb * a.top_k,
+            "beam step: nb %d x top_k %d (beam_sz %d, vocab %d) outside the kernel's limits", a.nb, a.top_k, a.beam_sz, a.V);
+  return launch_k(beam_step_kernel, dim3(1), dim3(SAMP_THREADS), 0, st, 1, a);
+}
+
 int sample_launch(const SampleArgs& a, int n, cudaStream_t st) {
   DMG_CHECK(a.V <= SAMP_MAXV, "sampler: vocab %d exceeds %d", a.V, SAMP_MAXV);
   if (n <= 0) return 0;

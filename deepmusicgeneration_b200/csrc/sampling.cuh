@@ -30,4 +30,15 @@ struct SampleArgs {
 
 int sample_launch(const SampleArgs& a, int n, cudaStream_t st);
 
+struct BeamArgs {
+  const float* logits;      // [nb, V] fp32: last-position logits of the live beams
+  int V, nb, top_k, beam_sz;
+  const float* scores_in;   // [n_scores]: accumulated negative log-probabilities (n_scores == 1: broadcast, the first step)
+  int n_scores;
+  float* scores_out;        // [beam_sz]
+  int* parents;             // [beam_sz] beam each survivor extends
+  int* tokens;              // [beam_sz] appended token
+};
+int beam_step_launch(const BeamArgs& a, cudaStream_t st);
+
 }  // namespace dmg

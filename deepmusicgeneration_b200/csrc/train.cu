@@ -416,6 +416,20 @@ int check_train(dmg_model* m, const char* who) {
 
 }  // namespace
 
+namespace dmg {
+int train_weights_reloaded(dmg_model* m, bool reset_optimizer) {
+  dmg_train* t = m->train;
+  if (t == nullptr) return 0;
+  if (ensure_wr_b16(m, t)) return -1;
+  if (reset_optimizer) {   // a loaded checkpoint carries no optimizer state here: fastai's learn.create_opt on the new weights
+    DMG_CUDA_OK(cudaMemset(t->m1, 0, (size_t)t->total * sizeof(float)));
+    DMG_CUDA_OK(cudaMemset(t->m2, 0, (size_t)t->total * sizeof(float)));
+    t->opt_steps = 0;
+  }
+  return 0;
+}
+}  // namespace dmg
+
 extern "C" {
 
 int64_t dmg_train_param_count(dmg_model* m) {
@@ -677,6 +691,33 @@ int dmg_train_get_grad(dmg_model* m, const char* name, float* out_host, int64_t 
     return 0;
   }
   return 1;
+}
+
+// Adam state of one parameter by its state-dict name: which = 1 (exp_avg) or 2 (exp_avg_sq); set = 0 reads into buf_host, 1 writes
+int dmg_train_opt_state(dmg_model* m, const char* name, int which, int set, float* buf_host, int64_t numel) {
+  if (check_train(m, "dmg_train_opt_state")) return -2;
+  DMG_CHECK(name && buf_host && (which == 1 || which == 2), "dmg_train_opt_state: bad arguments");
+  dmg_train* t = m->train;
+  std::string key = name;
+  if (key == "1.decoder.weight") key = "0.encoder.weight";
+  for (auto& p : t->params) {
+    if (p.name != key) continue;
+    DMG_CHECK(p.n == numel, "dmg_train_opt_state: %s has %lld elements, got %lld", name, p.n, (long long)numel);
+    DMG_CUDA_OK(cudaSetDevice(m->device));
+    DMG_CUDA_OK(cudaDeviceSynchronize());
+    float* dev = (which == 1 ? t->m1 : t->m2) + p.off;
+    if (set) DMG_CUDA_OK(cudaMemcpy(dev, buf_host, (size_t)numel * 4, cudaMemcpyHostToDevice));
+    else DMG_CUDA_OK(cudaMemcpy(buf_host, dev, (size_t)numel * 4, cudaMemcpyDeviceToHost));
+    return 0;
+  }
+  return 1;
+}
+
+// optimizer step counter (Adam bias correction): value < 0 reads it, otherwise sets it; returns the (new) value
+int64_t dmg_train_opt_steps(dmg_model* m, int64_t value) {
+  if (!m || !m->train) return -1;
+  if (value >= 0) m->train->opt_steps = (int)value;
+  return m->train->opt_steps;
 }
 
 float* dmg_train_grad_buffer(dmg_model* m) { return (m && m->train) ? m->train->G : nullptr; }

@@ -52,17 +52,25 @@ class MusicLearner:
 
     # -- checkpoints: {'model': state_dict (fastai key names), 'config': ...}  (:1812-1821, :1789-1805)
     def save(self, file=None, with_opt=True, config=None):
-        state = {'model': self.model.state_dict(), 'opt': None}
-        if config:
-            state['config'] = config
+        """{'model': state_dict (fastai key names), 'opt': Adam state of the live trainer (None before any training), 'config'}: the
+        file music_model_learner(pretrained_path=...) / createGenreContinuationModel(ckpt_path=...) reads back."""
+        tr = getattr(self, '_trainer', None)
+        state = {'model': self.model.state_dict(), 'opt': tr.opt_state_dict() if (with_opt and tr is not None) else None}
+        if config or self.config:
+            state['config'] = config or self.config
         torch.save(state, file)
         return file
+
+    def load_opt_state(self, opt_state, bs, bptt, **kw):
+        "learn.opt.load_state_dict(state['opt']) (deep_music_genre.py:1801-1803) onto the trainer of this (bs, bptt)."
+        if opt_state:
+            self.trainer(bs, bptt, **kw).load_opt_state_dict(opt_state)
 
     # -- training: what fastai's Learner.fit_one_cycle does for this learner (notebook cell 70-73, SURVEY.md 3.3)
     def trainer(self, bs, bptt, drop_mult=1., alpha=2., beta=1., seed=0, **kw):
         "The training-step engine for this model (RNNLearner adds RNNTrainer(alpha=2, beta=1)); created once per (bs, bptt)."
         from .training import TXLTrainer
-        key = (bs, bptt)
+        key = (bs, bptt, float(drop_mult), float(alpha), float(beta), int(seed), tuple(sorted(kw.items())))
         if getattr(self, '_trainer_key', None) != key:
             if getattr(self, '_trainer', None) is not None:
                 self._trainer.close()
@@ -83,6 +91,10 @@ class MusicLearner:
         n_b = batches.n_batches if is_pl else len(batches)
         tr = self.trainer(bs or (batches.local_bs if is_pl else batches[0][0].shape[0]),
                           bptt or (batches.bptt if is_pl else batches[0][0].shape[1]), drop_mult=drop_mult)
+        if getattr(self, 'pretrained_opt_state', None):
+            try:    tr.load_opt_state_dict(self.pretrained_opt_state)     # try / except: pass, like the reference
+            except Exception: pass
+            self.pretrained_opt_state = None
         total, i = cyc_len * n_b, 0
         for _ in range(cyc_len):
             tr.reset()
@@ -98,6 +110,12 @@ class MusicLearner:
         return tr.losses()
 
     def _prefill(self, x, pos):
+        max_seq = self.model._e.cfg.max_seq
+        if x.shape[1] > max_seq:
+            # the reference runs the whole seed as ONE forward (memory-less attention over every seed token); splitting it into
+            # segments would change the result, so the engine has to be built large enough
+            raise ValueError(f'seed of {x.shape[1]} tokens exceeds max_seq={max_seq}: build the learner with '
+                             f'music_model_learner(..., max_seq=<longest seed>) or cut the seed with item.trim_to_beat(...)')
         enc = self.model[0]
         enc._bs = x.shape[0]
         self.model._e.forward(x, pos if enc.encode_position else None, _lib.LOGITS_LAST)
@@ -158,32 +176,46 @@ class MusicLearner:
         params = sampler_params(self.data.vocab, n_words, temperatures, min_bars, top_k, top_p, None, flags=flags, seed=seed)
         return self._run_loop(n_words, x[:, -1].cpu().numpy(), pos[:, -1].cpu().numpy(), params)
 
-    def beam_search(self, xb, n_words, top_k=10, beam_sz=10, temperature=1.):
-        "deep_music_genre.py:1823-1851: beam search through model(xb) and select_hidden."
-        import torch.nn.functional as F
+    def beam_search(self, xb, n_words, top_k=10, beam_sz=10, temperature=1., return_beams=False):
+        """Return the `n_words` that come after `xb` using beam search (signature of deep_music_genre.py:1823-1851).
+
+        The beams live on the device: the K/V rings of the `top_k` copies of the seed are permuted by ``select_hidden`` (one
+        ``dmg_select_hidden`` per step), each step's log-softmax / per-beam top-k / global selection is one kernel
+        (``dmg_beam_step``) and only the survivors' (parent, token) pairs - a few dozen integers - come back to the host, which
+        keeps the token history.  Like the reference the final node is drawn with ``multinomial(exp(-scores / temperature))``."""
+        e = self.model._e
         self.model.reset()
         self.model.eval()
-        xb = xb.to(self.model._e.device)
-        xb_length = xb.shape[-1]
+        xb = xb.to(e.device)
+        seed_len = xb.shape[-1]
         if xb.shape[0] > 1: xb = xb[0][None]
-        xb = xb.repeat(top_k, 1)
-        nodes = xb.clone()
-        scores = xb.new_zeros(1).float()
-        for _ in range(n_words):
-            out = F.log_softmax(self.model(xb)[0][:, -1], dim=-1)
-            values, indices = out.topk(top_k, dim=-1)
-            scores = (-values + scores[:, None]).view(-1)
-            indices_idx = torch.arange(0, nodes.size(0))[:, None].expand(nodes.size(0), top_k).contiguous().view(-1)
-            sort_idx = scores.argsort()[:beam_sz]
-            scores = scores[sort_idx]
-            nodes = torch.cat([nodes[:, None].expand(nodes.size(0), top_k, nodes.size(1)),
-                               indices[:, :, None].expand(nodes.size(0), top_k, 1)], dim=2)
-            nodes = nodes.view(-1, nodes.size(2))[sort_idx]
-            self.model[0].select_hidden(indices_idx[sort_idx.cpu()])
-            xb = nodes[:, -1][:, None]
+        nb = top_k                                               # the reference starts from top_k identical copies of the seed
+        assert max(top_k, beam_sz) <= e.cfg.max_batch, f'beam search over {max(top_k, beam_sz)} beams needs max_batch >= that'
+        x = xb.repeat(nb, 1)
+        self.model[0]._bs = nb
+        e.forward(x, torch.zeros_like(x) if self.model[0].encode_position else None, _lib.LOGITS_LAST)
+        scores = torch.zeros(1, dtype=torch.float32, device=e.device)
+        new_scores = torch.empty(beam_sz, dtype=torch.float32, device=e.device)
+        parents = torch.empty(beam_sz, dtype=torch.int32, device=e.device)
+        tokens = torch.empty(beam_sz, dtype=torch.int32, device=e.device)
+        history = np.zeros((nb, 0), dtype=np.int64)
+        for step in range(n_words):
+            with torch.cuda.device(e.device):
+                check(e.lib.dmg_beam_step(e.h, _ptr(scores), scores.numel(), nb, top_k, beam_sz, _ptr(new_scores), _ptr(parents),
+                                          _ptr(tokens), _stream_ptr()), 'dmg_beam_step')
+            par, tok = parents.cpu().numpy(), tokens.cpu().numpy().astype(np.int64)
+            history = np.concatenate([history[par], tok[:, None]], axis=1)
+            self.model[0].select_hidden(par)                     # the survivors inherit their parents' memory (:1847)
+            nb = beam_sz
+            scores = new_scores.clone()
+            if step + 1 < n_words:
+                xs = torch.from_numpy(tok).to(e.device)[:, None]
+                e.forward(xs, torch.zeros_like(xs) if self.model[0].encode_position else None, _lib.LOGITS_LAST)
         if temperature != 1.: scores.div_(temperature)
+        if return_beams:
+            return history, scores.cpu()
         node_idx = torch.multinomial(torch.exp(-scores), 1).item()
-        return [i.item() for i in nodes[node_idx][xb_length:]]
+        return [int(i) for i in history[node_idx]]
 
 
 def music_model_learner(data, arch=None, config=None, drop_mult=1., pretrained_path=None, encode_position=True,
@@ -201,6 +233,7 @@ def music_model_learner(data, arch=None, config=None, drop_mult=1., pretrained_p
     learn = MusicLearner(data, model, config=config)
     if state is not None:
         model.load_state_dict(state['model'], strict=False)
+        learn.pretrained_opt_state = state.get('opt')      # applied by fit_one_cycle to the trainer it creates (:1801-1803)
     return learn
 
 

@@ -3,9 +3,10 @@
 
 The tokenised corpus is uploaded once as a flat ragged array; every batch is ONE kernel launch
 (``dmg_preload_fill``: all ``bs`` rows walk their items, apply the per-item random transpose and write x / y / pos).
-Only the per-epoch bookkeeping stays on the host, in numpy / torch exactly as the reference does it, so that the same
-seeds give the same shuffles and transposes: ``np.random.shuffle`` of the CircularIndex, ``torch.randint`` + ``torch.rand``
-for the transpose values, the initial (ro, ri) cursors of ``on_epoch_begin``.
+Only the per-epoch bookkeeping stays on the host (vectorised numpy / torch); it draws from the same generators in the same
+order as the reference, so the same seeds give the same shuffles and transposes: ``np.random.shuffle`` of the item permutation,
+``torch.randint`` + ``torch.rand`` for the transpose values; the initial row cursors (ro, ri) are a searchsorted over the
+cumulative item lengths.
 
     pl = MusicPreloader(items, vocab, bs=32, bptt=512, shuffle=True, transpose_range=(0, 12), encode_position=False)
     for x, y in pl:            # one epoch; x, y int64 [bs, bptt] on the GPU ({'x':…, 'pos':…}, y with encode_position)
@@ -28,20 +29,22 @@ def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-class CircularIndex:
-    "deep_music_genre.py:1005-1014"
+class _ItemOrder:
+    """The epoch's item order (the reference's ``CircularIndex``, deep_music_genre.py:1005-1014, as data instead of an indexer):
+    ``idx`` is the permutation ``np.random.shuffle`` acts on - same RNG call, same stream as the reference - and ``visit_order``
+    the order in which a row cursor walks the items (reversed when reading backwards, wrapping around)."""
 
     def __init__(self, length, forward):
         self.idx, self.forward = np.arange(length), forward
-
-    def __getitem__(self, i):
-        return self.idx[i % len(self.idx) if self.forward else len(self.idx) - 1 - i % len(self.idx)]
 
     def __len__(self):
         return len(self.idx)
 
     def shuffle(self):
         np.random.shuffle(self.idx)
+
+    def visit_order(self):
+        return self.idx if self.forward else self.idx[::-1]
 
 
 class MusicPreloader:
@@ -74,8 +77,10 @@ class MusicPreloader:
         self.bptt_len = self.bptt
         self.allocate_buffers()
 
-    # ---- host bookkeeping, verbatim logic of the reference ----------------------------------------------------------
-    def __len__(self):                                                               # :1032-1037 (items, = bs * batches)
+    # ---- host bookkeeping ------------------------------------------------------------------------------------------
+    # Same results as the reference's loops (tests/test_preloader_cpu.py checks them against batches the reference's own
+    # source produced); the random draws keep the reference's call order so equal seeds give equal epochs.
+    def __len__(self):                                                               # items per epoch = bs * batches (:1032-1037)
         if self.ite_len is None:
             self.totalToks = self.lengths.sum()
             self.ite_len = self.bs * int(math.ceil(self.totalToks / (self.bptt * self.bs)))
@@ -85,23 +90,27 @@ class MusicPreloader:
     def n_batches(self):
         return len(self) // self.bs
 
-    def allocate_buffers(self):                                                      # :1041-1055
+    def allocate_buffers(self):
         if self.ite_len is None:
             len(self)
-        self.idx = CircularIndex(self.n_items, not self.backwards)
+        self.idx = _ItemOrder(self.n_items, not self.backwards)
         self.ro = np.zeros(self.bs, dtype=np.int64)
         self.ri = np.zeros(self.bs, dtype=np.int64)
         self.transpose_values = self.get_random_transpose_values()
 
-    def get_random_transpose_values(self):                                           # :1057-1063
+    def get_random_transpose_values(self):
+        "per-item semitone shift: randint over transpose_range centred on zero, zeroed with probability 1 - transpose_p (:1057-1063)"
         if self.transpose_range is None:
             return None
-        rt_arr = torch.randint(*self.transpose_range, (self.n_items,)) - self.transpose_range[1] // 2
-        mask = torch.rand(rt_arr.shape) > self.transpose_p
-        rt_arr[mask] = 0
-        return rt_arr
+        lo, hi = self.transpose_range
+        shift = torch.randint(lo, hi, (self.n_items,)) - hi // 2          # torch RNG call 1 (same order as the reference)
+        keep = torch.rand(shift.shape) <= self.transpose_p                # torch RNG call 2
+        return torch.where(keep, shift, torch.zeros_like(shift))
 
-    def on_epoch_begin(self, **kwargs):                                              # :1065-1084
+    def on_epoch_begin(self, **kwargs):
+        """New epoch: reshuffle / redraw when `shuffle`, then place the bs row cursors at equal token distances along the epoch's
+        item stream: row i starts at token floor(i * totalToks / bs) of the concatenated stream - a searchsorted over the
+        cumulative lengths instead of the reference's nested loop (:1065-1084)."""
         if self.idx is None:
             self.allocate_buffers()
         elif self.shuffle:
@@ -111,15 +120,15 @@ class MusicPreloader:
             self.bptt_len = self.bptt
         self.idx.forward = not self.backwards
         len(self)
-        step = self.totalToks / self.bs
-        ln_rag, countTokens, i_rag = 0, 0, -1
-        for i in range(0, self.bs):
-            while ln_rag + countTokens <= int(step * i):
-                countTokens += ln_rag
-                i_rag += 1
-                ln_rag = self.lengths[self.idx[i_rag]]
-            self.ro[i] = i_rag
-            self.ri[i] = (ln_rag - int(step * i - countTokens)) if self.backwards else int(step * i - countTokens)
+        lens = self.lengths[self.idx.visit_order()]
+        ends = np.cumsum(lens)                                             # ends[k] = tokens in the first k+1 visited items
+        starts_at = (self.totalToks / self.bs * np.arange(self.bs)).astype(np.int64)     # int(step * i), step a Python float
+        item = np.searchsorted(ends, starts_at, side='right')              # first visited item whose end lies beyond the start
+        if self.totalToks == 0:
+            item[:] = -1
+        into = starts_at - (ends[item] - lens[item])                       # tokens already consumed inside that item
+        self.ro[:] = item
+        self.ri[:] = lens[item] - into if self.backwards else into
         self._epoch_uploaded = False
 
     def on_epoch_end(self, **kwargs):                                                # :1087

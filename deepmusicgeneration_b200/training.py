@@ -258,6 +258,41 @@ class TXLTrainer:
                                                   _stream_ptr()), 'dmg_train_dropout_mask')
         return out.view(*shape)
 
+    # ------------------------------------------------------------------ optimizer state (checkpoints)
+    def opt_state_dict(self):
+        """torch.optim.Adam-shaped state ({'state': {i: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_names': [...]}) - what fastai's
+        Learner.save(with_opt=True) stores under 'opt' (deep_music_genre.py:1812-1821); parameters in state-dict order."""
+        steps = int(self.lib.dmg_train_opt_steps(self.e.h, -1))
+        names, state = [], {}
+        for name, shape in self.e.weight_names().items():
+            if name == '1.decoder.weight':
+                continue
+            m1, m2 = torch.empty(shape, dtype=torch.float32), torch.empty(shape, dtype=torch.float32)
+            rc = self.lib.dmg_train_opt_state(self.e.h, name.encode(), 1, 0, C.c_void_p(m1.data_ptr()), m1.numel())
+            if rc == 1:
+                continue
+            check(rc, f'dmg_train_opt_state({name})')
+            check(self.lib.dmg_train_opt_state(self.e.h, name.encode(), 2, 0, C.c_void_p(m2.data_ptr()), m2.numel()), 'dmg_train_opt_state')
+            state[len(names)] = {'step': steps, 'exp_avg': m1, 'exp_avg_sq': m2}
+            names.append(name)
+        return {'state': state, 'param_names': names, 'step_count': self.step_count}
+
+    def load_opt_state_dict(self, sd):
+        "Inverse of opt_state_dict (best effort like the reference, deep_music_genre.py:1802-1803: unknown entries are skipped)."
+        steps = 0
+        for i, name in enumerate(sd.get('param_names', [])):
+            st = sd['state'].get(i)
+            if st is None:
+                continue
+            for which, key in ((1, 'exp_avg'), (2, 'exp_avg_sq')):
+                a = st[key].detach().to('cpu', torch.float32).contiguous()
+                rc = self.lib.dmg_train_opt_state(self.e.h, name.encode(), which, 1, C.c_void_p(a.data_ptr()), a.numel())
+                if rc not in (0, 1):
+                    check(rc, f'dmg_train_opt_state({name})')
+            steps = max(steps, int(st.get('step', 0)))
+        self.lib.dmg_train_opt_steps(self.e.h, steps)
+        self.step_count = int(sd.get('step_count', steps))
+
     def sync_for_inference(self):
         "Re-derive what inference caches from the trained weights (rel-pos key cache)."
         check(self.lib.dmg_commit_weights(self.e.h), 'dmg_commit_weights')

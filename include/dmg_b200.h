@@ -148,6 +148,13 @@ int dmg_sample_logits(dmg_model* m, const float* logits_dev, const int32_t* prev
                       const dmg_sampler_params* params, uint64_t offset, int32_t* out_dev, int32_t* num_choices_dev,
                       void* stream);
 
+/* One step of MusicLearner.beam_search (deep_music_genre.py:1834-1847) on the logits of the latest DMG_LOGITS_LAST forward over `nb`
+ * beams: log_softmax, top_k per beam, scores = -logp + previous score (scores_dev: fp32 [n_scores], n_scores = 1 broadcasts like the
+ * reference's zeros(1)), the beam_sz lowest scores survive.  Outputs (device): scores [beam_sz], the parent beam of each survivor
+ * (feed it to dmg_select_hidden) and the token it appends.  Exact ties go to the lower candidate index. */
+int dmg_beam_step(dmg_model* m, const float* scores_dev, int n_scores, int nb, int top_k, int beam_sz, float* scores_out_dev,
+                  int32_t* parents_out_dev, int32_t* tokens_out_dev, void* stream);
+
 /* Test hook: ONE sampling step for n independent rows that also returns the final probabilities probs_dev fp32 [n, V] (may be
  * NULL) - their support is the set kept by the grammar filter, top-k and top-p.  predict_loop = 0: predict_mask's step (as
  * dmg_sample_logits; last_xxsep_dev / pos_since_start_dev ignored).  predict_loop = 1: the step of MusicLearner.predict
@@ -222,6 +229,11 @@ int dmg_train_grad_unpack(dmg_model* m, int64_t offset, int64_t count, const voi
  * Inference entry points need dmg_commit_weights() again afterwards (the rel-pos key cache follows r_attn). */
 int dmg_train_optimizer_step(dmg_model* m, float lr, float beta1, float beta2, float eps, float wd, float clip,
                              float grad_scale, void* stream);
+/* MusicLearner.save(with_opt=True) / the optimizer half of music_model_learner(pretrained_path=...) (deep_music_genre.py:1801-1803,
+ * 1812-1821): Adam's exp_avg (which = 1) / exp_avg_sq (which = 2) of one parameter by its state-dict name, fp32 host buffer;
+ * set = 0 reads, 1 writes.  Unknown names return 1.  dmg_train_opt_steps: the step counter of the bias correction (value < 0 reads). */
+int dmg_train_opt_state(dmg_model* m, const char* name, int which, int set, float* buf_host, int64_t numel);
+int64_t dmg_train_opt_steps(dmg_model* m, int64_t value);
 /* Synchronises the stream and returns {cross-entropy (mean), alpha*AR, beta*TAR, gradient norm (after grad_scale; 0 before
  * the first optimizer step)} of the latest step. */
 int dmg_train_losses(dmg_model* m, float* out4_host, void* stream);

@@ -180,6 +180,37 @@ def predict(model, vocab, item_data, item_pos, n_words=128, temperatures=(1.0, 1
     return new_idx
 
 
+def beam_search(model, xb, n_words, top_k=10, beam_sz=10, temperature=1., return_beams=False):
+    """``MusicLearner.beam_search`` (deep_music_genre.py:1823-1851) over an oracle ``SequentialRNN``.  ``argsort`` is made stable
+    (the reference's is not, and its top_k identical copies of the seed produce exact ties); ``return_beams`` returns the surviving
+    (token history, score) pairs instead of drawing one of them."""
+    model.reset()
+    model.eval()
+    xb_length = xb.shape[-1]
+    if xb.shape[0] > 1: xb = xb[0][None]
+    xb = xb.repeat(top_k, 1)
+    nodes = xb.clone()
+    scores = xb.new_zeros(1).float()
+    with torch.no_grad():
+        for k in range(n_words):
+            out = F.log_softmax(model(xb)[0][:, -1], dim=-1)
+            values, indices = out.topk(top_k, dim=-1)
+            scores = (-values + scores[:, None]).view(-1)
+            indices_idx = torch.arange(0, nodes.size(0))[:, None].expand(nodes.size(0), top_k).contiguous().view(-1)
+            sort_idx = scores.argsort(stable=True)[:beam_sz]
+            scores = scores[sort_idx]
+            nodes = torch.cat([nodes[:, None].expand(nodes.size(0), top_k, nodes.size(1)),
+                               indices[:, :, None].expand(nodes.size(0), top_k, 1)], dim=2)
+            nodes = nodes.view(-1, nodes.size(2))[sort_idx]
+            model[0].select_hidden(indices_idx[sort_idx])
+            xb = nodes[:, -1][:, None]
+    if temperature != 1.: scores.div_(temperature)
+    if return_beams:
+        return nodes[:, xb_length:].numpy(), scores
+    node_idx = torch.multinomial(torch.exp(-scores), 1).item()
+    return [i.item() for i in nodes[node_idx][xb_length:]]
+
+
 def predict_mask(model, vocab, item_data, item_pos, temperatures=(1.0, 1.0), top_k=20, top_p=0.8):
     "``MultitaskLearner.predict_mask`` (deep_music_remix.py:2563-2613) over an oracle ``MultiTransformer`` (eval mode)."
     x = torch.as_tensor(np.asarray(item_data)).long().clone()

@@ -63,3 +63,17 @@ def test_edge_cases():
     assert list(masked.position) == [0, 0, 0, 0, 0, 0, 0, 0, 2, 2, 2]
     t = pc.MusicItem(np.array([0, 1, 72, 142, 301]), v).transpose(2)
     assert list(t.data) == [0, 1, 74, 142, 301]
+
+
+@pytest.mark.parametrize('name', ['ref_genre_output.mid', 'ref_remix_Notes_output.mid'])
+def test_midi_writer_reproduces_the_reference_outputs_byte_for_byte(golden_dir, tmp_path, name):
+    """outputs/genre_output.mid and outputs/remix_Notes_output.mid are files the reference itself wrote with
+    ``full.to_stream(bpm).write('midi', fp)`` (app.py:191, 275; music21 behind it).  Decoding them and writing them again with the
+    product's SMF writer must give the same bytes: tempo / key / time-signature track, track name + program + pitch-bend prelude,
+    1024 ticks per quarter, velocity 90, note-off ordering, chord grouping by duration (deep_music_genre.py:513-541), end-of-track gaps."""
+    v = pc.MusicVocab.create()
+    src = os.path.join(golden_dir, name)
+    item = pc.MusicItem.from_file(src, v)
+    out = tmp_path / 'again.mid'
+    item.to_stream(bpm=120).write('midi', fp=str(out))
+    assert open(src, 'rb').read() == open(out, 'rb').read()

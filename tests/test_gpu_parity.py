@@ -467,3 +467,23 @@ def test_generate_batch_equals_independent_oracle_predicts(golden_dir):
         mine = [int(t) for t in got[:, b] if t >= 0]
         assert (got[len(mine):, b] < 0).all()               # once stopped, always stopped
         assert mine == ref, (b, len(mine), len(ref))
+
+
+def test_beam_search_on_the_device_ring_matches_oracle():
+    """MusicLearner.beam_search (deep_music_genre.py:1823-1851): per-step log-softmax / top-k / selection kernel + select_hidden on the
+    K/V rings, against the oracle's restatement of the reference loop (fp32).  Compared: the surviving beams (token histories as a
+    multiset - the reference's top_k identical seed copies make duplicate beams, whose order is a tie) and their scores."""
+    from deepmusicgeneration_b200.codec import MusicDataBunch
+    from deepmusicgeneration_b200.learner import MusicLearner
+    om, pm = _pair(SMALL_M128, 'f32', 8, 128, keep_hidden=False)
+    g = torch.Generator().manual_seed(4)
+    xb = torch.randint(12, 300, (1, 40), generator=g)
+    for top_k, beam_sz, n_words in ((4, 6, 12), (8, 8, 20), (3, 2, 9)):
+        ref_nodes, ref_scores = osamp.beam_search(om, xb.clone(), n_words, top_k=top_k, beam_sz=beam_sz, return_beams=True)
+        nodes, scores = MusicLearner(MusicDataBunch.empty(''), pm).beam_search(xb.clone(), n_words, top_k=top_k, beam_sz=beam_sz,
+                                                                              return_beams=True)
+        assert nodes.shape == ref_nodes.shape == (beam_sz, n_words)
+        assert (scores.sort()[0] - ref_scores.sort()[0]).abs().max() < 2e-3, (top_k, beam_sz)
+        assert sorted(map(tuple, nodes.tolist())) == sorted(map(tuple, ref_nodes.tolist())), (top_k, beam_sz)
+    out = MusicLearner(MusicDataBunch.empty(''), pm).beam_search(xb.clone(), 10, top_k=4, beam_sz=4)
+    assert len(out) == 10 and all(isinstance(t, int) for t in out)

@@ -249,3 +249,74 @@ def test_loss_curve_50_steps_c3_geometry(monkeypatch):
     print('loss curve (oracle ce, cuda ce) every 10 steps:', [(round(c[0], 3), round(c[1], 3)) for c in curve[::10]], 'last', curve[-1])
     assert curve[-1][1] < curve[0][1] - 1.0                         # the model learns the four batches
     tr.close()
+
+
+def test_load_state_dict_over_live_trainer_refreshes_r_attn_and_restarts_adam(monkeypatch):
+    """fit -> load_state_dict(checkpoint) -> fit (resume): the first step after the reload must run with the NEW r_attn weights (their
+    bf16 copy is training-only state) and with fresh Adam moments, exactly like a trainer created on the loaded weights."""
+    cfg = small_config()
+    bs, bptt = 2, 64
+    om, pm, tr = build_pair(cfg, bs, bptt, 0.)
+    g = torch.Generator().manual_seed(2)
+    x, y = torch.randint(0, V, (bs, bptt), generator=g), torch.randint(0, V, (bs, bptt), generator=g)
+    tr.reset()
+    for _ in range(3):
+        tr.step(x, y, lr=1e-2, mask_size=(1, 1))            # moves every weight, fills the Adam moments
+    torch.manual_seed(123)
+    om2 = txl.get_language_model(V, cfg, drop_mult=0.).train()      # a different "checkpoint"
+    pm.load_state_dict(om2.state_dict())
+    om2.reset(); tr.reset()
+    set_oracle_mask(monkeypatch, (1, 1))
+    opt = otrain.AdamTrueWD(otrain.unique_params(om2), eps=1e-3)
+    ref = otrain.train_step(om2, x, y, opt, 1e-3, wd=0.01, clip=0.5)
+    sd0 = {k: v.clone() for k, v in pm.state_dict().items()}
+    tr.forward(x, y, None, mask_size=(1, 1)); tr.backward()
+    got = tr.losses()
+    assert abs(got['ce'] - ref['ce']) < 2e-2 * ref['ce'], (got, ref)
+    compare_grads(tr, om2, tol=2e-2)                          # includes every r_attn.weight gradient
+    tr.optimizer_step(1e-3, betas=(0.9, 0.99), eps=1e-3, wd=0.01, clip=0.5)
+    sd_ref, sd_got = om2.state_dict(), pm.state_dict()
+    for name, w in sd_got.items():                          # first Adam step of a FRESH optimizer (bias correction of step 1)
+        d_got, d_ref = w - sd0[name], sd_ref[name].reshape(w.shape) - sd0[name]
+        assert rel(d_got, d_ref) < 0.1, (name, rel(d_got, d_ref))
+    tr.close()
+
+
+def test_save_with_optimizer_state_and_reload_round_trip(tmp_path, golden_dir):
+    """MusicLearner.save(file, config=...) -> createGenreContinuationModel(ckpt_path=file) -> predict (deep_music_genre.py:1784-1821,
+    app_utils.py:68-75): weights, config and the Adam state come back; the reloaded learner generates the same greedy stream and its
+    next training step equals the original learner's next step."""
+    import os
+    from deepmusicgeneration_b200.app_utils import createGenreContinuationModel
+    from deepmusicgeneration_b200.codec import MusicDataBunch, MusicItem
+    from deepmusicgeneration_b200.learner import music_model_learner
+    cfg = small_config(mem_len=64)
+    data = MusicDataBunch.empty('')
+    learn = music_model_learner(data, config=dict(cfg), dtype='bf16', max_batch=4, max_seq=256, keep_hidden=False, seed=3)
+    base = (torch.arange(4 * 64 * 8) % 29 + 12).view(4, -1)
+    batches = [(base[:, i * 64:(i + 1) * 64], base[:, i * 64 + 1:(i + 1) * 64 + 1]) for i in range(7)]
+    learn.fit_one_cycle(1, 3e-3, batches)
+    path = str(tmp_path / 'ckpt.pth')
+    learn.save(path, config=dict(cfg))
+    state = torch.load(path, map_location='cpu', weights_only=False)
+    assert set(state) == {'model', 'opt', 'config'} and state['opt'] is not None and state['config']['d_model'] == cfg['d_model']
+    assert len(state['opt']['state']) == len(state['opt']['param_names']) > 10
+    # reload through the app-level entry point (config comes from the file when the caller passes none: :1790-1791)
+    learn2 = music_model_learner(data, config=None, pretrained_path=path, dtype='bf16', max_batch=4, max_seq=256, keep_hidden=False)
+    for k, v in learn.model.state_dict().items():
+        assert torch.equal(v, learn2.model.state_dict()[k]), k
+    item = MusicItem.from_file(os.path.join(golden_dir, 'Undertale_-_Megalovania.mid'), data.vocab).trim_to_beat(8)
+    a, _ = learn.predict(item, n_words=40, top_k=1, top_p=0.0, min_bars=100)
+    b, _ = learn2.predict(item, n_words=40, top_k=1, top_p=0.0, min_bars=100)
+    assert list(a.data) == list(b.data)
+    # resume: one more step on both (same seed / step counter -> same dropout masks) moves the weights identically
+    tr1 = learn.trainer(4, 64)
+    learn2.load_opt_state(state['opt'], 4, 64)
+    tr2 = learn2.trainer(4, 64)
+    assert tr2.step_count == tr1.step_count
+    for tr in (tr1, tr2):
+        tr.reset(); tr.step(batches[0][0], batches[0][1], lr=1e-3, mask_size=(1, 1))
+    sd1, sd2 = learn.model.state_dict(), learn2.model.state_dict()
+    for k in sd1:
+        assert (sd1[k] - sd2[k]).abs().max() < 1e-6, k
+    assert createGenreContinuationModel.__defaults__[1].endswith('lakh_genre_model.pth')
