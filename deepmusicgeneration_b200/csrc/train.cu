@@ -649,8 +649,8 @@ int dmg_train_optimizer_step(dmg_model* m, float lr, float beta1, float beta2, f
   dmg_train* t = m->train;
   DMG_CUDA_OK(cudaSetDevice(m->device));
   cudaStream_t st = (cudaStream_t)stream;
-  DMG_CUDA_OK(cudaMemsetAsync(t->acc + 3, 0, sizeof(float), st));
-  if (train_sumsq(t->G, t->total, t->acc + 3, st)) return -1;
+  // the norm of the (all-reduced) gradient, summed in a fixed order: every rank must scale its update by the same bits
+  if (train_sumsq_det(t->G, t->total, t->partial, 148 * 4, t->acc + 3, st)) return -1;
   t->opt_steps++;
   if (train_adam(t->adam_tensors, t->adam_chunks, t->n_adam_chunks, t->G, t->m1, t->m2, lr, beta1, beta2, eps, wd, t->opt_steps, clip,
                  t->acc + 3, grad_scale, st)) return -1;

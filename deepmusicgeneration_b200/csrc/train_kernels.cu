@@ -354,6 +354,41 @@ __global__ void __launch_bounds__(256) train_sumsq_kernel(const float* __restric
   }
 }
 
+// Deterministic two-stage sum of squares (the gradient norm that scales the Adam update): per-block partials in a fixed slot each,
+// then one block adds them in a fixed order - every data-parallel rank derives bit-identical clipping from the same reduced gradient.
+__global__ void __launch_bounds__(256) train_sumsq_part_kernel(const float* __restrict__ x, long long n, float* __restrict__ part) {
+  __shared__ float red[8];
+  float s = 0.f;
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const float4 v = ((const float4*)x)[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 * 4; i < n; i++) s += x[i] * x[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tsum = 0.f;
+    for (int i = 0; i < 8; i++) tsum += red[i];
+    part[blockIdx.x] = tsum;
+  }
+}
+__global__ void __launch_bounds__(256) train_sumsq_final_kernel(const float* __restrict__ part, int n, float* __restrict__ out) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) s += part[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tsum = 0.f;
+    for (int i = 0; i < 8; i++) tsum += red[i];
+    *out = tsum;
+  }
+}
+
 __global__ void __launch_bounds__(256) train_tar_kernel(const bf16* __restrict__ h, long long bstride, int B, int n, int d,
                                                         float* __restrict__ acc) {
   __shared__ float red[8];
@@ -576,6 +611,13 @@ int train_head_bwd(const bf16* dxd, const float* core_out, float* dx32, int B, i
 
 int train_sumsq(const float* x, long long n, float* acc, cudaStream_t st) {
   return launch_np(train_sumsq_kernel, dim3(grid_for(n / 4, 148 * 4)), dim3(256), 0, st, x, n, acc);
+}
+
+int train_sumsq_det(const float* x, long long n, float* part, int part_cap, float* out, cudaStream_t st) {
+  int g = grid_for(n / 4, 148 * 4);
+  if (g > part_cap) g = part_cap;
+  if (launch_np(train_sumsq_part_kernel, dim3(g), dim3(256), 0, st, x, n, part)) return -1;
+  return launch_np(train_sumsq_final_kernel, dim3(1), dim3(256), 0, st, (const float*)part, g, out);
 }
 
 int train_tar(const bf16* h, long long bstride, int B, int n, int d, float* acc, cudaStream_t st) {

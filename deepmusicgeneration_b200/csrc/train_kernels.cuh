@@ -171,6 +171,8 @@ int train_head_bwd(const bf16* dxd, const float* core_out, float* dx32, int B, i
                    uint32_t seed, float scale, float ar_coef, cudaStream_t st);
 // sum of squares of a fp32 buffer into acc[slot] (AR term, gradient norm)
 int train_sumsq(const float* x, long long n, float* acc, cudaStream_t st);
+// out = sum of squares, summed in a fixed order (part: scratch of part_cap floats)
+int train_sumsq_det(const float* x, long long n, float* part, int part_cap, float* out, cudaStream_t st);
 // TAR value: sum over b, t>=1 of (h[b,t]-h[b,t-1])^2 for h = bf16 [B, n, d] with stream stride bstride elements
 int train_tar(const bf16* h, long long bstride, int B, int n, int d, float* acc, cudaStream_t st);
 // embedding backward: demb[id] += mask * scale * (dx + dbr) (atomics); beat/bar likewise when pos != NULL

@@ -24,8 +24,10 @@ def _worker(rank, world, port, wire, q):
         sharding.init_distributed(backend='nccl')
         torch.cuda.set_device(rank)
         bptt, per = 128, 2
-        cfg = dict(txl.default_config(), n_layers=4, d_model=128, n_heads=2, d_head=64, d_inner=256, mem_len=bptt, ctx_len=bptt,
+        cfg = dict(txl.default_config(), n_layers=6, d_model=128, n_heads=2, d_head=64, d_inner=256, mem_len=bptt, ctx_len=bptt,
                    encode_position=False, mask_steps=1)
+        # train mode draws rand_window_mask on the host (p = 0.2 of a k = 0 window even with mask_steps = 1): pin both sides to (1, 1)
+        txl.rand_window_mask = lambda x_len, m_len, device, **kw: txl.window_mask(x_len, device, m_len, size=(1, 1))
         torch.manual_seed(0)
         om = txl.get_language_model(V, cfg, drop_mult=0.).train()
         pm = get_language_model(V, cfg, dtype='bf16', device=rank, max_batch=per, max_seq=bptt, keep_hidden=False, init=False)
@@ -36,7 +38,7 @@ def _worker(rank, world, port, wire, q):
         lo, hi = rank * per, (rank + 1) * per
         om.reset(); tr.reset()
         opt = otrain.AdamTrueWD(otrain.unique_params(om), eps=1e-3)
-        worst = 0.
+        worst, worst_at = 0., None
         for s in range(2):                                         # the second step runs over a warm memory
             x = torch.randint(0, V, (world * per, bptt), generator=g)
             y = torch.randint(0, V, (world * per, bptt), generator=g)
@@ -49,7 +51,7 @@ def _worker(rank, world, port, wire, q):
                 r = refg.get(name, refg.get('1.decoder.weight') if name == '0.encoder.weight' else None)
                 assert r is not None, name
                 e = ((gsum / world - r.reshape(gsum.shape)).norm() / r.norm().clamp_min(1e-20)).item()
-                worst = max(worst, e)
+                if e > worst: worst, worst_at = e, (s, name)
             tr.optimizer_step(1e-3, betas=(0.9, 0.99), eps=1e-3, wd=0.01, clip=0.5)
             gn = tr.losses()['grad_norm']
             assert abs(gn - ref['grad_norm']) < 4e-2 * ref['grad_norm'], (s, gn, ref['grad_norm'])
@@ -60,7 +62,7 @@ def _worker(rank, world, port, wire, q):
         same = all(torch.equal(both[0], b) for b in both)
         comm = tr.profile_comm(lambda: (tr.forward(x[lo:hi], y[lo:hi], None, mask_size=(1, 1)), tr.backward()), reps=1)
         tr.close()
-        q.put((rank, worst, same, comm['bytes_per_step'], None))
+        q.put((rank, worst, same, (comm['bytes_per_step'], worst_at), None))
     except Exception as e:                                         # surface the failure in the parent
         import traceback
         q.put((rank, None, None, None, traceback.format_exc()))
@@ -81,5 +83,5 @@ def test_two_rank_allreduced_gradient_equals_oracle_on_concatenated_batch(wire):
     for p in procs: p.join(timeout=120)
     for rank, worst, same, nbytes, err in res:
         assert err is None, err
-        print(f'rank {rank}: wire {wire}, worst gradient rel err vs oracle (whole batch) {worst:.3e}, {nbytes} bytes exchanged per step')
+        print(f'rank {rank}: wire {wire}, worst gradient rel err vs oracle (whole batch) {worst:.3e} at {nbytes[1]}, {nbytes[0]} bytes exchanged per step, same weights {same}')
         assert worst < 2.5e-2 and same
