@@ -30,27 +30,31 @@
 // 16-row clusters would run in two waves).
 #include <cuda.h>
 
+#include "attention_decode2.cuh"
 #include "kernels.cuh"
 #include "launch.cuh"
 
 namespace dmg {
 namespace {
 
-constexpr int DL_STAGES = 8;
-constexpr int DL_A_BYTES = 128 * 128;               // weight tile: up to 128 features x 64 bf16
-constexpr int DL_B_BYTES = DL_ROWS * 128;           // activation tile: 32 rows x 64 bf16
-constexpr int DL_STAGE = DL_A_BYTES + DL_B_BYTES;   // 20 KB (a multiple of 1024: every tile base keeps the 128B-swizzle phase)
+constexpr int DL_STAGES = 10;                       // weight ring: 10 x 16 KB in flight
+constexpr int DL_STAGE = 128 * 128;                 // one stage = one weight tile: up to 128 features x 64 bf16
+constexpr int DL_B_BYTES = DL_ROWS * 128;           // activation k-block: 32 rows x 64 bf16
 constexpr int DL_D = 512;                           // d_model this kernel is specialised for (LayerNorm thread mapping)
-constexpr int DL_XA_BYTES = DL_ROWS * DL_D * 2;     // resident B operand: the 32 rows after a LayerNorm, 8 k-blocks of 4 KB
-constexpr int DL_MMAW = 2;                           // MMA-issuing warps (round-robin over stage uses; measured: 1 -> 2 warps -30 % MMA time, 4 no better)
+constexpr int DL_XA_BYTES = DL_ROWS * DL_D * 2;     // resident B operand: 32 rows x 512 (attention output, then LayerNorm rows), 8 k-blocks of 4 KB
+constexpr int DL_HS_KB = 4;                         // k-blocks of this CTA's GeLU slice (d_inner / 8 / 64)
+constexpr int DL_HS_BYTES = DL_HS_KB * DL_B_BYTES;  // resident B operand of the FFN-down phase: 32 rows x 256
+constexpr int DL_OWN = DL_ROWS / DL_CLUSTER;        // rows whose second LayerNorm this CTA computes (4)
+constexpr int DL_X1_BYTES = DL_OWN * DL_D * 4;      // their LayerNorm-1 output (fp32 residual of LayerNorm 2)
+constexpr int DL_MMAW = 2;                          // MMA-issuing warps (round-robin over stage uses)
 constexpr int DL_THREADS = 32 * (1 + DL_MMAW + 8);  // producer warp + MMA-issuing warps + 8 epilogue warps
 constexpr int DL_EPI0 = 32 * (1 + DL_MMAW);         // first epilogue thread
-constexpr int DL_NCHAIN = 4 * DL_MMAW;                       // partial accumulators of a phase (all tiles together): 16 x 32 columns = TMEM
-constexpr int DL_EPI = 256;                         // epilogue / LayerNorm threads (8 per row)
+constexpr int DL_EPI = 256;                         // epilogue / LayerNorm threads
 constexpr int DL_LN_BYTES = 4 * DL_D * 4;           // ln1 w, b and ln2 w, b staged in shared memory
-constexpr int DL_SMEM = DL_STAGES * DL_STAGE + DL_XA_BYTES + DL_LN_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
-constexpr int DL_TMEM_COLS = 256;                   // phases reuse the columns: each phase's MMAs start after the previous epilogue
+constexpr int DL_SMEM = DL_STAGES * DL_STAGE + DL_XA_BYTES + DL_HS_BYTES + DL_X1_BYTES + DL_LN_BYTES + 512 /*barriers + reduction scratch*/ + 1024 /*alignment slack*/;
+constexpr int DL_TMEM_COLS = 512;                   // 16 partial accumulators x 32 columns; phases reuse the columns
 constexpr int DL_CHAIN = DL_ROWS;                   // TMEM columns of one partial accumulator (N = 32 rows)
+static_assert(DL_SMEM <= 227 * 1024, "decode_layer_kernel: shared memory budget");
 
 __device__ __forceinline__ uint64_t dl_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -86,7 +90,7 @@ __device__ __forceinline__ void dl_spin(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg((const float4*)p); }
 // optional per-role timeline (DecodeLayerArgs::dbg, scripts/probe_decode_layer.py): slot = role * 16 + mark, value = %globaltimer ns
 __device__ __forceinline__ void dl_mark(unsigned long long* dbg, int role, int mark) {
-  if (dbg == nullptr || blockIdx.x != 0) return;
+  if (dbg == nullptr) return;
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   dbg[role * 16 + mark] = t;
@@ -149,40 +153,60 @@ __device__ __forceinline__ void dl_gather(uint32_t taddr, int nacc, float (&out)
   }
 }
 
-__global__ void __launch_bounds__(DL_THREADS, 1)
-decode_layer_kernel(const __grid_constant__ CUtensorMap tmAttn, const __grid_constant__ CUtensorMap tmH,
-                    const __grid_constant__ CUtensorMap tmWo, const __grid_constant__ CUtensorMap tmW1,
-                    const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmWq, const DecodeLayerArgs a) {
-  extern __shared__ __align__(1024) uint8_t dl_smem[];
+__device__ __forceinline__ uint32_t dl_mapa(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void dl_st_cluster_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Phases of one launch (body = bit 0 of mode, next = bit 1):
+//   A  out-projection        64 features per CTA  x K = HD     B operand: the attention output rows (TMA -> XA)
+//      LayerNorm 1           all 32 rows in every CTA (redundant; the rows a CTA owns also go to X1 as fp32)
+//   B  FFN-up + GeLU         256 features per CTA x K = 512    B operand: XA;  result stays in this CTA's shared memory (HS)
+//   C  FFN-down, split-K     all 512 features     x K = this CTA's 256 GeLU features (HS); partial sums -> global scratch
+//      LayerNorm 2           each CTA reduces the 8 partials of its OWN 4 rows, normalises, broadcasts the bf16 rows into the XA
+//                            of all 8 CTAs through distributed shared memory
+//   D  next layer's q|k|v    192 features per CTA x K = 512    B operand: XA
+// Three cluster barriers per launch: #1 projection slices published, #2 partial sums published, #3 XA broadcast done.
+// `cluster` = index of this CTA's cluster among the clusters of the fused role (the stand-alone kernel: blockIdx.x / 8).
+__device__ __forceinline__ void decode_layer_body(const CUtensorMap& tmAttn, const CUtensorMap& tmWo, const CUtensorMap& tmW1,
+                                                  const CUtensorMap& tmW2, const CUtensorMap& tmWq, const DecodeLayerArgs& a_in, int cluster,
+                                                  uint8_t* dl_smem) {
+  DecodeLayerArgs a = a_in;
+  if (cluster != 0 || dl_cluster_ctarank() != 0) a.dbg = nullptr;      // the timeline probe follows CTA 0
   uint8_t* tiles = dl_smem + ((1024u - (smem_u32(dl_smem) & 1023u)) & 1023u);
   uint8_t* xa_s = tiles + DL_STAGES * DL_STAGE;
-  float* ln_s = (float*)(xa_s + DL_XA_BYTES);                // [4][512]: ln1 w, ln1 b, ln2 w, ln2 b
-  uint64_t* full = (uint64_t*)(xa_s + DL_XA_BYTES + DL_LN_BYTES);
+  uint8_t* hs_s = xa_s + DL_XA_BYTES;
+  float* x1_s = (float*)(hs_s + DL_HS_BYTES);                // [4][512] fp32: LayerNorm-1 output of the rows this CTA owns
+  float* ln_s = x1_s + DL_OWN * DL_D;                        // [4][512]: ln1 w, ln1 b, ln2 w, ln2 b
+  uint64_t* full = (uint64_t*)(ln_s + 4 * DL_D);
   uint64_t* empty = full + DL_STAGES;
   uint64_t* tmem_full = empty + DL_STAGES;   // [4]: one per phase, single use
-  uint64_t* xa_ready = tmem_full + 4;        // [2]: B operand written (after LayerNorm 1 / LayerNorm 2)
-  uint32_t* tmem_holder = (uint32_t*)(xa_ready + 2);
+  uint64_t* xa_ready = tmem_full + 4;        // [0]: LayerNorm-1 rows in XA; [1]: embedded rows in XA (first launch of a step)
+  uint64_t* hs_ready = xa_ready + 2;         // GeLU slice in HS
+  uint64_t* attn_full = hs_ready + 1;        // attention output rows in XA (TMA)
+  uint32_t* tmem_holder = (uint32_t*)(attn_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int crank = (int)dl_cluster_ctarank();
-  const int row0 = a.row_base + (blockIdx.x / DL_CLUSTER) * DL_ROWS;
+  const int row0 = a.row_base + cluster * DL_ROWS;
   const bool body = (a.mode & 1) != 0, next = (a.mode & 2) != 0;
-  const int nkb_A = a.HD >> 6, nkb_d = DL_D >> 6, nkb_C = a.di >> 6;
-  const int fB = a.di / DL_CLUSTER, nB = fB >> 7;                         // FFN-up features of this CTA, in 128-feature tiles
-  const int fD = a.n3 / DL_CLUSTER, nD128 = fD >> 7, nD64 = (fD & 127) >> 6;   // next-layer q|k|v features of this CTA
-  const int nD = nD128 + nD64;
-  // partial accumulators per tile: one per 16-wide K step of a k-block; single-tile phases also alternate two k-blocks
-  const int accB = DL_NCHAIN / nB, accD = DL_NCHAIN / (nD ? nD : 1);   // chains per tile (4); single-tile phases use all 8
+  const int nkb_A = a.HD >> 6, nkb_d = DL_D >> 6;
+  constexpr int nB = 2, nC = 4, nD = 2;                      // tiles per phase (decode_layer_supported): 2 x 128, 4 x 128, 128 + 64
+  const int fB = a.di / DL_CLUSTER, fD = a.n3 / DL_CLUSTER;  // 256 FFN-up features, 192 q|k|v features per CTA
+  const int nA_use = body ? nkb_A : 0, nB_use = body ? nB * nkb_d : 0, nC_use = body ? nC * DL_HS_KB : 0, nD_use = next ? nD * nkb_d : 0;
   pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmWo); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmWq);
-    tma_prefetch_desc(&tmAttn); tma_prefetch_desc(&tmH);
+    tma_prefetch_desc(&tmWo); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmWq); tma_prefetch_desc(&tmAttn);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < DL_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }   // 4 issuing lanes commit per stage
-    for (int p = 0; p < 4; p++) mbar_init(&tmem_full[p], 4 * DL_MMAW);   // every MMA-issuing lane commits
-    mbar_init(&xa_ready[0], DL_EPI); mbar_init(&xa_ready[1], DL_EPI);
+    for (int p = 0; p < 4; p++) mbar_init(&tmem_full[p], 4 * DL_MMAW);                          // every MMA-issuing lane commits
+    mbar_init(&xa_ready[0], DL_EPI); mbar_init(&xa_ready[1], DL_EPI); mbar_init(hs_ready, DL_EPI); mbar_init(attn_full, 1);
     mbar_fence_init();
   }
   if (warp == 1 + DL_MMAW) tmem_alloc<DL_TMEM_COLS>(tmem_holder);
@@ -193,153 +217,119 @@ decode_layer_kernel(const __grid_constant__ CUtensorMap tmAttn, const __grid_con
 
   if (warp == 0) {
     // ================================================================== TMA producer
-    // Eight lanes issue in lock-step, lane j serving the stage uses i with i % 8 == j of a round of eight consecutive uses: one
-    // thread's scalar issue loop (barrier wait, expect_tx, two TMA instructions) was measured to be the bottleneck of phase C.
+    // The weights depend on nothing: all stage uses of the launch stream through the ring as fast as stages free up.  Eight lanes
+    // issue in lock-step (lane j = use r + j of a round): one thread's scalar issue loop was measured to be a bottleneck.
     if (lane == 0) dl_mark(a.dbg, 0, 0);
-    const bool act_lane = lane < DL_STAGES;
-    auto stage = [&](int i) { return tiles + (i & (DL_STAGES - 1)) * DL_STAGE; };
-    auto wait_empty = [&](int i) { if (i >= DL_STAGES) dl_spin(&empty[i & (DL_STAGES - 1)], (uint32_t)((i / DL_STAGES) - 1) & 1u); };
-    // weights of stage use i: `boxes` 64-feature boxes starting at feature row `frow`, k-block kb; `extra` = bytes of an activation box
-    auto wload = [&](int i, const CUtensorMap* tm, int kb, int frow, int boxes, uint32_t extra) {
-      wait_empty(i);
-      uint64_t* fb = &full[i & (DL_STAGES - 1)];
-      mbar_expect_tx(fb, (uint32_t)(boxes * 64 * 128) + extra);
-      tma_load_2d(stage(i), tm, kb * 64, frow, fb);
-      if (boxes == 2) tma_load_2d(stage(i) + 64 * 128, tm, kb * 64, frow + 64, fb);
-    };
-    auto aload = [&](int i, const CUtensorMap* tm, int kb) { tma_load_2d(stage(i) + DL_A_BYTES, tm, kb * 64, row0, &full[i & (DL_STAGES - 1)]); };
-    int it = 0;
-    if (body) {
-      // ---- phase A: out-projection rows [64 crank, +64); the first round's weight boxes go out before the attention kernel has finished
-      for (int r = 0; r < nkb_A; r += DL_STAGES) {
-        const int kb = r + lane;
-        const bool on = act_lane && kb < nkb_A;
-        if (on) wload(it + kb, &tmWo, kb, 64 * crank, 1, DL_B_BYTES);
-        if (r == 0) pdl_wait();
-        if (on) aload(it + kb, &tmAttn, kb);
-        __syncwarp();
+    const int total = nA_use + nB_use + nC_use + nD_use;
+    int bar_state = 0;                                   // cluster barrier progress of this warp: 0, 1 = arrived #1, 2 = arrived #2, 3 = arrived #3
+    for (int r = 0; r < total; r += 8) {
+      // barrier duties first, at round granularity; never block on a stage whose release needs a barrier we have not served
+      if (body && bar_state == 0 && r >= nA_use) { dl_arrive(); bar_state = 1; }                                   // #1
+      if (body && bar_state == 1 && r >= nA_use + nB_use) { dl_wait(); dl_arrive(); bar_state = 2; }               // #2
+      if (body && bar_state == 2 && r + 8 > nA_use + nB_use + nC_use + DL_STAGES) { dl_wait(); dl_arrive(); bar_state = 3; }   // #3
+      const int i = r + lane;
+      if (lane < 8 && i < total) {
+        const int s = i % DL_STAGES;
+        if (i >= DL_STAGES) dl_spin(&empty[s], (uint32_t)((i / DL_STAGES) - 1) & 1u);
+        uint8_t* dst = tiles + s * DL_STAGE;
+        const CUtensorMap* tm; int c0, frow, boxes;
+        if (i < nA_use) { tm = &tmWo; c0 = i * 64; frow = 64 * crank; boxes = 1; }
+        else if (i < nA_use + nB_use) { const int j = i - nA_use; tm = &tmW1; c0 = (j / nB) * 64; frow = fB * crank + 128 * (j % nB); boxes = 2; }
+        else if (i < nA_use + nB_use + nC_use) { const int j = i - nA_use - nB_use; tm = &tmW2; c0 = fB * crank + (j / nC) * 64; frow = 128 * (j % nC); boxes = 2; }
+        else { const int j = i - nA_use - nB_use - nC_use; tm = &tmWq; c0 = (j / nD) * 64; frow = fD * crank + 128 * (j % nD); boxes = (j % nD) == 0 ? 2 : 1; }
+        mbar_expect_tx(&full[s], (uint32_t)(boxes * 64 * 128));
+        tma_load_2d(dst, tm, c0, frow, &full[s]);
+        if (boxes == 2) tma_load_2d(dst + 64 * 128, tm, c0, frow + 64, &full[s]);
       }
-      it += nkb_A;
-      if (lane == 0) dl_mark(a.dbg, 0, 1);
-      dl_arrive();                                                     // #1 (nothing of ours to publish)
-      // ---- phase B: FFN-up features [fB crank, +fB), tiles interleaved; B operand = the resident LayerNorm rows
-      for (int r = 0; r < nB * nkb_d; r += DL_STAGES) {
-        const int j = r + lane;
-        if (act_lane && j < nB * nkb_d) wload(it + j, &tmW1, j / nB, fB * crank + 128 * (j % nB), 2, 0);
+      if (r == 0 && body) {                              // the attention output rows: the only load that waits for the predecessor
+        pdl_wait();
+        if (lane == 0) mbar_expect_tx(attn_full, (uint32_t)(nkb_A * DL_B_BYTES));
         __syncwarp();
+        if (lane < nkb_A) tma_load_2d(xa_s + lane * DL_B_BYTES, &tmAttn, lane * 64, row0, attn_full);
       }
-      it += nB * nkb_d;
-      if (lane == 0) dl_mark(a.dbg, 0, 2);
-      // ---- phase C: FFN-down rows [64 crank, +64) over the whole K = d_inner; H rows come from all CTAs of the cluster
-      for (int r = 0; r < nkb_C; r += DL_STAGES) {
-        const int kb = r + lane;
-        const bool on = act_lane && kb < nkb_C;
-        if (on) wload(it + kb, &tmW2, kb, 64 * crank, 1, DL_B_BYTES);
-        if (r == 0) {
-          if (lane == 0) dl_mark(a.dbg, 0, 3);
-          __syncwarp();
-          dl_wait();                                                   // #1
-          dl_arrive();                                                 // #2
-          dl_wait();                                                   // #2: every CTA's slice of H is in global memory
-          if (lane == 0) dl_mark(a.dbg, 0, 4);
-        }
-        if (on) aload(it + kb, &tmH, kb);
-        __syncwarp();
-      }
-      it += nkb_C;
-      if (lane == 0) dl_mark(a.dbg, 0, 5);
-      dl_arrive();                                                     // #3
-    }
-    if (next) {
-      // ---- phase D: the next layer's q|k|v features [fD crank, +fD), tiles interleaved (128-feature tiles first, then 64)
-      for (int r = 0; r < nD * nkb_d; r += DL_STAGES) {
-        const int j = r + lane;
-        if (act_lane && j < nD * nkb_d) {
-          const int kb = j / nD, t = j % nD;
-          if (t < nD128) wload(it + j, &tmWq, kb, fD * crank + 128 * t, 2, 0);
-          else wload(it + j, &tmWq, kb, fD * crank + 128 * nD128 + 64 * (t - nD128), 1, 0);
-        }
-        __syncwarp();
-      }
-      it += nD * nkb_d;
+      __syncwarp();
     }
     if (lane == 0) dl_mark(a.dbg, 0, 6);
-    __syncwarp();
-    if (body) dl_wait();                                               // #3
+    if (body) {                                          // whatever barrier duty is left (short launches)
+      if (bar_state == 0) { dl_arrive(); bar_state = 1; }
+      if (bar_state == 1) { dl_wait(); dl_arrive(); bar_state = 2; }
+      if (bar_state == 2) { dl_wait(); dl_arrive(); bar_state = 3; }
+      dl_wait();
+    }
   } else if (warp <= DL_MMAW) {
     // ================================================================== tcgen05.mma issuers (warp w: stage uses i with i % DL_MMAW == w - 1)
-    // ONE lane runs the whole issue loop with as few scalar instructions per MMA as possible: at N = 32 the tensor core retires an
-    // MMA every 64 cycles (scripts/probes/probe_mma_rate.cu: 63 cycles for any N <= 128), so the issue thread is the bottleneck.
+    // Lanes 0-3 issue the four 16-wide K steps of a k-block at once, each into its own accumulator chain, and each commits its own MMA
+    // (tcgen05.commit tracks the issuing THREAD; the stage's `empty` barrier counts 4 arrivals).  A tensor-core MMA retires every ~63
+    // cycles whatever N <= 128 is (scripts/probes/probe_mma_rate.cu), so the scalar issue work has to be spread out.
     int it = 0;
     const int mine = warp - 1;
-    const uint32_t xa_addr = smem_u32(xa_s), tiles_addr = smem_u32(tiles);
+    const uint32_t xa_addr = smem_u32(xa_s), hs_addr = smem_u32(hs_s), tiles_addr = smem_u32(tiles);
     constexpr uint64_t DHI = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-    // k-block `kb` of a tile whose partial accumulators start at column `col`: MMA k goes to chain (kb & kbx) * 4 + k, where
-    // kbx + 1 = k-blocks that rotate through the tile's chains (DL_NCHAIN / 4 / tiles of the phase): stage uses that different
-    // warps issue concurrently never share an accumulator
-    auto kblock = [&](int i, uint32_t col, uint32_t idesc, uint32_t b_addr, int kb, int kbx) {   // b_addr == 0: the stage's activation tile
+    // k-block `kb` of a tile whose 4 (or, kbx = 1, 8) partial accumulators start at column `col`
+    auto kblock = [&](int i, uint32_t col, uint32_t idesc, uint32_t b_addr, int kb, int kbx) {
       if ((i & (DL_MMAW - 1)) != mine) return;
-      const int s = i & (DL_STAGES - 1);
+      const int s = i % DL_STAGES;
       dl_spin(&full[s], (uint32_t)(i / DL_STAGES) & 1u);
       tc_fence_after();
-      // lanes 0-3 issue the four 16-wide K steps of the k-block at once, each into its own accumulator chain, and each commits
-      // its own MMA to the stage's `empty` barrier (tcgen05.commit tracks the issuing THREAD; the barrier counts 4 arrivals)
       const uint32_t a_addr = tiles_addr + s * DL_STAGE + lane * 32;
-      const uint32_t b = (b_addr ? b_addr : tiles_addr + s * DL_STAGE + DL_A_BYTES) + lane * 32;
       const uint32_t d = tmem_base + col + (uint32_t)((((kb & kbx) << 2) + lane) * DL_CHAIN);
-      umma_bf16(d, DHI | (uint64_t)((a_addr & 0x3FFFFu) >> 4), DHI | (uint64_t)((b & 0x3FFFFu) >> 4), idesc, kb > kbx ? 1u : 0u);
+      umma_bf16(d, DHI | (uint64_t)((a_addr & 0x3FFFFu) >> 4), DHI | (uint64_t)(((b_addr + lane * 32) & 0x3FFFFu) >> 4), idesc, kb > kbx ? 1u : 0u);
       umma_commit(&empty[s]);
     };
     constexpr uint32_t ID64 = dl_idesc(64, DL_ROWS), ID128 = dl_idesc(128, DL_ROWS);
-    static_assert((DL_STAGES & (DL_STAGES - 1)) == 0, "stage ring must be a power of two");
     if (lane == 0 && mine == 0) dl_mark(a.dbg, 1, 0);
     if (body) {
       if (lane < 4) {
-        for (int kb = 0; kb < nkb_A; kb++) kblock(it++, 0, ID64, 0, kb, DL_NCHAIN / 4 - 1);
+        dl_spin(attn_full, 0);
+        tc_fence_after();
+        for (int kb = 0; kb < nkb_A; kb++) kblock(it++, 0, ID64, xa_addr + kb * DL_B_BYTES, kb, 1);       // 8 chains (alternating k-blocks)
         dl_mark(a.dbg, 1, 1);
         umma_commit(&tmem_full[0]);
       }
       __syncwarp();
       dl_arrive();                                                     // #1
       if (lane < 4) {
-        dl_spin(&xa_ready[0], 0);                                      // LayerNorm 1 rows are in shared memory
+        dl_spin(&xa_ready[0], 0);                                      // LayerNorm 1 rows are in XA
         tc_fence_after();
         dl_mark(a.dbg, 1, 2);
         for (int kb = 0; kb < nkb_d; kb++)
-          for (int t = 0; t < nB; t++) kblock(it++, (uint32_t)(t * accB * DL_CHAIN), ID128, xa_addr + kb * DL_B_BYTES, kb, accB / 4 - 1);
+          for (int t = 0; t < nB; t++) kblock(it++, (uint32_t)(t * 4 * DL_CHAIN), ID128, xa_addr + kb * DL_B_BYTES, kb, 0);
         dl_mark(a.dbg, 1, 3);
         umma_commit(&tmem_full[1]);
-      }
-      __syncwarp();
-      dl_wait();                                                       // #1
-      dl_arrive();                                                     // #2
-      if (lane < 4) {
-        for (int kb = 0; kb < nkb_C; kb++) kblock(it++, 0, ID64, 0, kb, DL_NCHAIN / 4 - 1);
+        dl_spin(hs_ready, 0);                                          // this CTA's GeLU slice is in HS (the B accumulators have been read)
+        tc_fence_after();
+        for (int kb = 0; kb < DL_HS_KB; kb++)
+          for (int t = 0; t < nC; t++) kblock(it++, (uint32_t)(t * 4 * DL_CHAIN), ID128, hs_addr + kb * DL_B_BYTES, kb, 0);
         dl_mark(a.dbg, 1, 5);
         umma_commit(&tmem_full[2]);
       }
       __syncwarp();
-      dl_wait();                                                       // #2
+      dl_wait();                                                       // #1
+      dl_arrive();                                                     // #2
+      dl_wait();
       dl_arrive();                                                     // #3
+      dl_wait();                                                       // every CTA's LayerNorm-2 rows have landed in this XA
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // remote generic-proxy stores -> this CTA's tensor-core reads
     }
     if (next && lane < 4) {
-      dl_spin(&xa_ready[1], 0);
+      if (!body) dl_spin(&xa_ready[1], 0);
       tc_fence_after();
       dl_mark(a.dbg, 1, 6);
       for (int kb = 0; kb < nkb_d; kb++) {
-        for (int t = 0; t < nD128; t++) kblock(it++, (uint32_t)(t * accD * DL_CHAIN), ID128, xa_addr + kb * DL_B_BYTES, kb, accD / 4 - 1);
-        for (int t = 0; t < nD64; t++) kblock(it++, (uint32_t)((nD128 + t) * accD * DL_CHAIN), ID64, xa_addr + kb * DL_B_BYTES, kb, accD / 4 - 1);
+        kblock(it++, 0, ID128, xa_addr + kb * DL_B_BYTES, kb, 0);
+        kblock(it++, (uint32_t)(4 * DL_CHAIN), ID64, xa_addr + kb * DL_B_BYTES, kb, 0);
       }
       dl_mark(a.dbg, 1, 7);
       umma_commit(&tmem_full[3]);
     }
     __syncwarp();
-    if (body) dl_wait();                                               // #3
   } else {
     // ================================================================== epilogues + LayerNorm (256 threads)
     const int q = warp & 3;                               // TMEM lane quarter this warp may read (warp % 4)
-    const int half = (warp - 1 - DL_MMAW) >> 2;                     // which 16 of the 32 rows (accumulator columns) this warp unloads
-    const int te = threadIdx.x - DL_EPI0, r = te >> 3, t = te & 7;   // LayerNorm role: row r, 16-byte chunk t of every k-block
+    const int half = (warp - 1 - DL_MMAW) >> 2;           // which 16 of the 32 rows (accumulator columns) this warp unloads
+    const int te = threadIdx.x - DL_EPI0;
+    const int r = te >> 3, t = te & 7;                    // LayerNorm-1 role: row r of the cluster's 32, 16-byte chunk t of every k-block
+    const int lr = te >> 6, lc = te & 63;                 // LayerNorm-2 role: own row lr (cluster row 4 crank + lr), columns [8 lc, +8)
     const int row = row0 + r;
     const bool valid = row < a.B;
     const int erow0 = row0 + 16 * half;                   // first row of this warp's epilogue columns
@@ -349,13 +339,11 @@ decode_layer_kernel(const __grid_constant__ CUtensorMap tmAttn, const __grid_con
     if (body) {                                           // LayerNorm parameters never change: stage them before the dependency wait
       const float* src[4] = {a.ln1w, a.ln1b, a.ln2w, a.ln2b};
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        *(float2*)(ln_s + i * DL_D + 2 * te) = __ldg((const float2*)(src[i] + 2 * te));
-      }
+      for (int i = 0; i < 4; i++) *(float2*)(ln_s + i * DL_D + 2 * te) = __ldg((const float2*)(src[i] + 2 * te));
       asm volatile("bar.sync 1, 256;" ::: "memory");     // the 256 epilogue threads only
     }
     if (mk) dl_mark(a.dbg, 2, 0);
-    pdl_wait();                                           // the residual stream and the attention output come from the predecessors
+    pdl_wait();                                           // the residual stream comes from the predecessors
     if (mk) dl_mark(a.dbg, 2, 1);
 #pragma unroll
     for (int kb = 0; kb < 8; kb++) {
@@ -370,7 +358,7 @@ decode_layer_kernel(const __grid_constant__ CUtensorMap tmAttn, const __grid_con
       mbar_wait(&tmem_full[0], 0);
       tc_fence_after();
       if (mk) dl_mark(a.dbg, 2, 2);
-      dl_gather(tq, 4 * nkb_A < DL_NCHAIN ? 4 * nkb_A : DL_NCHAIN, acc);
+      dl_gather(tq, 4 * nkb_A < 8 ? 4 * nkb_A : 8, acc);
       if (lane < 16) {                                    // M = 64: feature 16 q + lane sits in TMEM lane 32 q + lane
         const int f = 64 * crank + 16 * q + lane;
         const float bias = a.bo ? __ldg(a.bo + f) : 0.f;
@@ -392,78 +380,125 @@ decode_layer_kernel(const __grid_constant__ CUtensorMap tmAttn, const __grid_con
       }
       dl_layernorm(z, ln_s, ln_s + DL_D, t);
       dl_store_xa(xa_s, z, r, t);
+      if ((r >> 2) == crank) {                            // a row this CTA owns: keep the fp32 result as the residual of LayerNorm 2
+        float* dst = x1_s + (r & 3) * DL_D + 8 * t;
+#pragma unroll
+        for (int kb = 0; kb < 8; kb++) {
+          *(float4*)(dst + 64 * kb) = make_float4(z[8 * kb], z[8 * kb + 1], z[8 * kb + 2], z[8 * kb + 3]);
+          *(float4*)(dst + 64 * kb + 4) = make_float4(z[8 * kb + 4], z[8 * kb + 5], z[8 * kb + 6], z[8 * kb + 7]);
+        }
+      }
       dl_fence_async_smem();
       mbar_arrive(&xa_ready[0]);
       if (mk) dl_mark(a.dbg, 2, 5);
-      // ---- FFN-up slice: + b1, tanh-GeLU, bf16 -> scratch H[row][feature]
+      // ---- FFN-up slice: + b1, tanh-GeLU, bf16 -> HS (this CTA's K slice of the FFN-down GEMM), K-major 128B-swizzled k-blocks
       mbar_wait(&tmem_full[1], 0);
       tc_fence_after();
       if (mk) dl_mark(a.dbg, 2, 6);
-      for (int tt = 0; tt < nB; tt++) {
-        dl_gather(tq + tt * accB * DL_CHAIN, nkb_d * 4 < accB ? nkb_d * 4 : accB, acc);
-        const int f = fB * crank + 128 * tt + 32 * q + lane;
-        const float bias = a.b1 ? __ldg(a.b1 + f) : 0.f;
 #pragma unroll
-        for (int rr = 0; rr < 16; rr++) a.H[(size_t)(erow0 + rr) * a.di + f] = __float2bfloat16_rn(dl_gelu(acc[rr] + bias));
+      for (int tt = 0; tt < nB; tt++) {
+        dl_gather(tq + tt * 4 * DL_CHAIN, 4, acc);
+        const int fl = 128 * tt + 32 * q + lane;          // local feature = K index of the next GEMM
+        const float bias = a.b1 ? __ldg(a.b1 + fB * crank + fl) : 0.f;
+        uint8_t* base = hs_s + (fl >> 6) * DL_B_BYTES + (fl & 7) * 2;
+        const int ch = (fl & 63) >> 3;
+#pragma unroll
+        for (int rr = 0; rr < 16; rr++) {
+          const int rw = 16 * half + rr;
+          *(bf16*)(base + rw * 128 + ((ch ^ (rw & 7)) << 4)) = __float2bfloat16_rn(dl_gelu(acc[rr] + bias));
+        }
       }
       tc_fence_before();
-      dl_fence_async_all();                               // H is read by the TMA engine of the peer CTAs
-      __syncwarp();
+      dl_fence_async_smem();
+      mbar_arrive(hs_ready);
       if (mk) dl_mark(a.dbg, 2, 7);
-      dl_arrive();                                                     // #2
-      dl_wait();
-      if (mk) dl_mark(a.dbg, 2, 8);
-      // ---- FFN-down slice -> scratch P[row][feature] (every LayerNorm-1 read of P happened before barrier #2)
+      // ---- FFN-down partial sums over this CTA's K slice -> scratch PP[crank][row][feature]
       mbar_wait(&tmem_full[2], 0);
       tc_fence_after();
       if (mk) dl_mark(a.dbg, 2, 9);
-      dl_gather(tq, 4 * nkb_C < DL_NCHAIN ? 4 * nkb_C : DL_NCHAIN, acc);
-      if (lane < 16) {
-        const int f = 64 * crank + 16 * q + lane;
-        const float bias = a.b2 ? __ldg(a.b2 + f) : 0.f;
+      float* pp = a.PP + (size_t)crank * a.pp_stride;
 #pragma unroll
-        for (int rr = 0; rr < 16; rr++) a.P[(size_t)(erow0 + rr) * DL_D + f] = acc[rr] + bias;
+      for (int tt = 0; tt < nC; tt++) {
+        dl_gather(tq + tt * 4 * DL_CHAIN, 4, acc);
+        const int f = 128 * tt + 32 * q + lane;
+#pragma unroll
+        for (int rr = 0; rr < 16; rr++) pp[(size_t)(erow0 + rr) * DL_D + f] = acc[rr];
       }
       tc_fence_before();
       __syncwarp();
       if (mk) dl_mark(a.dbg, 2, 10);
-      dl_arrive();                                                     // #3
+      dl_arrive();                                                     // #2: partial sums published
       dl_wait();
       if (mk) dl_mark(a.dbg, 2, 11);
-      // ---- LayerNorm 2
+      // ---- LayerNorm 2 of the 4 rows this CTA owns: x1 + b2 + the 8 partial sums, 64 threads per row, 8 columns each
+      {
+        const int crow = DL_OWN * crank + lr;             // row inside the cluster
+        const int grow = row0 + crow;
+        const int c0 = 8 * lc;
+        float v[8];
+        const float4 xa0 = *(const float4*)(x1_s + lr * DL_D + c0), xa1 = *(const float4*)(x1_s + lr * DL_D + c0 + 4);
+        v[0] = xa0.x; v[1] = xa0.y; v[2] = xa0.z; v[3] = xa0.w; v[4] = xa1.x; v[5] = xa1.y; v[6] = xa1.z; v[7] = xa1.w;
+        if (a.b2) {
+          const float4 b0 = __ldg((const float4*)(a.b2 + c0)), b1 = __ldg((const float4*)(a.b2 + c0 + 4));
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
 #pragma unroll
-      for (int kb = 0; kb < 8; kb++) {
-        const float4 p0 = ldcg4(a.P + (size_t)row * DL_D + 64 * kb + 8 * t), p1 = ldcg4(a.P + (size_t)row * DL_D + 64 * kb + 8 * t + 4);
-        float* v = z + 8 * kb;
-        v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w; v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
-      }
-      dl_layernorm(z, ln_s + 2 * DL_D, ln_s + 3 * DL_D, t);
-      if (crank == 0 && valid) {                          // the residual stream of the next layer (one writer per row)
+        for (int p = 0; p < DL_CLUSTER; p++) {
+          const float* src = a.PP + (size_t)p * a.pp_stride + (size_t)grow * DL_D + c0;
+          const float4 p0 = ldcg4(src), p1 = ldcg4(src + 4);
+          v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w; v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+        }
+        // row statistics: 64 threads = 2 warps of the row; two-pass like every LayerNorm of the path
+        float* red = (float*)(tmem_holder + 4);           // 16 floats of scratch behind the barriers
+        float s1 = 0.f;
 #pragma unroll
-        for (int kb = 0; kb < 8; kb++) {
-          const float* v = z + 8 * kb;
-          float* dst = a.x32 + (size_t)row * DL_D + 64 * kb + 8 * t;
+        for (int i = 0; i < 8; i++) s1 += v[i];
+        s1 = warp_sum(s1);
+        if (lane == 0) red[(te >> 5)] = s1;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float mean = (red[2 * lr] + red[2 * lr + 1]) * (1.f / DL_D);
+        float s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const float c = v[i] - mean; s2 += c * c; }
+        s2 = warp_sum(s2);
+        if (lane == 0) red[8 + (te >> 5)] = s2;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float rstd = rsqrtf((red[8 + 2 * lr] + red[8 + 2 * lr + 1]) * (1.f / DL_D) + 1e-5f);
+        const float* w = ln_s + 2 * DL_D + c0;
+        const float* bb = ln_s + 3 * DL_D + c0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = (v[i] - mean) * rstd * w[i] + bb[i];
+        const uint4 packed = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        if (grow < a.B) {                                 // the residual stream of the next layer: one writer per row
+          float* dst = a.x32 + (size_t)grow * DL_D + c0;
           *(float4*)dst = make_float4(v[0], v[1], v[2], v[3]);
           *(float4*)(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-          if (a.xa_out)
-            *(uint4*)(a.xa_out + (size_t)row * DL_D + 64 * kb + 8 * t) =
-                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          if (a.xa_out) *(uint4*)(a.xa_out + (size_t)grow * DL_D + c0) = packed;
+        }
+        if (next) {                                       // the bf16 row chunk into the XA of all 8 CTAs (k-block lc / 8, chunk lc % 8, swizzled)
+          const uint32_t off = smem_u32(xa_s) + (uint32_t)((lc >> 3) * DL_B_BYTES + crow * 128 + (((lc & 7) ^ (crow & 7)) << 4));
+#pragma unroll
+          for (int p = 0; p < DL_CLUSTER; p++) dl_st_cluster_v4(dl_mapa(off, (uint32_t)p), packed);
         }
       }
-    }
-    if (next) {
-      dl_store_xa(xa_s, z, r, t);                         // body: LayerNorm 2 rows; first call of a step: the embedded rows
+      if (mk) dl_mark(a.dbg, 2, 12);
+      dl_arrive();                                                     // #3: the broadcast rows are published (release)
+      dl_wait();
+    } else if (next) {
+      dl_store_xa(xa_s, z, r, t);                         // first launch of a step: the embedded rows, every CTA for itself
       dl_fence_async_smem();
       mbar_arrive(&xa_ready[1]);
-      if (mk) dl_mark(a.dbg, 2, 12);
+    }
+    if (next) {
       // ---- next layer's q|k|v slice -> fp32 [row][3 HD] (the input of the decode-attention kernel)
       mbar_wait(&tmem_full[3], 0);
       tc_fence_after();
       if (mk) dl_mark(a.dbg, 2, 13);
+#pragma unroll
       for (int tt = 0; tt < nD; tt++) {
-        dl_gather(tq + tt * accD * DL_CHAIN, accD, acc);
-        const bool h64 = tt >= nD128;
-        const int f = fD * crank + (h64 ? 128 * nD128 + 64 * (tt - nD128) + 16 * q + lane : 128 * tt + 32 * q + lane);
+        dl_gather(tq + tt * 4 * DL_CHAIN, 4, acc);
+        const bool h64 = tt == 1;
+        const int f = fD * crank + (h64 ? 128 + 16 * q + lane : 32 * q + lane);
         if (!h64 || lane < 16) {
           const float bias = a.bq ? __ldg(a.bq + f) : 0.f;
 #pragma unroll
@@ -479,20 +514,45 @@ decode_layer_kernel(const __grid_constant__ CUtensorMap tmAttn, const __grid_con
   if (warp == 1 + DL_MMAW) tmem_dealloc<DL_TMEM_COLS>(tmem_base);
 }
 
+__global__ void __launch_bounds__(DL_THREADS, 1)
+decode_layer_kernel(const __grid_constant__ CUtensorMap tmAttn, const __grid_constant__ CUtensorMap tmWo,
+                    const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                    const __grid_constant__ CUtensorMap tmWq, const DecodeLayerArgs a) {
+  extern __shared__ __align__(1024) uint8_t dyn_smem[];
+  decode_layer_body(tmAttn, tmWo, tmW1, tmW2, tmWq, a, (int)blockIdx.x / DL_CLUSTER, dyn_smem);
+}
+
+// Dual-role launch: the first `n_fused` clusters run the fused layer step of ONE half of the streams, the other clusters are the
+// persistent CTAs of the decode attention of the OTHER half (a different layer phase of the software pipeline over the two halves,
+// model.cu).  The latency-bound layer step occupies 32 SMs and hardly any bandwidth; the HBM-bound attention gets the rest of the
+// machine; one launch instead of two streams, so the co-residency does not depend on the scheduler.
+constexpr int DUAL_G = 2;
+__global__ void __launch_bounds__(DL_THREADS, 1)
+decode_dual_kernel(const __grid_constant__ CUtensorMap tmAttn, const __grid_constant__ CUtensorMap tmWo,
+                   const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                   const __grid_constant__ CUtensorMap tmWq, const DecodeLayerArgs fa, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmR, const AttnDecodeArgs aa, int n_stages,
+                   int b0, int n_fused) {
+  extern __shared__ __align__(1024) uint8_t dyn_smem[];
+  const int cluster = (int)blockIdx.x / DL_CLUSTER;
+  if (cluster < n_fused) {
+    decode_layer_body(tmAttn, tmWo, tmW1, tmW2, tmWq, fa, cluster, dyn_smem);
+  } else if (threadIdx.x < (4 * DUAL_G + 1) * 32) {
+    attn_decode2_body<DUAL_G>(tmK, tmV, tmR, aa, n_stages, b0, (int)blockIdx.x - n_fused * DL_CLUSTER, (int)gridDim.x - n_fused * DL_CLUSTER,
+                              dyn_smem);
+  }
+}
+
 }  // namespace
 
 bool decode_layer_supported(int d, int HD, int di, int n3) {
-  if (d != DL_D || HD % 64 || HD <= 0) return false;
-  if (di % (DL_CLUSTER * 128)) return false;
-  const int nB = di / DL_CLUSTER / 128, nD = (n3 % (DL_CLUSTER * 64)) ? 0 : (n3 / DL_CLUSTER + 127) / 128;
-  // two tiles per multi-tile phase (d_inner 2048, 3 * HD = 1536): each tile owns 4 accumulator chains and one of the two
-  // MMA-issuing warps; other geometries take the unfused launches
-  if (nB != 2 || nD != 2) return false;
-  return true;
+  // the C2 geometry class: d_model 512, K of the out-projection a multiple of 64 (at most 8 k-blocks: XA holds the attention rows),
+  // d_inner 2048 (256 FFN-up features = 4 k-blocks per CTA), 3 HD = 1536 (128 + 64 q|k|v features per CTA); others: unfused launches
+  return d == DL_D && HD % 64 == 0 && HD >= 64 && HD <= DL_D && di == DL_CLUSTER * 64 * DL_HS_KB && n3 == DL_CLUSTER * 192;
 }
 
-int decode_layer(const TensorMap2D* tmAttn, const TensorMap2D* tmH, const TensorMap2D* tmWo, const TensorMap2D* tmW1,
-                 const TensorMap2D* tmW2, const TensorMap2D* tmWq, const DecodeLayerArgs& a, cudaStream_t st) {
+int decode_layer(const TensorMap2D* tmAttn, const TensorMap2D* tmWo, const TensorMap2D* tmW1, const TensorMap2D* tmW2,
+                 const TensorMap2D* tmWq, const DecodeLayerArgs& a, cudaStream_t st) {
   DMG_CHECK(decode_layer_supported(a.d, a.HD, a.di, a.n3), "decode_layer: geometry d=%d HD=%d di=%d n3=%d not supported", a.d, a.HD, a.di, a.n3);
   static bool configured = false;
   if (!configured) {
@@ -502,8 +562,53 @@ int decode_layer(const TensorMap2D* tmAttn, const TensorMap2D* tmH, const Tensor
   const int clusters = (a.B - a.row_base + DL_ROWS - 1) / DL_ROWS;
   if (clusters <= 0) return 0;
   return launch_k(decode_layer_kernel, dim3(clusters * DL_CLUSTER), dim3(DL_THREADS), (size_t)DL_SMEM, st, DL_CLUSTER,
-                  *(const CUtensorMap*)tmAttn->bytes, *(const CUtensorMap*)tmH->bytes, *(const CUtensorMap*)tmWo->bytes,
-                  *(const CUtensorMap*)tmW1->bytes, *(const CUtensorMap*)tmW2->bytes, *(const CUtensorMap*)tmWq->bytes, a);
+                  *(const CUtensorMap*)tmAttn->bytes, *(const CUtensorMap*)tmWo->bytes, *(const CUtensorMap*)tmW1->bytes,
+                  *(const CUtensorMap*)tmW2->bytes, *(const CUtensorMap*)tmWq->bytes, a);
+}
+
+
+bool decode_dual_supported(int M) { return d2_pick_groups(M) == DUAL_G && d2_pick_stages(M, DUAL_G) >= 2; }
+
+int decode_dual_max_clusters() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(DL_CLUSTER * 32); cfg.blockDim = dim3(DL_THREADS); cfg.dynamicSmemBytes = 227 * 1024;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = DL_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaFuncSetAttribute(decode_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+      cudaOccupancyMaxActiveClusters(&n, decode_dual_kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  cached = n;
+  return cached;
+}
+
+// fa: the fused layer step over rows [fa.row_base, fa.B); aa / b0: the decode attention of the other half (chunk-local pointers, ring
+// offset b0), on `attn_clusters` clusters of 8 persistent CTAs
+int decode_dual(const TensorMap2D* tmAttn, const TensorMap2D* tmWo, const TensorMap2D* tmW1, const TensorMap2D* tmW2, const TensorMap2D* tmWq,
+                const DecodeLayerArgs& fa, const TensorMap2D* tmK, const TensorMap2D* tmV, const TensorMap2D* tmR, const AttnDecodeArgs& aa,
+                int b0, int attn_clusters, cudaStream_t st) {
+  DMG_CHECK(decode_layer_supported(fa.d, fa.HD, fa.di, fa.n3) && decode_dual_supported(aa.M), "decode_dual: geometry not supported");
+  DMG_CHECK(aa.Dcap >= aa.M + 1, "decode_dual: rel-pos cache too small (%d < %d)", aa.Dcap, aa.M + 1);
+  const int ns = d2_pick_stages(aa.M, DUAL_G);
+  const D2Layout L = d2_layout(aa.M, DUAL_G, ns);
+  const int smem = L.total > DL_SMEM ? L.total : DL_SMEM;
+  static int configured = 0;
+  if (configured < smem) {
+    DMG_CUDA_OK(cudaFuncSetAttribute(decode_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  const int n_fused = (fa.B - fa.row_base + DL_ROWS - 1) / DL_ROWS;
+  DMG_CHECK(n_fused >= 1 && attn_clusters >= 1, "decode_dual: empty role");
+  return launch_k(decode_dual_kernel, dim3((n_fused + attn_clusters) * DL_CLUSTER), dim3(DL_THREADS), (size_t)smem, st, DL_CLUSTER,
+                  *(const CUtensorMap*)tmAttn->bytes, *(const CUtensorMap*)tmWo->bytes, *(const CUtensorMap*)tmW1->bytes,
+                  *(const CUtensorMap*)tmW2->bytes, *(const CUtensorMap*)tmWq->bytes, fa, *(const CUtensorMap*)tmK->bytes,
+                  *(const CUtensorMap*)tmV->bytes, *(const CUtensorMap*)tmR->bytes, aa, ns, b0, n_fused);
 }
 
 }  // namespace dmg

@@ -38,8 +38,9 @@ struct DecodeLayerArgs {
   float* x32;            // [rows, d] fp32 residual stream, in / out
   bf16* xa_out;          // [rows, d] bf16 copy of the final rows (input of the head GEMM) or NULL
   float* qkv;            // [rows, n3] fp32: the next layer's q|k|v (mode & 2)
-  float* P;              // scratch [rows padded to DL_ROWS, d] fp32: projection / FFN-down slices before their LayerNorm
-  bf16* H;               // scratch [rows padded to DL_ROWS, di] bf16: GeLU(FFN-up)
+  float* P;              // scratch [rows padded to DL_ROWS, d] fp32: out-projection slices before LayerNorm 1
+  float* PP;             // scratch [DL_CLUSTER][pp_stride] fp32: the FFN-down partial sums of the 8 K slices, [row, d] each
+  long long pp_stride;   // elements between two slabs of PP
   const float *bo, *b1, *b2, *bq;            // biases (any may be NULL)
   const float *ln1w, *ln1b, *ln2w, *ln2b;
   int row_base, B;       // rows [row_base, B) of the buffers belong to this launch (a stream lane of the step)
@@ -48,9 +49,18 @@ struct DecodeLayerArgs {
   unsigned long long* dbg = nullptr;   // optional timeline of CTA 0 (48 slots), see decode_layer.cu dl_mark
 };
 bool decode_layer_supported(int d, int HD, int di, int n3);
-// tmAttn / tmH: DL_ROWS-row boxes over the attention output [rows, HD] and the H scratch; tmWo, tmW1, tmW2, tmWq: 64-row boxes
-int decode_layer(const TensorMap2D* tmAttn, const TensorMap2D* tmH, const TensorMap2D* tmWo, const TensorMap2D* tmW1,
-                 const TensorMap2D* tmW2, const TensorMap2D* tmWq, const DecodeLayerArgs& a, cudaStream_t st);
+// tmAttn: DL_ROWS-row boxes over the attention output [rows, HD]; tmWo, tmW1, tmW2, tmWq: 64-row boxes
+int decode_layer(const TensorMap2D* tmAttn, const TensorMap2D* tmWo, const TensorMap2D* tmW1, const TensorMap2D* tmW2,
+                 const TensorMap2D* tmWq, const DecodeLayerArgs& a, cudaStream_t st);
+
+struct AttnDecodeArgs;
+// Dual-role launch (decode_layer.cu): the fused layer step of one half of the streams and the decode attention of the other half in
+// ONE kernel (software pipeline over two halves of the batch, model.cu).
+bool decode_dual_supported(int M);
+int decode_dual_max_clusters();      // clusters of 8 CTAs of that kernel that can be co-resident (15 on a B200)
+int decode_dual(const TensorMap2D* tmAttn, const TensorMap2D* tmWo, const TensorMap2D* tmW1, const TensorMap2D* tmW2, const TensorMap2D* tmWq,
+                const DecodeLayerArgs& fa, const TensorMap2D* tmK, const TensorMap2D* tmV, const TensorMap2D* tmR, const AttnDecodeArgs& aa,
+                int b0, int attn_clusters, cudaStream_t st);
 
 // ------------------------------------------------------------------ elementwise / small kernels
 // x32[row] = emb[id] (+ beat[pos%32] + bar[min(pos/32 % 1024, 1023)]); xa = T(x32)

@@ -80,36 +80,83 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
   const bool flash = m->is_bf16 && m->use_tc && T_len > 1 && (bert || (m->mem_count == 0 && win == 1 && k == 1)) &&
                      m->Dcap >= T_len && !(m->kflags & DMG_KF_NO_FLASH);
   // one-token step, product path: per layer ONE decode-attention launch + ONE fused layer launch (decode_layer.cu)
-  const bool fused = fast_decode && m->fused_decode && !c.keep_hidden && m->layers[0].wqkv.has_tm;
+  const bool fused = fast_decode && m->fused_decode && !c.keep_hidden && m->layers[0].wqkv.has_tm && rows <= m->dl_rows;
   if (fused) {
-    // Stream lanes (groups of streams on parallel CUDA streams, the attention of one group over the fused layer kernel of
-    // another) were measured on top of this path and rejected: profiles/README.md, round 2.
-    DecodeLayerArgs da;
-    da.x32 = m->x32; da.qkv = m->qkv; da.P = m->dl_P; da.H = m->dl_H;
-    da.row_base = 0; da.B = nb; da.d = d; da.HD = HD; da.di = c.d_inner; da.n3 = 3 * HD;
-    for (int l = 0; l <= c.n_layers; l++) {
+    // helpers: the fused layer step of layer l over rows [r0, r1) (l == 0 ... L: body of layer l-1, q|k|v of layer l) and the
+    // decode attention of layer l over the same kind of row range
+    auto layer_args = [&](int l, int r0, int r1, LayerW** Lb_out, LayerW** Ln_out) {
       const bool body = l > 0, next = l < c.n_layers;
       LayerW& Lb = m->layers[body ? l - 1 : 0];        // the layer whose body runs
       LayerW& Ln = m->layers[next ? l : 0];            // the layer whose q|k|v are produced
-      if (body) {
-        AttnDecodeArgs a;
-        a.qkv = m->qkv;
-        a.kring = (bf16*)Lb.kring + (size_t)b0 * c.n_heads * M * 64;
-        a.vring = (bf16*)Lb.vring + (size_t)b0 * c.n_heads * M * 64;
-        a.rd = (const bf16*)Lb.rd;
-        a.u = m->u; a.v = m->v;
-        a.out = (bf16*)m->attn;
-        a.dev_state = m->dev_state;
-        a.B = nb; a.H = c.n_heads; a.M = M; a.Dcap = m->Dcap;
-        a.scale = 1.f / sqrtf((float)c.d_head);
-        if (attn_decode2(&Lb.tmK, &Lb.tmV, &Lb.tmR, a, b0, m->num_sms, st)) return -1;
-      }
+      DecodeLayerArgs da;
+      da.x32 = m->x32; da.qkv = m->qkv; da.P = m->dl_P; da.PP = m->dl_PP; da.pp_stride = m->dl_pp_stride;
+      da.row_base = r0; da.B = r1; da.d = d; da.HD = HD; da.di = c.d_inner; da.n3 = 3 * HD;
       da.mode = (body ? 1 : 0) | (next ? 2 : 0);
-      da.dbg = l == c.n_layers / 2 ? m->dl_dbg : nullptr;      // timeline probe: one mid-stack launch
+      da.dbg = (l == c.n_layers / 2 && r0 == 0) ? m->dl_dbg : nullptr;      // timeline probe: one mid-stack launch
       da.xa_out = next ? nullptr : (bf16*)m->xa;
       da.bo = Lb.bo; da.b1 = Lb.b1; da.b2 = Lb.b2; da.ln1w = Lb.ln1w; da.ln1b = Lb.ln1b; da.ln2w = Lb.ln2w; da.ln2b = Lb.ln2b;
       da.bq = Ln.bqkv;
-      if (decode_layer(&m->tmAttn16, &m->tmH16, &Lb.wo.tm64, &Lb.w1.tm64, &Lb.w2.tm64, &Ln.wqkv.tm64, da, st)) return -1;
+      *Lb_out = &Lb; *Ln_out = &Ln;
+      return da;
+    };
+    auto attn_args = [&](int l, int r0, int r1) {
+      LayerW& La = m->layers[l];
+      AttnDecodeArgs a;
+      a.qkv = m->qkv + (size_t)r0 * 3 * HD;
+      a.kring = (bf16*)La.kring + (size_t)(b0 + r0) * c.n_heads * M * 64;
+      a.vring = (bf16*)La.vring + (size_t)(b0 + r0) * c.n_heads * M * 64;
+      a.rd = (const bf16*)La.rd;
+      a.u = m->u; a.v = m->v;
+      a.out = (bf16*)m->attn + (size_t)r0 * HD;
+      a.dev_state = m->dev_state;
+      a.B = r1 - r0; a.H = c.n_heads; a.M = M; a.Dcap = m->Dcap;
+      a.scale = 1.f / sqrtf((float)c.d_head);
+      return a;
+    };
+    auto fused_alone = [&](int l, int r0, int r1) -> int {
+      LayerW *Lb, *Ln;
+      const DecodeLayerArgs da = layer_args(l, r0, r1, &Lb, &Ln);
+      return decode_layer(&m->tmAttn16, &Lb->wo.tm64, &Lb->w1.tm64, &Lb->w2.tm64, &Ln->wqkv.tm64, da, st);
+    };
+    auto attn_alone = [&](int l, int r0, int r1) -> int {
+      LayerW& La = m->layers[l];
+      return attn_decode2(&La.tmK, &La.tmV, &La.tmR, attn_args(l, r0, r1), b0 + r0, m->num_sms, st);
+    };
+    // dual-role launch: fused step `lf` over rows [f0, f1) together with the attention of layer `la` over rows [a0, a1)
+    auto dual = [&](int lf, int f0, int f1, int la, int a0, int a1) -> int {
+      LayerW *Lb, *Ln;
+      const DecodeLayerArgs da = layer_args(lf, f0, f1, &Lb, &Ln);
+      LayerW& La = m->layers[la];
+      const int n_fused = (f1 - f0 + DL_ROWS - 1) / DL_ROWS;
+      int attn_clusters = m->dl_max_clusters - n_fused;
+      const long long items = (long long)(a1 - a0) * c.n_heads;
+      if ((long long)attn_clusters * DL_CLUSTER > items) attn_clusters = (int)((items + DL_CLUSTER - 1) / DL_CLUSTER);
+      return decode_dual(&m->tmAttn16, &Lb->wo.tm64, &Lb->w1.tm64, &Lb->w2.tm64, &Ln->wqkv.tm64, da, &La.tmK, &La.tmV, &La.tmR,
+                         attn_args(la, a0, a1), b0 + a0, attn_clusters, st);
+    };
+    const int L = c.n_layers;
+    const int groups = (nb + DL_ROWS - 1) / DL_ROWS;
+    const bool pipelined = m->dl_dual && groups >= 2 && (groups + 1) / 2 < m->dl_max_clusters;
+    if (!pipelined) {
+      // Stream lanes (groups of streams on parallel CUDA streams) were measured on top of this path and rejected (profiles/README.md).
+      for (int l = 0; l <= L; l++) {
+        if (l > 0 && attn_alone(l - 1, 0, nb)) return -1;
+        if (fused_alone(l, 0, nb)) return -1;
+      }
+    } else {
+      // Software pipeline over two halves X = [0, hx) and Y = [hx, nb) of the streams: while one half's attention streams its K/V
+      // rings (HBM-bound, wants bandwidth, not SMs), the other half runs its latency-bound fused layer step on 8 CTAs per 32 rows -
+      // in the SAME launch (decode_dual_kernel), so both really are resident together:
+      //   F_0(X+Y) | A_0(X) | A_0(Y)+F_1(X) | A_1(X)+F_1(Y) | A_1(Y)+F_2(X) | ... | A_{L-1}(Y)+F_L(X) | F_L(Y)
+      // (F_l = body of layer l-1 + q|k|v of layer l; A_l = attention of layer l).
+      const int hx = ((groups + 1) / 2) * DL_ROWS;
+      if (fused_alone(0, 0, nb)) return -1;
+      if (attn_alone(0, 0, hx)) return -1;
+      for (int l = 0; l < L; l++) {
+        if (dual(l + 1, 0, hx, l, hx, nb)) return -1;                       // A_l(Y) + F_{l+1}(X)
+        if (l + 1 < L) { if (dual(l + 1, hx, nb, l + 1, 0, hx)) return -1; }   // A_{l+1}(X) + F_{l+1}(Y)
+        else if (fused_alone(L, hx, nb)) return -1;
+      }
     }
   }
   for (int l = 0; l < c.n_layers && !fused; l++) {
@@ -343,7 +390,7 @@ int dmg_create(const dmg_config* cfg, int device, dmg_model** out) {
         {"DMG_NO_DECODE_KERNEL", DMG_KF_NO_DECODE_KERNEL}, {"DMG_NO_FLASH", DMG_KF_NO_FLASH}, {"DMG_NO_GRAPH", DMG_KF_NO_GRAPH},
         {"DMG_BERT_ATTN_MMA_SYNC", DMG_KF_BERT_MMA_SYNC}, {"DMG_BERT_TC_FP32_STRIP", DMG_KF_BERT_FP32_STRIP},
         {"DMG_NO_SPLITK", DMG_KF_NO_SPLITK}, {"DMG_NO_BIG_GEMM", DMG_KF_NO_BIG_GEMM}, {"DMG_GEMM_SIMT", DMG_KF_GEMM_SIMT},
-        {"DMG_NO_FUSED_DECODE", DMG_KF_NO_FUSED_DECODE}};
+        {"DMG_NO_FUSED_DECODE", DMG_KF_NO_FUSED_DECODE}, {"DMG_DUAL_DECODE", DMG_KF_DUAL_DECODE}};
     for (const auto& e : sw)
       if (getenv(e.env)) m->kflags |= e.flag;
   }
@@ -462,14 +509,17 @@ int dmg_create(const dmg_config* cfg, int device, dmg_model** out) {
       if (bufs[i] == nullptr || m->a_cols[i] % 64 != 0) continue;
       TRY(make_tmap_bf16(&m->tmA[i], bufs[i], m->a_cols[i], m->a_rows[i], m->a_cols[i], 128));
     }
-    // fused one-token layer step: the projection / FFN-down scratch is `proj`, the GeLU(FFN-up) scratch is `hbuf` (both unused
-    // by that path otherwise); 16-row boxes over the attention output and over H
+    // fused one-token layer step: the out-projection scratch is `proj` (unused by that path otherwise), the FFN-down partial sums
+    // get their own [8][rows, d] fp32 scratch; DL_ROWS-row boxes over the attention output
     if (!rc && !bert && c.mem_len > 0 && !(m->kflags & DMG_KF_NO_FUSED_DECODE) && decode_layer_supported(d, HD, c.d_inner, 3 * HD)) {
       m->dl_P = m->proj;
-      m->dl_H = (bf16*)m->hbuf;
+      m->dl_rows = (int)(R < 512 ? R : 512);                      // one-token steps run max_batch <= 512 rows through this path
+      m->dl_pp_stride = (long long)m->dl_rows * d;
+      TRY(dalloc(m, &m->dl_PP, (size_t)DL_CLUSTER * m->dl_pp_stride));
       TRY(make_tmap_bf16(&m->tmAttn16, m->attn, HD, (long long)R, HD, DL_ROWS));
-      TRY(make_tmap_bf16(&m->tmH16, m->hbuf, c.d_inner, (long long)R, c.d_inner, DL_ROWS));
       m->fused_decode = !rc;
+      m->dl_max_clusters = decode_dual_max_clusters();
+      m->dl_dual = m->fused_decode && (m->kflags & DMG_KF_DUAL_DECODE) && decode_dual_supported(c.mem_len) && m->dl_max_clusters >= 4;
       if (!rc && getenv("DMG_DECODE_TIMELINE")) TRY(dalloc(m, &m->dl_dbg, 64));
     }
   }

@@ -69,9 +69,11 @@ struct dmg_model {
   TensorMap2D tmA[A_COUNT];
   // fused one-token layer step (decode_layer.cu)
   bool fused_decode = false;
-  float* dl_P = nullptr;
-  bf16* dl_H = nullptr;
-  TensorMap2D tmAttn16, tmH16;
+  float *dl_P = nullptr, *dl_PP = nullptr;
+  long long dl_pp_stride = 0;
+  int dl_rows = 0, dl_max_clusters = 0;
+  bool dl_dual = false;                    // the two-half software pipeline with dual-role launches
+  TensorMap2D tmAttn16;
   unsigned long long* dl_dbg = nullptr;   // DMG_DECODE_TIMELINE=1: timeline of the fused kernel's CTA 0 (the LAST launch wins)
   int a_rows[A_COUNT], a_cols[A_COUNT];
   // generation loop

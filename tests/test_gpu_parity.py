@@ -218,25 +218,27 @@ def test_fused_decode_layer_kernel_matches_unfused_and_oracle(B):
     cfg = dict(txl.baseline_config(), n_layers=3, mem_len=128)
     om, pf = _pair(cfg, 'bf16', B, 128, keep_hidden=False, max_rows=max(B, 4 * 128))
     _, pu = _pair(cfg, 'bf16', B, 128, keep_hidden=False, max_rows=max(B, 4 * 128), kernel_flags=L.KF_NO_FUSED_DECODE)
+    _, pd = _pair(cfg, 'bf16', B, 128, keep_hidden=False, max_rows=max(B, 4 * 128), kernel_flags=L.KF_DUAL_DECODE)   # two-half pipeline
     g = torch.Generator().manual_seed(17)
     x0 = torch.randint(0, V, (B, 90), generator=g)
     with_oracle = B <= 40
     if with_oracle:
         om.reset()
         with torch.no_grad(): om(x0)
-    for pm in (pf, pu):
+    for pm in (pf, pu, pd):
         pm.reset(); pm[0].forward(x0.cuda(), logits_mode=2)
-    wfu = wfo = 0.
+    wfu = wfo = wfd = 0.
     for s in range(60):                                          # crosses the wrap-around of the 128-slot ring
         xs = torch.randint(0, V, (B, 1), generator=g)
         lf = pf[0].forward(xs.cuda(), logits_mode=1)[0].cpu()
         lu = pu[0].forward(xs.cuda(), logits_mode=1)[0].cpu()
         wfu = max(wfu, (lf - lu).abs().max().item())
+        wfd = max(wfd, (lf - pd[0].forward(xs.cuda(), logits_mode=1)[0].cpu()).abs().max().item())
         if with_oracle:
             with torch.no_grad(): lo = om(xs)[0]
             wfo = max(wfo, _rel(lf, lo))
-    print(f'B={B}: fused vs unfused max abs {wfu:.3e}; fused vs oracle max rel {wfo:.3e}')
-    assert wfu < 2e-2 and wfo <= 2e-2
+    print(f'B={B}: fused vs unfused max abs {wfu:.3e}; fused vs dual-role pipeline {wfd:.3e}; fused vs oracle max rel {wfo:.3e}')
+    assert wfu < 2e-2 and wfo <= 2e-2 and wfd < 1e-6               # the pipeline reorders launches, not arithmetic
 
 
 def test_greedy_token_stream_f32_bit_exact(golden_dir):
