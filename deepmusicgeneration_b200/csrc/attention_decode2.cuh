@@ -81,6 +81,17 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+#ifdef D2_PROFILE   // scripts/probes/probe_attn_decode.cu: cycles consumer warp 0 spends waiting, per CTA [total, q, K tiles, V tiles, barriers, items]
+__device__ unsigned long long* d2_prof_ptr;
+#define D2_MARK(k) do { if (warp == 0 && lane == 0) { const long long _n = clock64(); sec[k] += _n - t_last; t_last = _n; } } while (0)
+#define D2_T0() const long long _t0 = clock64()
+#define D2_ACC(k) do { if (warp == 0 && lane == 0) prof[k] += clock64() - _t0; } while (0)
+#else
+#define D2_MARK(k) do {} while (0)
+#define D2_T0() do {} while (0)
+#define D2_ACC(k) do {} while (0)
+#endif
+
 // The kernel body as a device function: `cta` of `ncta` persistent CTAs (the stand-alone kernel passes blockIdx.x / gridDim.x; the
 // dual-role decode kernel of decode_layer.cu gives it the CTAs that are not busy with the fused layer step of the other half of the
 // streams).  Runs on the first (4 G + 1) * 32 threads of the block; `d2_smem` is the block's dynamic shared memory.
@@ -196,6 +207,11 @@ __device__ __forceinline__ void attn_decode2_body(const CUtensorMap& tmK, const 
   }
 
   // ============================== consumers ==============================
+#ifdef D2_PROFILE
+  long long prof[6] = {0, 0, 0, 0, 0, 0}, sec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_begin = clock64();
+  long long t_last = t_begin;
+#endif
   pdl_wait();
   const int pos_total = a.dev_state[0], mc = a.dev_state[1];
   const int head = pos_total % M;
@@ -219,7 +235,9 @@ __device__ __forceinline__ void attn_decode2_body(const CUtensorMap& tmK, const 
       cur_h = h;
     }
     const int qs = n & 1;
-    mbar_wait(&q_full[qs], (uint32_t)((n >> 1) & 1));
+    D2_MARK(7);
+    { D2_T0(); mbar_wait(&q_full[qs], (uint32_t)((n >> 1) & 1)); D2_ACC(1); }
+    D2_MARK(0);
     const float* qb = qbuf + qs * 192;
     // B fragments of the query (replicated over the 8 columns): k = 16*ks + {2t, 2t+1} and {2t+8, 2t+9}
     uint32_t quf[4][2], qvf[4][2];
@@ -235,11 +253,12 @@ __device__ __forceinline__ void attn_decode2_body(const CUtensorMap& tmK, const 
       }
     }
     float* scb = sc + (n & 1) * (M + 8);
+    D2_MARK(1);
 
     // ---------------- phase 1: scores; group grp owns keys [TR j + 64 grp, +64) of tile j, warp w a 16-key block ----------------
     for (int j = 0; j < nT; ++j, ++tile_cnt) {
       const int s = tile_cnt & smask;
-      mbar_wait(&full[s], (tile_cnt >> sshift) & 1);
+      { D2_T0(); mbar_wait(&full[s], (tile_cnt >> sshift) & 1); D2_ACC(2); }
       const uint32_t kt = smem_u32(stages + s * L.tile_bytes) + grp * 8192;
       const int p = TR * j + 64 * grp + krow_l;          // ring slot of this lane's ldmatrix row
       const int dist = p < head ? head - p : M + head - p;
@@ -264,6 +283,7 @@ __device__ __forceinline__ void attn_decode2_body(const CUtensorMap& tmK, const 
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
     }
+    D2_MARK(2);
     if (warp == 0) {   // the new token itself (distance 0): fp32 q and k from the staged row, Rd[0] from the resident table
       const bf16* r0 = (const bf16*)Rres;   // row 0 is not permuted by the swizzle
       float acc = 0.f;
@@ -278,7 +298,8 @@ __device__ __forceinline__ void attn_decode2_body(const CUtensorMap& tmK, const 
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(r_free);
-    named_bar_sync(1, NW * 32);
+    { D2_T0(); named_bar_sync(1, NW * 32); D2_ACC(4); }
+    D2_MARK(3);
 
     // ---------------- exact softmax over M+1 scores: max redundantly per warp, p = exp2(s - max) shared as bf16 ----------------
     float mx = -INFINITY;
@@ -294,16 +315,17 @@ __device__ __forceinline__ void attn_decode2_body(const CUtensorMap& tmK, const 
     part = warp_sum(part);
     if (lane == 0) psum[warp] = part;
     const float p_cur = exp2f(scb[M] - mx);
-    named_bar_sync(2, NW * 32);
+    { D2_T0(); named_bar_sync(2, NW * 32); D2_ACC(4); }
     float sum = p_cur;
 #pragma unroll
     for (int ww = 0; ww < NW; ww++) sum += psum[ww];
+    D2_MARK(4);
 
     // ---------------- phase 2: partial out[16 w .. 16 w + 16) over the group's 64 keys of every V tile ----------------
     float oA[4] = {0.f, 0.f, 0.f, 0.f}, oB[4] = {0.f, 0.f, 0.f, 0.f};
     for (int j = 0; j < nT; ++j, ++tile_cnt) {
       const int s = tile_cnt & smask;
-      mbar_wait(&full[s], (tile_cnt >> sshift) & 1);
+      { D2_T0(); mbar_wait(&full[s], (tile_cnt >> sshift) & 1); D2_ACC(3); }
       const uint32_t vt = smem_u32(stages + s * L.tile_bytes) + grp * 8192;
       const bf16* pj = pw + TR * j + 64 * grp + 2 * t4;
 #pragma unroll
@@ -318,13 +340,14 @@ __device__ __forceinline__ void attn_decode2_body(const CUtensorMap& tmK, const 
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
     }
+    D2_MARK(5);
     // ---------------- epilogue: combine the groups, add the new token's own value, normalise, store; ring append ----------------
     if (G > 1) {
       if (t4 == 0) {
         ored[grp * 64 + 16 * w + g] = oA[0] + oB[0];
         ored[grp * 64 + 16 * w + g + 8] = oA[2] + oB[2];
       }
-      named_bar_sync(3, NW * 32);
+      { D2_T0(); named_bar_sync(3, NW * 32); D2_ACC(4); }
     }
     if (grp == 0 && t4 == 0) {
       const float inv = 1.f / sum;
@@ -346,7 +369,15 @@ __device__ __forceinline__ void attn_decode2_body(const CUtensorMap& tmK, const 
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&q_empty[qs]);
+    D2_MARK(6);
   }
+#ifdef D2_PROFILE
+  if (warp == 0 && lane == 0 && d2_prof_ptr) {
+    prof[0] = clock64() - t_begin; prof[5] = hi - lo;
+    for (int k = 0; k < 6; k++) d2_prof_ptr[cta * 14 + k] = prof[k];
+    for (int k = 0; k < 8; k++) d2_prof_ptr[cta * 14 + 6 + k] = sec[k];
+  }
+#endif
 }
 
 

@@ -137,6 +137,7 @@ struct AttnDecodeArgs {
   const int* dev_state; // [0] pos_total, [1] mem_count
   int B, H, M, Dcap;
   float scale;
+  int force_v2 = 0;     // 1 = the second-generation kernel even where the third one applies (DMG_KF_ATTN_DECODE_V2, parity tests)
   int no_early_kv = 0;  // v2 kernel: 1 = request the first K/V tiles only after the predecessor kernel has finished (DMG_NO_EARLY_KV)
 };
 // BERT-encoder attention on tcgen05 (attention_bert_tc.cu): T >= 128; same contract as attn_flash(..., bert = 1, ...)

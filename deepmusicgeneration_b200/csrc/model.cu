@@ -111,6 +111,7 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
       a.dev_state = m->dev_state;
       a.B = r1 - r0; a.H = c.n_heads; a.M = M; a.Dcap = m->Dcap;
       a.scale = 1.f / sqrtf((float)c.d_head);
+      a.force_v2 = (m->kflags & DMG_KF_ATTN_DECODE_V2) ? 1 : 0;
       return a;
     };
     auto fused_alone = [&](int l, int r0, int r1) -> int {
@@ -189,6 +190,7 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
       a.dev_state = m->dev_state;
       a.B = nb; a.H = c.n_heads; a.M = M; a.Dcap = m->Dcap;
       a.scale = 1.f / sqrtf((float)c.d_head);
+      a.force_v2 = (m->kflags & DMG_KF_ATTN_DECODE_V2) ? 1 : 0;
       if (attn_decode2(&L.tmK, &L.tmV, &L.tmR, a, b0, m->num_sms, st)) return -1;
     } else {
       AttnGeneralArgs a;
@@ -390,7 +392,7 @@ int dmg_create(const dmg_config* cfg, int device, dmg_model** out) {
         {"DMG_NO_DECODE_KERNEL", DMG_KF_NO_DECODE_KERNEL}, {"DMG_NO_FLASH", DMG_KF_NO_FLASH}, {"DMG_NO_GRAPH", DMG_KF_NO_GRAPH},
         {"DMG_BERT_ATTN_MMA_SYNC", DMG_KF_BERT_MMA_SYNC}, {"DMG_BERT_TC_FP32_STRIP", DMG_KF_BERT_FP32_STRIP},
         {"DMG_NO_SPLITK", DMG_KF_NO_SPLITK}, {"DMG_NO_BIG_GEMM", DMG_KF_NO_BIG_GEMM}, {"DMG_GEMM_SIMT", DMG_KF_GEMM_SIMT},
-        {"DMG_NO_FUSED_DECODE", DMG_KF_NO_FUSED_DECODE}, {"DMG_DUAL_DECODE", DMG_KF_DUAL_DECODE}};
+        {"DMG_NO_FUSED_DECODE", DMG_KF_NO_FUSED_DECODE}, {"DMG_DUAL_DECODE", DMG_KF_DUAL_DECODE}, {"DMG_ATTN_DECODE_V2", DMG_KF_ATTN_DECODE_V2}};
     for (const auto& e : sw)
       if (getenv(e.env)) m->kflags |= e.flag;
   }
