@@ -19,7 +19,7 @@ LOGITS_NONE, LOGITS_ALL, LOGITS_LAST = 0, 1, 2
 SAMPLE_EARLY_STOP, SAMPLE_MASK_UNUSED, SAMPLE_REMIX_FILTER = 1, 2, 4
 # dmg_config.kernel_flags (DMG_KF_*): non-default kernels for parity tests / reproducing measurements; 0 = the product path
 (KF_NO_DECODE_KERNEL, KF_NO_FLASH, KF_NO_GRAPH, KF_BERT_MMA_SYNC, KF_BERT_FP32_STRIP, KF_NO_SPLITK, KF_NO_BIG_GEMM, KF_GEMM_SIMT,
- KF_NO_FUSED_DECODE, KF_DUAL_DECODE, KF_ATTN_DECODE_V2) = (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024)
+ KF_NO_FUSED_DECODE, KF_NO_DUAL_DECODE, KF_ATTN_DECODE_V2) = (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024)
 
 
 class Config(C.Structure):

@@ -30,7 +30,7 @@
 // 16-row clusters would run in two waves).
 #include <cuda.h>
 
-#include "attention_decode2.cuh"
+#include "attention_decode3.cuh"
 #include "kernels.cuh"
 #include "launch.cuh"
 
@@ -526,7 +526,7 @@ decode_layer_kernel(const __grid_constant__ CUtensorMap tmAttn, const __grid_con
 // persistent CTAs of the decode attention of the OTHER half (a different layer phase of the software pipeline over the two halves,
 // model.cu).  The latency-bound layer step occupies 32 SMs and hardly any bandwidth; the HBM-bound attention gets the rest of the
 // machine; one launch instead of two streams, so the co-residency does not depend on the scheduler.
-constexpr int DUAL_G = 2;
+static_assert(D3_THREADS <= DL_THREADS, "the attention role runs on the first D3_THREADS threads of the block");
 __global__ void __launch_bounds__(DL_THREADS, 1)
 decode_dual_kernel(const __grid_constant__ CUtensorMap tmAttn, const __grid_constant__ CUtensorMap tmWo,
                    const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
@@ -537,9 +537,9 @@ decode_dual_kernel(const __grid_constant__ CUtensorMap tmAttn, const __grid_cons
   const int cluster = (int)blockIdx.x / DL_CLUSTER;
   if (cluster < n_fused) {
     decode_layer_body(tmAttn, tmWo, tmW1, tmW2, tmWq, fa, cluster, dyn_smem);
-  } else if (threadIdx.x < (4 * DUAL_G + 1) * 32) {
-    attn_decode2_body<DUAL_G>(tmK, tmV, tmR, aa, n_stages, b0, (int)blockIdx.x - n_fused * DL_CLUSTER, (int)gridDim.x - n_fused * DL_CLUSTER,
-                              dyn_smem);
+  } else if (threadIdx.x < D3_THREADS) {
+    attn_decode3_body<D3_TEAMS>(tmK, tmV, tmR, aa, n_stages, b0, (int)blockIdx.x - n_fused * DL_CLUSTER,
+                                (int)gridDim.x - n_fused * DL_CLUSTER, dyn_smem);
   }
 }
 
@@ -567,7 +567,8 @@ int decode_layer(const TensorMap2D* tmAttn, const TensorMap2D* tmWo, const Tenso
 }
 
 
-bool decode_dual_supported(int M) { return d2_pick_groups(M) == DUAL_G && d2_pick_stages(M, DUAL_G) >= 2; }
+bool decode_dual_supported(int M) { return attn_decode3_supported(64, M); }
+int decode_dual_max_items(int attn_clusters) { return attn_clusters * DL_CLUSTER * D3_CAP; }   // (stream, head) items of the attention role
 
 int decode_dual_max_clusters() {
   static int cached = -1;
@@ -595,8 +596,10 @@ int decode_dual(const TensorMap2D* tmAttn, const TensorMap2D* tmWo, const Tensor
                 int b0, int attn_clusters, cudaStream_t st) {
   DMG_CHECK(decode_layer_supported(fa.d, fa.HD, fa.di, fa.n3) && decode_dual_supported(aa.M), "decode_dual: geometry not supported");
   DMG_CHECK(aa.Dcap >= aa.M + 1, "decode_dual: rel-pos cache too small (%d < %d)", aa.Dcap, aa.M + 1);
-  const int ns = d2_pick_stages(aa.M, DUAL_G);
-  const D2Layout L = d2_layout(aa.M, DUAL_G, ns);
+  DMG_CHECK((long long)aa.B * aa.H <= decode_dual_max_items(attn_clusters), "decode_dual: %d x %d items do not fit %d attention clusters",
+            aa.B, aa.H, attn_clusters);
+  const int ns = d3_pick_stages(aa.M);
+  const D3Layout L = d3_layout(aa.M, ns);
   const int smem = L.total > DL_SMEM ? L.total : DL_SMEM;
   static int configured = 0;
   if (configured < smem) {

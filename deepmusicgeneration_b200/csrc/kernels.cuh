@@ -57,6 +57,8 @@ struct AttnDecodeArgs;
 // Dual-role launch (decode_layer.cu): the fused layer step of one half of the streams and the decode attention of the other half in
 // ONE kernel (software pipeline over two halves of the batch, model.cu).
 bool decode_dual_supported(int M);
+int decode_dual_max_items(int attn_clusters);
+bool attn_decode3_supported(int Dh, int M);
 int decode_dual_max_clusters();      // clusters of 8 CTAs of that kernel that can be co-resident (15 on a B200)
 int decode_dual(const TensorMap2D* tmAttn, const TensorMap2D* tmWo, const TensorMap2D* tmW1, const TensorMap2D* tmW2, const TensorMap2D* tmWq,
                 const DecodeLayerArgs& fa, const TensorMap2D* tmK, const TensorMap2D* tmV, const TensorMap2D* tmR, const AttnDecodeArgs& aa,

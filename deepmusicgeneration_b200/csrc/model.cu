@@ -137,7 +137,9 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
     };
     const int L = c.n_layers;
     const int groups = (nb + DL_ROWS - 1) / DL_ROWS;
-    const bool pipelined = m->dl_dual && groups >= 2 && (groups + 1) / 2 < m->dl_max_clusters;
+    const int half_groups = (groups + 1) / 2;
+    const bool pipelined = m->dl_dual && groups >= 2 && half_groups < m->dl_max_clusters &&
+                           (long long)half_groups * DL_ROWS * c.n_heads <= decode_dual_max_items(m->dl_max_clusters - half_groups);
     if (!pipelined) {
       // Stream lanes (groups of streams on parallel CUDA streams) were measured on top of this path and rejected (profiles/README.md).
       for (int l = 0; l <= L; l++) {
@@ -392,7 +394,7 @@ int dmg_create(const dmg_config* cfg, int device, dmg_model** out) {
         {"DMG_NO_DECODE_KERNEL", DMG_KF_NO_DECODE_KERNEL}, {"DMG_NO_FLASH", DMG_KF_NO_FLASH}, {"DMG_NO_GRAPH", DMG_KF_NO_GRAPH},
         {"DMG_BERT_ATTN_MMA_SYNC", DMG_KF_BERT_MMA_SYNC}, {"DMG_BERT_TC_FP32_STRIP", DMG_KF_BERT_FP32_STRIP},
         {"DMG_NO_SPLITK", DMG_KF_NO_SPLITK}, {"DMG_NO_BIG_GEMM", DMG_KF_NO_BIG_GEMM}, {"DMG_GEMM_SIMT", DMG_KF_GEMM_SIMT},
-        {"DMG_NO_FUSED_DECODE", DMG_KF_NO_FUSED_DECODE}, {"DMG_DUAL_DECODE", DMG_KF_DUAL_DECODE}, {"DMG_ATTN_DECODE_V2", DMG_KF_ATTN_DECODE_V2}};
+        {"DMG_NO_FUSED_DECODE", DMG_KF_NO_FUSED_DECODE}, {"DMG_NO_DUAL_DECODE", DMG_KF_NO_DUAL_DECODE}, {"DMG_ATTN_DECODE_V2", DMG_KF_ATTN_DECODE_V2}};
     for (const auto& e : sw)
       if (getenv(e.env)) m->kflags |= e.flag;
   }
@@ -521,7 +523,7 @@ int dmg_create(const dmg_config* cfg, int device, dmg_model** out) {
       TRY(make_tmap_bf16(&m->tmAttn16, m->attn, HD, (long long)R, HD, DL_ROWS));
       m->fused_decode = !rc;
       m->dl_max_clusters = decode_dual_max_clusters();
-      m->dl_dual = m->fused_decode && (m->kflags & DMG_KF_DUAL_DECODE) && decode_dual_supported(c.mem_len) && m->dl_max_clusters >= 4;
+      m->dl_dual = m->fused_decode && !(m->kflags & DMG_KF_NO_DUAL_DECODE) && decode_dual_supported(c.mem_len) && m->dl_max_clusters >= 4;
       if (!rc && getenv("DMG_DECODE_TIMELINE")) TRY(dalloc(m, &m->dl_dbg, 64));
     }
   }

@@ -42,8 +42,8 @@ enum { DMG_KF_NO_DECODE_KERNEL = 1,  /* one-token steps through the general atte
        DMG_KF_NO_BIG_GEMM = 64,      /* many-row GEMMs on gemm_tc_kernel instead of the persistent CTA-pair kernel                    */
        DMG_KF_GEMM_SIMT = 128,       /* every GEMM on the FFMA kernel                                                                 */
        DMG_KF_NO_FUSED_DECODE = 256, /* one-token step as separate GEMM / LayerNorm launches instead of the fused layer kernels       */
-       DMG_KF_DUAL_DECODE = 512,     /* two-half software pipeline: the fused layer step of one half of the streams and the attention of
-                                        the other half in ONE dual-role launch (measured slower while the attention is SM-bound) */
+       DMG_KF_NO_DUAL_DECODE = 512,  /* fused layer kernels and attention as separate launches over all streams instead of the two-half
+                                        software pipeline (fused step of one half + attention of the other half in ONE dual-role launch) */
        DMG_KF_ATTN_DECODE_V2 = 1024  /* one-token attention on the second-generation kernel (one consumer group, resident rel-pos keys)      */ };
 
 /* Model hyper-parameters: the keys of the reference config dicts (app_utils.py:13-63, fastai tfmerXL_lm_config). */

@@ -216,9 +216,9 @@ def test_fused_decode_layer_kernel_matches_unfused_and_oracle(B):
     40 (three clusters, the last one ragged), 256 (the benchmark's 16 clusters)."""
     from deepmusicgeneration_b200 import _lib as L
     cfg = dict(txl.baseline_config(), n_layers=3, mem_len=128)
-    om, pf = _pair(cfg, 'bf16', B, 128, keep_hidden=False, max_rows=max(B, 4 * 128))
+    om, pf = _pair(cfg, 'bf16', B, 128, keep_hidden=False, max_rows=max(B, 4 * 128))          # product: two-half pipeline when B > 32
     _, pu = _pair(cfg, 'bf16', B, 128, keep_hidden=False, max_rows=max(B, 4 * 128), kernel_flags=L.KF_NO_FUSED_DECODE)
-    _, pd = _pair(cfg, 'bf16', B, 128, keep_hidden=False, max_rows=max(B, 4 * 128), kernel_flags=L.KF_DUAL_DECODE)   # two-half pipeline
+    _, pd = _pair(cfg, 'bf16', B, 128, keep_hidden=False, max_rows=max(B, 4 * 128), kernel_flags=L.KF_NO_DUAL_DECODE)   # all streams per launch
     g = torch.Generator().manual_seed(17)
     x0 = torch.randint(0, V, (B, 90), generator=g)
     with_oracle = B <= 40
@@ -237,8 +237,8 @@ def test_fused_decode_layer_kernel_matches_unfused_and_oracle(B):
         if with_oracle:
             with torch.no_grad(): lo = om(xs)[0]
             wfo = max(wfo, _rel(lf, lo))
-    print(f'B={B}: fused vs unfused max abs {wfu:.3e}; fused vs dual-role pipeline {wfd:.3e}; fused vs oracle max rel {wfo:.3e}')
-    assert wfu < 2e-2 and wfo <= 2e-2 and wfd < 2e-2
+    print(f'B={B}: fused vs unfused max abs {wfu:.3e}; pipelined vs whole-batch launches {wfd:.3e}; fused vs oracle max rel {wfo:.3e}')
+    assert wfu < 2e-2 and wfo <= 2e-2 and wfd == 0.               # the pipeline reorders launches, not arithmetic
 
 
 def test_greedy_token_stream_f32_bit_exact(golden_dir):
