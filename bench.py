@@ -341,34 +341,58 @@ def measure_c2(args):
     e2e_ms = sharding.max_over_ranks(ev0.elapsed_time(ev1), device=dev)
     e2e_value = B * world * Ke / (e2e_ms / 1e3)
 
-    # ---- roofline of the dominant kernel (fused decode attention), timed alone with CUDA events on its stream.
-    # 16 launches touch 16 different layers' rings (4.3 GB) -> every launch reads cold data (L2 = 126 MB).
+    # ---- roofline of the dominant kernel, timed alone with CUDA events on its stream.  The pipelined step (B > 32 streams) spends
+    # its time in decode_dual_kernel: the attention of one half of the streams (HBM-bound: that half's K/V rings once) next to the
+    # fused layer step of the other half (one layer's weights once); 2 L - 1 such launches per step.  Launches over consecutive
+    # layers touch different rings and weights (4.4 GB per sweep) -> every launch reads cold data (L2 = 126 MB).
     L = cfg['n_layers']
-    for l in range(L):
-        _lib.check(lib.dmg_attn_decode_layer(e.h, l, stream), 'attn_decode_layer')
-    torch.cuda.synchronize()
-    reps = 8
-    ev0.record()
-    for _ in range(reps):
-        for l in range(L):
-            lib.dmg_attn_decode_layer(e.h, l, stream)
-    ev1.record()
-    torch.cuda.synchronize()
-    attn_ms = ev0.elapsed_time(ev1) / (reps * L)
     peak, peak_src = measured_peaks()
     geo = dict(H=shape['n_heads'], Dh=shape['d_head'], M=shape['mem_len'])
-    abytes = attention_bytes_per_launch(B, **geo)
     sbytes = step_bytes(B, L=shape['n_layers'], d=shape['d_model'], di=shape['d_inner'], **geo)
-    achieved = abytes / (attn_ms / 1e3) / 1e9
+    reps = 8
+    dual_on = lib.dmg_decode_dual_launch(e.h, 0, stream) == 0
     traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'attn_decode_traffic.json')
+    if dual_on:
+        for l in range(L - 1):
+            _lib.check(lib.dmg_decode_dual_launch(e.h, l, stream), 'decode_dual_launch')
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(reps):
+            for l in range(L - 1):
+                lib.dmg_decode_dual_launch(e.h, l, stream)
+        ev1.record()
+        torch.cuda.synchronize()
+        k_ms = ev0.elapsed_time(ev1) / (reps * (L - 1))
+        half = B - ((B + 31) // 32 + 1) // 2 * 32                                  # streams of the attention role (second half)
+        d_, di_, HD_ = shape['d_model'], shape['d_inner'], shape['n_heads'] * shape['d_head']
+        wbytes = (HD_ * d_ + 2 * d_ * di_ + d_ * 3 * HD_) * 2                      # out-proj, FFN up / down, next q|k|v (bf16)
+        abytes = attention_bytes_per_launch(half, **geo) + wbytes
+        per_step = 2 * L - 1
+        kname = 'decode_dual_kernel (decode_layer.cu): attn_decode3 body over half the streams + fused layer step of the other half'
+        tpath = os.path.join(ROOT, 'profiles', 'decode_dual_traffic.json')
+    else:
+        for l in range(L):
+            _lib.check(lib.dmg_attn_decode_layer(e.h, l, stream), 'attn_decode_layer')
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(reps):
+            for l in range(L):
+                lib.dmg_attn_decode_layer(e.h, l, stream)
+        ev1.record()
+        torch.cuda.synchronize()
+        k_ms = ev0.elapsed_time(ev1) / (reps * L)
+        abytes = attention_bytes_per_launch(B, **geo)
+        per_step = L
+        kname = 'attn_decode3_kernel (attention_decode2.cu / attention_decode3.cuh)'
+        tpath = os.path.join(ROOT, 'profiles', 'attn_decode_traffic.json')
+    achieved = abytes / (k_ms / 1e3) / 1e9
     if os.path.exists(tpath):
         try: traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
         except Exception: traffic = None
-    roofline = {'bound': 'hbm', 'kernel': 'attn_decode2_kernel<2> (attention_decode2.cu)', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+    roofline = {'bound': 'hbm', 'kernel': kname, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                'algorithmic_bytes_per_launch': abytes, 'kernel_ms': attn_ms,
-                'kernel_share_of_step': attn_ms * L / (ms / K),
+                'algorithmic_bytes_per_launch': abytes, 'kernel_ms': k_ms, 'launches_per_step': per_step,
+                'kernel_share_of_step': k_ms * per_step / (ms / K),
                 'step_algorithmic_bytes': sbytes, 'step_frac': sbytes / (ms / K / 1e3) / 1e9 / peak}
 
     uses_tc = bool(lib.dmg_uses_tcgen05(e.h))

@@ -69,6 +69,7 @@ SYMBOLS = {
     'dmg_launch_count': (c_i64, []),
     'dmg_uses_tcgen05': (c_i32, [c_vp]),
     'dmg_attn_decode_layer': (c_i32, [c_vp, c_i32, c_vp]),
+    'dmg_decode_dual_launch': (c_i32, [c_vp, c_i32, c_vp]),
     'dmg_decode_timeline': (c_i32, [c_vp, c_vp]),
     'dmg_gemm_bf16': (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     # training step

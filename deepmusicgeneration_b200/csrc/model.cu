@@ -65,6 +65,77 @@ static int linear(dmg_model* m, int abuf, const void* A, const Weight& w, const 
   return gemm_simt<bf16>((const bf16*)A, K, w.b16, K, bias, C, ldc, M, N, K, gelu, out_bf16, st);
 }
 
+// The launches of the one-token step (product path) over the streams [b0, b0 + nb) of the model: the fused layer step of layer l
+// over rows [r0, r1) (l == 0 ... L: body of layer l-1, q|k|v of layer l), the decode attention of layer l over the same kind of row
+// range, and the dual-role launch that runs one of each (for different halves of the streams) side by side.
+struct DecodeStep {
+  dmg_model* m;
+  int b0;
+  cudaStream_t st;
+
+  DecodeLayerArgs layer_args(int l, int r0, int r1, LayerW** Lb_out, LayerW** Ln_out) const {
+    const dmg_config& c = m->cfg;
+    const bool body = l > 0, next = l < c.n_layers;
+    LayerW& Lb = m->layers[body ? l - 1 : 0];        // the layer whose body runs
+    LayerW& Ln = m->layers[next ? l : 0];            // the layer whose q|k|v are produced
+    DecodeLayerArgs da;
+    da.x32 = m->x32; da.qkv = m->qkv; da.P = m->dl_P; da.PP = m->dl_PP; da.pp_stride = m->dl_pp_stride;
+    da.row_base = r0; da.B = r1; da.d = c.d_model; da.HD = m->HD; da.di = c.d_inner; da.n3 = 3 * m->HD;
+    da.mode = (body ? 1 : 0) | (next ? 2 : 0);
+    da.dbg = (l == c.n_layers / 2 && r0 == 0) ? m->dl_dbg : nullptr;      // timeline probe: one mid-stack launch
+    da.xa_out = next ? nullptr : (bf16*)m->xa;
+    da.bo = Lb.bo; da.b1 = Lb.b1; da.b2 = Lb.b2; da.ln1w = Lb.ln1w; da.ln1b = Lb.ln1b; da.ln2w = Lb.ln2w; da.ln2b = Lb.ln2b;
+    da.bq = Ln.bqkv;
+    *Lb_out = &Lb; *Ln_out = &Ln;
+    return da;
+  }
+  AttnDecodeArgs attn_args(int l, int r0, int r1) const {
+    const dmg_config& c = m->cfg;
+    const int M = c.mem_len, HD = m->HD;
+    LayerW& La = m->layers[l];
+    AttnDecodeArgs a;
+    a.qkv = m->qkv + (size_t)r0 * 3 * HD;
+    a.kring = (bf16*)La.kring + (size_t)(b0 + r0) * c.n_heads * M * 64;
+    a.vring = (bf16*)La.vring + (size_t)(b0 + r0) * c.n_heads * M * 64;
+    a.rd = (const bf16*)La.rd;
+    a.u = m->u; a.v = m->v;
+    a.out = (bf16*)m->attn + (size_t)r0 * HD;
+    a.dev_state = m->dev_state;
+    a.B = r1 - r0; a.H = c.n_heads; a.M = M; a.Dcap = m->Dcap;
+    a.scale = 1.f / sqrtf((float)c.d_head);
+    a.force_v2 = (m->kflags & DMG_KF_ATTN_DECODE_V2) ? 1 : 0;
+    return a;
+  }
+  int fused_alone(int l, int r0, int r1) const {
+    LayerW *Lb, *Ln;
+    const DecodeLayerArgs da = layer_args(l, r0, r1, &Lb, &Ln);
+    return decode_layer(&m->tmAttn16, &Lb->wo.tm64, &Lb->w1.tm64, &Lb->w2.tm64, &Ln->wqkv.tm64, da, st);
+  }
+  int attn_alone(int l, int r0, int r1) const {
+    LayerW& La = m->layers[l];
+    return attn_decode2(&La.tmK, &La.tmV, &La.tmR, attn_args(l, r0, r1), b0 + r0, m->num_sms, st);
+  }
+  // dual-role launch: fused step `lf` over rows [f0, f1) together with the attention of layer `la` over rows [a0, a1)
+  int dual(int lf, int f0, int f1, int la, int a0, int a1) const {
+    LayerW *Lb, *Ln;
+    const DecodeLayerArgs da = layer_args(lf, f0, f1, &Lb, &Ln);
+    LayerW& La = m->layers[la];
+    const int n_fused = (f1 - f0 + DL_ROWS - 1) / DL_ROWS;
+    int attn_clusters = m->dl_max_clusters - n_fused;
+    const long long items = (long long)(a1 - a0) * m->cfg.n_heads;
+    if ((long long)attn_clusters * DL_CLUSTER > items) attn_clusters = (int)((items + DL_CLUSTER - 1) / DL_CLUSTER);
+    return decode_dual(&m->tmAttn16, &Lb->wo.tm64, &Lb->w1.tm64, &Lb->w2.tm64, &Ln->wqkv.tm64, da, &La.tmK, &La.tmV, &La.tmR,
+                       attn_args(la, a0, a1), b0 + a0, attn_clusters, st);
+  }
+  // two-half software pipeline (see forward_chunk): is it on for nb streams, and where the halves split
+  bool pipelined(int nb, int* hx) const {
+    const int groups = (nb + DL_ROWS - 1) / DL_ROWS, half_groups = (groups + 1) / 2;
+    *hx = half_groups * DL_ROWS;
+    return m->dl_dual && groups >= 2 && half_groups < m->dl_max_clusters &&
+           (long long)half_groups * DL_ROWS * m->cfg.n_heads <= decode_dual_max_items(m->dl_max_clusters - half_groups);
+  }
+};
+
 template <class T>
 static int forward_chunk(dmg_model* m, const long long* ids, const long long* pos, int b0, int nb, int T_len, int win,
                          int k, int logits_mode, float* logits, float* core_out, cudaStream_t st) {
@@ -82,69 +153,15 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
   // one-token step, product path: per layer ONE decode-attention launch + ONE fused layer launch (decode_layer.cu)
   const bool fused = fast_decode && m->fused_decode && !c.keep_hidden && m->layers[0].wqkv.has_tm && rows <= m->dl_rows;
   if (fused) {
-    // helpers: the fused layer step of layer l over rows [r0, r1) (l == 0 ... L: body of layer l-1, q|k|v of layer l) and the
-    // decode attention of layer l over the same kind of row range
-    auto layer_args = [&](int l, int r0, int r1, LayerW** Lb_out, LayerW** Ln_out) {
-      const bool body = l > 0, next = l < c.n_layers;
-      LayerW& Lb = m->layers[body ? l - 1 : 0];        // the layer whose body runs
-      LayerW& Ln = m->layers[next ? l : 0];            // the layer whose q|k|v are produced
-      DecodeLayerArgs da;
-      da.x32 = m->x32; da.qkv = m->qkv; da.P = m->dl_P; da.PP = m->dl_PP; da.pp_stride = m->dl_pp_stride;
-      da.row_base = r0; da.B = r1; da.d = d; da.HD = HD; da.di = c.d_inner; da.n3 = 3 * HD;
-      da.mode = (body ? 1 : 0) | (next ? 2 : 0);
-      da.dbg = (l == c.n_layers / 2 && r0 == 0) ? m->dl_dbg : nullptr;      // timeline probe: one mid-stack launch
-      da.xa_out = next ? nullptr : (bf16*)m->xa;
-      da.bo = Lb.bo; da.b1 = Lb.b1; da.b2 = Lb.b2; da.ln1w = Lb.ln1w; da.ln1b = Lb.ln1b; da.ln2w = Lb.ln2w; da.ln2b = Lb.ln2b;
-      da.bq = Ln.bqkv;
-      *Lb_out = &Lb; *Ln_out = &Ln;
-      return da;
-    };
-    auto attn_args = [&](int l, int r0, int r1) {
-      LayerW& La = m->layers[l];
-      AttnDecodeArgs a;
-      a.qkv = m->qkv + (size_t)r0 * 3 * HD;
-      a.kring = (bf16*)La.kring + (size_t)(b0 + r0) * c.n_heads * M * 64;
-      a.vring = (bf16*)La.vring + (size_t)(b0 + r0) * c.n_heads * M * 64;
-      a.rd = (const bf16*)La.rd;
-      a.u = m->u; a.v = m->v;
-      a.out = (bf16*)m->attn + (size_t)r0 * HD;
-      a.dev_state = m->dev_state;
-      a.B = r1 - r0; a.H = c.n_heads; a.M = M; a.Dcap = m->Dcap;
-      a.scale = 1.f / sqrtf((float)c.d_head);
-      a.force_v2 = (m->kflags & DMG_KF_ATTN_DECODE_V2) ? 1 : 0;
-      return a;
-    };
-    auto fused_alone = [&](int l, int r0, int r1) -> int {
-      LayerW *Lb, *Ln;
-      const DecodeLayerArgs da = layer_args(l, r0, r1, &Lb, &Ln);
-      return decode_layer(&m->tmAttn16, &Lb->wo.tm64, &Lb->w1.tm64, &Lb->w2.tm64, &Ln->wqkv.tm64, da, st);
-    };
-    auto attn_alone = [&](int l, int r0, int r1) -> int {
-      LayerW& La = m->layers[l];
-      return attn_decode2(&La.tmK, &La.tmV, &La.tmR, attn_args(l, r0, r1), b0 + r0, m->num_sms, st);
-    };
-    // dual-role launch: fused step `lf` over rows [f0, f1) together with the attention of layer `la` over rows [a0, a1)
-    auto dual = [&](int lf, int f0, int f1, int la, int a0, int a1) -> int {
-      LayerW *Lb, *Ln;
-      const DecodeLayerArgs da = layer_args(lf, f0, f1, &Lb, &Ln);
-      LayerW& La = m->layers[la];
-      const int n_fused = (f1 - f0 + DL_ROWS - 1) / DL_ROWS;
-      int attn_clusters = m->dl_max_clusters - n_fused;
-      const long long items = (long long)(a1 - a0) * c.n_heads;
-      if ((long long)attn_clusters * DL_CLUSTER > items) attn_clusters = (int)((items + DL_CLUSTER - 1) / DL_CLUSTER);
-      return decode_dual(&m->tmAttn16, &Lb->wo.tm64, &Lb->w1.tm64, &Lb->w2.tm64, &Ln->wqkv.tm64, da, &La.tmK, &La.tmV, &La.tmR,
-                         attn_args(la, a0, a1), b0 + a0, attn_clusters, st);
-    };
+    const DecodeStep ds{m, b0, st};
     const int L = c.n_layers;
-    const int groups = (nb + DL_ROWS - 1) / DL_ROWS;
-    const int half_groups = (groups + 1) / 2;
-    const bool pipelined = m->dl_dual && groups >= 2 && half_groups < m->dl_max_clusters &&
-                           (long long)half_groups * DL_ROWS * c.n_heads <= decode_dual_max_items(m->dl_max_clusters - half_groups);
+    int hx = 0;
+    const bool pipelined = ds.pipelined(nb, &hx);
     if (!pipelined) {
       // Stream lanes (groups of streams on parallel CUDA streams) were measured on top of this path and rejected (profiles/README.md).
       for (int l = 0; l <= L; l++) {
-        if (l > 0 && attn_alone(l - 1, 0, nb)) return -1;
-        if (fused_alone(l, 0, nb)) return -1;
+        if (l > 0 && ds.attn_alone(l - 1, 0, nb)) return -1;
+        if (ds.fused_alone(l, 0, nb)) return -1;
       }
     } else {
       // Software pipeline over two halves X = [0, hx) and Y = [hx, nb) of the streams: while one half's attention streams its K/V
@@ -152,13 +169,12 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
       // in the SAME launch (decode_dual_kernel), so both really are resident together:
       //   F_0(X+Y) | A_0(X) | A_0(Y)+F_1(X) | A_1(X)+F_1(Y) | A_1(Y)+F_2(X) | ... | A_{L-1}(Y)+F_L(X) | F_L(Y)
       // (F_l = body of layer l-1 + q|k|v of layer l; A_l = attention of layer l).
-      const int hx = ((groups + 1) / 2) * DL_ROWS;
-      if (fused_alone(0, 0, nb)) return -1;
-      if (attn_alone(0, 0, hx)) return -1;
+      if (ds.fused_alone(0, 0, nb)) return -1;
+      if (ds.attn_alone(0, 0, hx)) return -1;
       for (int l = 0; l < L; l++) {
-        if (dual(l + 1, 0, hx, l, hx, nb)) return -1;                       // A_l(Y) + F_{l+1}(X)
-        if (l + 1 < L) { if (dual(l + 1, hx, nb, l + 1, 0, hx)) return -1; }   // A_{l+1}(X) + F_{l+1}(Y)
-        else if (fused_alone(L, hx, nb)) return -1;
+        if (ds.dual(l + 1, 0, hx, l, hx, nb)) return -1;                       // A_l(Y) + F_{l+1}(X)
+        if (l + 1 < L) { if (ds.dual(l + 1, hx, nb, l + 1, 0, hx)) return -1; }   // A_{l+1}(X) + F_{l+1}(Y)
+        else if (ds.fused_alone(L, hx, nb)) return -1;
       }
     }
   }
@@ -793,6 +809,18 @@ int dmg_attn_decode_layer(dmg_model* m, int layer, void* stream) {
   a.B = m->batch; a.H = c.n_heads; a.M = c.mem_len; a.Dcap = m->Dcap;
   a.scale = 1.f / sqrtf((float)c.d_head);
   return attn_decode2(&L.tmK, &L.tmV, &L.tmR, a, 0, m->num_sms, (cudaStream_t)stream);
+}
+
+int dmg_decode_dual_launch(dmg_model* m, int layer, void* stream) {
+  DMG_CHECK(m, "dmg_decode_dual_launch: null model");
+  const dmg_config& c = m->cfg;
+  DMG_CHECK(layer >= 0 && layer + 1 < c.n_layers, "dmg_decode_dual_launch: layer %d out of range", layer);
+  DMG_CHECK(m->batch >= 1 && m->batch <= m->dl_rows, "dmg_decode_dual_launch: no active streams");
+  DMG_CUDA_OK(cudaSetDevice(m->device));
+  const DecodeStep ds{m, 0, (cudaStream_t)stream};
+  int hx = 0;
+  DMG_CHECK(m->fused_decode && ds.pipelined(m->batch, &hx), "dmg_decode_dual_launch: the two-half pipeline is off for this model / batch");
+  return ds.dual(layer + 1, 0, hx, layer, hx, m->batch);      // A_layer(second half) + F_{layer+1}(first half), as in the step
 }
 
 int dmg_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_dev, void* c_dev, int M, int N, int K, int gelu,

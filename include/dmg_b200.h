@@ -181,6 +181,11 @@ int dmg_decode_timeline(dmg_model* m, uint64_t* out48_host);
  * current ring state and the q/k/v of the latest one-token forward (idempotent: the ring position is not advanced). */
 int dmg_attn_decode_layer(dmg_model* m, int layer, void* stream);
 
+/* The same for the dominant launch of the pipelined one-token step (decode_dual_kernel): the attention of `layer` over the second
+ * half of the streams together with the fused layer step (body of `layer`, q|k|v of `layer + 1`) of the first half, exactly as the
+ * step issues it.  Advances nothing on the host side, but rewrites the residual stream of the first half: call it after the run. */
+int dmg_decode_dual_launch(dmg_model* m, int layer, void* stream);
+
 /* Stand-alone GEMM entry (unit tests / micro-benchmarks): C[M,N] = A[M,K] * W[N,K]^T (+bias) (gelu),
  * bf16 inputs on the device, fp32 or bf16 output.  backend: DMG_GEMM_AUTO = tcgen05, DMG_GEMM_SIMT. */
 int dmg_gemm_bf16(const void* a_dev, const void* w_dev, const float* bias_dev, void* c_dev, int M, int N, int K,
