@@ -32,7 +32,7 @@ static int launch_d2(const TensorMap2D* tmK, const TensorMap2D* tmV, const Tenso
 }
 
 // ---- third generation (attention_decode3.cuh): two consumer teams, rel-pos scores from a per-CTA table ----
-bool attn_decode3_supported(int Dh, int M) { return Dh == 64 && M >= D3_KEYS && M <= 512 && M % D3_KEYS == 0 && d3_pick_stages(M) >= 3; }
+bool attn_decode3_supported(int Dh, int M) { return Dh == 64 && M >= D3_KEYS && M <= 512 && M % D3_KEYS == 0 && d3_pick_stages(M) >= 2; }
 
 __global__ void __launch_bounds__(D3_THREADS, 1)
 attn_decode3_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,

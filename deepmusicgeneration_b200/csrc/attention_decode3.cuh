@@ -35,26 +35,26 @@ struct D3Layout {
   int off_ring, off_r, off_tab, off_team, team_bytes, off_bar, total;
 };
 
-__host__ __device__ inline D3Layout d3_layout(int M, int n_stages) {
+__host__ __device__ inline D3Layout d3_layout(int M, int n_stages, int teams = D3_TEAMS) {
   D3Layout L;
   L.r_boxes = (M + 1 + 63) / 64;
   L.n_stages = n_stages;
   L.tab_stride = M + 4;                        // = 4 mod 32: the mma C fragments scatter into it without bank conflicts
-  const int ring = D3_TEAMS * n_stages * D3_TILE;
+  const int ring = teams * n_stages * D3_TILE;
   L.off_ring = 0;
   L.off_r = ring - L.r_boxes * 8192;           // the rel-pos keys alias the tail of the ring region
   L.free_bytes = L.off_r;
   L.off_tab = ring;
   L.off_team = L.off_tab + D3_CAP * L.tab_stride * 4;
   L.team_bytes = 2 * 768 + (((M + 16) * 2 + 15) & ~15) + 64;   // q/k/v slots, bf16 probabilities, warp maxima / sums / own score
-  L.off_bar = (L.off_team + D3_TEAMS * L.team_bytes + 15) & ~15;
-  L.total = L.off_bar + (D3_TEAMS * (2 * n_stages + 4) + 2) * 8 + 1024 /*alignment slack*/;
+  L.off_bar = (L.off_team + teams * L.team_bytes + 15) & ~15;
+  L.total = L.off_bar + (teams * (2 * n_stages + 4) + 2) * 8 + 1024 /*alignment slack*/;
   return L;
 }
 
-static inline int d3_pick_stages(int M) {
-  for (int s = 6; s >= 3; s--) {
-    const D3Layout L = d3_layout(M, s);
+static inline int d3_pick_stages(int M, int teams = D3_TEAMS) {
+  for (int s = 6; s >= 2; s--) {
+    const D3Layout L = d3_layout(M, s, teams);
     if (L.off_r >= 0 && L.total <= 227 * 1024) return s;
   }
   return 0;
@@ -66,7 +66,7 @@ __device__ __forceinline__ void attn_decode3_body(const CUtensorMap& tmK, const 
   constexpr int CW = 4 * T;                 // consumer warps [0, CW); producer warps [CW, CW + T)
   uint8_t* base = d3_smem + ((1024u - (smem_u32(d3_smem) & 1023u)) & 1023u);
   const int M = a.M, H = a.H, B = a.B, HD = H * 64;
-  const D3Layout L = d3_layout(M, n_stages);
+  const D3Layout L = d3_layout(M, n_stages, T);
   uint8_t* Rres = base + L.off_r;
   float* tab = (float*)(base + L.off_tab);
   const int S = L.tab_stride;

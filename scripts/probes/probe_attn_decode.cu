@@ -89,11 +89,12 @@ int main(int argc, char** argv) {
     printf("      sections (incl. their waits): q wait %5.0f | fragments %5.0f | K phase %5.0f | own key + bar1 %5.0f | softmax + bar2 %5.0f | V phase %5.0f | epilogue %5.0f | loop %5.0f\n",
            acc[6] / items, acc[7] / items, acc[8] / items, acc[9] / items, acc[10] / items, acc[11] / items, acc[12] / items, acc[13] / items);
   }
-  // third generation with the per-section cycle marks of team 0 / warp 0 (prologue reported under "loop")
-  for (int grid : {148, 88, 37}) {
-    const int ns = d3_pick_stages(M);
-    const D3Layout L = d3_layout(M, ns);
-    CK(cudaFuncSetAttribute(probe3_kernel<D3_TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+  // third generation with the per-section cycle marks of team 0 / warp 0, two and three teams
+  for (int T : {2, 3}) for (int grid : {148, 88, 37}) {
+    const int ns = d3_pick_stages(M, T);
+    const D3Layout L = d3_layout(M, ns, T);
+    if (T == 2) CK(cudaFuncSetAttribute(probe3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    else CK(cudaFuncSetAttribute(probe3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     const int per = D3_CAP * grid / H;
     float total = 0;
     const int reps = 8;
@@ -101,7 +102,8 @@ int main(int argc, char** argv) {
       const int s = r % NSETS;
       AttnDecodeArgs a{qkv, k[s], v[s], rd, u, vv, out, st, per < B ? per : B, H, M, Dcap, 0.125f, 0, 1};
       CK(cudaEventRecord(e0, stream));
-      launch_k(probe3_kernel<D3_TEAMS>, dim3(grid), dim3(D3_THREADS), L.total, stream, 1, *(const CUtensorMap*)tmK[s].bytes, *(const CUtensorMap*)tmV[s].bytes, *(const CUtensorMap*)tmR.bytes, a, ns);
+      if (T == 2) launch_k(probe3_kernel<2>, dim3(grid), dim3(2 * 160), L.total, stream, 1, *(const CUtensorMap*)tmK[s].bytes, *(const CUtensorMap*)tmV[s].bytes, *(const CUtensorMap*)tmR.bytes, a, ns);
+      else launch_k(probe3_kernel<3>, dim3(grid), dim3(3 * 160), L.total, stream, 1, *(const CUtensorMap*)tmK[s].bytes, *(const CUtensorMap*)tmV[s].bytes, *(const CUtensorMap*)tmR.bytes, a, ns);
       CK(cudaEventRecord(e1, stream));
       CK(cudaStreamSynchronize(stream));
       float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -111,9 +113,9 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(hp.data(), prof, grid * 14 * 8, cudaMemcpyDeviceToHost));
     double acc[14] = {0};
     for (int c = 0; c < grid; c++) for (int q = 0; q < 14; q++) acc[q] += (double)hp[c * 14 + q] / grid;
-    const double items = acc[5];
-    printf("v3 grid=%3d streams=%3d stages=%d: %7.2f us | team 0: %4.1f items, total %6.0f cycles; prologue %5.0f; per item: q wait %5.0f | fragments+own %5.0f | K phase %5.0f (waits %5.0f) | softmax %5.0f | V phase %5.0f (waits %5.0f) | epilogue %5.0f\n",
-           grid, per < B ? per : B, ns, total / reps * 1e3, items, acc[0], acc[13], acc[6] / items, acc[7] / items, acc[8] / items, acc[2] / items, acc[10] / items, acc[11] / items, acc[3] / items, acc[12] / items);
+    const double items = acc[5], nstreams = per < B ? per : B, us = total / reps * 1e3;
+    printf("v3 T=%d grid=%3d streams=%3.0f stages=%d: %7.2f us  %5.2f TB/s %5.1f GB/s per SM | team 0: %4.1f items, total %6.0f cycles; prologue %5.0f; per item: q wait %5.0f | fragments+own %5.0f | K phase %5.0f (waits %5.0f) | softmax %5.0f | V phase %5.0f (waits %5.0f) | epilogue %5.0f\n",
+           T, grid, nstreams, ns, us, nstreams * H * M * 256.0 / us / 1e6, nstreams * H * M * 256.0 / us / 1e3 / grid, items, acc[0], acc[13], acc[6] / items, acc[7] / items, acc[8] / items, acc[2] / items, acc[10] / items, acc[11] / items, acc[3] / items, acc[12] / items);
   }
   // the library's launchers: second generation (force_v2) against the third (teams + rel-pos table), same buffers
   for (int v2 : {1, 0}) for (int sms : {148, 88, 37}) {
