@@ -960,7 +960,9 @@ int attn_train_bwd(const AttnTrainBwdArgs& ba, int num_sms, cudaStream_t st) {
   const int rows = a.B * a.T;
   if (launch_np(attn_delta_kernel, dim3((rows * 32 + 255) / 256), dim3(256), 0, st, (const bf16*)a.out, ba.dout, ba.delta, rows, a.T, a.H))
     return -1;
-  if (a.p_save && a.m_save) {   // the tcgen05 forward saved the probabilities: no score recomputation
+  if (attn_bwd_dq_tc_supported(ba)) {   // saved probabilities, 128-aligned shapes: dQ on tcgen05
+    if (attn_bwd_dq_tc(ba, st)) return -1;
+  } else if (a.p_save && a.m_save) {   // the tcgen05 forward saved the probabilities: no score recomputation
     if (launch_np(attn_bwd_dq_kernel<true>, dim3(a.B * a.H * (a.T / 64)), dim3(128), (size_t)DQ_PS_SMEM, st, ba)) return -1;
   } else if (launch_np(attn_bwd_dq_kernel<false>, dim3(a.B * a.H * (a.T / 64)), dim3(128), (size_t)DQ_SMEM, st, ba)) {
     return -1;

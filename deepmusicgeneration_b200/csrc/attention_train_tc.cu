@@ -561,7 +561,401 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmPd, const __grid_co
   if (warp == 1) tmem_dealloc<128>(tmem_base);
 }
 
+
+// =============================================================================================
+// dQ on tcgen05 (replaces attn_bwd_dq_kernel<true> of attention_train.cu when T, M and mem_count are multiples of 128): the autograd of
+// fastai's _apply_attention with respect to the query side, from the probabilities the forward saved.
+//   dPd = dO V^T                         (tcgen05, TMEM, double-buffered)
+//   P = p_save * exp(m_save*scale - lse),  Pd = dropout(P),  dS = P * (dropout'(dPd) - delta) * scale       (softmax warps, one row each)
+//   dQ  = dS K  +  dS_dist Rk            (tcgen05; dS_dist = dS in (row, distance) coordinates = the transpose of _line_shift)
+// and, for the kernels downstream, Pd and dS tiles (dK/dV kernel) and dS_dist (dRk GEMM) leave through TMA stores.
+// One CTA = (stream, head, 128-query tile), key tiles of 128 from the oldest visible key up to the diagonal, 12 warps:
+//   warps 0-7  tile math: thread = one query row x 64 keys (key half = warp / 4)
+//   warp 8     TMA loads: dO once; per tile V, the saved probabilities (2 buffers), K, one 128-distance block of Rk
+//   warp 9     one thread issues every tcgen05.mma
+//   warp 10    TMA stores: dS tile, Pd tile (written in place over the saved probabilities), finished dS_dist blocks
+// The distance of (row r, key jl) inside a tile is D0 + r - jl (D0 = M + i0 - j0, a multiple of 128), so a tile touches two aligned
+// 128-distance blocks: the upper one (shared with the previous, older key tile) becomes complete with this tile, the lower one is
+// started.  A block lives in one of two [128 rows][128 distances] bf16 buffers (canonical K-major swizzled layout): every entry is
+// written exactly once by the two tiles that share the block, a finished block is the A operand of  dQ_bd += block . Rk[block]
+// and is stored to ds_dist as it lies.  The first (largest-distance) block only gets its upper-tile part: its buffer starts zeroed;
+// the blocks beyond it (distances no visible key produces) are stored as zeros from that buffer before the first tile.
+// TMEM: [0,128) / [128,256) dPd of even / odd tiles | [256,320) dQ content part | [320,384) dQ position part.
+// =============================================================================================
+constexpr int DQT_THREADS = 12 * 32;
+constexpr int DQO_DO = 0;
+constexpr int DQO_K = DQO_DO + T16K;
+constexpr int DQO_V = DQO_K + T16K;
+constexpr int DQO_R = DQO_V + T16K;
+constexpr int DQO_P = DQO_R + T16K;                  // 2 buffers x 2 key halves
+constexpr int DQO_DS = DQO_P + 4 * T16K;             // 2 key halves
+constexpr int DQO_STRIP = DQO_DS + 2 * T16K;         // 2 block buffers x 2 distance halves
+constexpr int DQO_BAR = DQO_STRIP + 4 * T16K;
+constexpr int DQT_SMEM = DQO_BAR + 512 + 1024 /*alignment slack*/;
+static_assert(DQT_SMEM <= 227 * 1024, "shared memory budget");
+enum { D_DOFULL = 0, D_KFULL, D_KEMPTY, D_VFULL, D_VEMPTY, D_RFULL, D_REMPTY, D_PFULL0, D_PFULL1, D_PFREE0, D_PFREE1, D_DPFULL0, D_DPFULL1,
+       D_DPFREE0, D_DPFREE1, D_DSFULL, D_DSFREE, D_SFREE0, D_SFREE1, D_ZINIT, D_ZDONE, D_DQFULL, D_COUNT };
+constexpr uint32_t DTM_DP = 0, DTM_AC = 256, DTM_BD = 320;
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t smem_addr, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(smem_addr), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(DQT_THREADS, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmR,
+                      const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmPB,
+                      const __grid_constant__ CUtensorMap tmDS, const __grid_constant__ CUtensorMap tmDD, const AttnTrainBwdArgs ba) {
+  const AttnTrainArgs& a = ba.f;
+  extern __shared__ __align__(1024) uint8_t dq_smem_raw[];
+  uint8_t* smem = dq_smem_raw + ((1024u - (smem_u32(dq_smem_raw) & 1023u)) & 1023u);
+  uint64_t* bar = (uint64_t*)(smem + DQO_BAR);
+  uint32_t* tmem_holder = (uint32_t*)(bar + D_COUNT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nT = a.T / 128;
+  const int it = nT - 1 - (blockIdx.x % nT);        // heavy (late) query tiles first
+  const int bh = blockIdx.x / nT, b = bh / a.H, h = bh % a.H;
+  const int i0 = it * 128, HD = a.H * 64, S = a.M + a.T;
+  const int jt_lo = (a.M - a.mem_count) / 128, jt_hi = (a.M + i0) / 128;
+  const int NT = jt_hi - jt_lo + 1;                 // key tiles of this CTA
+  const int blk0 = (a.M + i0) / 128 - jt_lo;        // upper distance block of the first (oldest) tile; tile n completes block blk0 - n
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmM); tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmP); tma_prefetch_desc(&tmPB); tma_prefetch_desc(&tmDS); tma_prefetch_desc(&tmDD);
+    for (int i = 0; i < D_COUNT; i++) {
+      uint32_t cnt = 1;
+      if (i == D_DPFREE0 || i == D_DPFREE1 || i == D_DSFULL || i == D_ZINIT) cnt = 8;
+      if (i == D_DSFREE || i == D_SFREE0 || i == D_SFREE1) cnt = 2;       // the MMA that read the buffer + the TMA store that read it
+      mbar_init(&bar[i], cnt);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_holder);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 8) {
+      // =========================================== TMA loads ===========================================
+      if (lane == 0) {
+        mbar_expect_tx(&bar[D_DOFULL], T16K);
+        tma_load_2d(smem + DQO_DO, &tmDO, h * 64, b * a.T + i0, &bar[D_DOFULL]);
+        auto load_kv = [&](int n, int which) {      // which: 0 = K, 1 = V
+          const int j0 = (jt_lo + n) * 128;
+          mbar_wait(&bar[which ? D_VEMPTY : D_KEMPTY], (n & 1) ^ 1);
+          uint64_t* full = &bar[which ? D_VFULL : D_KFULL];
+          mbar_expect_tx(full, T16K);
+          uint8_t* dst = smem + (which ? DQO_V : DQO_K);
+          if (j0 < a.M) tma_load_2d(dst, &tmM, which * HD + h * 64, b * a.M + j0, full);
+          else tma_load_2d(dst, &tmX, (1 + which) * HD + h * 64, b * a.T + (j0 - a.M), full);
+        };
+        auto load_r = [&](int n) {
+          mbar_wait(&bar[D_REMPTY], (n & 1) ^ 1);
+          mbar_expect_tx(&bar[D_RFULL], T16K);
+          tma_load_2d(smem + DQO_R, &tmR, h * 64, (blk0 - n) * 128, &bar[D_RFULL]);
+        };
+        auto load_p = [&](int n) {
+          const int s = n & 1, j0 = (jt_lo + n) * 128;
+          mbar_wait(&bar[D_PFREE0 + s], ((n >> 1) & 1) ^ 1);
+          mbar_expect_tx(&bar[D_PFULL0 + s], 2 * T16K);
+          tma_load_2d(smem + DQO_P + s * 2 * T16K, &tmP, j0, bh * a.T + i0, &bar[D_PFULL0 + s]);
+          tma_load_2d(smem + DQO_P + s * 2 * T16K + T16K, &tmP, j0 + 64, bh * a.T + i0, &bar[D_PFULL0 + s]);
+        };
+        load_kv(0, 1);
+        load_p(0);
+        load_kv(0, 0);
+        load_r(0);
+        if (NT > 1) load_p(1);
+        for (int n = 1; n < NT; n++) {
+          load_kv(n, 1);
+          if (n + 1 < NT) load_p(n + 1);
+          load_kv(n, 0);
+          load_r(n);
+        }
+      }
+    } else if (warp == 9) {
+      // =========================================== MMA issuer ===========================================
+      if (lane == 0) {
+        constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+        constexpr uint32_t idesc_n64 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t d_o = smem_u32(smem + DQO_DO), kk = smem_u32(smem + DQO_K), vv = smem_u32(smem + DQO_V), rr = smem_u32(smem + DQO_R),
+                       ds = smem_u32(smem + DQO_DS), st = smem_u32(smem + DQO_STRIP);
+        auto m1 = [&](int n) {                       // dPd(n) = dO V(n)^T
+          const int s = n & 1;
+          mbar_wait(&bar[D_VFULL], n & 1);
+          if (n >= 2) mbar_wait(&bar[D_DPFREE0 + s], ((n >> 1) & 1) ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; k++) umma_bf16(tmem_base + DTM_DP + 128 * s, desc_kmajor(d_o + k * 32), desc_kmajor(vv + k * 32), idesc_s, (uint32_t)(k > 0));
+          umma_commit(&bar[D_DPFULL0 + s]);
+          umma_commit(&bar[D_VEMPTY]);
+        };
+        mbar_wait(&bar[D_DOFULL], 0);
+        m1(0);
+        if (NT > 1) m1(1);
+        for (int n = 0; n < NT; n++) {
+          const int sb = (blk0 - n) & 1;
+          mbar_wait(&bar[D_DSFULL], n & 1);
+          mbar_wait(&bar[D_KFULL], n & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int hf = 0; hf < 2; hf++)
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              umma_bf16(tmem_base + DTM_AC, desc_kmajor(ds + hf * T16K + k * 32), desc_mnmajor(kk + hf * 8192 + k * 2048), idesc_n64,
+                        (uint32_t)(n > 0 || hf > 0 || k > 0));
+          umma_commit(&bar[D_DSFREE]);
+          umma_commit(&bar[D_KEMPTY]);
+          mbar_wait(&bar[D_RFULL], n & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int hf = 0; hf < 2; hf++)
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              umma_bf16(tmem_base + DTM_BD, desc_kmajor(st + sb * 2 * T16K + hf * T16K + k * 32), desc_mnmajor(rr + hf * 8192 + k * 2048),
+                        idesc_n64, (uint32_t)(n > 0 || hf > 0 || k > 0));
+          umma_commit(&bar[D_SFREE0 + sb]);
+          umma_commit(&bar[D_REMPTY]);
+          if (n + 2 < NT) m1(n + 2);
+        }
+        umma_commit(&bar[D_DQFULL]);
+      }
+    } else if (warp == 10) {
+      // =========================================== TMA stores ===========================================
+      if (lane == 0) {
+        const uint32_t ds = smem_u32(smem + DQO_DS), st = smem_u32(smem + DQO_STRIP), pp = smem_u32(smem + DQO_P);
+        const int row_bh = bh * a.T + i0, row_b = b * a.T + i0;
+        mbar_wait(&bar[D_ZINIT], 0);
+        for (int blk = blk0 + 1; blk < S / 128; blk++) {   // distances beyond the oldest visible key: zeros for the dRk GEMM
+          tma_store_2d(&tmDD, st + (blk0 & 1) * 2 * T16K, h * S + blk * 128, row_b);
+          tma_store_2d(&tmDD, st + (blk0 & 1) * 2 * T16K + T16K, h * S + blk * 128 + 64, row_b);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(&bar[D_ZDONE]);
+        for (int n = 0; n < NT; n++) {
+          const int j0 = (jt_lo + n) * 128, U = blk0 - n, sb = U & 1;
+          mbar_wait(&bar[D_DSFULL], n & 1);
+#pragma unroll
+          for (int hf = 0; hf < 2; hf++) {
+            tma_store_2d(&tmDS, ds + hf * T16K, j0 + 64 * hf, row_bh);
+            tma_store_2d(&tmPB, pp + (n & 1) * 2 * T16K + hf * T16K, j0 + 64 * hf, row_bh);
+            tma_store_2d(&tmDD, st + sb * 2 * T16K + hf * T16K, h * S + U * 128 + 64 * hf, row_b);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(&bar[D_PFREE0 + (n & 1)]);
+          mbar_arrive(&bar[D_DSFREE]);
+          mbar_arrive(&bar[D_SFREE0 + sb]);
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      }
+    }
+  } else {
+    // =========================================== tile math ===========================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int hf = warp >> 2, q4 = warp & 3;
+    const int r = q4 * 32 + lane;                   // query row of this thread inside the tile
+    const int row = i0 + r;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const uint32_t rowoff = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+    const int rsw = r & 7;
+    {   // both distance-block buffers start as zeros
+      uint4* z = (uint4*)(smem + DQO_STRIP) + threadIdx.x;
+#pragma unroll
+      for (int i = 0; i < 4 * T16K / 16 / 256; i++) z[i * 256] = make_uint4(0u, 0u, 0u, 0u);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[D_ZINIT]);
+    }
+    const long long bhrow = (long long)bh * a.T + row;
+    const float lse2 = a.lse[bhrow] * LOG2E, dl = ba.delta[bhrow];
+    const float c2 = a.scale * LOG2E;
+    const uint32_t drop_base = (uint32_t)((bhrow * S) >> 1);
+    const float* mrow = a.m_save + bhrow * (S >> 6);
+    const int C0 = 128 + r - 64 * hf;               // strip column of this thread's first key: c = C0 - jj
+    uint8_t* const strip = smem + DQO_STRIP;
+
+    for (int n = 0; n < NT; n++) {
+      const int j0h = (jt_lo + n) * 128 + 64 * hf;   // full-context index of this thread's first key
+      const float mblk = __ldg(mrow + (j0h >> 6));
+      const int s = n & 1, U = blk0 - n, sbU = U & 1;
+      const bool has_L = n + 1 < NT;                 // the diagonal tile's lower block would hold negative distances (masked keys)
+      mbar_wait(&bar[D_PFULL0 + s], (n >> 1) & 1);
+      mbar_wait(&bar[D_DPFULL0 + s], (n >> 1) & 1);
+      tc_fence_after();
+      float dpd[64];
+      {
+        uint32_t x0[32], x1[32];
+        tmem_ld_32x32(t_lane + DTM_DP + 128 * s + 64 * hf, x0);
+        tmem_ld_32x32(t_lane + DTM_DP + 128 * s + 64 * hf + 32, x1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i++) { dpd[i] = __uint_as_float(x0[i]); dpd[32 + i] = __uint_as_float(x1[i]); }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[D_DPFREE0 + s]);
+      const float fac = ex2_fast(mblk * c2 - lse2);
+      if (n >= 1) mbar_wait(&bar[D_DSFREE], (n - 1) & 1);
+      if (n == 0) mbar_wait(&bar[D_ZDONE], 0);
+      if (n >= 1 && has_L) mbar_wait(&bar[D_SFREE0 + (sbU ^ 1)], ((n - 1) >> 1) & 1);
+      uint8_t* const prow = smem + DQO_P + s * 2 * T16K + hf * T16K + rowoff;
+      uint8_t* const dsrow = smem + DQO_DS + hf * T16K + rowoff;
+      uint8_t* const bufU = strip + sbU * 2 * T16K + rowoff;
+      uint8_t* const bufL = strip + (sbU ^ 1) * 2 * T16K + rowoff;
+      uint32_t dsw[32];                               // dS of this thread's 64 keys, bf16 pairs (keys 2 i, 2 i + 1)
+#pragma unroll
+      for (int ck = 0; ck < 8; ck++) {
+        const uint32_t choff = (uint32_t)((ck ^ rsw) << 4);
+        const uint4 raw = *(const uint4*)(prow + choff);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+        uint32_t pk[4], dk[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int pp = 4 * ck + e;
+          float keep0 = 1.f, keep1 = 1.f;
+          if (a.drop_thresh) {
+            const uint32_t hb = drop_pair_bits(a.drop_seed, drop_base + (uint32_t)(j0h >> 1) + pp);
+            keep0 = ((hb & 0xFFFFu) >= a.drop_thresh) ? a.drop_scale : 0.f;
+            keep1 = ((hb >> 16) >= a.drop_thresh) ? a.drop_scale : 0.f;
+          }
+          const float p0 = bf16lo(w[e]) * fac, p1 = bf16hi(w[e]) * fac;
+          const float s0 = p0 * (dpd[2 * pp] * keep0 - dl) * a.scale, s1 = p1 * (dpd[2 * pp + 1] * keep1 - dl) * a.scale;
+          pk[e] = pack_bf16x2(keep0 * p0, keep1 * p1);
+          dk[e] = pack_bf16x2(s0, s1);
+          dsw[pp] = dk[e];
+        }
+        *(uint4*)(prow + choff) = make_uint4(pk[0], pk[1], pk[2], pk[3]);      // Pd over the saved probabilities (own row, own chunk)
+        *(uint4*)(dsrow + choff) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+      }
+      // ---- the same 64 values in (row, distance) coordinates: key jj sits in column C0 - jj of this tile's [128][256] window, i.e. the
+      // run of columns [C0 - 63, C0] in REVERSED key order.  The run starts at a lane-dependent offset a = (C0 - 63) & 7 inside an aligned
+      // 8-column chunk (16 bytes of the swizzled layout), so the reversed run is shifted right by `a` elements with a three-stage barrel
+      // shifter on the packed words (select + byte-permute), which leaves seven full chunks (one 16-byte store each) and two partial ones
+      // at the ends (element stores: the rest of those chunks belongs to the neighbouring key tile, possibly being written right now).
+      {
+        const int c_lo = C0 - 63, sh = c_lo & 7, cbase = c_lo - sh;
+        uint32_t y[36];
+#pragma unroll
+        for (int i = 0; i < 36; i++) {                // stage 0: reverse (word i = keys 63 - 2 i, 62 - 2 i), shifted by one element if sh & 1
+          const uint32_t cur = i < 32 ? __byte_perm(dsw[31 - i], 0u, 0x1032) : 0u;
+          const uint32_t prev = (i >= 1 && i <= 32) ? __byte_perm(dsw[32 - i], 0u, 0x1032) : 0u;
+          y[i] = (sh & 1) ? __byte_perm(prev, cur, 0x5432) : cur;
+        }
+        if (sh & 2) {
+#pragma unroll
+          for (int i = 35; i >= 1; i--) y[i] = y[i - 1];
+        }
+        if (sh & 4) {
+#pragma unroll
+          for (int i = 35; i >= 2; i--) y[i] = y[i - 2];
+        }
+        auto chunk_ptr = [&](int c) -> uint8_t* {     // address of the aligned 8-column chunk at window column c; nullptr: not stored
+          if (c >= 128) { const int cc = c - 128; return bufU + (cc >> 6) * T16K + ((((cc & 63) >> 3) ^ rsw) << 4); }
+          return has_L ? bufL + (c >> 6) * T16K + ((((c & 63) >> 3) ^ rsw) << 4) : nullptr;
+        };
+#pragma unroll
+        for (int j = 1; j < 8; j++) {
+          uint8_t* dst = chunk_ptr(cbase + 8 * j);
+          if (dst) *(uint4*)dst = make_uint4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+        }
+        uint8_t* d0 = chunk_ptr(cbase);
+        uint8_t* d8 = chunk_ptr(cbase + 64);
+        if (sh == 0) {
+          if (d0) *(uint4*)d0 = make_uint4(y[0], y[1], y[2], y[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            const uint16_t lo = (uint16_t)((e & 1) ? (y[e >> 1] >> 16) : (y[e >> 1] & 0xFFFFu));
+            const uint16_t hi = (uint16_t)((e & 1) ? (y[32 + (e >> 1)] >> 16) : (y[32 + (e >> 1)] & 0xFFFFu));
+            if (d0 && e >= sh) *(uint16_t*)(d0 + 2 * e) = lo;
+            if (d8 && e < sh) *(uint16_t*)(d8 + 2 * e) = hi;
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar[D_DSFULL]);
+    }
+
+    // ---- dq = content part + position part (columns 32 hf .. 32 hf + 31 of this row); du / dv = their column sums over all rows
+    mbar_wait(&bar[D_DQFULL], 0);
+    tc_fence_after();
+    uint32_t xa[32], xb[32];
+    tmem_ld_32x32(t_lane + DTM_AC + 32 * hf, xa);
+    tmem_ld_32x32(t_lane + DTM_BD + 32 * hf, xb);
+    tmem_ld_wait();
+    tc_fence_before();
+    bf16* qrow = ba.dqkv_x + ((long long)b * a.T + row) * a.ldx + h * 64 + 32 * hf;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int d0 = 8 * k + 2 * e;
+        o[e] = pack_bf16x2(__uint_as_float(xa[d0]) + __uint_as_float(xb[d0]), __uint_as_float(xa[d0 + 1]) + __uint_as_float(xb[d0 + 1]));
+      }
+      *(uint4*)(qrow + 8 * k) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    float* red = (float*)(smem + DQO_K);            // the K tile is dead (every MMA has retired): [8 warps][64] column sums
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+      const float sa = warp_sum(__uint_as_float(xa[i])), sbv = warp_sum(__uint_as_float(xb[i]));
+      if (lane == 0) { red[warp * 64 + i] = sa; red[warp * 64 + 32 + i] = sbv; }
+    }
+    softmax_bar_sync();
+    if (threadIdx.x < 128) {
+      const int t = threadIdx.x >> 6, cc = threadIdx.x & 63, w0 = (cc >> 5) * 4;
+      float sum = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; q++) sum += red[(w0 + q) * 64 + t * 32 + (cc & 31)];
+      atomicAdd((t ? ba.dv : ba.du) + h * 64 + cc, sum);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem_base);
+}
+
 }  // namespace
+
+bool attn_bwd_dq_tc_supported(const AttnTrainBwdArgs& ba) {
+  static const bool off = getenv("DMG_ATTN_DQ_MMA_SYNC") != nullptr;
+  const AttnTrainArgs& a = ba.f;
+  return !off && a.p_save && a.m_save && ba.p_buf && ba.ds_buf && a.T % 128 == 0 && a.M % 128 == 0 && a.mem_count % 128 == 0 &&
+         a.ldx % 8 == 0 && (a.M == 0 || a.ldm % 8 == 0);
+}
+
+int attn_bwd_dq_tc(const AttnTrainBwdArgs& ba, cudaStream_t st) {
+  const AttnTrainArgs& a = ba.f;
+  static bool configured = false;
+  if (!configured) {
+    DMG_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQT_SMEM));
+    configured = true;
+  }
+  const int HD = a.H * 64;
+  const long long S = (long long)a.M + a.T, rows_bh = (long long)a.B * a.H * a.T;
+  const TensorMap2D *tx = nullptr, *tm = nullptr, *tr = nullptr, *tdo = nullptr, *tp = nullptr, *tpb = nullptr, *tds = nullptr, *tdd = nullptr;
+  if (train_get_tmap(a.qkv_x, 3 * HD, (long long)a.B * a.T, a.ldx, 128, &tx)) return -1;
+  if (a.M > 0) { if (train_get_tmap(a.kv_m, 2 * HD, (long long)a.B * a.M, a.ldm, 128, &tm)) return -1; }
+  else tm = tx;
+  if (train_get_tmap(a.rk, HD, S, HD, 128, &tr)) return -1;
+  if (train_get_tmap(ba.dout, HD, (long long)a.B * a.T, HD, 128, &tdo)) return -1;
+  if (train_get_tmap(a.p_save, S, rows_bh, S, 128, &tp)) return -1;
+  if (train_get_tmap(ba.p_buf, S, rows_bh, S, 128, &tpb)) return -1;
+  if (train_get_tmap(ba.ds_buf, S, rows_bh, S, 128, &tds)) return -1;
+  if (train_get_tmap(ba.ds_dist, (long long)a.H * S, (long long)a.B * a.T, (long long)a.H * S, 128, &tdd)) return -1;
+  return launch_np(attn_bwd_dq_tc_kernel, dim3(a.B * a.H * (a.T / 128)), dim3(DQT_THREADS), (size_t)DQT_SMEM, st, *(const CUtensorMap*)tx->bytes,
+                   *(const CUtensorMap*)tm->bytes, *(const CUtensorMap*)tr->bytes, *(const CUtensorMap*)tdo->bytes, *(const CUtensorMap*)tp->bytes,
+                   *(const CUtensorMap*)tpb->bytes, *(const CUtensorMap*)tds->bytes, *(const CUtensorMap*)tdd->bytes, ba);
+}
+
 
 bool attn_bwd_dkv_tc_supported(const AttnTrainBwdArgs& ba) {
   static const bool off = getenv("DMG_ATTN_DKV_MMA_SYNC") != nullptr;

@@ -120,6 +120,9 @@ bool attn_train_fwd_tc_supported(const AttnTrainArgs& a);
 int attn_train_fwd_tc(const AttnTrainArgs& a, cudaStream_t st);
 struct AttnTrainBwdArgs;
 bool attn_bwd_dkv_tc_supported(const AttnTrainBwdArgs& ba);
+// dQ (+ the P / dS tiles and dS in distance coordinates) on tcgen05 from the saved probabilities; same shapes as the dK/dV kernel
+bool attn_bwd_dq_tc_supported(const AttnTrainBwdArgs& ba);
+int attn_bwd_dq_tc(const AttnTrainBwdArgs& ba, cudaStream_t st);
 int attn_bwd_dkv_tc(const AttnTrainBwdArgs& ba, cudaStream_t st);
 struct TensorMap2D;
 int train_get_tmap(const void* base, long long inner, long long rows, long long ld, int box_rows, const TensorMap2D** out);
