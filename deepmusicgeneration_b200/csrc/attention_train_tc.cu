@@ -741,17 +741,22 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         for (int n = 0; n < NT; n++) {
           const int j0 = (jt_lo + n) * 128, U = blk0 - n, sb = U & 1;
           mbar_wait(&bar[D_DSFULL], n & 1);
-#pragma unroll
-          for (int hf = 0; hf < 2; hf++) {
-            tma_store_2d(&tmDS, ds + hf * T16K, j0 + 64 * hf, row_bh);
-            tma_store_2d(&tmPB, pp + (n & 1) * 2 * T16K + hf * T16K, j0 + 64 * hf, row_bh);
-            tma_store_2d(&tmDD, st + sb * 2 * T16K + hf * T16K, h * S + U * 128 + 64 * hf, row_b);
-          }
+          // three bulk groups, released in the order the tile math needs the buffers back: dS tile, distance block, probabilities
+          tma_store_2d(&tmDS, ds, j0, row_bh);
+          tma_store_2d(&tmDS, ds + T16K, j0 + 64, row_bh);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          tma_store_2d(&tmDD, st + sb * 2 * T16K, h * S + U * 128, row_b);
+          tma_store_2d(&tmDD, st + sb * 2 * T16K + T16K, h * S + U * 128 + 64, row_b);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          tma_store_2d(&tmPB, pp + (n & 1) * 2 * T16K, j0, row_bh);
+          tma_store_2d(&tmPB, pp + (n & 1) * 2 * T16K + T16K, j0 + 64, row_bh);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+          mbar_arrive(&bar[D_DSFREE]);
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          mbar_arrive(&bar[D_SFREE0 + sb]);
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           mbar_arrive(&bar[D_PFREE0 + (n & 1)]);
-          mbar_arrive(&bar[D_DSFREE]);
-          mbar_arrive(&bar[D_SFREE0 + sb]);
         }
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       }
@@ -781,9 +786,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const int C0 = 128 + r - 64 * hf;               // strip column of this thread's first key: c = C0 - jj
     uint8_t* const strip = smem + DQO_STRIP;
 
+    float mnext = __ldg(mrow + ((jt_lo * 128 + 64 * hf) >> 6));
     for (int n = 0; n < NT; n++) {
       const int j0h = (jt_lo + n) * 128 + 64 * hf;   // full-context index of this thread's first key
-      const float mblk = __ldg(mrow + (j0h >> 6));
+      const float mblk = mnext;
+      if (n + 1 < NT) mnext = __ldg(mrow + ((j0h + 128) >> 6));
       const int s = n & 1, U = blk0 - n, sbU = U & 1;
       const bool has_L = n + 1 < NT;                 // the diagonal tile's lower block would hold negative distances (masked keys)
       mbar_wait(&bar[D_PFULL0 + s], (n >> 1) & 1);
@@ -802,9 +809,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[D_DPFREE0 + s]);
       const float fac = ex2_fast(mblk * c2 - lse2);
-      if (n >= 1) mbar_wait(&bar[D_DSFREE], (n - 1) & 1);
-      if (n == 0) mbar_wait(&bar[D_ZDONE], 0);
-      if (n >= 1 && has_L) mbar_wait(&bar[D_SFREE0 + (sbU ^ 1)], ((n - 1) >> 1) & 1);
       uint8_t* const prow = smem + DQO_P + s * 2 * T16K + hf * T16K + rowoff;
       uint8_t* const dsrow = smem + DQO_DS + hf * T16K + rowoff;
       uint8_t* const bufU = strip + sbU * 2 * T16K + rowoff;
@@ -815,7 +819,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         const uint32_t choff = (uint32_t)((ck ^ rsw) << 4);
         const uint4 raw = *(const uint4*)(prow + choff);
         const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-        uint32_t pk[4], dk[4];
+        uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const int pp = 4 * ck + e;
@@ -828,12 +832,18 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           const float p0 = bf16lo(w[e]) * fac, p1 = bf16hi(w[e]) * fac;
           const float s0 = p0 * (dpd[2 * pp] * keep0 - dl) * a.scale, s1 = p1 * (dpd[2 * pp + 1] * keep1 - dl) * a.scale;
           pk[e] = pack_bf16x2(keep0 * p0, keep1 * p1);
-          dk[e] = pack_bf16x2(s0, s1);
-          dsw[pp] = dk[e];
+          dsw[pp] = pack_bf16x2(s0, s1);
         }
         *(uint4*)(prow + choff) = make_uint4(pk[0], pk[1], pk[2], pk[3]);      // Pd over the saved probabilities (own row, own chunk)
-        *(uint4*)(dsrow + choff) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
       }
+      // the dS tile and the distance blocks are single buffers: the previous tile's MMAs and TMA stores must have read them (they had the
+      // whole tile math above to do so)
+      if (n >= 1) mbar_wait(&bar[D_DSFREE], (n - 1) & 1);
+#pragma unroll
+      for (int ck = 0; ck < 8; ck++)
+        *(uint4*)(dsrow + ((ck ^ rsw) << 4)) = make_uint4(dsw[4 * ck], dsw[4 * ck + 1], dsw[4 * ck + 2], dsw[4 * ck + 3]);
+      if (n == 0) mbar_wait(&bar[D_ZDONE], 0);
+      if (n >= 1 && has_L) mbar_wait(&bar[D_SFREE0 + (sbU ^ 1)], ((n - 1) >> 1) & 1);
       // ---- the same 64 values in (row, distance) coordinates: key jj sits in column C0 - jj of this tile's [128][256] window, i.e. the
       // run of columns [C0 - 63, C0] in REVERSED key order.  The run starts at a lane-dependent offset a = (C0 - 63) & 7 inside an aligned
       // 8-column chunk (16 bytes of the swizzled layout), so the reversed run is shifted right by `a` elements with a three-stage barrel
