@@ -66,7 +66,10 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // SAVE: also write the undropped probabilities / block maxima for the backward (AttnTrainArgs::p_save, m_save)
-template <bool SAVE>
+// RING: the inference engine's layout - the memory keys / values are the per-head K/V RINGS ([stream][head][slot][64]; tmM = K ring,
+//       tmP = V ring, logical memory row j = slot (ring_head + j) % M, ring_head a multiple of 128) and the relative-position keys the
+//       per-head cache Rd ([head][Dcap][64], tmR); multi-token segments over a warm memory (chunked prefill, validation passes)
+template <bool SAVE, bool RING>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmM,
                          const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmP,
@@ -89,7 +92,7 @@ attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmM);
     tma_prefetch_desc(&tmR);
-    if (SAVE) tma_prefetch_desc(&tmP);
+    if (SAVE || RING) tma_prefetch_desc(&tmP);
     for (int i = 0; i < B_COUNT; i++) {
       uint32_t cnt = 1;
       if (i == B_QREADY || i == B_SFREE) cnt = TC_SOFT_WARPS;
@@ -116,21 +119,31 @@ attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         const int s = n & 1, j0 = (jt_lo + n) * 128;
         mbar_wait(&bar[B_KEMPTY0 + s], ((n >> 1) & 1) ^ 1);
         mbar_expect_tx(&bar[B_KFULL0 + s], T16K);
-        if (j0 < a.M) tma_load_2d(smem + OFF_K + s * T16K, &tmM, h * 64, b * a.M + j0, &bar[B_KFULL0 + s]);
-        else tma_load_2d(smem + OFF_K + s * T16K, &tmX, HD + h * 64, b * a.T + (j0 - a.M), &bar[B_KFULL0 + s]);
+        if (j0 < a.M) {
+          if (RING) tma_load_2d(smem + OFF_K + s * T16K, &tmM, 0, ((a.ring_b0 + b) * a.H + h) * a.M + (a.ring_head + j0) % a.M, &bar[B_KFULL0 + s]);
+          else tma_load_2d(smem + OFF_K + s * T16K, &tmM, h * 64, b * a.M + j0, &bar[B_KFULL0 + s]);
+        } else {
+          tma_load_2d(smem + OFF_K + s * T16K, &tmX, HD + h * 64, b * a.T + (j0 - a.M), &bar[B_KFULL0 + s]);
+        }
       };
       auto load_r = [&](int k) {                    // k-th block load: block blk0 - k (may be -1: all rows out of bounds -> zeros)
         const int blk = blk0 - k, s = blk & 1;
         mbar_wait(&bar[B_REMPTY0 + s], ((k >> 1) & 1) ^ 1);
         mbar_expect_tx(&bar[B_RFULL0 + s], T16K);
-        tma_load_2d(smem + OFF_R + s * T16K, &tmR, h * 64, blk * 128, &bar[B_RFULL0 + s]);
+        // RING: block -1 of head h > 0 reads the previous head's rows instead of zeros - only masked (future) keys ever meet it
+        if (RING) tma_load_2d(smem + OFF_R + s * T16K, &tmR, 0, h * a.ring_dcap + blk * 128, &bar[B_RFULL0 + s]);
+        else tma_load_2d(smem + OFF_R + s * T16K, &tmR, h * 64, blk * 128, &bar[B_RFULL0 + s]);
       };
       auto load_v = [&](int n) {
         const int j0 = (jt_lo + n) * 128;
         mbar_wait(&bar[B_VEMPTY], (n & 1) ^ 1);
         mbar_expect_tx(&bar[B_VFULL], T16K);
-        if (j0 < a.M) tma_load_2d(smem + OFF_V, &tmM, HD + h * 64, b * a.M + j0, &bar[B_VFULL]);
-        else tma_load_2d(smem + OFF_V, &tmX, 2 * HD + h * 64, b * a.T + (j0 - a.M), &bar[B_VFULL]);
+        if (j0 < a.M) {
+          if (RING) tma_load_2d(smem + OFF_V, &tmP, 0, ((a.ring_b0 + b) * a.H + h) * a.M + (a.ring_head + j0) % a.M, &bar[B_VFULL]);
+          else tma_load_2d(smem + OFF_V, &tmM, HD + h * 64, b * a.M + j0, &bar[B_VFULL]);
+        } else {
+          tma_load_2d(smem + OFF_V, &tmX, 2 * HD + h * 64, b * a.T + (j0 - a.M), &bar[B_VFULL]);
+        }
       };
       load_k(0);
       load_r(0);
@@ -412,7 +425,7 @@ attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         }
         *(uint4*)(orow + 8 * k) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      a.lse[(long long)bh * a.T + row] = (m * c + log2f(l)) * LN2;
+      if (a.lse) a.lse[(long long)bh * a.T + row] = (m * c + log2f(l)) * LN2;
     }
   }
   tc_fence_before();
@@ -1003,8 +1016,8 @@ bool attn_train_fwd_tc_supported(const AttnTrainArgs& a) {
 int attn_train_fwd_tc(const AttnTrainArgs& a, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    DMG_CUDA_OK(cudaFuncSetAttribute(attn_train_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    DMG_CUDA_OK(cudaFuncSetAttribute(attn_train_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    DMG_CUDA_OK(cudaFuncSetAttribute(attn_train_fwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    DMG_CUDA_OK(cudaFuncSetAttribute(attn_train_fwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     configured = true;
   }
   DMG_CHECK((a.p_save == nullptr) == (a.m_save == nullptr), "training attention: p_save and m_save go together");
@@ -1023,12 +1036,42 @@ int attn_train_fwd_tc(const AttnTrainArgs& a, cudaStream_t st) {
       if (train_get_tmap(a.qu_save, HD, (long long)a.B * a.T, HD, 128, &tqu)) return -1;
       if (train_get_tmap(a.qv_save, HD, (long long)a.B * a.T, HD, 128, &tqv)) return -1;
     }
-    return launch_np(attn_train_fwd_tc_kernel<true>, grid, block, (size_t)TC_SMEM, st, *(const CUtensorMap*)tx->bytes,
+    return launch_np(attn_train_fwd_tc_kernel<true, false>, grid, block, (size_t)TC_SMEM, st, *(const CUtensorMap*)tx->bytes,
                      *(const CUtensorMap*)tm->bytes, *(const CUtensorMap*)tr->bytes, *(const CUtensorMap*)tp->bytes,
                      *(const CUtensorMap*)tqu->bytes, *(const CUtensorMap*)tqv->bytes, a);
   }
-  return launch_np(attn_train_fwd_tc_kernel<false>, grid, block, (size_t)TC_SMEM, st, *(const CUtensorMap*)tx->bytes,
+  return launch_np(attn_train_fwd_tc_kernel<false, false>, grid, block, (size_t)TC_SMEM, st, *(const CUtensorMap*)tx->bytes,
                    *(const CUtensorMap*)tm->bytes, *(const CUtensorMap*)tr->bytes, *(const CUtensorMap*)tx->bytes,
+                   *(const CUtensorMap*)tx->bytes, *(const CUtensorMap*)tx->bytes, a);
+}
+
+// The same kernel over the inference engine's K/V rings and per-head Rd cache (model.cu: bf16 segments of T % 128 == 0 tokens over a
+// warm memory with mem_count, the ring position and mem_len multiples of 128).  qkv16: [B*T, 3*H*64] bf16 of the current segment.
+bool attn_fwd_tc_ring_supported(int T, int Dh, int M, int mem_count, int pos_total) {
+  return Dh == 64 && T % 128 == 0 && M > 0 && M % 128 == 0 && mem_count > 0 && mem_count % 128 == 0 && pos_total % 128 == 0;
+}
+
+int attn_fwd_tc_ring(const bf16* qkv16, const bf16* kring, const bf16* vring, const bf16* rd, int Dcap, const float* u, const float* v,
+                     bf16* out, int B, int T, int H, int M, int mem_count, int win, int k, int pos_total, int b0, int max_batch, float scale,
+                     cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    DMG_CUDA_OK(cudaFuncSetAttribute(attn_train_fwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    configured = true;
+  }
+  const int HD = H * 64;
+  AttnTrainArgs a;
+  a.qkv_x = qkv16; a.ldx = 3 * HD; a.kv_m = nullptr; a.ldm = 0; a.rk = rd; a.u = u; a.v = v; a.out = out; a.lse = nullptr;
+  a.B = B; a.T = T; a.H = H; a.M = M; a.mem_count = mem_count; a.win = win; a.k = k; a.scale = scale;
+  a.drop_thresh = 0; a.drop_seed = 0; a.drop_scale = 1.f;
+  a.ring_head = pos_total % M; a.ring_b0 = b0; a.ring_dcap = Dcap;
+  const TensorMap2D *tx = nullptr, *tk = nullptr, *tv = nullptr, *tr = nullptr;
+  if (train_get_tmap(qkv16, 3 * HD, (long long)B * T, 3 * HD, 128, &tx)) return -1;
+  if (train_get_tmap(kring, 64, (long long)max_batch * H * M, 64, 128, &tk)) return -1;
+  if (train_get_tmap(vring, 64, (long long)max_batch * H * M, 64, 128, &tv)) return -1;
+  if (train_get_tmap(rd, 64, (long long)H * Dcap, 64, 128, &tr)) return -1;
+  return launch_np(attn_train_fwd_tc_kernel<false, true>, dim3(B * H * (T / 128)), dim3(TC_THREADS), (size_t)TC_SMEM, st,
+                   *(const CUtensorMap*)tx->bytes, *(const CUtensorMap*)tk->bytes, *(const CUtensorMap*)tr->bytes, *(const CUtensorMap*)tv->bytes,
                    *(const CUtensorMap*)tx->bytes, *(const CUtensorMap*)tx->bytes, a);
 }
 

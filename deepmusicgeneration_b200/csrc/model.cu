@@ -150,6 +150,10 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
   // segments without memory (prefill after reset(), every BERT forward) in bf16: flash attention on the tensor cores
   const bool flash = m->is_bf16 && m->use_tc && T_len > 1 && (bert || (m->mem_count == 0 && win == 1 && k == 1)) &&
                      m->Dcap >= T_len && !(m->kflags & DMG_KF_NO_FLASH);
+  // bf16 segments of whole 128-token tiles over a WARM memory (chunked prefill of long seeds, validation passes): the tcgen05 attention of
+  // the training forward reading the K/V rings and the per-head Rd cache in place (attention_train_tc.cu)
+  const bool tc_warm = m->is_bf16 && m->use_tc && !bert && !flash && !fast_decode && T_len > 1 && !(m->kflags & DMG_KF_NO_FLASH) &&
+                       m->qkv16 != nullptr && attn_fwd_tc_ring_supported(T_len, c.d_head, M, m->mem_count, m->pos_total);
   // one-token step, product path: per layer ONE decode-attention launch + ONE fused layer launch (decode_layer.cu)
   const bool fused = fast_decode && m->fused_decode && !c.keep_hidden && m->layers[0].wqkv.has_tm && rows <= m->dl_rows;
   if (fused) {
@@ -193,10 +197,16 @@ static int forward_chunk(dmg_model* m, const long long* ids, const long long* po
       }
       if (M > 0 && ring_append_kv<bf16, bf16>(m->qkv16, (bf16*)L.kring, (bf16*)L.vring, nb, T_len, c.n_heads, c.d_head, M,
                                                m->pos_total, b0, c.max_batch, st)) return -1;
+    } else if (tc_warm) {
+      if (linear(m, A_XA, xa, L.wqkv, L.bqkv, m->qkv16, 3 * HD, rows, 0, 1, st)) return -1;
+      if (attn_fwd_tc_ring(m->qkv16, (const bf16*)L.kring, (const bf16*)L.vring, (const bf16*)L.rd, m->Dcap, m->u, m->v, (bf16*)m->attn, nb,
+                           T_len, c.n_heads, M, m->mem_count, win, k, m->pos_total, b0, c.max_batch, 1.f / sqrtf((float)c.d_head), st)) return -1;
+      if (ring_append_kv<bf16, bf16>(m->qkv16, (bf16*)L.kring, (bf16*)L.vring, nb, T_len, c.n_heads, c.d_head, M, m->pos_total, b0,
+                                     c.max_batch, st)) return -1;
     } else if (linear(m, A_XA, xa, L.wqkv, L.bqkv, m->qkv, 3 * HD, rows, 0, 0, st)) {
       return -1;
     }
-    if (flash) {
+    if (flash || tc_warm) {
     } else if (fast_decode) {
       AttnDecodeArgs a;
       a.qkv = m->qkv;

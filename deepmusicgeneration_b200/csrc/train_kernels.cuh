@@ -113,11 +113,17 @@ struct AttnTrainArgs {
   // dK contraction (tcgen05 dK/dV kernel) and of the dRk GEMM in the backward
   bf16* qu_save = nullptr;
   bf16* qv_save = nullptr;
+  // inference engine (attn_fwd_tc_ring): memory keys / values in per-head rings, relative-position keys in the per-head Rd cache
+  int ring_head = 0, ring_b0 = 0, ring_dcap = 0;
 };
 int attn_train_fwd(const AttnTrainArgs& a, cudaStream_t st);
 // tcgen05 / TMEM / TMA forward (attention_train_tc.cu): T, M, mem_count multiples of 128; attn_train_fwd dispatches to it
 bool attn_train_fwd_tc_supported(const AttnTrainArgs& a);
 int attn_train_fwd_tc(const AttnTrainArgs& a, cudaStream_t st);
+bool attn_fwd_tc_ring_supported(int T, int Dh, int M, int mem_count, int pos_total);
+int attn_fwd_tc_ring(const bf16* qkv16, const bf16* kring, const bf16* vring, const bf16* rd, int Dcap, const float* u, const float* v,
+                     bf16* out, int B, int T, int H, int M, int mem_count, int win, int k, int pos_total, int b0, int max_batch, float scale,
+                     cudaStream_t st);
 struct AttnTrainBwdArgs;
 bool attn_bwd_dkv_tc_supported(const AttnTrainBwdArgs& ba);
 // dQ (+ the P / dS tiles and dS in distance coordinates) on tcgen05 from the saved probabilities; same shapes as the dK/dV kernel

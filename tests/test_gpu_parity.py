@@ -209,6 +209,33 @@ def test_decode_kernels_equal_general_kernel_and_oracle(M):
     assert w2g < 2e-2 and wug < 2e-2 and w2o <= 2e-2
 
 
+def test_warm_memory_segments_on_tcgen05_match_general_kernel_and_oracle():
+    """Multi-token bf16 segments over a WARM memory (chunked prefill, validation passes; deep_music_genre.py:1631-1643 with mems):
+    whole 128-token tiles at a 128-aligned ring position run the tcgen05 attention over the K/V rings (attn_fwd_tc_ring), everything
+    else the general kernel.  Logits of every segment against the all-general-kernel engine and against the fp32 oracle; the
+    sequence crosses a partly filled memory, a full one, ring wrap-arounds, a one-token step and an unaligned tail."""
+    from deepmusicgeneration_b200 import _lib as L
+    cfg = dict(txl.baseline_config(), n_layers=2, mem_len=256)
+    B = 3
+    om, pt = _pair(cfg, 'bf16', B, 256, keep_hidden=False)
+    _, pg = _pair(cfg, 'bf16', B, 256, keep_hidden=False, kernel_flags=L.KF_NO_FLASH | L.KF_NO_DECODE_KERNEL | L.KF_NO_FUSED_DECODE)
+    g = torch.Generator().manual_seed(21)
+    om.reset(); pt.reset(); pg.reset()
+    launches = []
+    wtg = wto = 0.
+    for T in (128, 128, 256, 128, 1, 128, 127, 128):      # mem_count 0 (flash), 128 (partly filled), 256 ..., then unaligned positions
+        x = torch.randint(0, V, (B, T), generator=g)
+        with torch.no_grad(): lo = om(x)[0]
+        n0 = L.load().dmg_launch_count()
+        lt = pt[0].forward(x.cuda(), logits_mode=1)[0].cpu()
+        launches.append(L.load().dmg_launch_count() - n0)
+        lg = pg[0].forward(x.cuda(), logits_mode=1)[0].cpu()
+        wtg = max(wtg, (lt - lg).abs().max().item())
+        wto = max(wto, _rel(lt, lo))
+    print(f'warm-memory segments: product vs general kernel max abs {wtg:.3e}; product vs oracle max rel {wto:.3e}; launches {launches}')
+    assert wtg < 2e-2 and wto <= 2e-2
+
+
 @pytest.mark.parametrize('B', [5, 40, 256])
 def test_fused_decode_layer_kernel_matches_unfused_and_oracle(B):
     """decode_layer.cu (out-projection + LayerNorm + FFN + LayerNorm + next q|k|v in one cluster kernel; d_model 512 geometry):
