@@ -11,6 +11,10 @@ Restates what ``Learner.fit`` does per batch for ``music_model_learner`` (``deep
 
 Dropout: the product draws counter-based masks on the device; ``install_dropout_masks`` replaces every dropout module of
 the oracle model by a multiplication with a caller-provided mask so that both sides see the same masks.
+Known deviation (shared by the product): ``clip_grad_norm_`` here runs ONCE over all parameters (one global
+norm).  fastai's ``MixedPrecision(clip=0.5)`` - the reference's only clip setting, notebook cell 62 - clips per master-parameter layer
+group of ``tfmerXL_lm_split``, so the clipped update differs from the reference whenever a single group's norm exceeds the threshold
+while the others do not.
 Parity status: unpinned at the fastai boundary (the reference stores no training artefacts); this file is the definition
 the CUDA path is tested against.
 """
