@@ -187,32 +187,41 @@ __device__ __forceinline__ void attn_decode3_body(const CUtensorMap& tmK, const 
       const int seg_end = min(n_items, (h + 1) * B - lo);
       mbar_wait(r_full, (uint32_t)(r_epoch & 1));
       r_epoch++;
-      for (int nb0 = seg; nb0 < seg_end; nb0 += 8) {
-        const int item = min(nb0 + g, seg_end - 1);        // column g of the block (a repeated column past the end is never stored)
+      // both column blocks (2 x 8 items, D3_CAP = 16) in one pass over the keys: the A fragments are loaded once
+      uint32_t qvf[2][4][2];
+#pragma unroll
+      for (int nb = 0; nb < 2; nb++) {
+        const int item = min(seg + 8 * nb + g, seg_end - 1);   // column g of the block (a repeated column past the end is never stored)
         const float* qrow = a.qkv + (size_t)(lo + item - h * B) * 3 * HD + h * 64;
-        uint32_t qvf[4][2];
 #pragma unroll
         for (int ks = 0; ks < 4; ks++) {
 #pragma unroll
           for (int hh = 0; hh < 2; hh++) {
             const int d = ks * 16 + 2 * t4 + 8 * hh;
             const float2 qq = *(const float2*)(qrow + d), vv = *(const float2*)(a.v + h * 64 + d);
-            qvf[ks][hh] = pack_bf16x2(qq.x + vv.x, qq.y + vv.y);
+            qvf[nb][ks][hh] = pack_bf16x2(qq.x + vv.x, qq.y + vv.y);
           }
         }
-        for (int blk = warp; blk < nblk; blk += CW) {
-          const int dr = 16 * blk + (lane & 15);
-          const uint32_t r_row = r_base + dr * 128;
-          const int rsw = dr & 7;
-          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      }
+      const bool two = seg_end - seg > 8;
+      for (int blk = warp; blk < nblk; blk += CW) {
+        const int dr = 16 * blk + (lane & 15);
+        const uint32_t r_row = r_base + dr * 128;
+        const int rsw = dr & 7;
+        float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int ks = 0; ks < 4; ks++) {
-            uint32_t c0, c1, c2, c3;
-            ldmatrix_x4(r_row + (((2 * ks + hi16) ^ rsw) << 4), c0, c1, c2, c3);
-            mma_bf16_16816(acc, c0, c1, c2, c3, qvf[ks][0], qvf[ks][1]);
-          }
-          // C fragment: [0] (dist g, item 2 t4), [1] (dist g, item 2 t4 + 1), [2] / [3] the same for dist g + 8
-          const int i0 = nb0 + 2 * t4, d0 = 16 * blk + g, d1 = d0 + 8;
+        for (int ks = 0; ks < 4; ks++) {
+          uint32_t c0, c1, c2, c3;
+          ldmatrix_x4(r_row + (((2 * ks + hi16) ^ rsw) << 4), c0, c1, c2, c3);
+          mma_bf16_16816(acc0, c0, c1, c2, c3, qvf[0][ks][0], qvf[0][ks][1]);
+          if (two) mma_bf16_16816(acc1, c0, c1, c2, c3, qvf[1][ks][0], qvf[1][ks][1]);
+        }
+        // C fragment: [0] (dist g, item 2 t4), [1] (dist g, item 2 t4 + 1), [2] / [3] the same for dist g + 8
+        const int d0 = 16 * blk + g, d1 = d0 + 8;
+#pragma unroll
+        for (int nb = 0; nb < 2; nb++) {
+          const float* acc = nb ? acc1 : acc0;
+          const int i0 = seg + 8 * nb + 2 * t4;
           if (i0 < seg_end) {
             if (d0 <= M) tab[i0 * S + d0] = acc[0];
             if (d1 <= M) tab[i0 * S + d1] = acc[2];
@@ -301,17 +310,17 @@ __device__ __forceinline__ void attn_decode3_body(const CUtensorMap& tmK, const 
       if (j < nT) {
         { D2_T0(); mbar_wait(&full[s], (uint32_t)(use & 1)); D2_ACC(2); }
         const uint32_t kt = smem_u32(ring + (s * T + team) * D3_TILE);
-        float accA[4] = {0.f, 0.f, 0.f, 0.f}, accB[4] = {0.f, 0.f, 0.f, 0.f};   // two independent mma chains
+        float accA[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, accB[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-        for (int ks = 0; ks < 4; ks++) {
+        for (int ks = 0; ks < 4; ks++) {                    // four independent mma chains of depth two
           uint32_t a0, a1, a2, a3, c0, c1, c2, c3;
           ldmatrix_x4(kt + koffA + (((2 * ks + hi16) ^ kswA) << 4), a0, a1, a2, a3);
           ldmatrix_x4(kt + koffB + (((2 * ks + hi16) ^ kswB) << 4), c0, c1, c2, c3);
-          mma_bf16_16816(accA, a0, a1, a2, a3, quf[ks][0], quf[ks][1]);
-          mma_bf16_16816(accB, c0, c1, c2, c3, quf[ks][0], quf[ks][1]);
+          mma_bf16_16816(accA[ks & 1], a0, a1, a2, a3, quf[ks][0], quf[ks][1]);
+          mma_bf16_16816(accB[ks & 1], c0, c1, c2, c3, quf[ks][0], quf[ks][1]);
         }
         // every column of the accumulator holds the same score: lane t4 of a quad finishes key 16 (t4 >> 1) + 8 (t4 & 1) + g
-        const float val = t4 == 0 ? accA[0] : t4 == 1 ? accA[2] : t4 == 2 ? accB[0] : accB[2];
+        const float val = t4 == 0 ? accA[0][0] + accA[1][0] : t4 == 1 ? accA[0][2] + accA[1][2] : t4 == 2 ? accB[0][0] + accB[1][0] : accB[0][2] + accB[1][2];
         const int p = D3_KEYS * j + my_row;                 // ring slot
         const int dist = p < head ? head - p : M + head - p;
         const float sc = dist <= mc ? (val + tabrow[dist]) * sscale : -INFINITY;
@@ -346,7 +355,7 @@ __device__ __forceinline__ void attn_decode3_body(const CUtensorMap& tmK, const 
     D2_MARK(4);
 
     // ---------------- V phase: warp w owns out[16 w .. 16 w + 16) over all 128 keys of every tile ----------------
-    float oA[4] = {0.f, 0.f, 0.f, 0.f}, oB[4] = {0.f, 0.f, 0.f, 0.f};
+    float oA[4] = {0.f, 0.f, 0.f, 0.f}, oB[4] = {0.f, 0.f, 0.f, 0.f}, oC[4] = {0.f, 0.f, 0.f, 0.f}, oD[4] = {0.f, 0.f, 0.f, 0.f};
     for (int j = 0; j < nT; ++j) {
       { D2_T0(); mbar_wait(&full[s], (uint32_t)(use & 1)); D2_ACC(3); }
       const uint32_t vt = smem_u32(ring + (s * T + team) * D3_TILE);
@@ -370,8 +379,8 @@ __device__ __forceinline__ void attn_decode3_body(const CUtensorMap& tmK, const 
       const float inv = 1.f / sum;
       const int dA = 16 * w + g, dB = dA + 8;
       bf16* o = a.out + (size_t)b * HD + h * 64;
-      o[dA] = __float2bfloat16_rn((oA[0] + oB[0] + p_cur * qb[128 + dA]) * inv);
-      o[dB] = __float2bfloat16_rn((oA[2] + oB[2] + p_cur * qb[128 + dB]) * inv);
+      o[dA] = __float2bfloat16_rn(((oA[0] + oB[0]) + (oC[0] + oD[0]) + p_cur * qb[128 + dA]) * inv);
+      o[dB] = __float2bfloat16_rn(((oA[2] + oB[2]) + (oC[2] + oD[2]) + p_cur * qb[128 + dB]) * inv);
     }
     if (w == 1 || w == 2) {   // ring append (K13): slot `head` has been fully read for this (stream, head)
       bf16* rg = (w == 1 ? a.kring : a.vring) + (((size_t)b * H + h) * M + head) * 64;
