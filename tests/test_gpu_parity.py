@@ -209,6 +209,32 @@ def test_decode_kernels_equal_general_kernel_and_oracle(M):
     assert w2g < 2e-2 and wug < 2e-2 and w2o <= 2e-2
 
 
+def test_decode_attention_kernels_agree_at_300_streams():
+    """300 streams x 8 heads = 2400 (stream, head) items: more than the 16 items x 148 CTAs one launch of the third decode-attention kernel
+    holds, so the whole-batch path issues it in two stream chunks, and the two-half pipeline runs with its attention role exactly full
+    (160 streams x 8 heads = 16 items x 80 CTAs).  Both against the second-generation kernel (one launch, any number of items)."""
+    from deepmusicgeneration_b200 import _lib as L
+    cfg = dict(txl.baseline_config(), n_layers=2, mem_len=128)
+    B = 300
+    _, pp = _pair(cfg, 'bf16', B, 128, keep_hidden=False, max_rows=512)                                        # pipelined, third kernel
+    _, ps = _pair(cfg, 'bf16', B, 128, keep_hidden=False, max_rows=512, kernel_flags=L.KF_NO_DUAL_DECODE)      # whole batch, two chunks
+    _, p2 = _pair(cfg, 'bf16', B, 128, keep_hidden=False, max_rows=512, kernel_flags=L.KF_NO_DUAL_DECODE | L.KF_ATTN_DECODE_V2)
+    g = torch.Generator().manual_seed(8)
+    x0 = torch.randint(0, V, (B, 100), generator=g)
+    for pm in (pp, ps, p2):
+        pm.reset(); pm[0].forward(x0.cuda(), logits_mode=2)
+    wps = wp2 = 0.
+    for s in range(40):
+        xs = torch.randint(0, V, (B, 1), generator=g).cuda()
+        lp = pp[0].forward(xs, logits_mode=1)[0]
+        ls = ps[0].forward(xs, logits_mode=1)[0]
+        l2 = p2[0].forward(xs, logits_mode=1)[0]
+        wps = max(wps, (lp - ls).abs().max().item())
+        wp2 = max(wp2, (lp - l2).abs().max().item())
+    print(f'B=300: pipelined vs two-chunk whole-batch launches {wps:.3e}; third vs second attention kernel max abs {wp2:.3e}')
+    assert wps == 0. and wp2 < 2e-2
+
+
 def test_warm_memory_segments_on_tcgen05_match_general_kernel_and_oracle():
     """Multi-token bf16 segments over a WARM memory (chunked prefill, validation passes; deep_music_genre.py:1631-1643 with mems):
     whole 128-token tiles at a 128-aligned ring position run the tcgen05 attention over the K/V rings (attn_fwd_tc_ring), everything
