@@ -383,10 +383,12 @@ def measure_c2(args):
         k_ms = ev0.elapsed_time(ev1) / (reps * L)
         abytes = attention_bytes_per_launch(B, **geo)
         per_step = L
-        kname = 'attn_decode3_kernel (attention_decode2.cu / attention_decode3.cuh)'
+        third = shape['mem_len'] % 128 == 0 and shape['mem_len'] <= 512 and shape['d_head'] == 64
+        kname = ('attn_decode3_kernel (attention_decode3.cuh)' if third else
+                 'attn_decode2_kernel<G> (attention_decode2.cuh; mem_len outside the third kernel\'s range)')
         tpath = os.path.join(ROOT, 'profiles', 'attn_decode_traffic.json')
     achieved = abytes / (k_ms / 1e3) / 1e9
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and not c5:                     # the ncu captures were taken at the C2 geometry
         try: traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
         except Exception: traffic = None
     roofline = {'bound': 'hbm', 'kernel': kname, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
