@@ -582,11 +582,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmPd, const __grid_co
 //   P = p_save * exp(m_save*scale - lse),  Pd = dropout(P),  dS = P * (dropout'(dPd) - delta) * scale       (softmax warps, one row each)
 //   dQ  = dS K  +  dS_dist Rk            (tcgen05; dS_dist = dS in (row, distance) coordinates = the transpose of _line_shift)
 // and, for the kernels downstream, Pd and dS tiles (dK/dV kernel) and dS_dist (dRk GEMM) leave through TMA stores.
-// One CTA = (stream, head, 128-query tile), key tiles of 128 from the oldest visible key up to the diagonal, 12 warps:
-//   warps 0-7  tile math: thread = one query row x 64 keys (key half = warp / 4)
-//   warp 8     TMA loads: dO once; per tile V, the saved probabilities (2 buffers), K, one 128-distance block of Rk
-//   warp 9     one thread issues every tcgen05.mma
-//   warp 10    TMA stores: dS tile, Pd tile (written in place over the saved probabilities), finished dS_dist blocks
+// One CTA = (stream, head, 128-query tile), key tiles of 128 from the oldest visible key up to the diagonal, 20 warps:
+//   warps 0-15 tile math: thread = one query row x 32 keys (key quarter = warp / 4)
+//   warp 16    TMA loads: dO once; per tile V, the saved probabilities (2 buffers), K, one 128-distance block of Rk
+//   warp 17    one thread issues every tcgen05.mma
+//   warp 18    TMA stores: dS tile, Pd tile (written in place over the saved probabilities), finished dS_dist blocks
 // The distance of (row r, key jl) inside a tile is D0 + r - jl (D0 = M + i0 - j0, a multiple of 128), so a tile touches two aligned
 // 128-distance blocks: the upper one (shared with the previous, older key tile) becomes complete with this tile, the lower one is
 // started.  A block lives in one of two [128 rows][128 distances] bf16 buffers (canonical K-major swizzled layout): every entry is
@@ -595,7 +595,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmPd, const __grid_co
 // the blocks beyond it (distances no visible key produces) are stored as zeros from that buffer before the first tile.
 // TMEM: [0,128) / [128,256) dPd of even / odd tiles | [256,320) dQ content part | [320,384) dQ position part.
 // =============================================================================================
-constexpr int DQT_THREADS = 12 * 32;
+constexpr int DQT_MATH_WARPS = 16;                // thread = one query row x 32 keys: four warps per scheduler hide the tile math's latencies
+constexpr int DQT_THREADS = (DQT_MATH_WARPS + 4) * 32;
 constexpr int DQO_DO = 0;
 constexpr int DQO_K = DQO_DO + T16K;
 constexpr int DQO_V = DQO_K + T16K;
@@ -634,26 +635,25 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   const int NT = jt_hi - jt_lo + 1;                 // key tiles of this CTA
   const int blk0 = (a.M + i0) / 128 - jt_lo;        // upper distance block of the first (oldest) tile; tile n completes block blk0 - n
 
-  if (warp == 8 && lane == 0) {
+  if (warp == DQT_MATH_WARPS && lane == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmM); tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmP); tma_prefetch_desc(&tmPB); tma_prefetch_desc(&tmDS); tma_prefetch_desc(&tmDD);
     for (int i = 0; i < D_COUNT; i++) {
       uint32_t cnt = 1;
-      if (i == D_DPFREE0 || i == D_DPFREE1 || i == D_DSFULL || i == D_ZINIT) cnt = 8;
+      if (i == D_DPFREE0 || i == D_DPFREE1 || i == D_DSFULL || i == D_ZINIT) cnt = DQT_MATH_WARPS;
       if (i == D_DSFREE || i == D_SFREE0 || i == D_SFREE1) cnt = 2;       // the MMA that read the buffer + the TMA store that read it
       mbar_init(&bar[i], cnt);
     }
     mbar_fence_init();
   }
-  if (warp == 9) tmem_alloc<512>(tmem_holder);
+  if (warp == DQT_MATH_WARPS + 1) tmem_alloc<512>(tmem_holder);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (warp == 8) {
+  if (warp >= DQT_MATH_WARPS) {
+    if (warp == DQT_MATH_WARPS) {
       // =========================================== TMA loads ===========================================
       if (lane == 0) {
         mbar_expect_tx(&bar[D_DOFULL], T16K);
@@ -691,7 +691,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           load_r(n);
         }
       }
-    } else if (warp == 9) {
+    } else if (warp == DQT_MATH_WARPS + 1) {
       // =========================================== MMA issuer ===========================================
       if (lane == 0) {
         constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
@@ -738,7 +738,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         }
         umma_commit(&bar[D_DQFULL]);
       }
-    } else if (warp == 10) {
+    } else if (warp == DQT_MATH_WARPS + 2) {
       // =========================================== TMA stores ===========================================
       if (lane == 0) {
         const uint32_t ds = smem_u32(smem + DQO_DS), st = smem_u32(smem + DQO_STRIP), pp = smem_u32(smem + DQO_P);
@@ -776,8 +776,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     }
   } else {
     // =========================================== tile math ===========================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    const int hf = warp >> 2, q4 = warp & 3;
+    const int qk = warp >> 2, q4 = warp & 3;        // key quarter (32 keys) of every tile, TMEM lane quarter
+    const int hf = qk >> 1, sub = qk & 1;           // ... = 64-key half tile hf, 16-byte chunks 4 sub .. 4 sub + 3 of its rows
     const int r = q4 * 32 + lane;                   // query row of this thread inside the tile
     const int row = i0 + r;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16);
@@ -786,7 +786,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     {   // both distance-block buffers start as zeros
       uint4* z = (uint4*)(smem + DQO_STRIP) + threadIdx.x;
 #pragma unroll
-      for (int i = 0; i < 4 * T16K / 16 / 256; i++) z[i * 256] = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = 0; i < 4 * T16K / 16 / (DQT_MATH_WARPS * 32); i++) z[i * DQT_MATH_WARPS * 32] = make_uint4(0u, 0u, 0u, 0u);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[D_ZINIT]);
@@ -796,28 +796,22 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const float c2 = a.scale * LOG2E;
     const uint32_t drop_base = (uint32_t)((bhrow * S) >> 1);
     const float* mrow = a.m_save + bhrow * (S >> 6);
-    const int C0 = 128 + r - 64 * hf;               // strip column of this thread's first key: c = C0 - jj
+    const int C0 = 128 + r - 32 * qk;               // strip column of this thread's first key: c = C0 - jj
     uint8_t* const strip = smem + DQO_STRIP;
 
-    float mnext = __ldg(mrow + ((jt_lo * 128 + 64 * hf) >> 6));
+    float mnext = __ldg(mrow + ((jt_lo * 128 + 32 * qk) >> 6));
     for (int n = 0; n < NT; n++) {
-      const int j0h = (jt_lo + n) * 128 + 64 * hf;   // full-context index of this thread's first key
+      const int j0q = (jt_lo + n) * 128 + 32 * qk;   // full-context index of this thread's first key
       const float mblk = mnext;
-      if (n + 1 < NT) mnext = __ldg(mrow + ((j0h + 128) >> 6));
+      if (n + 1 < NT) mnext = __ldg(mrow + ((j0q + 128) >> 6));
       const int s = n & 1, U = blk0 - n, sbU = U & 1;
       const bool has_L = n + 1 < NT;                 // the diagonal tile's lower block would hold negative distances (masked keys)
       mbar_wait(&bar[D_PFULL0 + s], (n >> 1) & 1);
       mbar_wait(&bar[D_DPFULL0 + s], (n >> 1) & 1);
       tc_fence_after();
-      float dpd[64];
-      {
-        uint32_t x0[32], x1[32];
-        tmem_ld_32x32(t_lane + DTM_DP + 128 * s + 64 * hf, x0);
-        tmem_ld_32x32(t_lane + DTM_DP + 128 * s + 64 * hf + 32, x1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i++) { dpd[i] = __uint_as_float(x0[i]); dpd[32 + i] = __uint_as_float(x1[i]); }
-      }
+      uint32_t dpd[32];
+      tmem_ld_32x32(t_lane + DTM_DP + 128 * s + 32 * qk, dpd);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[D_DPFREE0 + s]);
@@ -826,10 +820,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       uint8_t* const dsrow = smem + DQO_DS + hf * T16K + rowoff;
       uint8_t* const bufU = strip + sbU * 2 * T16K + rowoff;
       uint8_t* const bufL = strip + (sbU ^ 1) * 2 * T16K + rowoff;
-      uint32_t dsw[32];                               // dS of this thread's 64 keys, bf16 pairs (keys 2 i, 2 i + 1)
+      uint32_t dsw[16];                               // dS of this thread's 32 keys, bf16 pairs (keys 2 i, 2 i + 1)
 #pragma unroll
-      for (int ck = 0; ck < 8; ck++) {
-        const uint32_t choff = (uint32_t)((ck ^ rsw) << 4);
+      for (int ck = 0; ck < 4; ck++) {
+        const uint32_t choff = (uint32_t)(((4 * sub + ck) ^ rsw) << 4);
         const uint4 raw = *(const uint4*)(prow + choff);
         const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
         uint32_t pk[4];
@@ -838,12 +832,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           const int pp = 4 * ck + e;
           float keep0 = 1.f, keep1 = 1.f;
           if (a.drop_thresh) {
-            const uint32_t hb = drop_pair_bits(a.drop_seed, drop_base + (uint32_t)(j0h >> 1) + pp);
+            const uint32_t hb = drop_pair_bits(a.drop_seed, drop_base + (uint32_t)(j0q >> 1) + pp);
             keep0 = ((hb & 0xFFFFu) >= a.drop_thresh) ? a.drop_scale : 0.f;
             keep1 = ((hb >> 16) >= a.drop_thresh) ? a.drop_scale : 0.f;
           }
           const float p0 = bf16lo(w[e]) * fac, p1 = bf16hi(w[e]) * fac;
-          const float s0 = p0 * (dpd[2 * pp] * keep0 - dl) * a.scale, s1 = p1 * (dpd[2 * pp + 1] * keep1 - dl) * a.scale;
+          const float s0 = p0 * (__uint_as_float(dpd[2 * pp]) * keep0 - dl) * a.scale;
+          const float s1 = p1 * (__uint_as_float(dpd[2 * pp + 1]) * keep1 - dl) * a.scale;
           pk[e] = pack_bf16x2(keep0 * p0, keep1 * p1);
           dsw[pp] = pack_bf16x2(s0, s1);
         }
@@ -853,52 +848,52 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       // whole tile math above to do so)
       if (n >= 1) mbar_wait(&bar[D_DSFREE], (n - 1) & 1);
 #pragma unroll
-      for (int ck = 0; ck < 8; ck++)
-        *(uint4*)(dsrow + ((ck ^ rsw) << 4)) = make_uint4(dsw[4 * ck], dsw[4 * ck + 1], dsw[4 * ck + 2], dsw[4 * ck + 3]);
+      for (int ck = 0; ck < 4; ck++)
+        *(uint4*)(dsrow + (((4 * sub + ck) ^ rsw) << 4)) = make_uint4(dsw[4 * ck], dsw[4 * ck + 1], dsw[4 * ck + 2], dsw[4 * ck + 3]);
       if (n == 0) mbar_wait(&bar[D_ZDONE], 0);
       if (n >= 1 && has_L) mbar_wait(&bar[D_SFREE0 + (sbU ^ 1)], ((n - 1) >> 1) & 1);
-      // ---- the same 64 values in (row, distance) coordinates: key jj sits in column C0 - jj of this tile's [128][256] window, i.e. the
-      // run of columns [C0 - 63, C0] in REVERSED key order.  The run starts at a lane-dependent offset a = (C0 - 63) & 7 inside an aligned
-      // 8-column chunk (16 bytes of the swizzled layout), so the reversed run is shifted right by `a` elements with a three-stage barrel
-      // shifter on the packed words (select + byte-permute), which leaves seven full chunks (one 16-byte store each) and two partial ones
-      // at the ends (element stores: the rest of those chunks belongs to the neighbouring key tile, possibly being written right now).
+      // ---- the same 32 values in (row, distance) coordinates: key jj sits in column C0 - jj of this tile's [128][256] window, i.e. the
+      // run of columns [C0 - 31, C0] in REVERSED key order.  The run starts at a lane-dependent offset sh = (C0 - 31) & 7 inside an aligned
+      // 8-column chunk (16 bytes of the swizzled layout), so the reversed run is shifted right by `sh` elements with a three-stage barrel
+      // shifter on the packed words (select + byte-permute), which leaves three full chunks (one 16-byte store each) and two partial ones
+      // at the ends (element stores: the rest of those chunks belongs to a neighbouring thread or key tile, possibly being written now).
       {
-        const int c_lo = C0 - 63, sh = c_lo & 7, cbase = c_lo - sh;
-        uint32_t y[36];
+        const int c_lo = C0 - 31, sh = c_lo & 7, cbase = c_lo - sh;
+        uint32_t y[20];
 #pragma unroll
-        for (int i = 0; i < 36; i++) {                // stage 0: reverse (word i = keys 63 - 2 i, 62 - 2 i), shifted by one element if sh & 1
-          const uint32_t cur = i < 32 ? __byte_perm(dsw[31 - i], 0u, 0x1032) : 0u;
-          const uint32_t prev = (i >= 1 && i <= 32) ? __byte_perm(dsw[32 - i], 0u, 0x1032) : 0u;
+        for (int i = 0; i < 20; i++) {                // stage 0: reverse (word i = keys 31 - 2 i, 30 - 2 i), shifted by one element if sh & 1
+          const uint32_t cur = i < 16 ? __byte_perm(dsw[15 - i], 0u, 0x1032) : 0u;
+          const uint32_t prev = (i >= 1 && i <= 16) ? __byte_perm(dsw[16 - i], 0u, 0x1032) : 0u;
           y[i] = (sh & 1) ? __byte_perm(prev, cur, 0x5432) : cur;
         }
         if (sh & 2) {
 #pragma unroll
-          for (int i = 35; i >= 1; i--) y[i] = y[i - 1];
+          for (int i = 19; i >= 1; i--) y[i] = y[i - 1];
         }
         if (sh & 4) {
 #pragma unroll
-          for (int i = 35; i >= 2; i--) y[i] = y[i - 2];
+          for (int i = 19; i >= 2; i--) y[i] = y[i - 2];
         }
         auto chunk_ptr = [&](int c) -> uint8_t* {     // address of the aligned 8-column chunk at window column c; nullptr: not stored
           if (c >= 128) { const int cc = c - 128; return bufU + (cc >> 6) * T16K + ((((cc & 63) >> 3) ^ rsw) << 4); }
           return has_L ? bufL + (c >> 6) * T16K + ((((c & 63) >> 3) ^ rsw) << 4) : nullptr;
         };
 #pragma unroll
-        for (int j = 1; j < 8; j++) {
+        for (int j = 1; j < 4; j++) {
           uint8_t* dst = chunk_ptr(cbase + 8 * j);
           if (dst) *(uint4*)dst = make_uint4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
         }
         uint8_t* d0 = chunk_ptr(cbase);
-        uint8_t* d8 = chunk_ptr(cbase + 64);
+        uint8_t* d4 = chunk_ptr(cbase + 32);
         if (sh == 0) {
           if (d0) *(uint4*)d0 = make_uint4(y[0], y[1], y[2], y[3]);
         } else {
 #pragma unroll
           for (int e = 0; e < 8; e++) {
             const uint16_t lo = (uint16_t)((e & 1) ? (y[e >> 1] >> 16) : (y[e >> 1] & 0xFFFFu));
-            const uint16_t hi = (uint16_t)((e & 1) ? (y[32 + (e >> 1)] >> 16) : (y[32 + (e >> 1)] & 0xFFFFu));
+            const uint16_t hi = (uint16_t)((e & 1) ? (y[16 + (e >> 1)] >> 16) : (y[16 + (e >> 1)] & 0xFFFFu));
             if (d0 && e >= sh) *(uint16_t*)(d0 + 2 * e) = lo;
-            if (d8 && e < sh) *(uint16_t*)(d8 + 2 * e) = hi;
+            if (d4 && e < sh) *(uint16_t*)(d4 + 2 * e) = hi;
           }
         }
       }
@@ -907,17 +902,17 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       if (lane == 0) mbar_arrive(&bar[D_DSFULL]);
     }
 
-    // ---- dq = content part + position part (columns 32 hf .. 32 hf + 31 of this row); du / dv = their column sums over all rows
+    // ---- dq = content part + position part (columns 16 qk .. 16 qk + 15 of this row); du / dv = their column sums over all rows
     mbar_wait(&bar[D_DQFULL], 0);
     tc_fence_after();
-    uint32_t xa[32], xb[32];
-    tmem_ld_32x32(t_lane + DTM_AC + 32 * hf, xa);
-    tmem_ld_32x32(t_lane + DTM_BD + 32 * hf, xb);
+    uint32_t xa[32], xb[32];                        // 32-column loads, the first 16 are this thread's
+    tmem_ld_32x32(t_lane + DTM_AC + 16 * qk, xa);
+    tmem_ld_32x32(t_lane + DTM_BD + 16 * qk, xb);
     tmem_ld_wait();
     tc_fence_before();
-    bf16* qrow = ba.dqkv_x + ((long long)b * a.T + row) * a.ldx + h * 64 + 32 * hf;
+    bf16* qrow = ba.dqkv_x + ((long long)b * a.T + row) * a.ldx + h * 64 + 16 * qk;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < 2; k++) {
       uint32_t o[4];
 #pragma unroll
       for (int e = 0; e < 4; e++) {
@@ -926,24 +921,24 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       }
       *(uint4*)(qrow + 8 * k) = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    float* red = (float*)(smem + DQO_K);            // the K tile is dead (every MMA has retired): [8 warps][64] column sums
+    float* red = (float*)(smem + DQO_K);            // the K tile is dead (every MMA has retired): [16 warps][32] column sums
 #pragma unroll
-    for (int i = 0; i < 32; i++) {
+    for (int i = 0; i < 16; i++) {
       const float sa = warp_sum(__uint_as_float(xa[i])), sbv = warp_sum(__uint_as_float(xb[i]));
-      if (lane == 0) { red[warp * 64 + i] = sa; red[warp * 64 + 32 + i] = sbv; }
+      if (lane == 0) { red[warp * 32 + i] = sa; red[warp * 32 + 16 + i] = sbv; }
     }
-    softmax_bar_sync();
+    asm volatile("bar.sync 1, %0;" ::"n"(DQT_MATH_WARPS * 32) : "memory");
     if (threadIdx.x < 128) {
-      const int t = threadIdx.x >> 6, cc = threadIdx.x & 63, w0 = (cc >> 5) * 4;
+      const int t = threadIdx.x >> 6, cc = threadIdx.x & 63, w0 = (cc >> 4) * 4;
       float sum = 0.f;
 #pragma unroll
-      for (int q = 0; q < 4; q++) sum += red[(w0 + q) * 64 + t * 32 + (cc & 31)];
+      for (int q = 0; q < 4; q++) sum += red[(w0 + q) * 32 + t * 16 + (cc & 15)];
       atomicAdd((t ? ba.dv : ba.du) + h * 64 + cc, sum);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem_base);
+  if (warp == DQT_MATH_WARPS + 1) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace
