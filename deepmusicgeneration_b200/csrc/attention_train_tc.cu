@@ -584,7 +584,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmPd, const __grid_co
 // and, for the kernels downstream, Pd and dS tiles (dK/dV kernel) and dS_dist (dRk GEMM) leave through TMA stores.
 // One CTA = (stream, head, 128-query tile), key tiles of 128 from the oldest visible key up to the diagonal, 20 warps:
 //   warps 0-15 tile math: thread = one query row x 32 keys (key quarter = warp / 4)
-//   warp 16    TMA loads: dO once; per tile V, the saved probabilities (2 buffers), K, one 128-distance block of Rk
+//   warp 16    TMA loads: dO once; per tile the saved probabilities (2 buffers), K, one 128-distance block of Rk
+//   warp 19    TMA loads: V (its own thread: it runs two tiles ahead of the other streams)
 //   warp 17    one thread issues every tcgen05.mma
 //   warp 18    TMA stores: dS tile, Pd tile (written in place over the saved probabilities), finished dS_dist blocks
 // The distance of (row r, key jl) inside a tile is D0 + r - jl (D0 = M + i0 - j0, a multiple of 128), so a tile touches two aligned
@@ -679,16 +680,29 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           tma_load_2d(smem + DQO_P + s * 2 * T16K, &tmP, j0, bh * a.T + i0, &bar[D_PFULL0 + s]);
           tma_load_2d(smem + DQO_P + s * 2 * T16K + T16K, &tmP, j0 + 64, bh * a.T + i0, &bar[D_PFULL0 + s]);
         };
-        load_kv(0, 1);
+        // V has its own producer thread (warp 19): dPd runs two tiles ahead of the tile math, so V(n+2)'s buffer is free long before
+        // the buffers of this thread's streams are, and a request queued behind their waits arrived microseconds late
+        // (profiles/r2g_attn_bwd_dq_tc_timeline.txt).  The waits below come in the order their conditions become true: K (after dS K of
+        // tile n-1), Rk (after the position MMA of n-1), the probability buffer (after the TMA stores of n-1 have read it).
         load_p(0);
         load_kv(0, 0);
         load_r(0);
         if (NT > 1) load_p(1);
         for (int n = 1; n < NT; n++) {
-          load_kv(n, 1);
-          if (n + 1 < NT) load_p(n + 1);
           load_kv(n, 0);
           load_r(n);
+          if (n + 1 < NT) load_p(n + 1);
+        }
+      }
+    } else if (warp == DQT_MATH_WARPS + 3) {
+      // =========================================== TMA loads: V ===========================================
+      if (lane == 0) {
+        for (int n = 0; n < NT; n++) {
+          const int j0 = (jt_lo + n) * 128;
+          mbar_wait(&bar[D_VEMPTY], (n & 1) ^ 1);
+          mbar_expect_tx(&bar[D_VFULL], T16K);
+          if (j0 < a.M) tma_load_2d(smem + DQO_V, &tmM, HD + h * 64, b * a.M + j0, &bar[D_VFULL]);
+          else tma_load_2d(smem + DQO_V, &tmX, 2 * HD + h * 64, b * a.T + (j0 - a.M), &bar[D_VFULL]);
         }
       }
     } else if (warp == DQT_MATH_WARPS + 1) {
