@@ -683,15 +683,15 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         // V has its own producer thread (warp 19): dPd runs two tiles ahead of the tile math, so V(n+2)'s buffer is free long before
         // the buffers of this thread's streams are, and a request queued behind their waits arrived microseconds late
         // (profiles/r2g_attn_bwd_dq_tc_timeline.txt).  The waits below come in the order their conditions become true: K (after dS K of
-        // tile n-1), Rk (after the position MMA of n-1), the probability buffer (after the TMA stores of n-1 have read it).
+        // tile n-1), the probability buffer (after the first TMA store group of n-1 has read it), Rk (after the position MMA of n-1).
         load_p(0);
         load_kv(0, 0);
         load_r(0);
         if (NT > 1) load_p(1);
         for (int n = 1; n < NT; n++) {
           load_kv(n, 0);
-          load_r(n);
           if (n + 1 < NT) load_p(n + 1);
+          load_r(n);
         }
       }
     } else if (warp == DQT_MATH_WARPS + 3) {
@@ -768,22 +768,25 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         for (int n = 0; n < NT; n++) {
           const int j0 = (jt_lo + n) * 128, U = blk0 - n, sb = U & 1;
           mbar_wait(&bar[D_DSFULL], n & 1);
-          // three bulk groups, released in the order the tile math needs the buffers back: dS tile, distance block, probabilities
+          // three bulk groups, released in the order the pipeline needs the buffers back: the probability buffer first - its reload for
+          // tile n + 2 comes from HBM (~2 us) and must be requested before tile n + 1 is half done (the timeline in
+          // profiles/r2g_attn_bwd_dq_tc_timeline.txt: as the last group its read finished 2 us after the tile) - then the dS tile, then the
+          // distance block
+          tma_store_2d(&tmPB, pp + (n & 1) * 2 * T16K, j0, row_bh);
+          tma_store_2d(&tmPB, pp + (n & 1) * 2 * T16K + T16K, j0 + 64, row_bh);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           tma_store_2d(&tmDS, ds, j0, row_bh);
           tma_store_2d(&tmDS, ds + T16K, j0 + 64, row_bh);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           tma_store_2d(&tmDD, st + sb * 2 * T16K, h * S + U * 128, row_b);
           tma_store_2d(&tmDD, st + sb * 2 * T16K + T16K, h * S + U * 128 + 64, row_b);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          tma_store_2d(&tmPB, pp + (n & 1) * 2 * T16K, j0, row_bh);
-          tma_store_2d(&tmPB, pp + (n & 1) * 2 * T16K + T16K, j0 + 64, row_bh);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-          mbar_arrive(&bar[D_DSFREE]);
-          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          mbar_arrive(&bar[D_SFREE0 + sb]);
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           mbar_arrive(&bar[D_PFREE0 + (n & 1)]);
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          mbar_arrive(&bar[D_DSFREE]);
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(&bar[D_SFREE0 + sb]);
         }
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       }
