@@ -164,6 +164,7 @@ __device__ __forceinline__ void attn_decode3_body(const CUtensorMap& tmK, const 
   }
 
   // ============================== consumers ==============================
+  if (a.dbg && cta == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.dbg[48] = t; }
 #ifdef D2_PROFILE
   long long prof[6] = {0, 0, 0, 0, 0, 0}, sec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long t_begin = clock64();
@@ -243,6 +244,7 @@ __device__ __forceinline__ void attn_decode3_body(const CUtensorMap& tmK, const 
   }
 
   D2_MARK(7);   // prologue
+  if (a.dbg && cta == 0 && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.dbg[49] = t; }
   // ---------------- main loop: the team's items ----------------
   uint64_t* tb = bars + 2 + team * (2 * n_stages + 4);
   uint64_t *full = tb, *empty = tb + n_stages, *q_full = tb + 2 * n_stages, *q_empty = q_full + 2;
@@ -391,6 +393,7 @@ __device__ __forceinline__ void attn_decode3_body(const CUtensorMap& tmK, const 
     if (lane == 0) mbar_arrive(&q_empty[qs]);
     D2_MARK(6);
   }
+  if (a.dbg && tid == 0 && (cta == 0 || cta == ncta - 1)) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.dbg[cta == 0 ? 50 : 51] = t; }
 #ifdef D2_PROFILE
   if (warp == 0 && lane == 0 && d2_prof_ptr) {
     prof[0] = clock64() - t_begin; prof[5] = (n_items + T - 1) / T;

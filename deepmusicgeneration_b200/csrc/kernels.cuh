@@ -139,6 +139,7 @@ struct AttnDecodeArgs {
   const int* dev_state; // [0] pos_total, [1] mem_count
   int B, H, M, Dcap;
   float scale;
+  unsigned long long* dbg = nullptr;   // timeline probe (third kernel, CTA 0 and the last CTA): [48] start, [49] table built, [50] end, [51] last CTA's end
   int force_v2 = 0;     // 1 = the second-generation kernel even where the third one applies (DMG_KF_ATTN_DECODE_V2, parity tests)
   int no_early_kv = 0;  // v2 kernel: 1 = request the first K/V tiles only after the predecessor kernel has finished (DMG_NO_EARLY_KV)
 };

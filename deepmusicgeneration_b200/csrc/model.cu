@@ -124,8 +124,10 @@ struct DecodeStep {
     int attn_clusters = m->dl_max_clusters - n_fused;
     const long long items = (long long)(a1 - a0) * m->cfg.n_heads;
     if ((long long)attn_clusters * DL_CLUSTER > items) attn_clusters = (int)((items + DL_CLUSTER - 1) / DL_CLUSTER);
+    AttnDecodeArgs aa = attn_args(la, a0, a1);
+    aa.dbg = da.dbg;                               // the same mid-stack launch carries both roles' timeline marks
     return decode_dual(&m->tmAttn16, &Lb->wo.tm64, &Lb->w1.tm64, &Lb->w2.tm64, &Ln->wqkv.tm64, da, &La.tmK, &La.tmV, &La.tmR,
-                       attn_args(la, a0, a1), b0 + a0, attn_clusters, st);
+                       aa, b0 + a0, attn_clusters, st);
   }
   // two-half software pipeline (see forward_chunk): is it on for nb streams, and where the halves split
   bool pipelined(int nb, int* hx) const {
@@ -795,12 +797,12 @@ int dmg_sample_probs(dmg_model* m, int predict_loop, const float* logits_dev, co
   return sample_launch(a, n, (cudaStream_t)stream);
 }
 
-int dmg_decode_timeline(dmg_model* m, uint64_t* out48_host) {
-  DMG_CHECK(m && out48_host, "dmg_decode_timeline: null argument");
+int dmg_decode_timeline(dmg_model* m, uint64_t* out64_host) {
+  DMG_CHECK(m && out64_host, "dmg_decode_timeline: null argument");
   DMG_CHECK(m->dl_dbg != nullptr, "dmg_decode_timeline: create the model with DMG_DECODE_TIMELINE=1 in the environment");
   DMG_CUDA_OK(cudaSetDevice(m->device));
   DMG_CUDA_OK(cudaDeviceSynchronize());
-  DMG_CUDA_OK(cudaMemcpy(out48_host, m->dl_dbg, 48 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  DMG_CUDA_OK(cudaMemcpy(out64_host, m->dl_dbg, 64 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return 0;
 }
 

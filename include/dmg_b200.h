@@ -174,8 +174,10 @@ int64_t dmg_launch_count(void);                  /* kernels launched by this lib
 int dmg_uses_tcgen05(dmg_model* m);              /* 1 when GEMMs run on the tcgen05 kernel */
 
 /* Measurement hook: %globaltimer marks (ns) of CTA 0 of one mid-stack launch of the fused one-token layer kernel (decode_layer.cu):
- * 3 roles (TMA producer, MMA issuer, epilogue thread) x 16 marks.  Needs DMG_DECODE_TIMELINE=1 in the environment at dmg_create. */
-int dmg_decode_timeline(dmg_model* m, uint64_t* out48_host);
+ * 3 roles (TMA producer, MMA issuer, epilogue thread) x 16 marks, then - when that launch is a dual-role launch - 4 marks of the attention
+ * role ([48] first attention CTA starts, [49] its rel-pos table is built, [50] it ends, [51] the last attention CTA ends): 64 values.
+ * Needs DMG_DECODE_TIMELINE=1 in the environment at dmg_create. */
+int dmg_decode_timeline(dmg_model* m, uint64_t* out64_host);
 
 /* Measurement hook for bench.py's roofline: re-launch ONLY the fused decode-attention kernel of `layer` on the
  * current ring state and the q/k/v of the latest one-token forward (idempotent: the ring position is not advanced). */

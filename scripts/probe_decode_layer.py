@@ -23,9 +23,9 @@ m._e.forward(x, None, _lib.LOGITS_LAST)
 for _ in range(20):
     m._e.forward(torch.randint(0, 324, (B, 1), generator=g).cuda(), None, _lib.LOGITS_LAST)
 torch.cuda.synchronize()
-out = np.zeros(48, dtype=np.uint64)
+out = np.zeros(64, dtype=np.uint64)
 _lib.check(m._e.lib.dmg_decode_timeline(m._e.h, out.ctypes.data_as(C.c_void_p)), 'timeline')
-t0 = int(min(v for v in out if v > 0))
+t0 = int(min(v for v in out[:48] if v > 0))
 names = {0: ['start', 'A issued', 'B issued', 'C weights pre-issued', 'barrier 2 passed', 'C issued', 'D issued'],
          1: ['start', 'A mma issued', 'xa_ready0 seen', 'B mma issued', 'C kb0 issued', 'C mma issued', 'xa_ready1 seen', 'D mma issued', 'C kb7 issued'],
          2: ['start', 'pdl_wait done', 'tmem_full A', 'A epilogue done', 'barrier 1 passed', 'LN1 done', 'tmem_full B', 'B epilogue done', 'barrier 2 passed',
@@ -35,3 +35,8 @@ for role, label in ((0, 'producer'), (1, 'mma'), (2, 'epilogue')):
     for i, n in enumerate(names[role]):
         v = int(out[role * 16 + i])
         if v: print(f'   {n:24s} {(v - t0) / 1e3:8.2f} us')
+
+if out[48]:
+    print('attention role of the same dual-role launch')
+    for i, n in ((48, 'first CTA starts'), (49, 'rel-pos table built'), (50, 'first CTA ends'), (51, 'last CTA ends')):
+        print(f'   {n:24s} {(int(out[i]) - t0) / 1e3:8.2f} us')
