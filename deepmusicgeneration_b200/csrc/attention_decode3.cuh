@@ -117,6 +117,7 @@ __device__ __forceinline__ void attn_decode3_body(const CUtensorMap& tmK, const 
       // stage s of team t lives at slot s * T + t of the ring region: the first stages of every team are outside the rel-pos alias
       int s = 0, use = 0, pre = 0;
       bool alias_ok = false;
+      const uint64_t kv_policy = l2_policy_evict_first();
       // The K/V ring of this layer was last written by this layer's attention kernel of the PREVIOUS step (long retired), so the
       // first item's tiles do not depend on the predecessor kernel: request them while it drains.
       if (team < n_items && !a.no_early_kv) {
@@ -127,8 +128,8 @@ __device__ __forceinline__ void attn_decode3_body(const CUtensorMap& tmK, const 
           uint8_t* dst = ring + (s * T + team) * D3_TILE;
           const CUtensorMap* tm = pre < nT ? &tmK : &tmV;
           const int r0 = row0 + (pre < nT ? pre : pre - nT) * D3_KEYS;
-          tma_load_2d(dst, tm, 0, r0, &full[s]);
-          tma_load_2d(dst + 8192, tm, 0, r0 + 64, &full[s]);
+          tma_load_2d_hint(dst, tm, 0, r0, &full[s], kv_policy);          // read once per step: evict-first, the weights stay in L2
+          tma_load_2d_hint(dst + 8192, tm, 0, r0 + 64, &full[s], kv_policy);
           ++pre; ++s;
         }
         if (s == n_stages) { s = 0; use = 1; }
@@ -154,8 +155,8 @@ __device__ __forceinline__ void attn_decode3_body(const CUtensorMap& tmK, const 
           uint8_t* dst = ring + (s * T + team) * D3_TILE;
           const CUtensorMap* tm = t < nT ? &tmK : &tmV;
           const int r0 = row0 + (t < nT ? t : t - nT) * D3_KEYS;
-          tma_load_2d(dst, tm, 0, r0, &full[s]);
-          tma_load_2d(dst + 8192, tm, 0, r0 + 64, &full[s]);
+          tma_load_2d_hint(dst, tm, 0, r0, &full[s], kv_policy);          // read once per step: evict-first, the weights stay in L2
+          tma_load_2d_hint(dst + 8192, tm, 0, r0 + 64, &full[s], kv_policy);
           if (++s == n_stages) { s = 0; ++use; }
         }
       }

@@ -222,6 +222,7 @@ __device__ __forceinline__ void decode_layer_body(const CUtensorMap& tmAttn, con
     if (lane == 0) dl_mark(a.dbg, 0, 0);
     const int total = nA_use + nB_use + nC_use + nD_use;
     int bar_state = 0;                                   // cluster barrier progress of this warp: 0, 1 = arrived #1, 2 = arrived #2, 3 = arrived #3
+    const uint64_t w_policy = l2_policy_evict_last();
     for (int r = 0; r < total; r += 8) {
       // barrier duties first, at round granularity; never block on a stage whose release needs a barrier we have not served
       if (body && bar_state == 0 && r >= nA_use) { dl_arrive(); bar_state = 1; }                                   // #1
@@ -238,8 +239,9 @@ __device__ __forceinline__ void decode_layer_body(const CUtensorMap& tmAttn, con
         else if (i < nA_use + nB_use + nC_use) { const int j = i - nA_use - nB_use; tm = &tmW2; c0 = fB * crank + (j / nC) * 64; frow = 128 * (j % nC); boxes = 2; }
         else { const int j = i - nA_use - nB_use - nC_use; tm = &tmWq; c0 = (j / nD) * 64; frow = fD * crank + 128 * (j % nD); boxes = (j % nD) == 0 ? 2 : 1; }
         mbar_expect_tx(&full[s], (uint32_t)(boxes * 64 * 128));
-        tma_load_2d(dst, tm, c0, frow, &full[s]);
-        if (boxes == 2) tma_load_2d(dst + 64 * 128, tm, c0, frow + 64, &full[s]);
+        // weights: keep them in L2 across steps (101 MB of bf16 weights against a 126 MB L2; the K/V streams are loaded evict-first)
+        tma_load_2d_hint(dst, tm, c0, frow, &full[s], w_policy);
+        if (boxes == 2) tma_load_2d_hint(dst + 64 * 128, tm, c0, frow + 64, &full[s], w_policy);
       }
       if (r == 0 && body) {                              // the attention output rows: the only load that waits for the predecessor
         pdl_wait();
