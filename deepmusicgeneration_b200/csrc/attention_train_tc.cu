@@ -462,7 +462,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmPd, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nS = (a.M + a.T) / 128;
   const int jt = (int)(blockIdx.x % nS);            // memory tiles (most query rows) first
-  const int bh = blockIdx.x / nS, b = bh / a.H, h = bh % a.H;
+  // (stream, head) pairs in the REVERSE of the dQ kernel's order: the Pd / dS tiles it wrote last are still in L2 (the 537 MB of a layer's
+  // tiles do not fit, the most recent ~100 MB do)
+  const int bh = a.B * a.H - 1 - (int)(blockIdx.x / nS), b = bh / a.H, h = bh % a.H;
   const int j0 = jt * 128, HD = a.H * 64;
   const bool in_x = j0 >= a.M;
   bf16 *dk_dst, *dv_dst;
