@@ -221,13 +221,15 @@ __device__ __forceinline__ void decode_layer_body(const CUtensorMap& tmAttn, con
     // issue in lock-step (lane j = use r + j of a round): one thread's scalar issue loop was measured to be a bottleneck.
     if (lane == 0) dl_mark(a.dbg, 0, 0);
     const int total = nA_use + nB_use + nC_use + nD_use;
-    int bar_state = 0;                                   // cluster barrier progress of this warp: 0, 1 = arrived #1, 2 = arrived #2, 3 = arrived #3
+    int bar_state = 0;                                   // cluster barrier progress of this warp: n = arrived at barrier #n (#1, #2: LayerNorm 1)
     const uint64_t w_policy = l2_policy_evict_last();
     for (int r = 0; r < total; r += 8) {
       // barrier duties first, at round granularity; never block on a stage whose release needs a barrier we have not served
       if (body && bar_state == 0 && r >= nA_use) { dl_arrive(); bar_state = 1; }                                   // #1
-      if (body && bar_state == 1 && r >= nA_use + nB_use) { dl_wait(); dl_arrive(); bar_state = 2; }               // #2
-      if (body && bar_state == 2 && r + 8 > nA_use + nB_use + nC_use + DL_STAGES) { dl_wait(); dl_arrive(); bar_state = 3; }   // #3
+      // stages released by the FFN-up MMAs need LayerNorm 1, i.e. barrier #2 with this warp's arrival
+      if (body && bar_state == 1 && r + 8 > nA_use + DL_STAGES) { dl_wait(); dl_arrive(); bar_state = 2; }         // #2
+      if (body && bar_state == 2 && r >= nA_use + nB_use) { dl_wait(); dl_arrive(); bar_state = 3; }               // #3
+      if (body && bar_state == 3 && r + 8 > nA_use + nB_use + nC_use + DL_STAGES) { dl_wait(); dl_arrive(); bar_state = 4; }   // #4
       const int i = r + lane;
       if (lane < 8 && i < total) {
         const int s = i % DL_STAGES;
@@ -256,6 +258,7 @@ __device__ __forceinline__ void decode_layer_body(const CUtensorMap& tmAttn, con
       if (bar_state == 0) { dl_arrive(); bar_state = 1; }
       if (bar_state == 1) { dl_wait(); dl_arrive(); bar_state = 2; }
       if (bar_state == 2) { dl_wait(); dl_arrive(); bar_state = 3; }
+      if (bar_state == 3) { dl_wait(); dl_arrive(); bar_state = 4; }
       dl_wait();
     }
   } else if (warp <= DL_MMAW) {
@@ -290,6 +293,8 @@ __device__ __forceinline__ void decode_layer_body(const CUtensorMap& tmAttn, con
       }
       __syncwarp();
       dl_arrive();                                                     // #1
+      dl_wait();
+      dl_arrive();                                                     // #2 (before waiting for LayerNorm 1: its broadcast needs every thread's arrival)
       if (lane < 4) {
         dl_spin(&xa_ready[0], 0);                                      // LayerNorm 1 rows are in XA
         tc_fence_after();
@@ -306,10 +311,10 @@ __device__ __forceinline__ void decode_layer_body(const CUtensorMap& tmAttn, con
         umma_commit(&tmem_full[2]);
       }
       __syncwarp();
-      dl_wait();                                                       // #1
-      dl_arrive();                                                     // #2
-      dl_wait();
+      dl_wait();                                                       // #2
       dl_arrive();                                                     // #3
+      dl_wait();
+      dl_arrive();                                                     // #4
       dl_wait();                                                       // every CTA's LayerNorm-2 rows have landed in this XA
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // remote generic-proxy stores -> this CTA's tensor-core reads
     }
@@ -347,12 +352,20 @@ __device__ __forceinline__ void decode_layer_body(const CUtensorMap& tmAttn, con
     if (mk) dl_mark(a.dbg, 2, 0);
     pdl_wait();                                           // the residual stream comes from the predecessors
     if (mk) dl_mark(a.dbg, 2, 1);
+    float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // body: this CTA's 64-feature slice of the residual row (LayerNorm 1 is column-sliced)
+    if (body) {
+      if (valid) {
+        const float4 x0 = ldcg4(a.x32 + (size_t)row * DL_D + 64 * crank + 8 * t), x1 = ldcg4(a.x32 + (size_t)row * DL_D + 64 * crank + 8 * t + 4);
+        rs[0] = x0.x; rs[1] = x0.y; rs[2] = x0.z; rs[3] = x0.w; rs[4] = x1.x; rs[5] = x1.y; rs[6] = x1.z; rs[7] = x1.w;
+      }
+    } else {
 #pragma unroll
-    for (int kb = 0; kb < 8; kb++) {
-      float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-      if (valid) { x0 = ldcg4(a.x32 + (size_t)row * DL_D + 64 * kb + 8 * t); x1 = ldcg4(a.x32 + (size_t)row * DL_D + 64 * kb + 8 * t + 4); }
-      float* v = z + 8 * kb;
-      v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+      for (int kb = 0; kb < 8; kb++) {
+        float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+        if (valid) { x0 = ldcg4(a.x32 + (size_t)row * DL_D + 64 * kb + 8 * t); x1 = ldcg4(a.x32 + (size_t)row * DL_D + 64 * kb + 8 * t + 4); }
+        float* v = z + 8 * kb;
+        v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+      }
     }
     float acc[16];
     if (body) {
@@ -361,36 +374,72 @@ __device__ __forceinline__ void decode_layer_body(const CUtensorMap& tmAttn, con
       tc_fence_after();
       if (mk) dl_mark(a.dbg, 2, 2);
       dl_gather(tq, 4 * nkb_A < 8 ? 4 * nkb_A : 8, acc);
+      // ---- out-projection slice + bias -> T[row][feature of this CTA] (fp32, in the not yet used HS buffer)
+      float* T = (float*)hs_s;                            // [32][64]
+      float4* stats = (float4*)(hs_s + DL_ROWS * 64 * 4); // [8 CTAs][32 rows]: (mean, M2) of the CTA's 64-feature slice of the row
       if (lane < 16) {                                    // M = 64: feature 16 q + lane sits in TMEM lane 32 q + lane
-        const int f = 64 * crank + 16 * q + lane;
-        const float bias = a.bo ? __ldg(a.bo + f) : 0.f;
+        const int fl = 16 * q + lane;
+        const float bias = a.bo ? __ldg(a.bo + 64 * crank + fl) : 0.f;
 #pragma unroll
-        for (int rr = 0; rr < 16; rr++) a.P[(size_t)(erow0 + rr) * DL_D + f] = acc[rr] + bias;
+        for (int rr = 0; rr < 16; rr++) T[(16 * half + rr) * 64 + fl] = acc[rr] + bias;
       }
       tc_fence_before();
-      __syncwarp();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (mk) dl_mark(a.dbg, 2, 3);
-      dl_arrive();                                                     // #1: P slices published
+      // ---- LayerNorm 1, column-sliced: this CTA normalises ITS 64 features of all 32 rows.  Row statistics: every CTA's (mean, M2) of
+      // its slice goes to all 8 CTAs through distributed shared memory, the slices are merged exactly (Chan et al.); then the bf16 slice
+      // goes into k-block `crank` of every CTA's XA and the fp32 slice to the CTA that owns the row in LayerNorm 2.
+      float v[8];
+      {
+        const float4 t0 = *(const float4*)(T + r * 64 + 8 * t), t1 = *(const float4*)(T + r * 64 + 8 * t + 4);
+        v[0] = t0.x + rs[0]; v[1] = t0.y + rs[1]; v[2] = t0.z + rs[2]; v[3] = t0.w + rs[3];
+        v[4] = t1.x + rs[4]; v[5] = t1.y + rs[5]; v[6] = t1.z + rs[6]; v[7] = t1.w + rs[7];
+      }
+      float s1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; i++) s1 += v[i];
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 4);
+      const float mj = s1 * (1.f / 64.f);
+      float s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; i++) { const float c = v[i] - mj; s2 += c * c; }
+      s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 2); s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
+      {   // lane t of the row's 8 sends the pair to CTA t
+        const uint32_t off = smem_u32(stats + crank * DL_ROWS + r);
+        dl_st_cluster_v4(dl_mapa(off, (uint32_t)t), make_uint4(__float_as_uint(mj), __float_as_uint(s2), 0u, 0u));
+      }
+      dl_arrive();                                                     // #1: slice statistics published; every CTA is done reading its attention rows
       dl_wait();
       if (mk) dl_mark(a.dbg, 2, 4);
-      // ---- LayerNorm 1 (every CTA, all 512 features of its cluster's 32 rows)
+      {
+        float ms[DL_CLUSTER], qs[DL_CLUSTER], mean = 0.f;
 #pragma unroll
-      for (int kb = 0; kb < 8; kb++) {
-        const float4 p0 = ldcg4(a.P + (size_t)row * DL_D + 64 * kb + 8 * t), p1 = ldcg4(a.P + (size_t)row * DL_D + 64 * kb + 8 * t + 4);
-        float* v = z + 8 * kb;
-        v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w; v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
-      }
-      dl_layernorm(z, ln_s, ln_s + DL_D, t);
-      dl_store_xa(xa_s, z, r, t);
-      if ((r >> 2) == crank) {                            // a row this CTA owns: keep the fp32 result as the residual of LayerNorm 2
-        float* dst = x1_s + (r & 3) * DL_D + 8 * t;
+        for (int p = 0; p < DL_CLUSTER; p++) { const float4 st = stats[p * DL_ROWS + r]; ms[p] = st.x; qs[p] = st.y; mean += st.x; }
+        mean *= (1.f / DL_CLUSTER);
+        float m2 = 0.f;
 #pragma unroll
-        for (int kb = 0; kb < 8; kb++) {
-          *(float4*)(dst + 64 * kb) = make_float4(z[8 * kb], z[8 * kb + 1], z[8 * kb + 2], z[8 * kb + 3]);
-          *(float4*)(dst + 64 * kb + 4) = make_float4(z[8 * kb + 4], z[8 * kb + 5], z[8 * kb + 6], z[8 * kb + 7]);
-        }
+        for (int p = 0; p < DL_CLUSTER; p++) { const float dm = ms[p] - mean; m2 += qs[p] + 64.f * dm * dm; }
+        const float rstd = rsqrtf(m2 * (1.f / DL_D) + 1e-5f);
+        const float* w = ln_s + 64 * crank + 8 * t;
+        const float* bb = ln_s + DL_D + 64 * crank + 8 * t;
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = (v[i] - mean) * rstd * w[i] + bb[i];
       }
-      dl_fence_async_smem();
+      {
+        // fp32 slice -> X1 of the row's LayerNorm-2 owner (CTA r / 4, its row r % 4)
+        const uint32_t xoff = smem_u32(x1_s + (r & 3) * DL_D + 64 * crank + 8 * t);
+        const uint32_t xo = dl_mapa(xoff, (uint32_t)(r >> 2));
+        dl_st_cluster_v4(xo, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
+        dl_st_cluster_v4(xo + 16, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
+        // bf16 slice -> k-block `crank` of every CTA's XA (row r, 16-byte chunk t, swizzled)
+        const uint4 packed = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        const uint32_t off = smem_u32(xa_s) + (uint32_t)(crank * DL_B_BYTES + r * 128 + ((t ^ (r & 7)) << 4));
+#pragma unroll
+        for (int p = 0; p < DL_CLUSTER; p++) dl_st_cluster_v4(dl_mapa(off, (uint32_t)p), packed);
+      }
+      dl_arrive();                                                     // #2: the LayerNorm-1 rows (XA of all CTAs) and residual rows (X1 of the owners) are published
+      dl_wait();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // remote generic-proxy stores -> this CTA's tensor-core reads
       mbar_arrive(&xa_ready[0]);
       if (mk) dl_mark(a.dbg, 2, 5);
       // ---- FFN-up slice: + b1, tanh-GeLU, bf16 -> HS (this CTA's K slice of the FFN-down GEMM), K-major 128B-swizzled k-blocks
@@ -429,7 +478,7 @@ __device__ __forceinline__ void decode_layer_body(const CUtensorMap& tmAttn, con
       tc_fence_before();
       __syncwarp();
       if (mk) dl_mark(a.dbg, 2, 10);
-      dl_arrive();                                                     // #2: partial sums published
+      dl_arrive();                                                     // #3: partial sums published
       dl_wait();
       if (mk) dl_mark(a.dbg, 2, 11);
       // ---- LayerNorm 2 of the 4 rows this CTA owns: x1 + b2 + the 8 partial sums, 64 threads per row, 8 columns each
@@ -484,7 +533,7 @@ __device__ __forceinline__ void decode_layer_body(const CUtensorMap& tmAttn, con
         }
       }
       if (mk) dl_mark(a.dbg, 2, 12);
-      dl_arrive();                                                     // #3: the broadcast rows are published (release)
+      dl_arrive();                                                     // #4: the broadcast rows are published (release)
       dl_wait();
     } else if (next) {
       dl_store_xa(xa_s, z, r, t);                         // first launch of a step: the embedded rows, every CTA for itself
