@@ -44,11 +44,9 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint32_t* tmem_holder = (uint32_t*)(bar + Q_COUNT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nT = (a.T + 127) / 128;                  // a ragged last tile: keys >= T are masked, rows >= T are not stored
-  const int it = blockIdx.x % nT;                   // every query tile sees all nT key tiles: uniform work
-  const int bh = blockIdx.x / nT, b = bh / a.H, h = bh % a.H;
-  const int i0 = it * 128, HD = a.H * 64;
-  const int NT = nT;
+  const int NT = (a.T + 127) / 128;                  // a ragged last tile: keys >= T are masked, rows >= T are not stored
+  const int n_items = a.B * a.H * NT;               // every query tile sees all NT key tiles: uniform work
+  const int HD = a.H * 64;
 
   if (warp == BT_SOFT_WARPS && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -63,23 +61,31 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   pdl_launch_dependents();
 
   if (warp >= BT_SOFT_WARPS) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    // register pool of the CTA: 384 threads x 168 at launch; 128 auxiliary threads give back 104 each (13312), the 256 softmax threads
+    // take 48 each (12288) - an increase beyond what was given back would wait forever
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == BT_SOFT_WARPS) {
       // =========================================== TMA producer ===========================================
-      if (lane == 0) bt_producer(smem, bar, tmX, tmR, a, b, h, it, NT);
+      if (lane == 0) bt_producer(smem, bar, tmX, tmR, a, NT, n_items);
     } else if (warp == BT_SOFT_WARPS + 1) {
       // =========================================== MMA issuer ===========================================
-      if (lane == 0) bt_mma_issuer(smem, bar, tmem_base, it, NT);
+      if (lane == 0) bt_mma_issuer(smem, bar, tmem_base, NT, n_items, a.H);
     }
   } else {
     // =========================================== softmax warps ===========================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int hf = warp >> 2, q4 = warp & 3;
     const int r = q4 * 32 + lane;                   // query row of this thread inside the tile
-    const int row = i0 + r;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16);
     float* strip = (float*)(smem + BO_STRIP) + (size_t)(warp * 32 + lane) * BT_STRIP_LD;
     const float c = a.scale * BT_LOG2E;
+    uint8_t* prow = smem + BO_P + hf * BT16K + (r >> 3) * 1024 + (r & 7) * 128;
+
+    int kit = 0;                                    // items this CTA has finished: the barriers count on across items
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, kit++) {
+    const BtItem wi = bt_item(item, NT, a.H);
+    const int b = wi.b, h = wi.h, it = wi.it, i0 = it * 128, row = i0 + r;
+    const int g0 = kit * NT;
 
     {   // q + u, q + v and q_next + v in the canonical swizzled layout.  Eight consecutive threads take the eight 16-byte chunks of
         // one row (128 contiguous bytes: no bank conflicts); a thread's rows are 32 apart, so its physical chunk maps to the same
@@ -89,7 +95,7 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const float4 ua = __ldg((const float4*)(a.u + h * 64 + col)), ub = __ldg((const float4*)(a.u + h * 64 + col + 4));
       const float4 va = __ldg((const float4*)(a.v + h * 64 + col)), vb = __ldg((const float4*)(a.v + h * 64 + col + 4));
       const float uu[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w}, vv8[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-      mbar_wait(&bar[Q_QFULL], 0);
+      bt_wait(&bar[Q_QFULL], kit & 1);
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const int qr = rb + 32 * k;
@@ -118,14 +124,13 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 #pragma unroll
     for (int i = 0; i < 64; i++) o[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 1.f;
-    uint8_t* prow = smem + BO_P + hf * BT16K + (r >> 3) * 1024 + (r & 7) * 128;
     // the zero pad of _line_shift: key j = i + 1 (tile (row+1)/128, local key (row+1)%128; for the last row of a tile that is key 0
     // of the NEXT tile)
     const int zero_tile = (row + 1) >> 7, zero_jj = ((((row + 1) & 127) >> 6) == hf) ? ((row + 1) & 63) : -1000;
 
     for (int n = 0; n < NT; n++) {
       float s[64];
-      mbar_wait(&bar[Q_SFULL], n & 1);
+      bt_wait(&bar[Q_SFULL], (g0 + n) & 1);
       tc_fence_after();
       const int zj = n == zero_tile ? zero_jj : -1000;
       if constexpr (H16) {
@@ -226,7 +231,7 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       }
 
       if (n > 0) {                                   // fold the previous tile's P V into the running output
-        mbar_wait(&bar[Q_OFULL0 + hf], (n - 1) & 1);
+        bt_wait(&bar[Q_OFULL0 + hf], (g0 + n - 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int ch = 0; ch < 2; ch++) {
@@ -267,7 +272,7 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[Q_PFULL0 + hf]);
     }
-    mbar_wait(&bar[Q_OFULL0 + hf], (NT - 1) & 1);
+    bt_wait(&bar[Q_OFULL0 + hf], (g0 + NT - 1) & 1);
     tc_fence_after();
 #pragma unroll
     for (int ch = 0; ch < 2; ch++) {
@@ -278,6 +283,8 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       for (int i = 0; i < 32; i++) o[32 * ch + i] = fmaf(o[32 * ch + i], alpha_prev, __uint_as_float(x[i]));
     }
     tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar[Q_OFREE0 + hf]);   // the next item's first P V may overwrite the accumulator
 
     // merge the two key halves of every row: half 1 leaves its output, maximum and row sum in its strip line (fp32 strip) or in the q
     // tiles (fp16 strip: the lines are too short; every MMA that reads the q tiles has completed once the last P V has)
@@ -307,6 +314,8 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         *(uint4*)(orow + 8 * k) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // the merge buffer is the next item's q + u tile / strip lines
+    }   // items
   }
   tc_fence_before();
   __syncthreads();
@@ -334,7 +343,18 @@ int attn_bert_tc(const bf16* qkv, const bf16* rd, int Dcap, const float* u, cons
   if (train_get_tmap(rd, 64, (long long)H * Dcap, 64, 128, &tr)) return -1;
   BertTcArgs a;
   a.u = u; a.v = v; a.out = out; a.B = B; a.T = T; a.H = H; a.Dcap = Dcap; a.scale = scale;
-  const dim3 grid(B * H * ((T + 127) / 128));
+  // persistent: one CTA per SM (shared memory and all 512 TMEM columns allow one), items dealt round-robin.  DMG_BERT_TC_ONE_ITEM=1
+  // (measurement only) launches one CTA per item, the schedule of rounds 1 and 2.
+  static int num_sms = 0, one_item = -1;
+  if (num_sms == 0) {
+    int dev = 0;
+    DMG_CUDA_OK(cudaGetDevice(&dev));
+    DMG_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    const char* e = getenv("DMG_BERT_TC_ONE_ITEM");
+    one_item = e && e[0] == '1';
+  }
+  const int n_items = B * H * ((T + 127) / 128);
+  const dim3 grid(one_item || n_items < num_sms ? n_items : num_sms);
   if (fp32_strip)
     return launch_k(attn_bert_tc_kernel<false>, grid, dim3(BT_THREADS), (size_t)BT_SMEM, st, 1, *(const CUtensorMap*)tx->bytes,
                     *(const CUtensorMap*)tr->bytes, a);

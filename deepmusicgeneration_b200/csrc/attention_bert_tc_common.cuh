@@ -60,60 +60,98 @@ __device__ __forceinline__ void bt_init_barriers(uint64_t* bar, int soft_warps) 
   mbar_fence_init();
 }
 
-// TMA producer (one thread): q / q_next, then per key tile K, the position-key blocks and V
+// bounded wait without the printf of mbar_wait (its argument buffer and call cost the 64-register one-lane roles a dozen spills): a
+// protocol bug still traps (-> CUDA error on the host) instead of hanging the GPU box
+__device__ __forceinline__ void bt_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t n = 0;
+  while (!mbar_try_wait(bar, parity))
+    if (++n > (1u << 26)) __trap();
+}
+
+// Work decomposition of the persistent kernel: item = (stream, head, query tile), items are dealt round-robin over the CTAs
+// (item = blockIdx.x + k * gridDim.x: CTAs that run side by side work on neighbouring query tiles of one (stream, head) and share
+// its K / V / position-key tiles in L2).  Every mbarrier keeps counting across items: a role derives the phase parity from the
+// number of uses so far (g = k * NT + n for the per-tile barriers, k * (NT + 1) + j for the position-key loads).
+struct BtItem {
+  int b, h, it;
+};
+__device__ __forceinline__ BtItem bt_item(int item, int nT, int H) {
+  const int bh = item / nT;
+  return {bh / H, bh % H, item % nT};
+}
+
+// TMA producer (one thread): per item q / q_next, then per key tile K, the position-key blocks and V
 __device__ __forceinline__ void bt_producer(uint8_t* smem, uint64_t* bar, const CUtensorMap& tmX, const CUtensorMap& tmR, const BertTcArgs& a,
-                                            int b, int h, int it, int NT) {
-  const int i0 = it * 128, HD = a.H * 64;
+                                            int NT, int n_items) {
+  const int HD = a.H * 64;
   pdl_wait();                                  // q | k | v come from the predecessor kernel (the QKV GEMM)
-  mbar_expect_tx(&bar[Q_QFULL], 2 * BT16K);
-  tma_load_2d(smem + BO_P, &tmX, h * 64, b * a.T + i0, &bar[Q_QFULL]);
-  tma_load_2d(smem + BO_P + BT16K, &tmX, h * 64, b * a.T + i0 + 1, &bar[Q_QFULL]);   // rows i+1 (the last row of the last tile is never used)
-  auto load_k = [&](int n) {
-    mbar_wait(&bar[Q_KEMPTY], (n & 1) ^ 1);
-    mbar_expect_tx(&bar[Q_KFULL], BT16K);
-    tma_load_2d(smem + BO_K, &tmX, HD + h * 64, b * a.T + n * 128, &bar[Q_KFULL]);
-  };
-  auto load_r = [&](int k) {                  // load 0 = upper block of tile 0; load k >= 1 = lower block of tile k-1
-    const int s = k & 1;
-    // line 1: Rk rows (it-k)*128 ...; line 3: Rk rows T + 1 + (it-k)*128 ... (distance T + 1 + i - j; rows below 0 or past T - 1
-    // only meet masked keys or the zero pad)
-    const int row = k <= it ? (it - k) * 128 : a.T + 1 + (it - k) * 128;
-    mbar_wait(&bar[Q_REMPTY0 + s], ((k >> 1) & 1) ^ 1);
-    mbar_expect_tx(&bar[Q_RFULL0 + s], BT16K);
-    tma_load_2d(smem + BO_R + s * BT16K, &tmR, 0, h * a.Dcap + row, &bar[Q_RFULL0 + s]);
-  };
-  auto load_v = [&](int n) {
-    mbar_wait(&bar[Q_VEMPTY], (n & 1) ^ 1);
-    mbar_expect_tx(&bar[Q_VFULL], BT16K);
-    tma_load_2d(smem + BO_V, &tmX, 2 * HD + h * 64, b * a.T + n * 128, &bar[Q_VFULL]);
-  };
-  load_k(0);
-  load_r(0);
-  load_r(1);
-  load_v(0);
-  // waits in the order the MMAs retire: S(n-1) is issued half a tile before PV(n-2), so the V requests trail the K / R requests
-  // by one tile (a V request waiting for PV(n-1) in front of them would hold the operands of S(n+1) back until half a tile before
-  // use: measured 70.8 -> 64.5 ms per C4 forward)
-  for (int n = 1; n < NT; n++) {
-    load_k(n);
-    load_r(n + 1);
-    if (n >= 2) load_v(n - 1);
+  int k = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, k++) {
+    const BtItem w = bt_item(item, NT, a.H);
+    const int b = w.b, h = w.h, it = w.it, i0 = it * 128;
+    const int g0 = k * NT, r0 = k * (NT + 1);  // tiles / position-key loads of the earlier items
+    auto load_q = [&]() {
+      if (k > 0) {                             // the raw q tiles land in the P buffers: the last P V of the previous item has to be done
+        bt_wait(&bar[Q_OFULL0], (g0 - 1) & 1);
+        bt_wait(&bar[Q_OFULL1], (g0 - 1) & 1);
+      }
+      mbar_expect_tx(&bar[Q_QFULL], 2 * BT16K);
+      tma_load_2d(smem + BO_P, &tmX, h * 64, b * a.T + i0, &bar[Q_QFULL]);
+      tma_load_2d(smem + BO_P + BT16K, &tmX, h * 64, b * a.T + i0 + 1, &bar[Q_QFULL]);   // rows i+1 (the last row of the last tile is never used)
+    };
+    auto load_k = [&](int n) {
+      const int g = g0 + n;
+      bt_wait(&bar[Q_KEMPTY], (g & 1) ^ 1);
+      mbar_expect_tx(&bar[Q_KFULL], BT16K);
+      tma_load_2d(smem + BO_K, &tmX, HD + h * 64, b * a.T + n * 128, &bar[Q_KFULL]);
+    };
+    auto load_r = [&](int j) {                  // load 0 = upper block of tile 0; load j >= 1 = lower block of tile j-1
+      const int gl = r0 + j, s = gl & 1;
+      // line 1: Rk rows (it-j)*128 ...; line 3: Rk rows T + 1 + (it-j)*128 ... (distance T + 1 + i - j; rows below 0 or past T - 1
+      // only meet masked keys or the zero pad)
+      const int row = j <= it ? (it - j) * 128 : a.T + 1 + (it - j) * 128;
+      bt_wait(&bar[Q_REMPTY0 + s], ((gl >> 1) & 1) ^ 1);
+      mbar_expect_tx(&bar[Q_RFULL0 + s], BT16K);
+      tma_load_2d(smem + BO_R + s * BT16K, &tmR, 0, h * a.Dcap + row, &bar[Q_RFULL0 + s]);
+    };
+    auto load_v = [&](int n) {
+      const int g = g0 + n;
+      bt_wait(&bar[Q_VEMPTY], (g & 1) ^ 1);
+      mbar_expect_tx(&bar[Q_VFULL], BT16K);
+      tma_load_2d(smem + BO_V, &tmX, 2 * HD + h * 64, b * a.T + n * 128, &bar[Q_VFULL]);
+    };
+    // the first item asks for q first; later items already have their K / position-key buffers free while the previous item's last
+    // P V (which the q landing zone waits for) is still running
+    if (k == 0) load_q();
+    load_k(0);
+    load_r(0);
+    load_r(1);
+    if (k > 0) load_q();
+    load_v(0);
+    // waits in the order the MMAs retire: S(n-1) is issued half a tile before PV(n-2), so the V requests trail the K / R requests
+    // by one tile (a V request waiting for PV(n-1) in front of them would hold the operands of S(n+1) back until half a tile before
+    // use: measured 70.8 -> 64.5 ms per C4 forward)
+    for (int n = 1; n < NT; n++) {
+      load_k(n);
+      load_r(n + 1);
+      if (n >= 2) load_v(n - 1);
+    }
+    if (NT >= 2) load_v(NT - 1);
   }
-  if (NT >= 2) load_v(NT - 1);
 }
 
 // MMA issuer (one thread): S(n) = AC | strip, then P V of the previous tile
-__device__ __forceinline__ void bt_mma_issuer(uint8_t* smem, uint64_t* bar, uint32_t tmem_base, int it, int NT) {
+__device__ __forceinline__ void bt_mma_issuer(uint8_t* smem, uint64_t* bar, uint32_t tmem_base, int NT, int n_items, int H) {
   constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
   constexpr uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
   const uint32_t qu = smem_u32(smem + BO_QU), qv = smem_u32(smem + BO_QV), qvn = smem_u32(smem + BO_QVN), kk = smem_u32(smem + BO_K),
                  vv = smem_u32(smem + BO_V), rr = smem_u32(smem + BO_R), pp = smem_u32(smem + BO_P);
-  auto issue_pv = [&](int m) {
-    mbar_wait(&bar[Q_VFULL], m & 1);
+  auto issue_pv = [&](int g) {                 // g: tile count over all items of this CTA
+    bt_wait(&bar[Q_VFULL], g & 1);
 #pragma unroll
     for (int hf = 0; hf < 2; hf++) {
-      mbar_wait(&bar[Q_PFULL0 + hf], m & 1);
-      if (m > 0) mbar_wait(&bar[Q_OFREE0 + hf], (m - 1) & 1);
+      bt_wait(&bar[Q_PFULL0 + hf], g & 1);
+      if (g > 0) bt_wait(&bar[Q_OFREE0 + hf], (g - 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < 4; k++)
@@ -123,30 +161,37 @@ __device__ __forceinline__ void bt_mma_issuer(uint8_t* smem, uint64_t* bar, uint
     }
     umma_commit(&bar[Q_VEMPTY]);
   };
-  mbar_wait(&bar[Q_QREADY], 0);
-  for (int n = 0; n < NT; n++) {
-    mbar_wait(&bar[Q_KFULL], n & 1);
-    mbar_wait(&bar[Q_RFULL0 + (n & 1)], (n >> 1) & 1);                 // load n   = this tile's upper block
-    mbar_wait(&bar[Q_RFULL0 + ((n + 1) & 1)], ((n + 1) >> 1) & 1);     // load n+1 = this tile's lower block
-    if (n > 0) mbar_wait(&bar[Q_SFREE], (n - 1) & 1);
-    tc_fence_after();
-    const uint32_t ru = rr + (n & 1) * BT16K, rl = rr + ((n + 1) & 1) * BT16K;
-    const uint32_t au = n <= it ? qv : qvn, al = (n + 1) <= it ? qv : qvn;     // line 1 below / on the diagonal, line 3 above
-    // (separate ready / free barriers for AC and the strip - AC(n+1) issued right after the AC reads of tile n - were measured
-    // slower: 68.4 vs 64.4 ms per C4 forward; the extra arrive sits in the softmax warps' critical path)
+  int k = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, k++) {
+    const int it = item % NT;
+    const int g0 = k * NT, r0 = k * (NT + 1);
+    bt_wait(&bar[Q_QREADY], k & 1);
+    for (int n = 0; n < NT; n++) {
+      const int g = g0 + n, gu = r0 + n, gl = gu + 1;                   // load gu = this tile's upper block, gl = its lower block
+      bt_wait(&bar[Q_KFULL], g & 1);
+      bt_wait(&bar[Q_RFULL0 + (gu & 1)], (gu >> 1) & 1);
+      bt_wait(&bar[Q_RFULL0 + (gl & 1)], (gl >> 1) & 1);
+      if (g > 0) bt_wait(&bar[Q_SFREE], (g - 1) & 1);
+      tc_fence_after();
+      const uint32_t ru = rr + (gu & 1) * BT16K, rl = rr + (gl & 1) * BT16K;
+      const uint32_t au = n <= it ? qv : qvn, al = (n + 1) <= it ? qv : qvn;     // line 1 below / on the diagonal, line 3 above
+      // (separate ready / free barriers for AC and the strip - AC(n+1) issued right after the AC reads of tile n - were measured
+      // slower: 68.4 vs 64.4 ms per C4 forward; the extra arrive sits in the softmax warps' critical path)
 #pragma unroll
-    for (int k = 0; k < 4; k++) umma_bf16(tmem_base + BTM_AC, bt_desc_k(qu + k * 32), bt_desc_k(kk + k * 32), idesc_s, (uint32_t)(k > 0));
+      for (int k4 = 0; k4 < 4; k4++) umma_bf16(tmem_base + BTM_AC, bt_desc_k(qu + k4 * 32), bt_desc_k(kk + k4 * 32), idesc_s, (uint32_t)(k4 > 0));
 #pragma unroll
-    for (int k = 0; k < 4; k++) umma_bf16(tmem_base + BTM_STRIP, bt_desc_k(al + k * 32), bt_desc_k(rl + k * 32), idesc_s, (uint32_t)(k > 0));
+      for (int k4 = 0; k4 < 4; k4++) umma_bf16(tmem_base + BTM_STRIP, bt_desc_k(al + k4 * 32), bt_desc_k(rl + k4 * 32), idesc_s, (uint32_t)(k4 > 0));
 #pragma unroll
-    for (int k = 0; k < 4; k++)
-      umma_bf16(tmem_base + BTM_STRIP + 128, bt_desc_k(au + k * 32), bt_desc_k(ru + k * 32), idesc_s, (uint32_t)(k > 0));
-    umma_commit(&bar[Q_SFULL]);
-    umma_commit(&bar[Q_KEMPTY]);
-    umma_commit(&bar[Q_REMPTY0 + (n & 1)]);   // the upper block is dead after this tile; the lower one serves the next
-    if (n > 0) issue_pv(n - 1);
+      for (int k4 = 0; k4 < 4; k4++)
+        umma_bf16(tmem_base + BTM_STRIP + 128, bt_desc_k(au + k4 * 32), bt_desc_k(ru + k4 * 32), idesc_s, (uint32_t)(k4 > 0));
+      umma_commit(&bar[Q_SFULL]);
+      umma_commit(&bar[Q_KEMPTY]);
+      umma_commit(&bar[Q_REMPTY0 + (gu & 1)]);   // the upper block is dead after this tile; the lower one serves the next
+      if (n == NT - 1) umma_commit(&bar[Q_REMPTY0 + (gl & 1)]);   // ... or nobody: the next item starts with two fresh blocks
+      if (n > 0) issue_pv(g - 1);
+    }
+    issue_pv(g0 + NT - 1);
   }
-  issue_pv(NT - 1);
 }
 
 }  // namespace bert_tc

@@ -434,6 +434,27 @@ def test_bert_tcgen05_attention_bf16(T, variant):
     assert _rel(pl, ol) <= 2e-2 and (pl - pg).abs().max() < 3e-2
 
 
+@pytest.mark.parametrize('variant', ['default', 'fp32_strip'])
+@pytest.mark.parametrize('B,T', [(100, 128), (40, 257), (24, 1000), (24, 1024)])
+def test_bert_tcgen05_attention_persistent_items(B, T, variant):
+    """attention_bert_tc.cu is persistent: with more (stream, head, query tile) items than SMs every CTA walks several items and its
+    mbarrier phases, buffers and TMEM columns carry over - 1 / 3 / 8 key tiles per item (odd and even tile and position-key load
+    counts), ragged last tiles, 200 to 384 items on 148 SMs, against the oracle and the FFMA general kernel."""
+    from deepmusicgeneration_b200 import _lib as L
+    cfg = dict(obert.multitask_config(), enc_layers=2, d_model=128, n_heads=2, d_head=64, d_inner=256)
+    om, pm = _bert_pair(cfg, 'bf16', B, 1024, kernel_flags=L.KF_BERT_FP32_STRIP if variant == 'fp32_strip' else 0)
+    _, pgm = _bert_pair(cfg, 'bf16', B, 1024, kernel_flags=L.KF_NO_FLASH)
+    g = torch.Generator().manual_seed(B + T)
+    x = torch.randint(0, V, (B, T), generator=g)
+    pos = torch.cumsum(torch.randint(0, 9, (B, T), generator=g), 1)
+    with torch.no_grad():
+        ol = om({'msk': {'x': x, 'pos': pos.clone()}})['msk']
+    pl = pm({'msk': {'x': x.cuda(), 'pos': pos.cuda()}})['msk'].cpu()
+    pg = pgm({'msk': {'x': x.cuda(), 'pos': pos.cuda()}})['msk'].cpu()
+    print(f'B={B} T={T}: tcgen05 vs oracle {_rel(pl, ol):.3e}, general vs oracle {_rel(pg, ol):.3e}, tcgen05 vs general {(pl - pg).abs().max():.3e}')
+    assert _rel(pl, ol) <= 2e-2 and (pl - pg).abs().max() < 3e-2
+
+
 @pytest.mark.parametrize('T', [2, 63, 64, 100, 300, 320])
 def test_txl_flash_prefill_bf16_ragged_lengths(T):
     "attention_flash.cu, causal mode: prefill of a ragged seed after reset(), then ring decode continues from its K/V"
