@@ -23,13 +23,13 @@ namespace {
 using namespace bert_tc;
 
 constexpr int BT_SOFT_WARPS = 8;
-constexpr int BT_THREADS = (BT_SOFT_WARPS + 4) * 32;   // + one auxiliary warpgroup: TMA warp, MMA warp, two idle warps
+constexpr int BT_THREADS = (BT_SOFT_WARPS + 4) * 32;   // + one auxiliary warpgroup: TMA warp, MMA warp, two q-transform warps
 constexpr int BT_STRIP_LD = 68;
 constexpr int BO_BAR = BO_STRIP + BT_SOFT_WARPS * 32 * BT_STRIP_LD * 4;
 constexpr int BT_SMEM = BO_BAR + 256 + 1024;
 static_assert(BT_SMEM <= 227 * 1024, "shared memory budget");
 static_assert(BT_SOFT_WARPS * 32 * BT_LINE16 <= BT_SOFT_WARPS * 32 * BT_STRIP_LD * 4 && 128 * 68 * 4 <= 3 * BT16K, "fp16 lines / merge buffer fit");
-constexpr int BT_MROW = 68;                            // floats per row of the final merge buffer of the fp16-strip kernel (in the dead q tiles)
+constexpr int BT_MROW = 68;                            // floats per row of the final merge buffer of the fp16-strip kernel (over the strip lines)
 
 // H16: the position strip goes through shared memory as fp16 (|BD| < 65504 saturates; 11 bits of mantissa against the 8 of the bf16
 // operands): the thread's two 64-column windows overlap in 32 columns, so it reads 96 distinct columns once (three tcgen05.ld.x32
@@ -70,6 +70,9 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     } else if (warp == BT_SOFT_WARPS + 1) {
       // =========================================== MMA issuer ===========================================
       if (lane == 0) bt_mma_issuer(smem, bar, tmem_base, NT, n_items, a.H);
+    } else {
+      // =========================================== transform warps ===========================================
+      bt_transform(smem, bar, a, NT, n_items, threadIdx.x - 32 * (BT_SOFT_WARPS + 2));
     }
   } else {
     // =========================================== softmax warps ===========================================
@@ -86,39 +89,6 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const BtItem wi = bt_item(item, NT, a.H);
     const int b = wi.b, h = wi.h, it = wi.it, i0 = it * 128, row = i0 + r;
     const int g0 = kit * NT;
-
-    {   // q + u, q + v and q_next + v in the canonical swizzled layout.  Eight consecutive threads take the eight 16-byte chunks of
-        // one row (128 contiguous bytes: no bank conflicts); a thread's rows are 32 apart, so its physical chunk maps to the same
-        // logical columns in all of them and it needs one 8-wide slice of u and v only (requested before the wait for q).
-      const int tid = threadIdx.x, pc = tid & 7, rb = tid >> 3;
-      const int col = 8 * (pc ^ (rb & 7));
-      const float4 ua = __ldg((const float4*)(a.u + h * 64 + col)), ub = __ldg((const float4*)(a.u + h * 64 + col + 4));
-      const float4 va = __ldg((const float4*)(a.v + h * 64 + col)), vb = __ldg((const float4*)(a.v + h * 64 + col + 4));
-      const float uu[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w}, vv8[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-      bt_wait(&bar[Q_QFULL], kit & 1);
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int qr = rb + 32 * k;
-        const uint32_t off = (uint32_t)((qr >> 3) * 1024 + (qr & 7) * 128 + pc * 16);
-        const uint4 raw = *(const uint4*)(smem + BO_P + off);
-        const uint4 rawn = *(const uint4*)(smem + BO_P + BT16K + off);
-        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w}, wn[4] = {rawn.x, rawn.y, rawn.z, rawn.w};
-        uint32_t ou[4], ov[4], on[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const float u0 = uu[2 * e], u1 = uu[2 * e + 1], v0 = vv8[2 * e], v1 = vv8[2 * e + 1];
-          ou[e] = pack_bf16x2(bf16lo(w[e]) + u0, bf16hi(w[e]) + u1);
-          ov[e] = pack_bf16x2(bf16lo(w[e]) + v0, bf16hi(w[e]) + v1);
-          on[e] = pack_bf16x2(bf16lo(wn[e]) + v0, bf16hi(wn[e]) + v1);
-        }
-        *(uint4*)(smem + BO_QU + off) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
-        *(uint4*)(smem + BO_QV + off) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
-        *(uint4*)(smem + BO_QVN + off) = make_uint4(on[0], on[1], on[2], on[3]);
-      }
-      bt_fence_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar[Q_QREADY]);
-    }
 
     float o[64];
 #pragma unroll
@@ -286,9 +256,10 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     __syncwarp();
     if (lane == 0) mbar_arrive(&bar[Q_OFREE0 + hf]);   // the next item's first P V may overwrite the accumulator
 
-    // merge the two key halves of every row: half 1 leaves its output, maximum and row sum in its strip line (fp32 strip) or in the q
-    // tiles (fp16 strip: the lines are too short; every MMA that reads the q tiles has completed once the last P V has)
-    float* mine = H16 ? (float*)(smem + BO_QU) + (size_t)r * BT_MROW : strip;
+    // merge the two key halves of every row: half 1 leaves its output, maximum and row sum in its strip line (fp32 strip) or in
+    // merge rows laid over all strip lines (fp16 strip: one line is too short; the q tiles already belong to the next item)
+    float* mine = H16 ? (float*)(smem + BO_STRIP) + (size_t)r * BT_MROW : strip;
+    if constexpr (H16) asm volatile("bar.sync 1, 256;" ::: "memory");   // every thread is done with its line: the merge rows overlay them
     if (hf == 1) {
 #pragma unroll
       for (int k = 0; k < 16; k++) *(float4*)(mine + 4 * k) = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);

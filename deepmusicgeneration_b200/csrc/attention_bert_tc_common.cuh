@@ -20,8 +20,8 @@ constexpr int BO_QV = BO_QU + BT16K;
 constexpr int BO_QVN = BO_QV + BT16K;
 constexpr int BO_K = BO_QVN + BT16K;                   // one stage
 constexpr int BO_V = BO_K + BT16K;
-constexpr int BO_R = BO_V + BT16K;                     // 2 slots (slot = load index & 1)
-constexpr int BO_P = BO_R + 2 * BT16K;                 // 2 key halves; the raw q / q_next tiles land here first
+constexpr int BO_R = BO_V + BT16K;                     // 2 slots (slot = load index & 1): per item the raw q and q_next tiles, then the position-key blocks
+constexpr int BO_P = BO_R + 2 * BT16K;                 // 2 key halves
 constexpr int BO_STRIP = BO_P + 2 * BT16K;             // the kernels' own strip lines, exchange buffers and barriers follow
 
 enum { Q_QFULL = 0, Q_QREADY, Q_KFULL, Q_KEMPTY, Q_RFULL0, Q_RFULL1, Q_REMPTY0, Q_REMPTY1, Q_VFULL, Q_VEMPTY, Q_SFULL, Q_SFREE,
@@ -53,7 +53,7 @@ struct BertTcArgs {
 __device__ __forceinline__ void bt_init_barriers(uint64_t* bar, int soft_warps) {
   for (int i = 0; i < Q_COUNT; i++) {
     uint32_t cnt = 1;
-    if (i == Q_QREADY || i == Q_SFREE) cnt = soft_warps;
+    if (i == Q_SFREE) cnt = soft_warps;
     if (i == Q_PFULL0 || i == Q_PFULL1 || i == Q_OFREE0 || i == Q_OFREE1) cnt = soft_warps / 2;
     mbar_init(&bar[i], cnt);
   }
@@ -71,7 +71,14 @@ __device__ __forceinline__ void bt_wait(uint64_t* bar, uint32_t parity) {
 // Work decomposition of the persistent kernel: item = (stream, head, query tile), items are dealt round-robin over the CTAs
 // (item = blockIdx.x + k * gridDim.x: CTAs that run side by side work on neighbouring query tiles of one (stream, head) and share
 // its K / V / position-key tiles in L2).  Every mbarrier keeps counting across items: a role derives the phase parity from the
-// number of uses so far (g = k * NT + n for the per-tile barriers, k * (NT + 1) + j for the position-key loads).
+// number of uses so far (g = k * NT + n for the per-tile barriers, k * (NT + 3) + j for the loads into the two position-key slots:
+// j = 0, 1 are the item's raw q and q_next tiles, j = 2 + m is position-key load m).
+//
+// Item boundary: the slots are released when the last S MMA of an item completes, one tile time before the softmax warps are done with
+// the item.  In that time the producer brings the next item's q / q_next into the slots, the two transform warps turn them into the
+// q + u / q + v / q_next + v operand tiles (free: every MMA that read them has completed) and release the slots, the first two
+// position-key blocks follow, and the issuer runs S(0) of the next item right behind the last P V of this one - the softmax warps
+// find their first scores waiting when they return from the item's epilogue.
 struct BtItem {
   int b, h, it;
 };
@@ -89,15 +96,11 @@ __device__ __forceinline__ void bt_producer(uint8_t* smem, uint64_t* bar, const 
   for (int item = blockIdx.x; item < n_items; item += gridDim.x, k++) {
     const BtItem w = bt_item(item, NT, a.H);
     const int b = w.b, h = w.h, it = w.it, i0 = it * 128;
-    const int g0 = k * NT, r0 = k * (NT + 1);  // tiles / position-key loads of the earlier items
-    auto load_q = [&]() {
-      if (k > 0) {                             // the raw q tiles land in the P buffers: the last P V of the previous item has to be done
-        bt_wait(&bar[Q_OFULL0], (g0 - 1) & 1);
-        bt_wait(&bar[Q_OFULL1], (g0 - 1) & 1);
-      }
-      mbar_expect_tx(&bar[Q_QFULL], 2 * BT16K);
-      tma_load_2d(smem + BO_P, &tmX, h * 64, b * a.T + i0, &bar[Q_QFULL]);
-      tma_load_2d(smem + BO_P + BT16K, &tmX, h * 64, b * a.T + i0 + 1, &bar[Q_QFULL]);   // rows i+1 (the last row of the last tile is never used)
+    const int g0 = k * NT, r0 = k * (NT + 3);  // tiles / slot loads of the earlier items
+    auto slot_wait = [&](int j) {               // the slot of load j of this item, once its previous tenant has been released
+      const int gl = r0 + j, s = gl & 1;
+      bt_wait(&bar[Q_REMPTY0 + s], ((gl >> 1) & 1) ^ 1);
+      return s;
     };
     auto load_k = [&](int n) {
       const int g = g0 + n;
@@ -106,11 +109,10 @@ __device__ __forceinline__ void bt_producer(uint8_t* smem, uint64_t* bar, const 
       tma_load_2d(smem + BO_K, &tmX, HD + h * 64, b * a.T + n * 128, &bar[Q_KFULL]);
     };
     auto load_r = [&](int j) {                  // load 0 = upper block of tile 0; load j >= 1 = lower block of tile j-1
-      const int gl = r0 + j, s = gl & 1;
       // line 1: Rk rows (it-j)*128 ...; line 3: Rk rows T + 1 + (it-j)*128 ... (distance T + 1 + i - j; rows below 0 or past T - 1
       // only meet masked keys or the zero pad)
       const int row = j <= it ? (it - j) * 128 : a.T + 1 + (it - j) * 128;
-      bt_wait(&bar[Q_REMPTY0 + s], ((gl >> 1) & 1) ^ 1);
+      const int s = slot_wait(2 + j);
       mbar_expect_tx(&bar[Q_RFULL0 + s], BT16K);
       tma_load_2d(smem + BO_R + s * BT16K, &tmR, 0, h * a.Dcap + row, &bar[Q_RFULL0 + s]);
     };
@@ -120,13 +122,16 @@ __device__ __forceinline__ void bt_producer(uint8_t* smem, uint64_t* bar, const 
       mbar_expect_tx(&bar[Q_VFULL], BT16K);
       tma_load_2d(smem + BO_V, &tmX, 2 * HD + h * 64, b * a.T + n * 128, &bar[Q_VFULL]);
     };
-    // the first item asks for q first; later items already have their K / position-key buffers free while the previous item's last
-    // P V (which the q landing zone waits for) is still running
-    if (k == 0) load_q();
+    {   // the raw q tiles complete on their own barrier (one phase per item): a waiter on RFULL that skips the position-key phases in
+        // between would find the parity of an older phase and walk through
+      const int s0 = slot_wait(0), s1 = slot_wait(1);
+      mbar_expect_tx(&bar[Q_QFULL], 2 * BT16K);
+      tma_load_2d(smem + BO_R + s0 * BT16K, &tmX, h * 64, b * a.T + i0, &bar[Q_QFULL]);
+      tma_load_2d(smem + BO_R + s1 * BT16K, &tmX, h * 64, b * a.T + i0 + 1, &bar[Q_QFULL]);   // rows i+1 (the last row of the last tile is never used)
+    }
     load_k(0);
     load_r(0);
     load_r(1);
-    if (k > 0) load_q();
     load_v(0);
     // waits in the order the MMAs retire: S(n-1) is issued half a tile before PV(n-2), so the V requests trail the K / R requests
     // by one tile (a V request waiting for PV(n-1) in front of them would hold the operands of S(n+1) back until half a tile before
@@ -137,6 +142,53 @@ __device__ __forceinline__ void bt_producer(uint8_t* smem, uint64_t* bar, const 
       if (n >= 2) load_v(n - 1);
     }
     if (NT >= 2) load_v(NT - 1);
+  }
+}
+
+// Transform warps (64 threads): the item's raw q / q_next tiles (position-key slots) -> q + u, q + v and q_next + v in the canonical
+// swizzled layout.  Eight consecutive threads take the eight 16-byte chunks of one row (128 contiguous bytes: no bank conflicts); a
+// thread's rows are 8 apart, so its physical chunk maps to the same logical columns in all of them and it needs one 8-wide slice of
+// u and v only (requested before the wait for q).
+__device__ __forceinline__ void bt_transform(uint8_t* smem, uint64_t* bar, const BertTcArgs& a, int NT, int n_items, int tid) {
+  const int pc = tid & 7, rb = tid >> 3;
+  const int col = 8 * (pc ^ rb);
+  int k = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, k++) {
+    const int h = (item / NT) % a.H;
+    const float4 ua = __ldg((const float4*)(a.u + h * 64 + col)), ub = __ldg((const float4*)(a.u + h * 64 + col + 4));
+    const float4 va = __ldg((const float4*)(a.v + h * 64 + col)), vb = __ldg((const float4*)(a.v + h * 64 + col + 4));
+    const float uu[8] = {ua.x, ua.y, ua.z, ua.w, ub.x, ub.y, ub.z, ub.w}, vv8[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+    const int g0 = k * (NT + 3), g1 = g0 + 1;
+    // the slots were released by the last S MMA of the previous item: nothing reads the three operand tiles any more
+    bt_wait(&bar[Q_QFULL], k & 1);
+    const uint8_t* q_raw = smem + BO_R + (g0 & 1) * BT16K;
+    const uint8_t* qn_raw = smem + BO_R + (g1 & 1) * BT16K;
+#pragma unroll 4
+    for (int i = 0; i < 16; i++) {
+      const int qr = rb + 8 * i;
+      const uint32_t off = (uint32_t)((qr >> 3) * 1024 + (qr & 7) * 128 + pc * 16);
+      const uint4 raw = *(const uint4*)(q_raw + off);
+      const uint4 rawn = *(const uint4*)(qn_raw + off);
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w}, wn[4] = {rawn.x, rawn.y, rawn.z, rawn.w};
+      uint32_t ou[4], ov[4], on[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const float u0 = uu[2 * e], u1 = uu[2 * e + 1], v0 = vv8[2 * e], v1 = vv8[2 * e + 1];
+        ou[e] = pack_bf16x2(bf16lo(w[e]) + u0, bf16hi(w[e]) + u1);
+        ov[e] = pack_bf16x2(bf16lo(w[e]) + v0, bf16hi(w[e]) + v1);
+        on[e] = pack_bf16x2(bf16lo(wn[e]) + v0, bf16hi(wn[e]) + v1);
+      }
+      *(uint4*)(smem + BO_QU + off) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+      *(uint4*)(smem + BO_QV + off) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+      *(uint4*)(smem + BO_QVN + off) = make_uint4(on[0], on[1], on[2], on[3]);
+    }
+    bt_fence_async();
+    asm volatile("bar.sync 2, 64;" ::: "memory");   // the two transform warps
+    if (tid == 0) {
+      mbar_arrive(&bar[Q_REMPTY0]);            // the raw tiles are consumed: the slots go back to the producer
+      mbar_arrive(&bar[Q_REMPTY1]);
+      mbar_arrive(&bar[Q_QREADY]);
+    }
   }
 }
 
@@ -164,13 +216,14 @@ __device__ __forceinline__ void bt_mma_issuer(uint8_t* smem, uint64_t* bar, uint
   int k = 0;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x, k++) {
     const int it = item % NT;
-    const int g0 = k * NT, r0 = k * (NT + 1);
+    const int g0 = k * NT, r0 = k * (NT + 3) + 2;
     bt_wait(&bar[Q_QREADY], k & 1);
     for (int n = 0; n < NT; n++) {
       const int g = g0 + n, gu = r0 + n, gl = gu + 1;                   // load gu = this tile's upper block, gl = its lower block
       bt_wait(&bar[Q_KFULL], g & 1);
-      bt_wait(&bar[Q_RFULL0 + (gu & 1)], (gu >> 1) & 1);
-      bt_wait(&bar[Q_RFULL0 + (gl & 1)], (gl >> 1) & 1);
+      // RFULL counts position-key loads only: every earlier item and this one put one raw q tile into each slot
+      bt_wait(&bar[Q_RFULL0 + (gu & 1)], ((gu >> 1) - (k + 1)) & 1);
+      bt_wait(&bar[Q_RFULL0 + (gl & 1)], ((gl >> 1) - (k + 1)) & 1);
       if (g > 0) bt_wait(&bar[Q_SFREE], (g - 1) & 1);
       tc_fence_after();
       const uint32_t ru = rr + (gu & 1) * BT16K, rl = rr + (gl & 1) * BT16K;
