@@ -28,6 +28,7 @@ constexpr int BT_STRIP_LD = 68;
 constexpr int BO_BAR = BO_STRIP + BT_SOFT_WARPS * 32 * BT_STRIP_LD * 4;
 constexpr int BT_SMEM = BO_BAR + 256 + 1024;
 static_assert(BT_SMEM <= 227 * 1024, "shared memory budget");
+static_assert(BO_V2 + BT16K <= BO_BAR && BO_V2 % 1024 == 0, "second V stage of the fp16-strip kernel");
 static_assert(BT_SOFT_WARPS * 32 * BT_LINE16 <= BT_SOFT_WARPS * 32 * BT_STRIP_LD * 4 && 128 * 68 * 4 <= 3 * BT16K, "fp16 lines / merge buffer fit");
 constexpr int BT_MROW = 68;                            // floats per row of the final merge buffer of the fp16-strip kernel (over the strip lines)
 
@@ -66,10 +67,10 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == BT_SOFT_WARPS) {
       // =========================================== TMA producer ===========================================
-      if (lane == 0) bt_producer(smem, bar, tmX, tmR, a, NT, n_items);
+      if (lane == 0) bt_producer<H16 ? 2 : 1>(smem, bar, tmX, tmR, a, NT, n_items);
     } else if (warp == BT_SOFT_WARPS + 1) {
       // =========================================== MMA issuer ===========================================
-      if (lane == 0) bt_mma_issuer(smem, bar, tmem_base, NT, n_items, a.H);
+      bt_mma_issuer<H16 ? 2 : 1>(smem, bar, tmem_base, NT, n_items, a.H, a.dbg);   // the whole warp: uniform control flow
     } else {
       // =========================================== transform warps ===========================================
       bt_transform(smem, bar, a, NT, n_items, threadIdx.x - 32 * (BT_SOFT_WARPS + 2));
@@ -100,8 +101,12 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
     for (int n = 0; n < NT; n++) {
       float s[64];
+      const int mslot = 256 * hf + 48 * kit + 5 * n;
+      const bool mk = q4 == 0 && lane == 0 && NT <= 8;
+      if (mk) bt_mark(a.dbg, mslot, kit);
       bt_wait(&bar[Q_SFULL], (g0 + n) & 1);
       tc_fence_after();
+      if (mk) bt_mark(a.dbg, mslot + 1, kit);
       const int zj = n == zero_tile ? zero_jj : -1000;
       if constexpr (H16) {
         // strip columns [wbase, wbase + 96) -> fp16 -> this thread's line; score of local key jj (0..63) = line[64 + lane - jj]
@@ -138,6 +143,7 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar[Q_SFREE]);
+          if (mk) bt_mark(a.dbg, mslot + 2, kit);
 #pragma unroll
           for (int i = 0; i < 32; i++) { s[i] = __uint_as_float(x1[i]); s[32 + i] = __uint_as_float(x0[i]); }
         }
@@ -215,6 +221,7 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar[Q_OFREE0 + hf]);
       }
+      if (mk) bt_mark(a.dbg, mslot + 3, kit);
 
       float mx = -INFINITY;
 #pragma unroll
@@ -241,8 +248,11 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       bt_fence_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar[Q_PFULL0 + hf]);
+      if (mk) bt_mark(a.dbg, mslot + 4, kit);
+      if (lane == 0 && NT <= 8) bt_mark(a.dbg, 1024 + 64 * kit + 8 * n + warp, kit);
     }
     bt_wait(&bar[Q_OFULL0 + hf], (g0 + NT - 1) & 1);
+    if (q4 == 0 && lane == 0 && NT <= 8) bt_mark(a.dbg, 256 * hf + 48 * kit + 40, kit);
     tc_fence_after();
 #pragma unroll
     for (int ch = 0; ch < 2; ch++) {
@@ -286,6 +296,7 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");   // the merge buffer is the next item's q + u tile / strip lines
+    if (q4 == 0 && lane == 0 && NT <= 8) bt_mark(a.dbg, 256 * hf + 48 * kit + 41, kit);
     }   // items
   }
   tc_fence_before();
@@ -314,6 +325,7 @@ int attn_bert_tc(const bf16* qkv, const bf16* rd, int Dcap, const float* u, cons
   if (train_get_tmap(rd, 64, (long long)H * Dcap, 64, 128, &tr)) return -1;
   BertTcArgs a;
   a.u = u; a.v = v; a.out = out; a.B = B; a.T = T; a.H = H; a.Dcap = Dcap; a.scale = scale;
+  a.dbg = nullptr;
   // persistent: one CTA per SM (shared memory and all 512 TMEM columns allow one), items dealt round-robin.  DMG_BERT_TC_ONE_ITEM=1
   // (measurement only) launches one CTA per item, the schedule of rounds 1 and 2.
   static int num_sms = 0, one_item = -1;
@@ -326,6 +338,25 @@ int attn_bert_tc(const bf16* qkv, const bf16* rd, int Dcap, const float* u, cons
   }
   const int n_items = B * H * ((T + 127) / 128);
   const dim3 grid(one_item || n_items < num_sms ? n_items : num_sms);
+  // DMG_BERT_TC_TIMELINE=<file> (measurement only, scripts/probe_bert_tc.py): marks of CTA 0 of every launch, the last one is kept
+  static const char* tl_path = getenv("DMG_BERT_TC_TIMELINE");
+  static unsigned long long* tl_dev = nullptr;
+  if (tl_path && tl_path[0]) {
+    if (!tl_dev) DMG_CUDA_OK(cudaMalloc(&tl_dev, 2048 * sizeof(unsigned long long)));
+    DMG_CUDA_OK(cudaMemsetAsync(tl_dev, 0, 2048 * sizeof(unsigned long long), st));
+    a.dbg = tl_dev;
+    const int rc = fp32_strip ? launch_k(attn_bert_tc_kernel<false>, grid, dim3(BT_THREADS), (size_t)BT_SMEM, st, 1, *(const CUtensorMap*)tx->bytes,
+                                         *(const CUtensorMap*)tr->bytes, a)
+                              : launch_k(attn_bert_tc_kernel<true>, grid, dim3(BT_THREADS), (size_t)BT_SMEM, st, 1, *(const CUtensorMap*)tx->bytes,
+                                         *(const CUtensorMap*)tr->bytes, a);
+    if (rc) return rc;
+    static unsigned long long host[2048];
+    DMG_CUDA_OK(cudaStreamSynchronize(st));
+    DMG_CUDA_OK(cudaMemcpy(host, tl_dev, sizeof(host), cudaMemcpyDeviceToHost));
+    FILE* f = fopen(tl_path, "wb");
+    if (f) { fwrite(host, sizeof(host), 1, f); fclose(f); }
+    return 0;
+  }
   if (fp32_strip)
     return launch_k(attn_bert_tc_kernel<false>, grid, dim3(BT_THREADS), (size_t)BT_SMEM, st, 1, *(const CUtensorMap*)tx->bytes,
                     *(const CUtensorMap*)tr->bytes, a);

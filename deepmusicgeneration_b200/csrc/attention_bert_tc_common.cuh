@@ -25,9 +25,10 @@ constexpr int BO_P = BO_R + 2 * BT16K;                 // 2 key halves
 constexpr int BO_STRIP = BO_P + 2 * BT16K;             // the kernels' own strip lines, exchange buffers and barriers follow
 
 enum { Q_QFULL = 0, Q_QREADY, Q_KFULL, Q_KEMPTY, Q_RFULL0, Q_RFULL1, Q_REMPTY0, Q_REMPTY1, Q_VFULL, Q_VEMPTY, Q_SFULL, Q_SFREE,
-       Q_PFULL0, Q_PFULL1, Q_OFULL0, Q_OFULL1, Q_OFREE0, Q_OFREE1, Q_COUNT };
+       Q_PFULL0, Q_PFULL1, Q_OFULL0, Q_OFULL1, Q_OFREE0, Q_OFREE1, Q_VFULL1, Q_VEMPTY1, Q_COUNT };
 constexpr uint32_t BTM_AC = 0, BTM_STRIP = 128, BTM_O = 384;
 constexpr int BT_LINE16 = 208;                         // bytes of an fp16 strip line: 96 halves + 16 (16-byte stores of 8 lanes hit 8 bank groups)
+constexpr int BO_V2 = BO_STRIP + 256 * BT_LINE16;      // second V stage of the fp16-strip kernel: the 16 KB its lines leave of the fp32 lines' space
 
 __device__ __forceinline__ uint64_t bt_desc_k(uint32_t addr) {          // K-major, 128B swizzle: rows of 128 B, 8-row groups 1024 B apart
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -47,7 +48,16 @@ struct BertTcArgs {
   bf16* out;                        // [B*T, H*64]
   int B, T, H, Dcap;
   float scale;
+  unsigned long long* dbg;          // measurement only (DMG_BERT_TC_TIMELINE): %globaltimer marks of CTA 0, nullptr in the product path
 };
+// timeline slots: softmax warp 0 / 4 at [256 hf + 48 item + 5 tile + mark], issuer at [512 + 48 item + 6 tile + mark], transform warps at
+// [768 + 4 item + mark], producer at [832 + 4 item + mark]; the first four items of CTA 0
+__device__ __forceinline__ void bt_mark(unsigned long long* dbg, int slot, int item) {
+  if (dbg == nullptr || blockIdx.x != 0 || item >= 4) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  dbg[slot] = t;
+}
 
 // mbarrier arrival counts: soft_warps = number of softmax warps (half of them per key half)
 __device__ __forceinline__ void bt_init_barriers(uint64_t* bar, int soft_warps) {
@@ -88,6 +98,7 @@ __device__ __forceinline__ BtItem bt_item(int item, int nT, int H) {
 }
 
 // TMA producer (one thread): per item q / q_next, then per key tile K, the position-key blocks and V
+template <int VS>
 __device__ __forceinline__ void bt_producer(uint8_t* smem, uint64_t* bar, const CUtensorMap& tmX, const CUtensorMap& tmR, const BertTcArgs& a,
                                             int NT, int n_items) {
   const int HD = a.H * 64;
@@ -116,15 +127,17 @@ __device__ __forceinline__ void bt_producer(uint8_t* smem, uint64_t* bar, const 
       mbar_expect_tx(&bar[Q_RFULL0 + s], BT16K);
       tma_load_2d(smem + BO_R + s * BT16K, &tmR, 0, h * a.Dcap + row, &bar[Q_RFULL0 + s]);
     };
-    auto load_v = [&](int n) {
-      const int g = g0 + n;
-      bt_wait(&bar[Q_VEMPTY], (g & 1) ^ 1);
-      mbar_expect_tx(&bar[Q_VFULL], BT16K);
-      tma_load_2d(smem + BO_V, &tmX, 2 * HD + h * 64, b * a.T + n * 128, &bar[Q_VFULL]);
+    auto load_v = [&](int n) {                  // VS stages: stage g % VS, its use g / VS
+      const int g = g0 + n, vs = g % VS, vu = g / VS;
+      uint64_t* full = &bar[vs ? Q_VFULL1 : Q_VFULL];
+      bt_wait(&bar[vs ? Q_VEMPTY1 : Q_VEMPTY], (vu & 1) ^ 1);
+      mbar_expect_tx(full, BT16K);
+      tma_load_2d(smem + (vs ? BO_V2 : BO_V), &tmX, 2 * HD + h * 64, b * a.T + n * 128, full);
     };
     {   // the raw q tiles complete on their own barrier (one phase per item): a waiter on RFULL that skips the position-key phases in
         // between would find the parity of an older phase and walk through
       const int s0 = slot_wait(0), s1 = slot_wait(1);
+      bt_mark(a.dbg, 832 + 4 * k, k);
       mbar_expect_tx(&bar[Q_QFULL], 2 * BT16K);
       tma_load_2d(smem + BO_R + s0 * BT16K, &tmX, h * 64, b * a.T + i0, &bar[Q_QFULL]);
       tma_load_2d(smem + BO_R + s1 * BT16K, &tmX, h * 64, b * a.T + i0 + 1, &bar[Q_QFULL]);   // rows i+1 (the last row of the last tile is never used)
@@ -132,16 +145,20 @@ __device__ __forceinline__ void bt_producer(uint8_t* smem, uint64_t* bar, const 
     load_k(0);
     load_r(0);
     load_r(1);
+    bt_mark(a.dbg, 832 + 4 * k + 1, k);
     load_v(0);
-    // waits in the order the MMAs retire: S(n-1) is issued half a tile before PV(n-2), so the V requests trail the K / R requests
-    // by one tile (a V request waiting for PV(n-1) in front of them would hold the operands of S(n+1) back until half a tile before
-    // use: measured 70.8 -> 64.5 ms per C4 forward)
+    bt_mark(a.dbg, 832 + 4 * k + 2, k);
+    // One V stage: the request for V(n) can only go out when P V(n-1) has retired, and P V(n) cannot be issued before it lands - the
+    // kernel then runs at one TMA latency + one P V per tile (2.05 us measured, profiles/r2h_attn_bert_tc_timeline_single_v.txt),
+    // and the requests trail the K / R requests by one tile so that they do not hold those back as well (70.8 -> 64.5 ms per C4
+    // forward).  Two stages: V(n) waits for P V(n-2), a whole tile before it is needed.
     for (int n = 1; n < NT; n++) {
       load_k(n);
       load_r(n + 1);
-      if (n >= 2) load_v(n - 1);
+      if (VS == 2) load_v(n);
+      else if (n >= 2) load_v(n - 1);
     }
-    if (NT >= 2) load_v(NT - 1);
+    if (VS == 1 && NT >= 2) load_v(NT - 1);
   }
 }
 
@@ -161,6 +178,7 @@ __device__ __forceinline__ void bt_transform(uint8_t* smem, uint64_t* bar, const
     const int g0 = k * (NT + 3), g1 = g0 + 1;
     // the slots were released by the last S MMA of the previous item: nothing reads the three operand tiles any more
     bt_wait(&bar[Q_QFULL], k & 1);
+    if (tid == 0) bt_mark(a.dbg, 768 + 4 * k, k);
     const uint8_t* q_raw = smem + BO_R + (g0 & 1) * BT16K;
     const uint8_t* qn_raw = smem + BO_R + (g1 & 1) * BT16K;
 #pragma unroll 4
@@ -168,23 +186,35 @@ __device__ __forceinline__ void bt_transform(uint8_t* smem, uint64_t* bar, const
       const int qr = rb + 8 * i;
       const uint32_t off = (uint32_t)((qr >> 3) * 1024 + (qr & 7) * 128 + pc * 16);
       const uint4 raw = *(const uint4*)(q_raw + off);
-      const uint4 rawn = *(const uint4*)(qn_raw + off);
-      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w}, wn[4] = {rawn.x, rawn.y, rawn.z, rawn.w};
-      uint32_t ou[4], ov[4], on[4];
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+      uint32_t ou[4], ov[4];
 #pragma unroll
       for (int e = 0; e < 4; e++) {
         const float u0 = uu[2 * e], u1 = uu[2 * e + 1], v0 = vv8[2 * e], v1 = vv8[2 * e + 1];
         ou[e] = pack_bf16x2(bf16lo(w[e]) + u0, bf16hi(w[e]) + u1);
         ov[e] = pack_bf16x2(bf16lo(w[e]) + v0, bf16hi(w[e]) + v1);
-        on[e] = pack_bf16x2(bf16lo(wn[e]) + v0, bf16hi(wn[e]) + v1);
       }
       *(uint4*)(smem + BO_QU + off) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
       *(uint4*)(smem + BO_QV + off) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+      // row qr of q + v is row qr - 1 of q_next + v: same logical chunk, the swizzle of the row above
+      if (qr > 0) {
+        const int pr = qr - 1;
+        *(uint4*)(smem + BO_QVN + (pr >> 3) * 1024 + (pr & 7) * 128 + ((pc ^ (qr & 7) ^ (pr & 7)) << 4)) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+      }
+    }
+    if (rb == 7) {                             // the last row of q_next + v is the only one the raw q_next tile is needed for
+      const uint32_t off = (uint32_t)(15 * 1024 + 7 * 128 + pc * 16);
+      const uint4 rawn = *(const uint4*)(qn_raw + off);
+      const uint32_t wn[4] = {rawn.x, rawn.y, rawn.z, rawn.w};
+      uint32_t on[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) on[e] = pack_bf16x2(bf16lo(wn[e]) + vv8[2 * e], bf16hi(wn[e]) + vv8[2 * e + 1]);
       *(uint4*)(smem + BO_QVN + off) = make_uint4(on[0], on[1], on[2], on[3]);
     }
     bt_fence_async();
     asm volatile("bar.sync 2, 64;" ::: "memory");   // the two transform warps
     if (tid == 0) {
+      bt_mark(a.dbg, 768 + 4 * k + 1, k);
       mbar_arrive(&bar[Q_REMPTY0]);            // the raw tiles are consumed: the slots go back to the producer
       mbar_arrive(&bar[Q_REMPTY1]);
       mbar_arrive(&bar[Q_QREADY]);
@@ -192,26 +222,42 @@ __device__ __forceinline__ void bt_transform(uint8_t* smem, uint64_t* bar, const
   }
 }
 
-// MMA issuer (one thread): S(n) = AC | strip, then P V of the previous tile
-__device__ __forceinline__ void bt_mma_issuer(uint8_t* smem, uint64_t* bar, uint32_t tmem_base, int NT, int n_items, int H) {
+// MMA issuer: S(n) = AC | strip, then P V of the previous tile.  Executed by the WHOLE warp in uniform control flow (waits by all
+// lanes, tcgen05.mma / commit by the elected lane): descriptors and barrier addresses stay in uniform registers.  As the body of an
+// `if (lane == 0)` branch the same loop cost ~400 instructions per tile (per MMA a vector-to-uniform move loop, elect, predicate
+// shuffles, descriptor rebuild) = 2 us of one thread's time - and THAT was the tile period of the kernel, with the tensor pipe
+// 24 % busy and the softmax warps waiting for scores (profiles/r2h_attn_bert_tc_timeline_single_v.txt).
+template <int VS>
+__device__ __forceinline__ void bt_mma_issuer(uint8_t* smem, uint64_t* bar, uint32_t tmem_base, int NT, int n_items, int H,
+                                              unsigned long long* dbg) {
   constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
   constexpr uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-  const uint32_t qu = smem_u32(smem + BO_QU), qv = smem_u32(smem + BO_QV), qvn = smem_u32(smem + BO_QVN), kk = smem_u32(smem + BO_K),
-                 vv = smem_u32(smem + BO_V), rr = smem_u32(smem + BO_R), pp = smem_u32(smem + BO_P);
-  auto issue_pv = [&](int g) {                 // g: tile count over all items of this CTA
-    bt_wait(&bar[Q_VFULL], g & 1);
+  // descriptors of the operand tiles; a 16-element K step is +32 bytes (K-major) / +2048 bytes (MN-major V) in the address field
+  const uint64_t d_qu = bt_desc_k(smem_u32(smem + BO_QU)), d_qv = bt_desc_k(smem_u32(smem + BO_QV)), d_qvn = bt_desc_k(smem_u32(smem + BO_QVN)),
+                 d_k = bt_desc_k(smem_u32(smem + BO_K)), d_r0 = bt_desc_k(smem_u32(smem + BO_R)), d_r1 = bt_desc_k(smem_u32(smem + BO_R + BT16K)),
+                 d_p0 = bt_desc_k(smem_u32(smem + BO_P)), d_p1 = bt_desc_k(smem_u32(smem + BO_P + BT16K)),
+                 d_v0 = bt_desc_mn(smem_u32(smem + BO_V)), d_v1 = bt_desc_mn(smem_u32(smem + (VS == 2 ? BO_V2 : BO_V)));
+  auto issue_pv = [&](int g, int ms, int k) {  // g: tile count over all items of this CTA; ms, k: timeline slot / item
+    const int vs = g % VS, vu = g / VS;
+    bt_wait(&bar[vs ? Q_VFULL1 : Q_VFULL], vu & 1);
 #pragma unroll
     for (int hf = 0; hf < 2; hf++) {
       bt_wait(&bar[Q_PFULL0 + hf], g & 1);
       if (g > 0) bt_wait(&bar[Q_OFREE0 + hf], (g - 1) & 1);
       tc_fence_after();
+      if (elect_one()) {
+        const uint64_t dp = hf ? d_p1 : d_p0, dv = (vs ? d_v1 : d_v0) + (uint64_t)(hf * (8192 >> 4));
 #pragma unroll
-      for (int k = 0; k < 4; k++)
-        umma_bf16(tmem_base + BTM_O + 64 * hf, bt_desc_k(pp + hf * BT16K + k * 32), bt_desc_mn(vv + hf * 8192 + k * 2048), idesc_pv,
-                  (uint32_t)(k > 0));
-      umma_commit(&bar[Q_OFULL0 + hf]);
+        for (int k4 = 0; k4 < 4; k4++)
+          umma_bf16(tmem_base + BTM_O + 64 * hf, dp + (uint64_t)(2 * k4), dv + (uint64_t)(128 * k4), idesc_pv, (uint32_t)(k4 > 0));
+        umma_commit(&bar[Q_OFULL0 + hf]);
+        if (hf == 1) {
+          umma_commit(&bar[vs ? Q_VEMPTY1 : Q_VEMPTY]);
+          bt_mark(dbg, ms + 4, k);
+        }
+      }
+      __syncwarp();
     }
-    umma_commit(&bar[Q_VEMPTY]);
   };
   int k = 0;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x, k++) {
@@ -226,24 +272,28 @@ __device__ __forceinline__ void bt_mma_issuer(uint8_t* smem, uint64_t* bar, uint
       bt_wait(&bar[Q_RFULL0 + (gl & 1)], ((gl >> 1) - (k + 1)) & 1);
       if (g > 0) bt_wait(&bar[Q_SFREE], (g - 1) & 1);
       tc_fence_after();
-      const uint32_t ru = rr + (gu & 1) * BT16K, rl = rr + (gl & 1) * BT16K;
-      const uint32_t au = n <= it ? qv : qvn, al = (n + 1) <= it ? qv : qvn;     // line 1 below / on the diagonal, line 3 above
-      // (separate ready / free barriers for AC and the strip - AC(n+1) issued right after the AC reads of tile n - were measured
-      // slower: 68.4 vs 64.4 ms per C4 forward; the extra arrive sits in the softmax warps' critical path)
+      if (elect_one()) {
+        const uint64_t ru = (gu & 1) ? d_r1 : d_r0, rl = (gl & 1) ? d_r1 : d_r0;
+        const uint64_t au = n <= it ? d_qv : d_qvn, al = (n + 1) <= it ? d_qv : d_qvn;   // line 1 below / on the diagonal, line 3 above
+        // (separate ready / free barriers for AC and the strip - AC(n+1) issued right after the AC reads of tile n - were measured
+        // slower: 68.4 vs 64.4 ms per C4 forward; the extra arrive sits in the softmax warps' critical path)
 #pragma unroll
-      for (int k4 = 0; k4 < 4; k4++) umma_bf16(tmem_base + BTM_AC, bt_desc_k(qu + k4 * 32), bt_desc_k(kk + k4 * 32), idesc_s, (uint32_t)(k4 > 0));
+        for (int k4 = 0; k4 < 4; k4++) umma_bf16(tmem_base + BTM_AC, d_qu + (uint64_t)(2 * k4), d_k + (uint64_t)(2 * k4), idesc_s, (uint32_t)(k4 > 0));
 #pragma unroll
-      for (int k4 = 0; k4 < 4; k4++) umma_bf16(tmem_base + BTM_STRIP, bt_desc_k(al + k4 * 32), bt_desc_k(rl + k4 * 32), idesc_s, (uint32_t)(k4 > 0));
+        for (int k4 = 0; k4 < 4; k4++) umma_bf16(tmem_base + BTM_STRIP, al + (uint64_t)(2 * k4), rl + (uint64_t)(2 * k4), idesc_s, (uint32_t)(k4 > 0));
 #pragma unroll
-      for (int k4 = 0; k4 < 4; k4++)
-        umma_bf16(tmem_base + BTM_STRIP + 128, bt_desc_k(au + k4 * 32), bt_desc_k(ru + k4 * 32), idesc_s, (uint32_t)(k4 > 0));
-      umma_commit(&bar[Q_SFULL]);
-      umma_commit(&bar[Q_KEMPTY]);
-      umma_commit(&bar[Q_REMPTY0 + (gu & 1)]);   // the upper block is dead after this tile; the lower one serves the next
-      if (n == NT - 1) umma_commit(&bar[Q_REMPTY0 + (gl & 1)]);   // ... or nobody: the next item starts with two fresh blocks
-      if (n > 0) issue_pv(g - 1);
+        for (int k4 = 0; k4 < 4; k4++)
+          umma_bf16(tmem_base + BTM_STRIP + 128, au + (uint64_t)(2 * k4), ru + (uint64_t)(2 * k4), idesc_s, (uint32_t)(k4 > 0));
+        umma_commit(&bar[Q_SFULL]);
+        umma_commit(&bar[Q_KEMPTY]);
+        umma_commit(&bar[Q_REMPTY0 + (gu & 1)]);   // the upper block is dead after this tile; the lower one serves the next
+        if (n == NT - 1) umma_commit(&bar[Q_REMPTY0 + (gl & 1)]);   // ... or nobody: the next item starts with two fresh blocks
+        bt_mark(dbg, 512 + 48 * k + 6 * n, k);
+      }
+      __syncwarp();
+      if (n > 0) issue_pv(g - 1, 512 + 48 * k + 6 * (n - 1), k);
     }
-    issue_pv(g0 + NT - 1);
+    issue_pv(g0 + NT - 1, 512 + 48 * k + 6 * (NT - 1), k);
   }
 }
 
