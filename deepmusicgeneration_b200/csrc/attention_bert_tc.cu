@@ -30,7 +30,7 @@ constexpr int BT_SMEM = BO_BAR + 256 + 1024;
 static_assert(BT_SMEM <= 227 * 1024, "shared memory budget");
 static_assert(BO_V2 + BT16K <= BO_BAR && BO_V2 % 1024 == 0, "second V stage of the fp16-strip kernel");
 static_assert(BT_SOFT_WARPS * 32 * BT_LINE16 <= BT_SOFT_WARPS * 32 * BT_STRIP_LD * 4 && 128 * 68 * 4 <= 3 * BT16K, "fp16 lines / merge buffer fit");
-constexpr int BT_MROW = 68;                            // floats per row of the final merge buffer of the fp16-strip kernel (over the strip lines)
+constexpr int BT_MROW = 68;                            // floats per row of the final merge buffer of the fp16-strip kernel (over the strip lines): 64 accumulators + two (m, l) pairs
 
 // H16: the position strip goes through shared memory as fp16 (|BD| < 65504 saturates; 11 bits of mantissa against the 8 of the bf16
 // operands): the thread's two 64-column windows overlap in 32 columns, so it reads 96 distinct columns once (three tcgen05.ld.x32
@@ -266,31 +266,40 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     __syncwarp();
     if (lane == 0) mbar_arrive(&bar[Q_OFREE0 + hf]);   // the next item's first P V may overwrite the accumulator
 
-    // merge the two key halves of every row: half 1 leaves its output, maximum and row sum in its strip line (fp32 strip) or in
-    // merge rows laid over all strip lines (fp16 strip: one line is too short; the q tiles already belong to the next item)
-    float* mine = H16 ? (float*)(smem + BO_STRIP) + (size_t)r * BT_MROW : strip;
-    if constexpr (H16) asm volatile("bar.sync 1, 256;" ::: "memory");   // every thread is done with its line: the merge rows overlay them
-    if (hf == 1) {
-#pragma unroll
-      for (int k = 0; k < 16; k++) *(float4*)(mine + 4 * k) = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
-      mine[64] = m_run;
-      mine[65] = l_run;
+    // merge the two key halves of every row, both halves at work: half 0 finishes output columns 0-31, half 1 columns 32-63; each
+    // leaves the 32 accumulators the other one needs, its maximum and its row sum in its strip line (fp32 strip) or in merge rows laid
+    // over all strip lines (fp16 strip: one line is too short; the q tiles already belong to the next item)
+    float* wr_o; float* wr_s; const float* rd_o; const float* rd_s;
+    if constexpr (H16) {
+      float* mrow = (float*)(smem + BO_STRIP) + (size_t)r * BT_MROW;   // [0,32): half 1's columns 0-31; [32,64): half 0's columns 32-63; (m, l) pairs
+      wr_o = mrow + (hf ? 0 : 32); wr_s = mrow + (hf ? 64 : 66);
+      rd_o = mrow + (hf ? 32 : 0); rd_s = mrow + (hf ? 66 : 64);
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // every thread is done with its line: the merge rows overlay them
+    } else {
+      const float* partner = hf ? strip - (size_t)4 * 32 * BT_STRIP_LD : strip + (size_t)4 * 32 * BT_STRIP_LD;   // same row: same lane of warp +- 4
+      wr_o = strip; wr_s = strip + 64; rd_o = partner; rd_s = partner + 64;
     }
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      *(float4*)(wr_o + 4 * k) = make_float4(hf ? o[4 * k] : o[32 + 4 * k], hf ? o[4 * k + 1] : o[32 + 4 * k + 1],
+                                             hf ? o[4 * k + 2] : o[32 + 4 * k + 2], hf ? o[4 * k + 3] : o[32 + 4 * k + 3]);
+    wr_s[0] = m_run;
+    wr_s[1] = l_run;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (hf == 0 && row < a.T) {
-      const float* other = H16 ? mine : strip + (size_t)4 * 32 * BT_STRIP_LD;       // same row: same lane of warp + 4
-      const float m1 = other[64], l1 = other[65];
+    if (row < a.T) {
+      const float m1 = rd_s[0], l1 = rd_s[1];
       const float m = fmaxf(m_run, m1);
       const float w0 = ex2_fast((m_run - m) * c), w1 = ex2_fast((m1 - m) * c);
       const float inv = 1.f / (l_run * w0 + l1 * w1);
-      bf16* orow = a.out + ((long long)b * a.T + row) * HD + h * 64;
+      bf16* orow = a.out + ((long long)b * a.T + row) * HD + h * 64 + 32 * hf;
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
+      for (int k = 0; k < 4; k++) {
         uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
           const int d0 = 8 * k + 2 * e;
-          w[e] = pack_bf16x2((o[d0] * w0 + other[d0] * w1) * inv, (o[d0 + 1] * w0 + other[d0 + 1] * w1) * inv);
+          const float mine0 = hf ? o[32 + d0] : o[d0], mine1 = hf ? o[32 + d0 + 1] : o[d0 + 1];
+          w[e] = pack_bf16x2((mine0 * w0 + rd_o[d0] * w1) * inv, (mine1 * w0 + rd_o[d0 + 1] * w1) * inv);
         }
         *(uint4*)(orow + 8 * k) = make_uint4(w[0], w[1], w[2], w[3]);
       }
