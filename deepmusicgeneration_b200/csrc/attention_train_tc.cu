@@ -56,6 +56,16 @@ enum { B_QFULL = 0, B_QREADY, B_KFULL0, B_KFULL1, B_KEMPTY0, B_KEMPTY1, B_RFULL0
 constexpr uint32_t TM_AC = 0, TM_STRIP = 128, TM_O = 384;
 
 // shared-memory matrix descriptors (sm_100 version bit 46, SWIZZLE_128B)
+// bounded wait without the printf of mbar_wait, for the MMA-issuing warps: they run the issue loop as a WHOLE warp in uniform control flow
+// (waits by all lanes, tcgen05.mma / commit by the elected lane), so that descriptors and barrier addresses stay in uniform registers.
+// As the body of an `if (lane == 0)` branch every tcgen05.mma cost ~20 instructions (vector-to-uniform move loop, elect, predicate
+// shuffles, descriptor rebuild): ~0.1 us per MMA of one thread's time, 2 us per tile in the attention kernels
+// (profiles/r2h_attn_bert_tc_timeline_single_v.txt, profiles/r2g_attn_bwd_dq_tc_timeline.txt).
+__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t n = 0;
+  while (!mbar_try_wait(bar, parity))
+    if (++n > (1u << 26)) __trap();
+}
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {          // rows of 128 B, 8-row groups 1024 B apart
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
@@ -109,7 +119,7 @@ attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
 
   // register budget: 384 threads start with 168 registers each; the auxiliary warpgroup hands its share to the softmax warpgroups
   if (warp >= TC_SOFT_WARPS) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == TC_SOFT_WARPS) {
     // =========================================== TMA producer ===========================================
     if (lane == 0) {
@@ -160,65 +170,82 @@ attn_train_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
       if (NT >= 2) load_v(NT - 1);
     }
   } else if (warp == TC_SOFT_WARPS + 1) {
-    // =========================================== MMA issuer ===========================================
-    if (lane == 0) {
+    // =========================================== MMA issuer (whole warp, elected lane issues) ===========================================
+    {
       // instruction descriptors: D fp32, A/B bf16, N>>3 @17, M>>4 @24; bit 16: B is MN-major
       constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
       constexpr uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t qu = smem_u32(smem + OFF_QU), qv = smem_u32(smem + OFF_QV), kk = smem_u32(smem + OFF_K),
-                     vv = smem_u32(smem + OFF_V), rr = smem_u32(smem + OFF_R), pp = smem_u32(smem + OFF_P);
+      const uint32_t qu = smem_u32(smem + OFF_QU), qv = smem_u32(smem + OFF_QV);
+      // operand descriptors; a 16-element K step is +32 bytes (K-major) / +2048 bytes (MN-major V) in the address field
+      const uint64_t d_qu = desc_kmajor(qu), d_qv = desc_kmajor(qv), d_k0 = desc_kmajor(smem_u32(smem + OFF_K)),
+                     d_k1 = desc_kmajor(smem_u32(smem + OFF_K + T16K)), d_r0 = desc_kmajor(smem_u32(smem + OFF_R)),
+                     d_r1 = desc_kmajor(smem_u32(smem + OFF_R + T16K)), d_p0 = desc_kmajor(smem_u32(smem + OFF_P)),
+                     d_p1 = desc_kmajor(smem_u32(smem + OFF_P + T16K)), d_v = desc_mnmajor(smem_u32(smem + OFF_V));
       auto issue_pv = [&](int m) {
-        mbar_wait(&bar[B_VFULL], m & 1);
+        tc_wait(&bar[B_VFULL], m & 1);
 #pragma unroll
         for (int hf = 0; hf < 2; hf++) {
-          mbar_wait(&bar[B_PFULL0 + hf], m & 1);
-          if (m > 0) mbar_wait(&bar[B_OFREE0 + hf], (m - 1) & 1);
+          tc_wait(&bar[B_PFULL0 + hf], m & 1);
+          if (m > 0) tc_wait(&bar[B_OFREE0 + hf], (m - 1) & 1);
           tc_fence_after();
+          if (elect_one()) {
+            const uint64_t dp = hf ? d_p1 : d_p0, dv = d_v + (uint64_t)(hf * (8192 >> 4));
 #pragma unroll
-          for (int k = 0; k < 4; k++)
-            umma_bf16(tmem_base + TM_O + 64 * hf, desc_kmajor(pp + hf * T16K + k * 32), desc_mnmajor(vv + hf * 8192 + k * 2048), idesc_pv,
-                      (uint32_t)(k > 0));
-          umma_commit(&bar[B_OFULL0 + hf]);
+            for (int k = 0; k < 4; k++)
+              umma_bf16(tmem_base + TM_O + 64 * hf, dp + (uint64_t)(2 * k), dv + (uint64_t)(128 * k), idesc_pv, (uint32_t)(k > 0));
+            umma_commit(&bar[B_OFULL0 + hf]);
+            if (hf == 1) umma_commit(&bar[B_VEMPTY]);
+          }
+          __syncwarp();
         }
-        umma_commit(&bar[B_VEMPTY]);
       };
-      mbar_wait(&bar[B_QREADY], 0);
+      tc_wait(&bar[B_QREADY], 0);
       if (SAVE && a.qu_save) {                       // the biased query tiles are the backward's operands as well: store them as they lie
-        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmQU), "r"(qu), "r"(h * 64),
-                     "r"(b * a.T + i0)
-                     : "memory");
-        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmQV), "r"(qv), "r"(h * 64),
-                     "r"(b * a.T + i0)
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (elect_one()) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmQU), "r"(qu), "r"(h * 64),
+                       "r"(b * a.T + i0)
+                       : "memory");
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmQV), "r"(qv), "r"(h * 64),
+                       "r"(b * a.T + i0)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        __syncwarp();
       }
       for (int n = 0; n < NT; n++) {
         const int s = n & 1, blkU = blk0 - n, blkL = blkU - 1;
-        mbar_wait(&bar[B_KFULL0 + s], (n >> 1) & 1);
-        mbar_wait(&bar[B_RFULL0 + (blkU & 1)], (n >> 1) & 1);
-        mbar_wait(&bar[B_RFULL0 + (blkL & 1)], ((n + 1) >> 1) & 1);
-        if (n > 0) mbar_wait(&bar[B_SFREE], (n - 1) & 1);
+        tc_wait(&bar[B_KFULL0 + s], (n >> 1) & 1);
+        tc_wait(&bar[B_RFULL0 + (blkU & 1)], (n >> 1) & 1);
+        tc_wait(&bar[B_RFULL0 + (blkL & 1)], ((n + 1) >> 1) & 1);
+        if (n > 0) tc_wait(&bar[B_SFREE], (n - 1) & 1);
         tc_fence_after();
-        const uint32_t ks = kk + s * T16K, rl = rr + (blkL & 1) * T16K, ru = rr + (blkU & 1) * T16K;
+        if (elect_one()) {
+          const uint64_t ks = s ? d_k1 : d_k0, rl = (blkL & 1) ? d_r1 : d_r0, ru = (blkU & 1) ? d_r1 : d_r0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) umma_bf16(tmem_base + TM_AC, desc_kmajor(qu + k * 32), desc_kmajor(ks + k * 32), idesc_s, (uint32_t)(k > 0));
+          for (int k = 0; k < 4; k++) umma_bf16(tmem_base + TM_AC, d_qu + (uint64_t)(2 * k), ks + (uint64_t)(2 * k), idesc_s, (uint32_t)(k > 0));
 #pragma unroll
-        for (int k = 0; k < 4; k++) umma_bf16(tmem_base + TM_STRIP, desc_kmajor(qv + k * 32), desc_kmajor(rl + k * 32), idesc_s, (uint32_t)(k > 0));
+          for (int k = 0; k < 4; k++) umma_bf16(tmem_base + TM_STRIP, d_qv + (uint64_t)(2 * k), rl + (uint64_t)(2 * k), idesc_s, (uint32_t)(k > 0));
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-          umma_bf16(tmem_base + TM_STRIP + 128, desc_kmajor(qv + k * 32), desc_kmajor(ru + k * 32), idesc_s, (uint32_t)(k > 0));
-        umma_commit(&bar[B_SFULL]);
-        umma_commit(&bar[B_KEMPTY0 + s]);
-        umma_commit(&bar[B_REMPTY0 + (blkU & 1)]);   // the upper block is dead after this tile; the lower one serves the next
+          for (int k = 0; k < 4; k++)
+            umma_bf16(tmem_base + TM_STRIP + 128, d_qv + (uint64_t)(2 * k), ru + (uint64_t)(2 * k), idesc_s, (uint32_t)(k > 0));
+          umma_commit(&bar[B_SFULL]);
+          umma_commit(&bar[B_KEMPTY0 + s]);
+          umma_commit(&bar[B_REMPTY0 + (blkU & 1)]);   // the upper block is dead after this tile; the lower one serves the next
+        }
+        __syncwarp();
         if (n > 0) issue_pv(n - 1);
       }
       issue_pv(NT - 1);
-      if (SAVE && a.qu_save) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      // the bulk group belongs to the lane that issued it
+      if (SAVE && a.qu_save) {
+        if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+      }
     }
     }
   } else {
     // =========================================== softmax warps ===========================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int hf = warp >> 2, q4 = warp & 3;
     const int r = q4 * 32 + lane;                   // query row of this thread inside the tile
     const int row = i0 + r;                         // ... inside the segment
@@ -519,24 +546,27 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmPd, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp in uniform control flow, the elected lane issues (see tc_wait)
       // D fp32, A / B bf16, both MN-major (bits 15, 16), N = 64, M = 128
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-      if (in_x) mbar_wait(&bar[DB_ZERO], 0);
+      if (in_x) tc_wait(&bar[DB_ZERO], 0);
       for (int n = 0; n < NI; n++) {
         const int s = n % DKV_STAGES;
-        mbar_wait(&bar[DB_FULL0 + s], (n / DKV_STAGES) & 1);
+        tc_wait(&bar[DB_FULL0 + s], (n / DKV_STAGES) & 1);
         tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * DKV_STAGE_BYTES);
+        if (elect_one()) {
+          const uint32_t st = smem_u32(smem + s * DKV_STAGE_BYTES);
+          const uint64_t d0 = desc_mn64(st), d2 = desc_mn64(st + 2 * DKV_BOX), d4 = desc_mn64(st + 4 * DKV_BOX), d5 = desc_mn64(st + 5 * DKV_BOX);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          umma_bf16(tmem_base, desc_mn64(st + k * 2048), desc_mn64(st + 4 * DKV_BOX + k * 2048), idesc, (uint32_t)(n > 0 || k > 0));
-          umma_bf16(tmem_base + 64, desc_mn64(st + 2 * DKV_BOX + k * 2048), desc_mn64(st + 5 * DKV_BOX + k * 2048), idesc,
-                    (uint32_t)(n > 0 || k > 0));
+          for (int k = 0; k < 4; k++) {
+            umma_bf16(tmem_base, d0 + (uint64_t)(128 * k), d4 + (uint64_t)(128 * k), idesc, (uint32_t)(n > 0 || k > 0));
+            umma_bf16(tmem_base + 64, d2 + (uint64_t)(128 * k), d5 + (uint64_t)(128 * k), idesc, (uint32_t)(n > 0 || k > 0));
+          }
+          umma_commit(&bar[DB_EMPTY0 + s]);
+          if (n == NI - 1) umma_commit(&bar[DB_ACC]);
         }
-        umma_commit(&bar[DB_EMPTY0 + s]);
+        __syncwarp();
       }
-      umma_commit(&bar[DB_ACC]);
     }
   } else {
     const int q4 = warp & 3;
@@ -708,51 +738,63 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         }
       }
     } else if (warp == DQT_MATH_WARPS + 1) {
-      // =========================================== MMA issuer ===========================================
-      if (lane == 0) {
+      // =========================================== MMA issuer (whole warp, elected lane issues) ===========================================
+      {
         constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
         constexpr uint32_t idesc_n64 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t d_o = smem_u32(smem + DQO_DO), kk = smem_u32(smem + DQO_K), vv = smem_u32(smem + DQO_V), rr = smem_u32(smem + DQO_R),
-                       ds = smem_u32(smem + DQO_DS), st = smem_u32(smem + DQO_STRIP);
+        const uint64_t d_do = desc_kmajor(smem_u32(smem + DQO_DO)), d_v = desc_kmajor(smem_u32(smem + DQO_V)),
+                       d_k = desc_mnmajor(smem_u32(smem + DQO_K)), d_r = desc_mnmajor(smem_u32(smem + DQO_R)),
+                       d_ds = desc_kmajor(smem_u32(smem + DQO_DS)), d_st0 = desc_kmajor(smem_u32(smem + DQO_STRIP)),
+                       d_st1 = desc_kmajor(smem_u32(smem + DQO_STRIP + 2 * T16K));
         auto m1 = [&](int n) {                       // dPd(n) = dO V(n)^T
           const int s = n & 1;
-          mbar_wait(&bar[D_VFULL], n & 1);
-          if (n >= 2) mbar_wait(&bar[D_DPFREE0 + s], ((n >> 1) & 1) ^ 1);
+          tc_wait(&bar[D_VFULL], n & 1);
+          if (n >= 2) tc_wait(&bar[D_DPFREE0 + s], ((n >> 1) & 1) ^ 1);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; k++) umma_bf16(tmem_base + DTM_DP + 128 * s, desc_kmajor(d_o + k * 32), desc_kmajor(vv + k * 32), idesc_s, (uint32_t)(k > 0));
-          umma_commit(&bar[D_DPFULL0 + s]);
-          umma_commit(&bar[D_VEMPTY]);
+            for (int k = 0; k < 4; k++) umma_bf16(tmem_base + DTM_DP + 128 * s, d_do + (uint64_t)(2 * k), d_v + (uint64_t)(2 * k), idesc_s, (uint32_t)(k > 0));
+            umma_commit(&bar[D_DPFULL0 + s]);
+            umma_commit(&bar[D_VEMPTY]);
+          }
+          __syncwarp();
         };
-        mbar_wait(&bar[D_DOFULL], 0);
+        tc_wait(&bar[D_DOFULL], 0);
         m1(0);
         if (NT > 1) m1(1);
         for (int n = 0; n < NT; n++) {
           const int sb = (blk0 - n) & 1;
-          mbar_wait(&bar[D_DSFULL], n & 1);
-          mbar_wait(&bar[D_KFULL], n & 1);
+          tc_wait(&bar[D_DSFULL], n & 1);
+          tc_wait(&bar[D_KFULL], n & 1);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int hf = 0; hf < 2; hf++)
+            for (int hf = 0; hf < 2; hf++)
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-              umma_bf16(tmem_base + DTM_AC, desc_kmajor(ds + hf * T16K + k * 32), desc_mnmajor(kk + hf * 8192 + k * 2048), idesc_n64,
-                        (uint32_t)(n > 0 || hf > 0 || k > 0));
-          umma_commit(&bar[D_DSFREE]);
-          umma_commit(&bar[D_KEMPTY]);
-          mbar_wait(&bar[D_RFULL], n & 1);
+              for (int k = 0; k < 4; k++)
+                umma_bf16(tmem_base + DTM_AC, d_ds + (uint64_t)(hf * (T16K >> 4) + 2 * k), d_k + (uint64_t)(hf * (8192 >> 4) + 128 * k), idesc_n64,
+                          (uint32_t)(n > 0 || hf > 0 || k > 0));
+            umma_commit(&bar[D_DSFREE]);
+            umma_commit(&bar[D_KEMPTY]);
+          }
+          __syncwarp();
+          tc_wait(&bar[D_RFULL], n & 1);
           tc_fence_after();
+          if (elect_one()) {
+            const uint64_t d_st = sb ? d_st1 : d_st0;
 #pragma unroll
-          for (int hf = 0; hf < 2; hf++)
+            for (int hf = 0; hf < 2; hf++)
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-              umma_bf16(tmem_base + DTM_BD, desc_kmajor(st + sb * 2 * T16K + hf * T16K + k * 32), desc_mnmajor(rr + hf * 8192 + k * 2048),
-                        idesc_n64, (uint32_t)(n > 0 || hf > 0 || k > 0));
-          umma_commit(&bar[D_SFREE0 + sb]);
-          umma_commit(&bar[D_REMPTY]);
+              for (int k = 0; k < 4; k++)
+                umma_bf16(tmem_base + DTM_BD, d_st + (uint64_t)(hf * (T16K >> 4) + 2 * k), d_r + (uint64_t)(hf * (8192 >> 4) + 128 * k),
+                          idesc_n64, (uint32_t)(n > 0 || hf > 0 || k > 0));
+            umma_commit(&bar[D_SFREE0 + sb]);
+            umma_commit(&bar[D_REMPTY]);
+            if (n == NT - 1) umma_commit(&bar[D_DQFULL]);
+          }
+          __syncwarp();
           if (n + 2 < NT) m1(n + 2);
         }
-        umma_commit(&bar[D_DQFULL]);
       }
     } else if (warp == DQT_MATH_WARPS + 2) {
       // =========================================== TMA stores ===========================================
