@@ -204,8 +204,8 @@ __device__ __forceinline__ void decode_layer_body(const CUtensorMap& tmAttn, con
     tma_prefetch_desc(&tmWo); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmWq); tma_prefetch_desc(&tmAttn);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < DL_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }   // 4 issuing lanes commit per stage
-    for (int p = 0; p < 4; p++) mbar_init(&tmem_full[p], 4 * DL_MMAW);                          // every MMA-issuing lane commits
+    for (int s = 0; s < DL_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }   // the issuing lane commits per stage
+    for (int p = 0; p < 4; p++) mbar_init(&tmem_full[p], DL_MMAW);                              // the issuing lane of every MMA warp commits
     mbar_init(&xa_ready[0], DL_EPI); mbar_init(&xa_ready[1], DL_EPI); mbar_init(hs_ready, DL_EPI); mbar_init(attn_full, 1);
     mbar_fence_init();
   }
@@ -263,9 +263,11 @@ __device__ __forceinline__ void decode_layer_body(const CUtensorMap& tmAttn, con
     }
   } else if (warp <= DL_MMAW) {
     // ================================================================== tcgen05.mma issuers (warp w: stage uses i with i % DL_MMAW == w - 1)
-    // Lanes 0-3 issue the four 16-wide K steps of a k-block at once, each into its own accumulator chain, and each commits its own MMA
-    // (tcgen05.commit tracks the issuing THREAD; the stage's `empty` barrier counts 4 arrivals).  A tensor-core MMA retires every ~63
-    // cycles whatever N <= 128 is (scripts/probes/probe_mma_rate.cu), so the scalar issue work has to be spread out.
+    // The whole warp runs the issue loop in uniform control flow (waits by all lanes); the elected lane issues the four 16-wide K steps of
+    // a k-block back to back, each into its own accumulator chain, and commits the stage.  A tensor-core MMA retires every ~63 cycles
+    // whatever N <= 128 is (scripts/probes/probe_mma_rate.cu); in uniform control flow the operands of tcgen05.mma stay in uniform registers
+    // and an issue costs a 64-bit add, where the body of a divergent `if (lane < 4)` branch paid a vector-to-uniform move loop with elect
+    // and predicate shuffles per MMA (profiles/README.md, round 2h).
     int it = 0;
     const int mine = warp - 1;
     const uint32_t xa_addr = smem_u32(xa_s), hs_addr = smem_u32(hs_s), tiles_addr = smem_u32(tiles);
@@ -276,39 +278,51 @@ __device__ __forceinline__ void decode_layer_body(const CUtensorMap& tmAttn, con
       const int s = i % DL_STAGES;
       dl_spin(&full[s], (uint32_t)(i / DL_STAGES) & 1u);
       tc_fence_after();
-      const uint32_t a_addr = tiles_addr + s * DL_STAGE + lane * 32;
-      const uint32_t d = tmem_base + col + (uint32_t)((((kb & kbx) << 2) + lane) * DL_CHAIN);
-      umma_bf16(d, DHI | (uint64_t)((a_addr & 0x3FFFFu) >> 4), DHI | (uint64_t)(((b_addr + lane * 32) & 0x3FFFFu) >> 4), idesc, kb > kbx ? 1u : 0u);
-      umma_commit(&empty[s]);
+      if (elect_one()) {
+        const uint64_t da = DHI | (uint64_t)(((tiles_addr + s * DL_STAGE) & 0x3FFFFu) >> 4), db = DHI | (uint64_t)((b_addr & 0x3FFFFu) >> 4);
+        const uint32_t d = tmem_base + col + (uint32_t)(((kb & kbx) << 2) * DL_CHAIN);
+#pragma unroll
+        for (int l = 0; l < 4; l++)               // K step l: +32 bytes in both operands, its own accumulator chain
+          umma_bf16(d + (uint32_t)(l * DL_CHAIN), da + (uint64_t)(2 * l), db + (uint64_t)(2 * l), idesc, kb > kbx ? 1u : 0u);
+        umma_commit(&empty[s]);
+      }
+      __syncwarp();
     };
     constexpr uint32_t ID64 = dl_idesc(64, DL_ROWS), ID128 = dl_idesc(128, DL_ROWS);
     if (lane == 0 && mine == 0) dl_mark(a.dbg, 1, 0);
     if (body) {
-      if (lane < 4) {
+      {
         dl_spin(attn_full, 0);
         tc_fence_after();
         for (int kb = 0; kb < nkb_A; kb++) kblock(it++, 0, ID64, xa_addr + kb * DL_B_BYTES, kb, 1);       // 8 chains (alternating k-blocks)
-        dl_mark(a.dbg, 1, 1);
-        umma_commit(&tmem_full[0]);
+        if (elect_one()) {
+          dl_mark(a.dbg, 1, 1);
+          umma_commit(&tmem_full[0]);
+        }
       }
       __syncwarp();
       dl_arrive();                                                     // #1
       dl_wait();
       dl_arrive();                                                     // #2 (before waiting for LayerNorm 1: its broadcast needs every thread's arrival)
-      if (lane < 4) {
+      {
         dl_spin(&xa_ready[0], 0);                                      // LayerNorm 1 rows are in XA
         tc_fence_after();
-        dl_mark(a.dbg, 1, 2);
+        if (lane == 0) dl_mark(a.dbg, 1, 2);
         for (int kb = 0; kb < nkb_d; kb++)
           for (int t = 0; t < nB; t++) kblock(it++, (uint32_t)(t * 4 * DL_CHAIN), ID128, xa_addr + kb * DL_B_BYTES, kb, 0);
-        dl_mark(a.dbg, 1, 3);
-        umma_commit(&tmem_full[1]);
+        if (elect_one()) {
+          dl_mark(a.dbg, 1, 3);
+          umma_commit(&tmem_full[1]);
+        }
+        __syncwarp();
         dl_spin(hs_ready, 0);                                          // this CTA's GeLU slice is in HS (the B accumulators have been read)
         tc_fence_after();
         for (int kb = 0; kb < DL_HS_KB; kb++)
           for (int t = 0; t < nC; t++) kblock(it++, (uint32_t)(t * 4 * DL_CHAIN), ID128, hs_addr + kb * DL_B_BYTES, kb, 0);
-        dl_mark(a.dbg, 1, 5);
-        umma_commit(&tmem_full[2]);
+        if (elect_one()) {
+          dl_mark(a.dbg, 1, 5);
+          umma_commit(&tmem_full[2]);
+        }
       }
       __syncwarp();
       dl_wait();                                                       // #2
@@ -318,16 +332,18 @@ __device__ __forceinline__ void decode_layer_body(const CUtensorMap& tmAttn, con
       dl_wait();                                                       // every CTA's LayerNorm-2 rows have landed in this XA
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // remote generic-proxy stores -> this CTA's tensor-core reads
     }
-    if (next && lane < 4) {
+    if (next) {
       if (!body) dl_spin(&xa_ready[1], 0);
       tc_fence_after();
-      dl_mark(a.dbg, 1, 6);
+      if (lane == 0) dl_mark(a.dbg, 1, 6);
       for (int kb = 0; kb < nkb_d; kb++) {
         kblock(it++, 0, ID128, xa_addr + kb * DL_B_BYTES, kb, 0);
         kblock(it++, (uint32_t)(4 * DL_CHAIN), ID64, xa_addr + kb * DL_B_BYTES, kb, 0);
       }
-      dl_mark(a.dbg, 1, 7);
-      umma_commit(&tmem_full[3]);
+      if (elect_one()) {
+        dl_mark(a.dbg, 1, 7);
+        umma_commit(&tmem_full[3]);
+      }
     }
     __syncwarp();
   } else {
