@@ -237,13 +237,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t ph = (kb / STAGES) & 1;
       mbar_wait(&full[s], ph);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(tiles + s * L::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + L::A_BYTES;
+      // descriptors in uniform control flow, issue under elect_one (gemm_train.cu: behind `if (lane == 0)` every MMA is wrapped in a
+      // vector-to-uniform move loop)
+      const uint32_t a_addr = smem_u32(tiles + s * L::STAGE_BYTES);
+      const uint64_t da0 = umma_desc_sw128(a_addr), db0 = umma_desc_sw128(a_addr + L::A_BYTES);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {   // UMMA_K = 16 bf16 = 32 bytes inside the 128B swizzle atom
-          umma_bf16(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                    (uint32_t)((kb | k) != 0));
+          umma_bf16(tmem_base, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
         }
         umma_commit(&empty[s]);                       // frees the smem stage when these MMAs retire
         if (kb == num_kb - 1) umma_commit(tmem_full);  // accumulator complete
@@ -426,13 +427,12 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     for (int kb = 0; kb < num_kb; kb++) {
       mbar_wait(&full[kb], 0);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(tiles + kb * STAGE);
-        const uint32_t b_addr = a_addr + 128 * 64 * 2;
+      const uint32_t a_addr = smem_u32(tiles + kb * STAGE);
+      const uint64_t da0 = umma_desc_sw128(a_addr), db0 = umma_desc_sw128(a_addr + 128 * 64 * 2);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; k++)
-          umma_bf16(tmem_base, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                    (uint32_t)((kb | k) != 0));
+          umma_bf16(tmem_base, da0 + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
         if (kb == num_kb - 1) umma_commit(tmem_full);
       }
       __syncwarp();

@@ -248,12 +248,15 @@ gemm_train_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_addr = smem_u32(tiles + s * STAGE_BYTES);
-            const uint32_t b_addr = a_addr + A_BYTES;
+          // descriptors in uniform control flow, issue under elect_one: the operands of tcgen05.mma live in uniform registers, and behind
+          // an `if (lane == 0)` ptxas wraps every MMA in a vector-to-uniform move loop (5 R2UR + elect + predicate shuffles + branch) and
+          // rebuilds both descriptors - ~19 instructions per MMA of one thread against the 128 cycles a 256 x 256 x 16 pair MMA takes
+          const uint32_t a_addr = smem_u32(tiles + s * STAGE_BYTES);
+          const uint64_t da0 = umma_desc(a_addr, a_lbo, 1024u), db0 = umma_desc(a_addr + A_BYTES, b_lbo, 1024u);
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-              const uint64_t da = umma_desc(a_addr + k * a_kstep, a_lbo, 1024u), db = umma_desc(b_addr + k * b_kstep, b_lbo, 1024u);
+              const uint64_t da = da0 + (uint64_t)(k * (a_kstep >> 4)), db = db0 + (uint64_t)(k * (b_kstep >> 4));
               const uint32_t accum = (uint32_t)((kb > kb_lo) || k > 0);
               if (CG == 2) umma_bf16_pair(d_tmem, da, db, idesc, accum);
               else umma_bf16(d_tmem, da, db, idesc, accum);
