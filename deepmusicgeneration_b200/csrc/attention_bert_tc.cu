@@ -42,8 +42,7 @@ constexpr int BO_BAR = BO_STRIP + BT_SOFT_WARPS * 32 * BT_STRIP_LD * 4;
 constexpr int BT_SMEM = BO_BAR + 256 + 1024;
 static_assert(BT_SMEM <= 227 * 1024, "shared memory budget");
 static_assert(BO_V2 + BT16K <= BO_BAR && BO_V2 % 1024 == 0, "second V stage of the fp16-strip kernel");
-static_assert(BT_SOFT_WARPS * 32 * BT_LINE16 <= BT_SOFT_WARPS * 32 * BT_STRIP_LD * 4 && 128 * 68 * 4 <= 3 * BT16K, "fp16 lines / merge buffer fit");
-constexpr int BT_MROW = 68;                            // floats per row of the final merge buffer of the fp16-strip kernel (over the strip lines): 64 accumulators + two (m, l) pairs
+static_assert(BT_SOFT_WARPS * 32 * BT_LINE16 <= BT_SOFT_WARPS * 32 * BT_STRIP_LD * 4 && 34 * 4 <= BT_LINE16, "fp16 lines fit; a line holds the merge record");
 
 // H16: the position strip goes through shared memory as fp16 (|BD| < 65504 saturates; 11 bits of mantissa against the 8 of the bf16
 // operands): the thread's two 64-column windows overlap in 32 columns, so it reads 96 distinct columns once (three tcgen05.ld.x32
@@ -281,18 +280,19 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (lane == 0) mbar_arrive(&bar[Q_OFREE0 + hf]);   // the next item's first P V may overwrite the accumulator
 
     // merge the two key halves of every row, both halves at work: half 0 finishes output columns 0-31, half 1 columns 32-63; each
-    // leaves the 32 accumulators the other one needs, its maximum and its row sum in its strip line (fp32 strip) or in merge rows laid
-    // over all strip lines (fp16 strip: one line is too short; the q tiles already belong to the next item)
-    float* wr_o; float* wr_s; const float* rd_o; const float* rd_s;
+    // leaves the 32 accumulators the other one needs, its maximum and its row sum in ITS OWN strip line (dead since the last skew; 136
+    // of its 208 / 272 bytes) and reads the line of the same row's thread in the other half (same lane, warp +- 4)
+    float* wr_o; const float* rd_o;
     if constexpr (H16) {
-      float* mrow = (float*)(smem + BO_STRIP) + (size_t)r * BT_MROW;   // [0,32): half 1's columns 0-31; [32,64): half 0's columns 32-63; (m, l) pairs
-      wr_o = mrow + (hf ? 0 : 32); wr_s = mrow + (hf ? 64 : 66);
-      rd_o = mrow + (hf ? 32 : 0); rd_s = mrow + (hf ? 66 : 64);
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // every thread is done with its line: the merge rows overlay them
+      uint8_t* line = smem + BO_STRIP + (size_t)(warp * 32 + lane) * BT_LINE16;
+      wr_o = (float*)line;
+      rd_o = (const float*)(hf ? line - (size_t)4 * 32 * BT_LINE16 : line + (size_t)4 * 32 * BT_LINE16);
     } else {
-      const float* partner = hf ? strip - (size_t)4 * 32 * BT_STRIP_LD : strip + (size_t)4 * 32 * BT_STRIP_LD;   // same row: same lane of warp +- 4
-      wr_o = strip; wr_s = strip + 64; rd_o = partner; rd_s = partner + 64;
+      wr_o = strip;
+      rd_o = hf ? strip - (size_t)4 * 32 * BT_STRIP_LD : strip + (size_t)4 * 32 * BT_STRIP_LD;
     }
+    float* wr_s = wr_o + 32;
+    const float* rd_s = rd_o + 32;
 #pragma unroll
     for (int k = 0; k < 8; k++)
       *(float4*)(wr_o + 4 * k) = make_float4(hf ? o[4 * k] : o[32 + 4 * k], hf ? o[4 * k + 1] : o[32 + 4 * k + 1],
@@ -318,7 +318,7 @@ attn_bert_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         *(uint4*)(orow + 8 * k) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");   // the merge buffer is the next item's q + u tile / strip lines
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // the partner has read this line before the next item's first skew overwrites it
     if (q4 == 0 && lane == 0 && NT <= 8) bt_mark(a.dbg, 256 * hf + 48 * kit + 41, kit);
     }   // items
   }
