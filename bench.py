@@ -439,6 +439,7 @@ def main():
     ap.add_argument('--batch', type=int, default=B_PER_GPU, help='c2: streams per GPU')
     ap.add_argument('--train-batch', type=int, default=32, help='c3: sequences per GPU and step')
     ap.add_argument('--bert-batch', type=int, default=512, help='c4: sequences per GPU and forward')
+    ap.add_argument('--bert-chunk', type=int, default=32, help='c4: sequences per activation chunk of the encoder forward (max_rows / 1024)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.workload == 'c1':

@@ -56,7 +56,7 @@ def measure(args, sample_clocks=True, cpu_leg=True):
     B, K, W = args.bert_batch, args.steps, max(args.warmup, 3)
     lib = _lib.load()
     cfg = multitask_config()
-    pm = get_multitask_model(V, cfg, pad_idx=1, dtype='bf16', device=local_rank, max_batch=B, max_seq=T, max_rows=32 * T, seed=0)
+    pm = get_multitask_model(V, cfg, pad_idx=1, dtype='bf16', device=local_rank, max_batch=B, max_seq=T, max_rows=getattr(args, 'bert_chunk', 32) * T, seed=0)
     e = pm._e
     gen = torch.Generator().manual_seed(1234 + rank)
     xh, ph = synthetic(B, gen)

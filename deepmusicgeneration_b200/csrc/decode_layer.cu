@@ -6,7 +6,7 @@
 //
 // The unfused path runs these as 6 dependent launches per layer (4 split-K GEMMs + 2 LayerNorms, ~6 us each: every one of them
 // is bound by its launch-to-launch latency chain, not by bytes or flops - profiles/README.md).  Here a CLUSTER of 8 CTAs owns 32
-// generation streams ("rows") for the whole chain, so nothing but those 16 rows ever has to be exchanged:
+// generation streams ("rows") for the whole chain, so nothing but those 32 rows ever has to be exchanged:
 //
 //  * operands are swapped: D[feature, row] = W[feature, k] * X[row, k]^T - the weights are the M = 64 / 128 operand of
 //    tcgen05.mma (K-major as nn.Linear stores them), the 32 rows are the N = 32 operand; accumulators live in TMEM, lane = feature.
@@ -15,16 +15,18 @@
 //    step of a k-block, times two alternating k-blocks for single-tile phases; tiles of a phase are interleaved) that the
 //    epilogue adds up;
 //  * every GEMM's output features are split over the 8 CTAs of the cluster, so each CTA streams 1/8 of the layer's weights
-//    (768 KB at C2) through an 8-stage TMA ring - the weight stream never waits for activations and runs ahead across phases;
-//  * the three exchanges per layer (out-projection -> LayerNorm, FFN-up -> FFN-down, FFN-down -> LayerNorm) go through small
-//    L2-resident scratch rows and a hardware cluster barrier (release / acquire); LayerNorm is computed redundantly by all 8 CTAs
-//    (32 x 512 elements), its fp32 result stays in registers as the residual of the next LayerNorm and is written as the bf16
-//    B operand straight into shared memory in the canonical 128B-swizzled K-major layout;
+//    (768 KB at C2) through a 10-stage TMA ring - the weight stream never waits for activations and runs ahead across phases;
+//  * the exchanges of a layer: out-projection -> LayerNorm 1 stays inside the cluster's shared memory (every CTA normalises the 64
+//    features it computed for all 32 rows; only the (mean, M2) pairs of the slices and then the finished bf16 / fp32 slices travel,
+//    over distributed shared memory); FFN-up -> FFN-down needs none (a CTA's GeLU slice is its own K slice of the split-K FFN-down);
+//    FFN-down -> LayerNorm 2 goes through an L2-resident scratch of partial sums and the second LayerNorm of the 4 rows a CTA owns
+//    is broadcast as the bf16 B operand into all 8 CTAs' shared memory (canonical 128B-swizzled K-major layout); four hardware
+//    cluster barriers (release / acquire) per layer;
 //  * launched with programmatic dependent launch: barrier init, TMEM allocation and the first weight tiles overlap the tail of
 //    the attention kernel.
 //
-// Warp roles: warp 0 = TMA producer (one lane), warps 1-4 = tcgen05.mma issuers (one lane each, round-robin over stage uses: at this tile size
-// the scalar issue loop of ONE thread - barrier wait, descriptors, commit - costs more than the tensor core needs per MMA),
+// Warp roles: warp 0 = TMA producer (eight lanes per round of stage uses), warps 1-2 = tcgen05.mma issuers (stage uses alternate between
+// them; each runs its loop as a whole warp in uniform control flow and its elected lane issues the four K steps of a k-block),
 // the last 8 warps = TMEM epilogues + LayerNorm.
 // Grid: 8 CTAs per 32 streams - 64 CTAs at the benchmark's 256 streams (at most 15 clusters of 8 are co-resident on a B200, so
 // 16-row clusters would run in two waves).
@@ -164,13 +166,15 @@ __device__ __forceinline__ void dl_st_cluster_v4(uint32_t addr, uint4 v) {
 
 // Phases of one launch (body = bit 0 of mode, next = bit 1):
 //   A  out-projection        64 features per CTA  x K = HD     B operand: the attention output rows (TMA -> XA)
-//      LayerNorm 1           all 32 rows in every CTA (redundant; the rows a CTA owns also go to X1 as fp32)
+//      LayerNorm 1           column-sliced: the CTA's 64 features of all 32 rows; statistics merged over DSMEM; the bf16 slice goes to every
+//                            CTA's XA, the fp32 slice to the X1 of the row's LayerNorm-2 owner
 //   B  FFN-up + GeLU         256 features per CTA x K = 512    B operand: XA;  result stays in this CTA's shared memory (HS)
 //   C  FFN-down, split-K     all 512 features     x K = this CTA's 256 GeLU features (HS); partial sums -> global scratch
 //      LayerNorm 2           each CTA reduces the 8 partials of its OWN 4 rows, normalises, broadcasts the bf16 rows into the XA
 //                            of all 8 CTAs through distributed shared memory
 //   D  next layer's q|k|v    192 features per CTA x K = 512    B operand: XA
-// Three cluster barriers per launch: #1 projection slices published, #2 partial sums published, #3 XA broadcast done.
+// Four cluster barriers per launch: #1 slice statistics published, #2 LayerNorm-1 slices in every XA / X1, #3 partial sums published,
+// #4 LayerNorm-2 broadcast done.
 // `cluster` = index of this CTA's cluster among the clusters of the fused role (the stand-alone kernel: blockIdx.x / 8).
 __device__ __forceinline__ void decode_layer_body(const CUtensorMap& tmAttn, const CUtensorMap& tmWo, const CUtensorMap& tmW1,
                                                   const CUtensorMap& tmW2, const CUtensorMap& tmWq, const DecodeLayerArgs& a_in, int cluster,
