@@ -6,7 +6,9 @@
 //   j <= i   : BD[i, j] = (q_i + v)     . Rk[i - j]                (line 1)
 //   j == i+1 : BD[i, j] = 0                                        (line 2, the zero pad)
 //   j >  i+1 : BD[i, j] = (q_{i+1} + v) . Rk[T + 1 + i - j]        (line 3: the NEXT query row, wrapped distance)
-// Same scheme as attn_train_fwd_tc_kernel (attention_train_tc.cu): one CTA per (stream, head, 128-query tile), row-per-thread
+// Same scheme as attn_train_fwd_tc_kernel (attention_train_tc.cu) per work item (stream, head, 128-query tile) - but the grid is
+// PERSISTENT: one CTA per SM walks its items, barriers / buffers / TMEM carry over, the next item's operands are prepared under the
+// current item's last tile (attention_bert_tc_common.cuh).  Row-per-thread
 // softmax warps, AC and a 256-column position strip in TMEM, skew through thread-private shared-memory lines, P as the A operand
 // of the PV MMA.  The strip is strip[r][c] = BD[r, jj] with c = 128 + r - jj; below the diagonal both 128-column halves come from
 // (q+v) and two consecutive 128-row blocks of Rk, above it from (q_next+v) and blocks of Rk3[x] = Rk[x + T + 1 - 128 nT] (nT key tiles;

@@ -1,6 +1,5 @@
-// Shared by the tcgen05 attention kernels of the masked-BERT remix encoder (attention_bert_tc.cu: eight softmax warps;
-// attention_bert_tc16.cu: sixteen): the operand tiles in shared memory, the TMEM columns, the mbarriers, the TMA producer and the MMA
-// issuer.  Replaces MemMultiHeadRelativeAttentionKV._apply_attention (deep_music_remix.py:2078-2104); the scheme is described at the
+// The roles around the softmax warps of the tcgen05 attention kernel of the masked-BERT remix encoder (attention_bert_tc.cu): the operand
+// tiles in shared memory, the TMEM columns, the mbarriers, the TMA producer, the q-transform warps and the MMA issuer.  Replaces MemMultiHeadRelativeAttentionKV._apply_attention (deep_music_remix.py:2078-2104); the scheme is described at the
 // top of attention_bert_tc.cu.
 #pragma once
 #include <cuda.h>
